@@ -1,0 +1,344 @@
+"""ctypes binding of the CPU oracle (oracle/tdoa_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(tdoa-geolocation_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "libtdoa_oracle.so"
+REF_BINARY = _HERE / "_ref" / "processor"
+
+
+def build(force: bool = False) -> Path:
+    """Compile the oracle (and stage oracle/_ref when /root/reference exists)."""
+    src = _HERE / "tdoa_oracle.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "libtdoa_oracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    if Path("/root/reference/processor").exists():
+        subprocess.run(["make", "-C", str(_HERE), "ref"], check=True, stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+_i64 = C.c_int64
+_f64 = C.c_double
+_vp = C.c_void_p
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_LIB_PATH))
+        L = _lib
+        L.orc_unpack_u8.argtypes = [_vp, _i64, _vp]
+        L.orc_extract_reference.argtypes = [_vp, _i64, _vp]
+        L.orc_extract_reference.restype = _i64
+        L.orc_extract_target.argtypes = [_vp, _i64, _vp]
+        L.orc_extract_target.restype = _i64
+        L.orc_signal_power.argtypes = [_vp, _i64]
+        L.orc_signal_power.restype = _f64
+        L.orc_remove_dc.argtypes = [_vp, _i64, _vp, _vp]
+        L.orc_lowpass.argtypes = [_vp, _i64, C.c_int, _vp]
+        L.orc_cutoff_window.argtypes = [_f64, _f64]
+        L.orc_cutoff_window.restype = C.c_int
+        L.orc_bandpass.argtypes = [_vp, _i64, _f64, _f64, _f64, _vp]
+        L.orc_notch.argtypes = [_vp, _i64, _f64, _f64, _f64, _vp]
+        L.orc_normalize.argtypes = [_vp, _i64, _vp]
+        L.orc_normalize.restype = _f64
+        L.orc_enhance_weak.argtypes = [_vp, _i64, _vp]
+        L.orc_preprocess_source.argtypes = [_vp, _i64, _vp]
+        L.orc_preprocess_source.restype = C.c_int
+        L.orc_discriminator.argtypes = [_vp, _i64, _vp]
+        L.orc_envelope.argtypes = [_vp, _i64, _vp]
+        L.orc_preprocess_binary.argtypes = [_vp, _i64, _vp]
+        L.orc_preprocess_binary.restype = C.c_int
+        L.orc_tdcorr_source.argtypes = [_vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp]
+        L.orc_tdcorr_source.restype = _i64
+        L.orc_tdcorr_binary.argtypes = [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]
+        L.orc_tdcorr_binary.restype = _i64
+        L.orc_cross_correlate_source.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp]
+        L.orc_cross_correlate_binary.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _vp]
+        L.orc_tdcorr_binary_lags_mt.argtypes = [_vp, _i64, _vp, _i64, _i64, _i64, _vp]
+        L.orc_xcorr_two_sided.argtypes = [_vp, _vp, _i64, _i64, _vp]
+        L.orc_peak_parabolic.argtypes = [_vp, _i64, _vp, _vp, _vp]
+        L.orc_llh_to_ecef.argtypes = [_f64, _f64, _f64, _vp]
+        L.orc_ecef_to_llh.argtypes = [_f64, _f64, _f64, _vp]
+        L.orc_baseline.argtypes = [_vp, _vp]
+        L.orc_baseline.restype = _f64
+        L.orc_solve_tdoa.argtypes = [_vp, _vp, _vp, _vp]
+        L.orc_solve_tdoa.restype = C.c_int
+        L.orc_grid_solve.argtypes = [_vp, C.c_int, _vp, _f64, _f64, _f64, _f64, C.c_int, C.c_int,
+                                     _f64, _vp, _vp, _vp]
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+def _c64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.complex64)
+
+
+# ------------------------------------------------------------------ load
+def unpack_u8(raw: np.ndarray) -> np.ndarray:
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    n = raw.size // 2
+    out = np.empty(n, np.complex64)
+    lib().orc_unpack_u8(_p(raw), n, _p(out))
+    return out
+
+
+def extract_reference(data: np.ndarray) -> np.ndarray:
+    data = _c64(data)
+    out = np.empty(max(data.size, 1), np.complex64)
+    n = lib().orc_extract_reference(_p(data), data.size, _p(out))
+    return out[:n].copy()
+
+
+def extract_target(data: np.ndarray) -> np.ndarray:
+    data = _c64(data)
+    out = np.empty(max(data.size, 1), np.complex64)
+    n = lib().orc_extract_target(_p(data), data.size, _p(out))
+    return out[:n].copy()
+
+
+# ------------------------------------------------------------ primitives
+def signal_power(s) -> float:
+    s = _c64(s)
+    return lib().orc_signal_power(_p(s), s.size)
+
+
+def remove_dc(s):
+    s = _c64(s)
+    out = np.empty_like(s)
+    dc = np.zeros(1, np.complex64)
+    lib().orc_remove_dc(_p(s), s.size, _p(out), _p(dc))
+    return out, dc[0]
+
+
+def lowpass(s, window: int):
+    s = _c64(s)
+    out = np.empty_like(s)
+    lib().orc_lowpass(_p(s), s.size, int(window), _p(out))
+    return out
+
+
+def cutoff_window(cutoff: float, fs: float) -> int:
+    return lib().orc_cutoff_window(cutoff, fs)
+
+
+def bandpass(s, lo, hi, fs):
+    s = _c64(s)
+    out = np.empty_like(s)
+    lib().orc_bandpass(_p(s), s.size, lo, hi, fs, _p(out))
+    return out
+
+
+def notch(s, f0, bw, fs):
+    s = _c64(s)
+    out = np.empty_like(s)
+    lib().orc_notch(_p(s), s.size, f0, bw, fs, _p(out))
+    return out
+
+
+def normalize(s):
+    s = _c64(s)
+    out = np.empty_like(s)
+    p = lib().orc_normalize(_p(s), s.size, _p(out))
+    return out, p
+
+
+def preprocess_source(s):
+    s = _c64(s)
+    out = np.empty_like(s)
+    br = lib().orc_preprocess_source(_p(s), s.size, _p(out))
+    return out, br
+
+
+def discriminator(s):
+    s = _c64(s)
+    out = np.empty_like(s)
+    lib().orc_discriminator(_p(s), s.size, _p(out))
+    return out
+
+
+def envelope(s):
+    s = _c64(s)
+    out = np.empty_like(s)
+    lib().orc_envelope(_p(s), s.size, _p(out))
+    return out
+
+
+def preprocess_binary(s):
+    s = _c64(s)
+    out = np.empty_like(s)
+    br = lib().orc_preprocess_binary(_p(s), s.size, _p(out))
+    return out, br
+
+
+# ----------------------------------------------------------- correlators
+def tdcorr_source(s1, s2, max_lag=20000, block=1000, want_all=False):
+    s1, s2 = _c64(s1), _c64(s2)
+    d = np.zeros(1, np.int64)
+    c = np.zeros(1, np.float64)
+    allv = np.zeros(max(int(max_lag), 1), np.float64) if want_all else None
+    n = lib().orc_tdcorr_source(_p(s1), s1.size, _p(s2), s2.size, max_lag, block, _p(d), _p(c),
+                                _p(allv) if want_all else None)
+    if want_all:
+        return int(d[0]), float(c[0]), allv[:n]
+    return int(d[0]), float(c[0])
+
+
+def tdcorr_binary(s1, s2, max_lag=2000, block=10000, sanity=120, want_all=False):
+    s1, s2 = _c64(s1), _c64(s2)
+    d = np.zeros(1, np.int64)
+    c = np.zeros(1, np.float64)
+    r = np.zeros(1, np.int32)
+    allv = np.zeros(max(int(max_lag), 1), np.float64) if want_all else None
+    n = lib().orc_tdcorr_binary(_p(s1), s1.size, _p(s2), s2.size, max_lag, block, sanity,
+                                _p(d), _p(c), _p(r), _p(allv) if want_all else None)
+    if want_all:
+        return int(d[0]), float(c[0]), bool(r[0]), allv[:n]
+    return int(d[0]), float(c[0]), bool(r[0])
+
+
+def cross_correlate_source(s1, s2):
+    s1, s2 = _c64(s1), _c64(s2)
+    d = np.zeros(1, np.int64)
+    c = np.zeros(1, np.float64)
+    lib().orc_cross_correlate_source(_p(s1), s1.size, _p(s2), s2.size, _p(d), _p(c))
+    return int(d[0]), float(c[0])
+
+
+def cross_correlate_binary(s1, s2):
+    s1, s2 = _c64(s1), _c64(s2)
+    d = np.zeros(1, np.int64)
+    c = np.zeros(1, np.float64)
+    r = np.zeros(1, np.int32)
+    lib().orc_cross_correlate_binary(_p(s1), s1.size, _p(s2), s2.size, _p(d), _p(c), _p(r))
+    return int(d[0]), float(c[0]), bool(r[0])
+
+
+def tdcorr_binary_lags_mt(tpl, sig, tl_eff, n_lags, block=10000):
+    tpl, sig = _c64(tpl), _c64(sig)
+    out = np.zeros(n_lags, np.float64)
+    lib().orc_tdcorr_binary_lags_mt(_p(tpl), tl_eff, _p(sig), sig.size, n_lags, block, _p(out))
+    return out
+
+
+def xcorr_two_sided(y1, y2, max_lag: int):
+    y1, y2 = _c64(y1), _c64(y2)
+    assert y1.size == y2.size
+    out = np.zeros(2 * max_lag + 1, np.float64)
+    lib().orc_xcorr_two_sided(_p(y1), _p(y2), y1.size, max_lag, _p(out))
+    return out
+
+
+def peak_parabolic(c):
+    c = np.ascontiguousarray(c, np.float64)
+    i = np.zeros(1, np.int64)
+    f = np.zeros(1, np.float64)
+    v = np.zeros(1, np.float64)
+    lib().orc_peak_parabolic(_p(c), c.size, _p(i), _p(f), _p(v))
+    return int(i[0]), float(f[0]), float(v[0])
+
+
+# --------------------------------------------------------------- geodesy
+def llh_to_ecef(lat, lon, elev):
+    out = np.zeros(3, np.float64)
+    lib().orc_llh_to_ecef(lat, lon, elev, _p(out))
+    return out
+
+
+def ecef_to_llh(x, y, z):
+    out = np.zeros(3, np.float64)
+    lib().orc_ecef_to_llh(x, y, z, _p(out))
+    return out
+
+
+def baseline(llh1, llh2) -> float:
+    a = np.ascontiguousarray(llh1, np.float64)
+    b = np.ascontiguousarray(llh2, np.float64)
+    return lib().orc_baseline(_p(a), _p(b))
+
+
+def solve_tdoa(stations_llh, range_diffs):
+    st = np.ascontiguousarray(stations_llh, np.float64)
+    rd = np.ascontiguousarray(range_diffs, np.float64)
+    out = np.zeros(3, np.float64)
+    it = np.zeros(1, np.int32)
+    status = lib().orc_solve_tdoa(_p(st), _p(rd), _p(out), _p(it))
+    return out, status, int(it[0])
+
+
+def grid_solve(stations_llh, range_diffs, lat0, lon0, dlat, dlon, nlat, nlon, elev):
+    st = np.ascontiguousarray(stations_llh, np.float64)
+    rd = np.ascontiguousarray(range_diffs, np.float64)
+    idx = np.zeros(1, np.int64)
+    cost = np.zeros(1, np.float64)
+    llh = np.zeros(3, np.float64)
+    lib().orc_grid_solve(_p(st), st.shape[0], _p(rd), lat0, lon0, dlat, dlon, nlat, nlon, elev,
+                         _p(idx), _p(cost), _p(llh))
+    return int(idx[0]), float(cost[0]), llh
+
+
+# ------------------------------------------------ whole-capture drivers
+def process_capture_binary(raws, chunk=1_000_000):
+    """BINARY ProcessTDOA pair loops (ELF ProcessTDOA; pair order processor.go:816-817).
+
+    raws: list of uint8 arrays (one .dat per station).  Returns (ref, tgt) lists of
+    (delay, corr, researched) in i<j lexicographic order.
+    """
+    refs, tgts = [], []
+    for raw in raws:
+        data = unpack_u8(raw)
+        refs.append(extract_reference(data)[:chunk])
+        tgts.append(extract_target(data)[:chunk])
+    out_ref, out_tgt = [], []
+    n = len(raws)
+    for i in range(n):
+        for j in range(i + 1, n):
+            out_ref.append(cross_correlate_binary(refs[i], refs[j]))
+    for i in range(n):
+        for j in range(i + 1, n):
+            out_tgt.append(cross_correlate_binary(tgts[i], tgts[j]))
+    return out_ref, out_tgt
+
+
+def process_capture_source(raws, chunk=2_000_000):
+    """SOURCE ProcessTDOA pair loops (processor.go:756-850)."""
+    refs, tgts = [], []
+    for raw in raws:
+        data = unpack_u8(raw)
+        refs.append(extract_reference(data)[:chunk])
+        tgts.append(extract_target(data)[:chunk])
+    out_ref, out_tgt = [], []
+    n = len(raws)
+    for i in range(n):
+        for j in range(i + 1, n):
+            out_ref.append(cross_correlate_source(refs[i], refs[j]))
+    for i in range(n):
+        for j in range(i + 1, n):
+            out_tgt.append(cross_correlate_source(tgts[i], tgts[j]))
+    return out_ref, out_tgt
+
+
+def run_reference_binary(dat_paths, csv_path, ref_hz="162400000", tgt_hz="92300000", timeout=600):
+    """Run the staged reference ELF (oracle/_ref/processor); returns its stdout."""
+    if not REF_BINARY.exists():
+        raise FileNotFoundError(str(REF_BINARY))
+    res = subprocess.run([str(REF_BINARY), ref_hz, tgt_hz, str(csv_path), *map(str, dat_paths)],
+                         capture_output=True, text=True, timeout=timeout)
+    return res.stdout, res.stderr, res.returncode

@@ -1,0 +1,613 @@
+/*
+ * tdoa_oracle.c -- CPU restatement of the reference's TDOA processing path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under tdoa-geolocation_b200/ may include,
+ * link or call this file; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, and only as the checker.
+ *
+ * Two reference revisions are restated ("Oracle"):
+ *   SOURCE  = /root/reference/processor.go as committed (complex64 path, box-car
+ *             filters, 1000-sample blocks, sqrt(N) gain, 2x2 damped Newton).
+ *   BINARY  = /root/reference/processor (shipped ELF, Go 1.22.2) whose hot path
+ *             was recovered from its disassembly: 3-way preprocess (FM
+ *             discriminator / envelope / weak band-pass), real-only
+ *             correlator over a template shortened by maxLag, 10000-sample
+ *             blocks, 120-sample sanity re-search.
+ * Parity status: PINNED for the BINARY correlator/preprocess (golden stdout of
+ * the shipped binary, tests/golden/), for geodesy (PROJECT_NOTES.md:25-27) and
+ * for the us->m diagnostic (processor.go:885-889).  The SOURCE solver, the
+ * extended two-sided/sub-sample definitions and the grid solve have no
+ * runnable reference here ("parity unpinned" rows).
+ *
+ * Go numeric semantics that matter:
+ *   - complex64 +,- are component-wise f32; complex64 * is computed in f64 and
+ *     rounded once to f32; complex64 / complex(f32(n),0) is a correctly rounded
+ *     f32 divide per component (f64 quotient of f32 operands, rounded to f32).
+ *   - amd64 Go never fuses a*b+c: build with -ffp-contract=off.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { float re, im; } c64;
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------ load */
+
+/* processor.go:193-201  loadIQData: (f32(b) - 127.5) / 127.5, true division. */
+ORC_API void orc_unpack_u8(const uint8_t *raw, int64_t nsamp, c64 *out)
+{
+    for (int64_t i = 0; i < nsamp; i++) {
+        float iv = ((float)raw[2 * i] - 127.5f) / 127.5f;
+        float qv = ((float)raw[2 * i + 1] - 127.5f) / 127.5f;
+        out[i].re = iv;
+        out[i].im = qv;
+    }
+}
+
+/* processor.go:208-238  extractReferenceSignal: blocks 1 and 3 concatenated. */
+ORC_API int64_t orc_extract_reference(const c64 *data, int64_t n, c64 *out)
+{
+    int64_t b = n / 3;
+    if (b == 0) { memcpy(out, data, (size_t)n * sizeof(c64)); return n; }
+    memcpy(out, data, (size_t)b * sizeof(c64));
+    memcpy(out + b, data + 2 * b, (size_t)b * sizeof(c64));
+    return 2 * b;
+}
+
+/* processor.go:241-267  extractTargetSignal: block 2. */
+ORC_API int64_t orc_extract_target(const c64 *data, int64_t n, c64 *out)
+{
+    int64_t b = n / 3;
+    if (b == 0) { memcpy(out, data, (size_t)n * sizeof(c64)); return n; }
+    memcpy(out, data + b, (size_t)b * sizeof(c64));
+    return b;
+}
+
+/* ------------------------------------------------------------ primitives */
+
+/* processor.go:322-333  calculateSignalPower: f32 re*re+im*im, f64 running sum. */
+ORC_API double orc_signal_power(const c64 *s, int64_t n)
+{
+    if (n == 0) return 0.0;
+    double p = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        float a = s[i].re * s[i].re;
+        float b = s[i].im * s[i].im;
+        float t = a + b;
+        p += (double)t;
+    }
+    return p / (double)n;
+}
+
+static inline float div_f32_via_f64(float a, float c)
+{
+    /* runtime.complex128div with imag(m)==0 reduces to a/c in f64, then the
+     * result is narrowed to f32 (== correctly rounded f32 divide). */
+    return (float)((double)a / (double)c);
+}
+
+/* processor.go:299-319  removeDCBias: sequential complex64 sum, divide, subtract. */
+ORC_API void orc_remove_dc(const c64 *in, int64_t n, c64 *out, c64 *dc_out)
+{
+    c64 dc = {0.f, 0.f};
+    if (n == 0) { if (dc_out) *dc_out = dc; return; }
+    float sr = 0.f, si = 0.f;
+    for (int64_t i = 0; i < n; i++) { sr += in[i].re; si += in[i].im; }
+    dc.re = div_f32_via_f64(sr, (float)n);
+    dc.im = div_f32_via_f64(si, (float)n);
+    for (int64_t i = 0; i < n; i++) {
+        out[i].re = in[i].re - dc.re;
+        out[i].im = in[i].im - dc.im;
+    }
+    if (dc_out) *dc_out = dc;
+}
+
+/* processor.go:270-296  applyLowPassFilter: centred box-car, edge-normalised,
+ * taps summed in ascending j starting from a zero accumulator. */
+ORC_API void orc_lowpass(const c64 *in, int64_t n, int window, c64 *out)
+{
+    if (window <= 1) { if (out != in) memcpy(out, in, (size_t)n * sizeof(c64)); return; }
+    int64_t h = window / 2;
+    for (int64_t i = 0; i < n; i++) {
+        float sr = 0.f, si = 0.f;
+        int64_t lo = i - h, hi = i + h, cnt = 0;
+        if (lo < 0) lo = 0;
+        if (hi > n - 1) hi = n - 1;
+        for (int64_t j = lo; j <= hi; j++) { sr += in[j].re; si += in[j].im; cnt++; }
+        if (cnt > 0) {
+            out[i].re = div_f32_via_f64(sr, (float)cnt);
+            out[i].im = div_f32_via_f64(si, (float)cnt);
+        } else {
+            out[i].re = 0.f; out[i].im = 0.f;
+        }
+    }
+}
+
+/* processor.go:397-409: window = int(fs/(2 fc)) clamped to [3,1000]. */
+ORC_API int orc_cutoff_window(double cutoff, double fs)
+{
+    int w = (int)(fs / (2 * cutoff));
+    if (w < 3) w = 3;
+    if (w > 1000) w = 1000;
+    return w;
+}
+
+static void lowpass_cutoff(const c64 *in, int64_t n, double fc, double fs, c64 *out)
+{
+    orc_lowpass(in, n, orc_cutoff_window(fc, fs), out);
+}
+
+/* processor.go:384-394  applyHighPassFilter: s - LP(s). */
+static void highpass(const c64 *in, int64_t n, double fc, double fs, c64 *out)
+{
+    c64 *lp = (c64 *)malloc((size_t)(n ? n : 1) * sizeof(c64));
+    lowpass_cutoff(in, n, fc, fs, lp);
+    for (int64_t i = 0; i < n; i++) {
+        out[i].re = in[i].re - lp[i].re;
+        out[i].im = in[i].im - lp[i].im;
+    }
+    free(lp);
+}
+
+/* processor.go:354-381  applyBandpassFilter: HP(lo) if lo>0, LP(hi) if hi<fs/2. */
+ORC_API void orc_bandpass(const c64 *in, int64_t n, double lo, double hi, double fs, c64 *out)
+{
+    if (n == 0) return;
+    c64 *tmp = (c64 *)malloc((size_t)n * sizeof(c64));
+    if (lo > 0) highpass(in, n, lo, fs, tmp);
+    else memcpy(tmp, in, (size_t)n * sizeof(c64));
+    if (hi < fs / 2) lowpass_cutoff(tmp, n, hi, fs, out);
+    else memcpy(out, tmp, (size_t)n * sizeof(c64));
+    free(tmp);
+}
+
+/* processor.go:412-434  applyNotchFilter: s - 0.8*BP(f0 +- bw/2)(s).  The 0.8 is
+ * a complex64 constant (0.8f+0i): product in f64, one rounding == f32 multiply. */
+ORC_API void orc_notch(const c64 *in, int64_t n, double f0, double bw, double fs, c64 *out)
+{
+    double lo = f0 - bw / 2, hi = f0 + bw / 2;
+    if (lo < 0) lo = 0;
+    if (hi > fs / 2) hi = fs / 2;
+    c64 *band = (c64 *)malloc((size_t)(n ? n : 1) * sizeof(c64));
+    orc_bandpass(in, n, lo, hi, fs, band);
+    const float k = 0.8f;
+    for (int64_t i = 0; i < n; i++) {
+        float br = (float)((double)band[i].re * (double)k);
+        float bi = (float)((double)band[i].im * (double)k);
+        out[i].re = in[i].re - br;
+        out[i].im = in[i].im - bi;
+    }
+    free(band);
+}
+
+/* processor.go:336-351  normalizeSignal: scale = f32(1/sqrt(power)). */
+ORC_API double orc_normalize(const c64 *in, int64_t n, c64 *out)
+{
+    double p = orc_signal_power(in, n);
+    if (p <= 0) { if (out != in) memcpy(out, in, (size_t)n * sizeof(c64)); return p; }
+    float scale = (float)(1.0 / sqrt(p));
+    for (int64_t i = 0; i < n; i++) {
+        out[i].re = in[i].re * scale;
+        out[i].im = in[i].im * scale;
+    }
+    return p;
+}
+
+/* ------------------------------------------------- SOURCE preprocessing */
+
+/* processor.go:437-466  enhanceWeakSignal. */
+ORC_API void orc_enhance_weak(const c64 *in, int64_t n, c64 *out)
+{
+    const double fs = 2000000.0;
+    c64 *a = (c64 *)malloc((size_t)(n ? n : 1) * sizeof(c64));
+    c64 *b = (c64 *)malloc((size_t)(n ? n : 1) * sizeof(c64));
+    orc_remove_dc(in, n, a, NULL);
+    orc_notch(a, n, 60, 5, fs, b);
+    orc_notch(b, n, 120, 5, fs, a);
+    orc_notch(a, n, 1000000, 50000, fs, b);
+    orc_bandpass(b, n, 100.0, 40000.0, fs, a);
+    orc_lowpass(a, n, 50, b);
+    orc_normalize(b, n, out);
+    free(a); free(b);
+}
+
+/* processor.go:469-499  preprocessSignal.  Returns 1 for the weak branch. */
+ORC_API int orc_preprocess_source(const c64 *in, int64_t n, c64 *out)
+{
+    double p = orc_signal_power(in, n);
+    if (p < 0.001) { orc_enhance_weak(in, n, out); return 1; }
+    c64 *a = (c64 *)malloc((size_t)(n ? n : 1) * sizeof(c64));
+    c64 *b = (c64 *)malloc((size_t)(n ? n : 1) * sizeof(c64));
+    orc_remove_dc(in, n, a, NULL);
+    orc_bandpass(a, n, 500, 50000, 2000000.0, b);
+    orc_lowpass(b, n, 100, a);
+    orc_normalize(a, n, out);
+    free(a); free(b);
+    return 0;
+}
+
+/* ------------------------------------------------- BINARY preprocessing */
+
+/* ELF 0x49d120  convertToInstantaneousFrequency (no source):
+ *   n<2 -> input returned; out[i] = atan2(Im p, Re p), p = s[i]*conj(s[i-1])
+ *   (f64 products, rounded once to f32); gates: s[i-1]==0, p==0, |p|^2<=1e-10f
+ *   leave out[i]=0; out[0]=out[1]. */
+ORC_API void orc_discriminator(const c64 *in, int64_t n, c64 *out)
+{
+    if (n < 2) { if (out != in) memcpy(out, in, (size_t)n * sizeof(c64)); return; }
+    const float gate = 1e-10f; /* 0x2EDBE6FF */
+    out[0].re = 0.f; out[0].im = 0.f;
+    for (int64_t i = 1; i < n; i++) {
+        out[i].re = 0.f; out[i].im = 0.f;
+        float pr = in[i - 1].re, pi = in[i - 1].im;
+        if (pr == 0.f && pi == 0.f) continue;
+        float cr = in[i].re, ci = in[i].im;
+        float npi = -pi;
+        double re = (double)pr * (double)cr - (double)ci * (double)npi;
+        double im = (double)npi * (double)cr + (double)ci * (double)pr;
+        float fre = (float)re, fim = (float)im;
+        if (fre == 0.f && fim == 0.f) continue;
+        float m = fre * fre;
+        float m2 = fim * fim;
+        m = m + m2;
+        if (!(m > gate)) continue;
+        out[i].re = (float)atan2((double)fim, (double)fre);
+    }
+    out[0] = out[1];
+}
+
+/* ELF 0x49d021  envelope: f32 sqrt(f32(re*re+im*im)). */
+ORC_API void orc_envelope(const c64 *in, int64_t n, c64 *out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        float a = in[i].re * in[i].re;
+        float b = in[i].im * in[i].im;
+        float s = a + b;
+        out[i].re = sqrtf(s);
+        out[i].im = 0.f;
+    }
+}
+
+/* ELF 0x49cd40  preprocessSignal (binary): power>0.01 strong, >0.001 moderate,
+ * else weak (removeDC -> bandpass(100,200000,2e6) -> normalise).
+ * Returns 0 strong / 1 moderate / 2 weak. */
+ORC_API int orc_preprocess_binary(const c64 *in, int64_t n, c64 *out)
+{
+    double p = orc_signal_power(in, n);
+    c64 *a = (c64 *)malloc((size_t)(n ? n : 1) * sizeof(c64));
+    c64 *b = (c64 *)malloc((size_t)(n ? n : 1) * sizeof(c64));
+    int branch;
+    if (p > 0.01) {
+        orc_discriminator(in, n, a);
+        orc_remove_dc(a, n, b, NULL);
+        orc_lowpass(b, n, 10, a);
+        orc_normalize(a, n, out);
+        branch = 0;
+    } else if (p > 0.001) {
+        orc_envelope(in, n, a);
+        orc_remove_dc(a, n, b, NULL);
+        orc_normalize(b, n, out);
+        branch = 1;
+    } else {
+        orc_remove_dc(in, n, a, NULL);
+        orc_bandpass(a, n, 100.0, 200000.0, 2000000.0, b);
+        orc_normalize(b, n, out);
+        branch = 2;
+    }
+    free(a); free(b);
+    return branch;
+}
+
+/* ---------------------------------------------------------- correlators */
+
+/* processor.go:646-736  timeDomainCorrelation (SOURCE).  `all` (optional) gets
+ * the correlation of every evaluated lag, length = returned lag count. */
+ORC_API int64_t orc_tdcorr_source(const c64 *s1, int64_t n1, const c64 *s2, int64_t n2,
+                                  int64_t max_lag, int64_t block, int64_t *delay_out,
+                                  double *corr_out, double *all)
+{
+    const c64 *tpl = s1, *sig = s2;
+    int64_t tl = n1, sl = n2;
+    if (n1 > n2) { tpl = s2; sig = s1; tl = n2; sl = n1; }
+    *delay_out = 0; *corr_out = 0.0;
+    if (tl > sl) return 0;
+    if (max_lag > sl - tl) max_lag = sl - tl;
+    if (max_lag < 1) max_lag = 1;
+    int64_t best_delay = 0; double best = 0.0;
+    for (int64_t d = 0; d < max_lag; d++) {
+        double corr = 0.0; int64_t nb = 0;
+        for (int64_t bs = 0; bs < tl - block; bs += block) {
+            int64_t be = bs + block;
+            if (d + be > sl) break;
+            double bc = 0.0;
+            for (int64_t i = bs; i < be; i++) {
+                float a = tpl[i].re * sig[d + i].re;
+                float b = tpl[i].im * sig[d + i].im;
+                float t = a + b;
+                bc += (double)t;
+            }
+            bc /= (double)block;
+            corr += bc;
+            nb++;
+        }
+        if (nb > 0) {
+            corr /= (double)nb;
+            corr *= sqrt((double)(nb * block));
+            if (fabs(corr) > fabs(best)) { best = corr; best_delay = d; }
+        }
+        if (all) all[d] = (nb > 0) ? corr : 0.0;
+    }
+    *delay_out = best_delay; *corr_out = best;
+    return max_lag;
+}
+
+/* one lag of the BINARY correlator (ELF 0x49e027 loop): real parts only. */
+static double binary_lag(const c64 *tpl, int64_t tl, const c64 *sig, int64_t sl,
+                         int64_t d, int64_t block, int64_t *nb_out)
+{
+    double corr = 0.0; int64_t nb = 0;
+    for (int64_t bs = 0; bs < tl - block; bs += block) {
+        if (d + bs + block > sl) break;
+        double bc = 0.0;
+        for (int64_t i = bs; i < bs + block; i++) {
+            float t = tpl[i].re * sig[d + i].re;
+            bc += (double)t;
+        }
+        bc /= (double)block;
+        corr += bc;
+        nb++;
+    }
+    if (nb > 0) corr /= (double)nb;
+    *nb_out = nb;
+    return corr;
+}
+
+/* ELF 0x49d6a0  timeDomainCorrelation (BINARY): equal lengths -> template
+ * shortened by max_lag; block 10000; no sqrt gain; if best delay > sanity(120)
+ * re-search [0,sanity) and accept it when |c| > 0.5*|best|.
+ * Returns number of lags evaluated in the first search; *researched = 1 when
+ * the sanity result replaced the first-pass peak. */
+ORC_API int64_t orc_tdcorr_binary(const c64 *s1, int64_t n1, const c64 *s2, int64_t n2,
+                                  int64_t max_lag, int64_t block, int64_t sanity,
+                                  int64_t *delay_out, double *corr_out, int *researched,
+                                  double *all)
+{
+    const c64 *tpl = s1, *sig = s2;
+    int64_t tl = n1, sl = n2;
+    if (n1 > n2) { tpl = s2; sig = s1; tl = n2; sl = n1; }
+    *delay_out = 0; *corr_out = 0.0; if (researched) *researched = 0;
+    if (sl < tl) return 0;
+    int64_t tl_eff = tl;
+    if (sl == tl) tl_eff = tl - max_lag;
+    int64_t ml = max_lag;
+    if (ml > sl - tl_eff) ml = sl - tl_eff;
+    if (ml <= 0) ml = 1;
+    int64_t best_delay = 0; double best = 0.0;
+    for (int64_t d = 0; d < ml; d++) {
+        int64_t nb;
+        double c = binary_lag(tpl, tl_eff, sig, sl, d, block, &nb);
+        if (nb > 0 && fabs(c) > fabs(best)) { best = c; best_delay = d; }
+        if (all) all[d] = (nb > 0) ? c : 0.0;
+    }
+    *delay_out = best_delay; *corr_out = best;
+    if (best_delay > sanity) {
+        /* ELF 0x49dda7: template length for the re-search is tl-2000 when the
+         * inputs have equal length (2000 is hard-coded there), else tl. */
+        int64_t tl2 = (sl == tl) ? tl - 2000 : tl;
+        int64_t rbest_delay = 0; double rbest = 0.0;
+        for (int64_t d = 0; d < sanity; d++) {
+            int64_t nb;
+            double c = binary_lag(tpl, tl2, sig, sl, d, block, &nb);
+            if (nb > 0 && fabs(c) > fabs(rbest)) { rbest = c; rbest_delay = d; }
+        }
+        if (rbest_delay < sanity && fabs(rbest) > 0.5 * fabs(best)) {
+            *delay_out = rbest_delay; *corr_out = rbest;
+            if (researched) *researched = 1;
+        }
+    }
+    return ml;
+}
+
+/* processor.go:619-643  crossCorrelate (SOURCE): preprocess both, maxLag 20000,
+ * block 1000. */
+ORC_API void orc_cross_correlate_source(const c64 *s1, int64_t n1, const c64 *s2, int64_t n2,
+                                        int64_t *delay, double *corr)
+{
+    *delay = 0; *corr = 0.0;
+    if (n1 == 0 || n2 == 0) return;
+    c64 *p1 = (c64 *)malloc((size_t)n1 * sizeof(c64));
+    c64 *p2 = (c64 *)malloc((size_t)n2 * sizeof(c64));
+    orc_preprocess_source(s1, n1, p1);
+    orc_preprocess_source(s2, n2, p2);
+    orc_tdcorr_source(p1, n1, p2, n2, 20000, 1000, delay, corr, NULL);
+    free(p1); free(p2);
+}
+
+/* BINARY crossCorrelate: 3-way preprocess, maxLag 2000, block 10000, sanity 120. */
+ORC_API void orc_cross_correlate_binary(const c64 *s1, int64_t n1, const c64 *s2, int64_t n2,
+                                        int64_t *delay, double *corr, int *researched)
+{
+    *delay = 0; *corr = 0.0; if (researched) *researched = 0;
+    if (n1 == 0 || n2 == 0) return;
+    c64 *p1 = (c64 *)malloc((size_t)n1 * sizeof(c64));
+    c64 *p2 = (c64 *)malloc((size_t)n2 * sizeof(c64));
+    orc_preprocess_binary(s1, n1, p1);
+    orc_preprocess_binary(s2, n2, p2);
+    orc_tdcorr_binary(p1, n1, p2, n2, 2000, 10000, 120, delay, corr, researched, NULL);
+    free(p1); free(p2);
+}
+
+/* Multi-threaded helper for the CPU baseline only: evaluates the BINARY
+ * correlator's first-pass lags with OpenMP over lags (the arithmetic of each
+ * lag is unchanged, so the result equals orc_tdcorr_binary's first pass). */
+ORC_API void orc_tdcorr_binary_lags_mt(const c64 *tpl, int64_t tl_eff, const c64 *sig, int64_t sl,
+                                       int64_t n_lags, int64_t block, double *all)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t d = 0; d < n_lags; d++) {
+        int64_t nb;
+        double c = binary_lag(tpl, tl_eff, sig, sl, d, block, &nb);
+        all[d] = (nb > 0) ? c : 0.0;
+    }
+}
+
+/* ------------------------------------------ extended (engine-defined) path
+ * No reference equivalent ("parity unpinned"): two-sided valid-support
+ * correlation of the real parts of two equal-length preprocessed chunks,
+ *   c(l) = (1/n) sum_{i<n} y1[L+i] * y2[L+i+l],  n = W-2L, l in [-L,+L],
+ * f64 accumulation of the exact f32xf32 products.  out has 2L+1 entries. */
+ORC_API void orc_xcorr_two_sided(const c64 *y1, const c64 *y2, int64_t w, int64_t max_lag,
+                                 double *out)
+{
+    int64_t n = w - 2 * max_lag;
+#pragma omp parallel for schedule(static)
+    for (int64_t l = -max_lag; l <= max_lag; l++) {
+        double acc = 0.0;
+        if (n > 0) {
+            const c64 *a = y1 + max_lag, *b = y2 + max_lag + l;
+            for (int64_t i = 0; i < n; i++) acc += (double)a[i].re * (double)b[i].re;
+            acc /= (double)n;
+        }
+        out[l + max_lag] = acc;
+    }
+}
+
+/* arg-max of |c| (strict >, ascending index => first maximum wins, as
+ * processor.go:722-725) with a 3-point parabolic vertex on |c|. */
+ORC_API void orc_peak_parabolic(const double *c, int64_t n, int64_t *idx_out, double *frac_out,
+                                double *val_out)
+{
+    int64_t best = 0; double bv = 0.0;
+    for (int64_t i = 0; i < n; i++)
+        if (fabs(c[i]) > fabs(bv)) { bv = c[i]; best = i; }
+    double frac = 0.0;
+    if (best > 0 && best < n - 1) {
+        double a = fabs(c[best - 1]), b = fabs(c[best]), d = fabs(c[best + 1]);
+        double den = a - 2 * b + d;
+        if (den != 0.0) frac = 0.5 * (a - d) / den;
+    }
+    *idx_out = best; *frac_out = frac; *val_out = bv;
+}
+
+/* --------------------------------------------------------------- geodesy */
+
+/* processor.go:125-148  latLonToECEF. */
+ORC_API void orc_llh_to_ecef(double lat, double lon, double elev, double *xyz)
+{
+    const double a = 6378137.0, f = 1.0 / 298.257223563;
+    double e2 = 2 * f - f * f;
+    double lr = lat * M_PI / 180, lo = lon * M_PI / 180;
+    double sl = sin(lr), cl = cos(lr), so = sin(lo), co = cos(lo);
+    double N = a / sqrt(1 - e2 * sl * sl);
+    xyz[0] = (N + elev) * cl * co;
+    xyz[1] = (N + elev) * cl * so;
+    xyz[2] = (N * (1 - e2) + elev) * sl;
+}
+
+/* processor.go:1023-1045  ecefToLatLon: 5 fixed iterations. */
+ORC_API void orc_ecef_to_llh(double x, double y, double z, double *llh)
+{
+    const double a = 6378137.0, f = 1.0 / 298.257223563, e2 = 2 * f - f * f;
+    double p = sqrt(x * x + y * y);
+    double lon = atan2(y, x);
+    double lat = atan2(z, p * (1 - e2));
+    for (int i = 0; i < 5; i++) {
+        double N = a / sqrt(1 - e2 * sin(lat) * sin(lat));
+        double elev = p / cos(lat) - N;
+        lat = atan2(z, p * (1 - e2 * N / (N + elev)));
+    }
+    double N = a / sqrt(1 - e2 * sin(lat) * sin(lat));
+    double elev = p / cos(lat) - N;
+    llh[0] = lat * 180.0 / M_PI; llh[1] = lon * 180.0 / M_PI; llh[2] = elev;
+}
+
+/* processor.go:151-163  distance3D / calculateBaseline. */
+ORC_API double orc_baseline(const double *llh1, const double *llh2)
+{
+    double p1[3], p2[3];
+    orc_llh_to_ecef(llh1[0], llh1[1], llh1[2], p1);
+    orc_llh_to_ecef(llh2[0], llh2[1], llh2[2], p2);
+    double dx = p2[0] - p1[0], dy = p2[1] - p1[1], dz = p2[2] - p1[2];
+    return sqrt(dx * dx + dy * dy + dz * dz);
+}
+
+/* processor.go:932-1020  solveTDOA: stations 0..2 only, rd[0], rd[1] only,
+ * 10 iterations, damped (0.5) 2x2 Newton in ECEF X,Y; Z frozen.
+ * Returns 0 ok, 1 singular Jacobian (|det|<1e-10). */
+ORC_API int orc_solve_tdoa(const double *st_llh, const double *rd, double *out_llh, int *iters)
+{
+    double s[3][3];
+    for (int k = 0; k < 3; k++) orc_llh_to_ecef(st_llh[3 * k], st_llh[3 * k + 1], st_llh[3 * k + 2], s[k]);
+    double clat = (st_llh[0] + st_llh[3] + st_llh[6]) / 3.0;
+    double clon = (st_llh[1] + st_llh[4] + st_llh[7]) / 3.0;
+    double cel = (st_llh[2] + st_llh[5] + st_llh[8]) / 3.0;
+    double x[3];
+    orc_llh_to_ecef(clat, clon, cel, x);
+    int it;
+    for (it = 0; it < 10; it++) {
+        double r[3];
+        for (int k = 0; k < 3; k++)
+            r[k] = sqrt((x[0] - s[k][0]) * (x[0] - s[k][0]) + (x[1] - s[k][1]) * (x[1] - s[k][1]) +
+                        (x[2] - s[k][2]) * (x[2] - s[k][2]));
+        double res1 = (r[1] - r[0]) - rd[0];
+        double res2 = (r[2] - r[0]) - rd[1];
+        if (fabs(res1) < 1.0 && fabs(res2) < 1.0) break;
+        double dx1 = (x[0] - s[0][0]) / r[0], dy1 = (x[1] - s[0][1]) / r[0];
+        double dx2 = (x[0] - s[1][0]) / r[1], dy2 = (x[1] - s[1][1]) / r[1];
+        double dx3 = (x[0] - s[2][0]) / r[2], dy3 = (x[1] - s[2][1]) / r[2];
+        double J11 = dx2 - dx1, J12 = dy2 - dy1, J21 = dx3 - dx1, J22 = dy3 - dy1;
+        double det = J11 * J22 - J12 * J21;
+        if (fabs(det) < 1e-10) { if (iters) *iters = it; return 1; }
+        double dx = (-res1 * J22 + res2 * J12) / det;
+        double dy = (res1 * J21 - res2 * J11) / det;
+        x[0] += 0.5 * dx;
+        x[1] += 0.5 * dy;
+    }
+    if (iters) *iters = it;
+    orc_ecef_to_llh(x[0], x[1], x[2], out_llh);
+    return 0;
+}
+
+/* ------------------------------------------------- grid multilateration
+ * No reference equivalent ("parity unpinned").  Cost of a cell =
+ *   sum over pairs i<j (lexicographic) of ((r_j - r_i) - rd_ij)^2, f64,
+ * cells at lat0+a*dlat, lon0+b*dlon, fixed elevation; arg-min with lowest
+ * linear index (a*nlon+b) winning ties. */
+ORC_API void orc_grid_solve(const double *st_llh, int n_st, const double *rd,
+                            double lat0, double lon0, double dlat, double dlon,
+                            int nlat, int nlon, double elev,
+                            int64_t *best_idx, double *best_cost, double *best_llh)
+{
+    double (*s)[3] = malloc(sizeof(double[3]) * (size_t)n_st);
+    for (int k = 0; k < n_st; k++) orc_llh_to_ecef(st_llh[3 * k], st_llh[3 * k + 1], st_llh[3 * k + 2], s[k]);
+    double *r = malloc(sizeof(double) * (size_t)n_st);
+    int64_t bi = -1; double bc = 0.0;
+    for (int a = 0; a < nlat; a++) {
+        for (int b = 0; b < nlon; b++) {
+            double x[3];
+            orc_llh_to_ecef(lat0 + a * dlat, lon0 + b * dlon, elev, x);
+            for (int k = 0; k < n_st; k++) {
+                double dx = x[0] - s[k][0], dy = x[1] - s[k][1], dz = x[2] - s[k][2];
+                r[k] = sqrt(dx * dx + dy * dy + dz * dz);
+            }
+            double cost = 0.0; int p = 0;
+            for (int i = 0; i < n_st; i++)
+                for (int j = i + 1; j < n_st; j++, p++) {
+                    double e = (r[j] - r[i]) - rd[p];
+                    cost += e * e;
+                }
+            int64_t idx = (int64_t)a * nlon + b;
+            if (bi < 0 || cost < bc) { bi = idx; bc = cost; }
+        }
+    }
+    *best_idx = bi; *best_cost = bc;
+    if (best_llh && bi >= 0) {
+        best_llh[0] = lat0 + (double)(bi / nlon) * dlat;
+        best_llh[1] = lon0 + (double)(bi % nlon) * dlon;
+        best_llh[2] = elev;
+    }
+    free(s); free(r);
+}
