@@ -1,0 +1,179 @@
+/*
+ * tdoa_b200.h -- C ABI of libtdoa_b200.so, the B200 (sm_100a) TDOA correlation engine.
+ *
+ * Drop-in boundary for the processing stage of KX0U-Jim/tdoa-geolocation.  The
+ * reference has no FFI seam of its own (a single `package main`), so each entry
+ * point below names the reference method it replaces (file:line in the reference
+ * tree).  Plain pointers and sizes only; the caller owns every host pointer and the
+ * library never retains one after a call returns (cgo pointer rules).
+ *
+ * Error convention: every function returns 0 on success or a negative TDOA_E_* code;
+ * tdoa_last_error() returns the message of the last failure on that engine
+ * (NULL engine: the last tdoa_create failure of the calling thread).  There is no
+ * CPU fallback: without an sm_100 device tdoa_create fails with TDOA_E_NODEVICE.
+ *
+ * Threading: one caller at a time per engine (the reference is single-threaded);
+ * every entry point selects the engine's device itself, so it is safe to call from
+ * migrating goroutines/threads without pinning.
+ */
+#ifndef TDOA_B200_H
+#define TDOA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDOA_API __attribute__((visibility("default")))
+
+/* error codes */
+#define TDOA_OK 0
+#define TDOA_E_INVALID (-1)   /* bad argument                                      */
+#define TDOA_E_NODEVICE (-2)  /* no sm_100 CUDA device / CUDA runtime unusable     */
+#define TDOA_E_CUDA (-3)      /* a CUDA call failed (message has the CUDA error)   */
+#define TDOA_E_NOMEM (-4)     /* device or pinned-host allocation failed           */
+#define TDOA_E_STATE (-5)     /* call sequence error (e.g. station not loaded)     */
+#define TDOA_E_SINGULAR (-6)  /* solveTDOA: singular Jacobian (processor.go:997)   */
+
+/* processing modes (tdoa_config.mode) */
+#define TDOA_MODE_SOURCE 0   /* processor.go as committed: complex64 box-car path,
+                                1000-sample blocks, sqrt(N) gain, maxLag 20000      */
+#define TDOA_MODE_BINARY 1   /* shipped `processor` ELF: FM discriminator / envelope /
+                                weak 3-way preprocess, real correlator over a template
+                                shortened by maxLag, 10000-sample blocks, 120-sample
+                                sanity re-search                                     */
+#define TDOA_MODE_EXTENDED 2 /* BINARY preprocessing + two-sided lag search with
+                                parabolic sub-sample refinement (engine-defined)     */
+
+/* signal kinds of the dual-frequency capture (processor.go:208-267) */
+#define TDOA_KIND_REF 0 /* blocks 1 and 3 concatenated */
+#define TDOA_KIND_TGT 1 /* block 2 */
+
+/* tdoa_peak.flags */
+#define TDOA_PEAK_RESEARCHED 0x1u /* sanity re-search replaced the first-pass peak   */
+#define TDOA_PEAK_EDGE 0x2u       /* peak on the edge of the lag range (frac = 0)    */
+#define TDOA_PEAK_BRUTE 0x4u      /* every lag was evaluated in the time domain      */
+#define TDOA_PEAK_EMPTY 0x8u      /* empty input: (0, 0.0) as processor.go:622-625   */
+#define TDOA_PEAK_BRANCH1(f) (((f) >> 8) & 3u)  /* preprocess branch of signal 1      */
+#define TDOA_PEAK_BRANCH2(f) (((f) >> 10) & 3u) /* 0 strong/std, 1 moderate, 2 weak   */
+
+typedef struct tdoa_engine tdoa_engine; /* opaque: device memory, streams, plans */
+
+/* One correlation peak; 32 bytes; also the record exchanged between GPUs. */
+typedef struct {
+    int32_t lag;       /* integer lag of the peak, samples (delay of signal 2)       */
+    uint32_t flags;    /* TDOA_PEAK_*                                                */
+    double corr;       /* correlation at the peak, signed (the Go float64 return)    */
+    float frac;        /* sub-sample offset in [-0.5,0.5]; 0 in SOURCE/BINARY modes  */
+    float margin;      /* (|peak|-|runner-up|)/|peak| among exactly evaluated lags   */
+    int32_t first_lag; /* first-pass lag before the sanity re-search                 */
+    int32_t n_blocks;  /* whole blocks that contributed (processor.go:691-712)       */
+} tdoa_peak;
+
+typedef struct {
+    double sample_rate;    /* 2e6 (processor.go:821)                                 */
+    int32_t mode;          /* TDOA_MODE_*                                            */
+    int32_t n_stations;    /* stations the engine holds (>= 2)                       */
+    int32_t chunk_samples; /* "test chunk": 2000000 source (processor.go:772),
+                              1000000 binary; 0 = whole signal                       */
+    int32_t max_lag;       /* 20000 source (processor.go:633), 2000 binary;
+                              EXTENDED: lags -max_lag..+max_lag                      */
+    int32_t block_size;    /* 1000 source (processor.go:682), 10000 binary           */
+    int32_t sanity_lag;    /* 120 (binary re-search window); 0 disables              */
+    int32_t fast_demod;    /* 0: f64 products + f64 atan2 as the reference;
+                              1: f32 discriminator (<= 2 ulp), EXTENDED only default */
+    int32_t use_fft;       /* 1: FFT candidate search + exact re-evaluation;
+                              0: evaluate every lag in the time domain               */
+    int32_t device;        /* CUDA device ordinal                                    */
+    int32_t reserved[7];
+} tdoa_config;
+
+/* Fill *cfg with the reference-matching defaults of `mode`. */
+TDOA_API int tdoa_default_config(int32_t mode, tdoa_config *cfg);
+
+TDOA_API int tdoa_create(tdoa_engine **out, const tdoa_config *cfg);
+TDOA_API void tdoa_destroy(tdoa_engine *e);
+TDOA_API const char *tdoa_last_error(const tdoa_engine *e);
+
+/* Pinned host buffers for callers that want full PCIe rate (optional). */
+TDOA_API void *tdoa_host_alloc(size_t nbytes);
+TDOA_API void tdoa_host_free(void *p);
+
+/* loadIQData + extractReferenceSignal + extractTargetSignal (processor.go:166-267):
+ * hands one station's whole .dat capture (interleaved uint8 I,Q) to the engine.
+ * The bytes are copied to the device before the call returns. */
+TDOA_API int tdoa_load_u8(tdoa_engine *e, int32_t station, const uint8_t *iq, size_t nbytes);
+/* Same, capture already resident in device memory; not copied, caller keeps it alive. */
+TDOA_API int tdoa_load_u8_device(tdoa_engine *e, int32_t station, const uint8_t *d_iq, size_t nbytes);
+
+/* loadIQData parity probe (processor.go:193-201): complex64 samples
+ * [first, first+count) of a station's capture, written to host out_c64[2*count]. */
+TDOA_API int tdoa_unpack(tdoa_engine *e, int32_t station, int64_t first, int64_t count, float *out_c64);
+
+/* preprocessSignal probe (processor.go:469-499 / ELF 0x49cd40): preprocesses samples
+ * [start, start+len) of `kind` of `station` in the engine's mode and returns the
+ * normalised complex64 signal, its initial power and the branch taken. */
+TDOA_API int tdoa_preprocess(tdoa_engine *e, int32_t station, int32_t kind, int64_t start, int64_t len,
+                             float *out_c64, double *power, int32_t *branch);
+
+/* ProcessTDOA pair loops (processor.go:816-850): correlates every station pair i<j
+ * (lexicographic, = argv order) of `kind` over n_windows windows
+ * [win_start + w*hop, +win_len).  win_len = 0 means the config's chunk (0 = whole
+ * signal).  out[w * P + p], P = S(S-1)/2. */
+TDOA_API int tdoa_xcorr(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
+                        int32_t n_windows, int64_t hop, tdoa_peak *out);
+/* Same, peaks left in device memory (e.g. an NCCL send buffer); d_out[n_windows*P]. */
+TDOA_API int tdoa_xcorr_device(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
+                               int32_t n_windows, int64_t hop, tdoa_peak *d_out);
+
+/* crossCorrelate seam (processor.go:619-643): two host complex64 slices
+ * (interleaved re,im), returns (delay, correlation).  Empty input -> (0, 0.0). */
+TDOA_API int tdoa_cross_correlate(tdoa_engine *e, const float *sig1_c64, int64_t n1,
+                                  const float *sig2_c64, int64_t n2, tdoa_peak *out);
+
+/* latLonToECEF / calculateBaseline (processor.go:125-163): baselines[p] in metres
+ * for pairs i<j of stations_llh[S][3] (lat deg, lon deg, elev m). */
+TDOA_API int tdoa_baselines(tdoa_engine *e, const double *stations_llh, int32_t n_stations, double *baselines);
+
+/* solveTDOA (processor.go:932-1020) batched: n_sets range-difference sets,
+ * range_diffs[set * rd_stride + p].  out_llh[set][3]; status[set] = 0 ok,
+ * TDOA_E_SINGULAR singular Jacobian; iters[set] (may be NULL). */
+TDOA_API int tdoa_solve(tdoa_engine *e, const double *stations_llh, int32_t n_stations,
+                        const double *range_diffs, int32_t n_sets, int32_t rd_stride,
+                        double *out_llh, int32_t *status, int32_t *iters);
+
+/* Dense lat-lon grid multilateration (no reference equivalent): for each set the
+ * cell minimising sum_{i<j} ((r_j - r_i) - rd_ij)^2.
+ * grid_desc = {lat0, lon0, dlat, dlon, nlat, nlon, elev}. */
+TDOA_API int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_stations,
+                       const double *grid_desc, const double *range_diffs, int32_t n_sets,
+                       int32_t rd_stride, double *out_llh, double *out_cost, int64_t *out_index);
+
+/* Introspection for the benchmark: kernels launched and device time of the last
+ * tdoa_xcorr call, per stage (CUDA events on the engine's stream). */
+typedef struct {
+    int64_t launches_total;   /* kernels launched by this engine since creation   */
+    int64_t launches_last;    /* ... by the last xcorr / cross_correlate call     */
+    float ms_preprocess;      /* stats + demod + box-car of the last call         */
+    float ms_fft;             /* segmented FFT cross-spectrum + inverse           */
+    float ms_exact;           /* exact time-domain re-evaluation + peak select    */
+    float ms_total;
+    int64_t fft_launches;     /* launches of the segmented FFT kernel, last call  */
+    float ms_fft_seg;         /* device time of those launches                    */
+    int64_t fft_pair_samples; /* template samples they covered                    */
+    int64_t brute_pairs;      /* pair-windows that fell back to every-lag search  */
+} tdoa_stats;
+TDOA_API int tdoa_get_stats(tdoa_engine *e, tdoa_stats *out);
+
+/* Raw CUDA stream of the engine (cudaStream_t as void*), for callers that time or
+ * chain work on it. */
+TDOA_API void *tdoa_stream(tdoa_engine *e);
+/* Block until everything queued on the engine's stream is done. */
+TDOA_API int tdoa_synchronize(tdoa_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDOA_B200_H */

@@ -1,0 +1,91 @@
+"""Pins the CPU oracle (oracle/tdoa_oracle.c) against what the reference's own shipped
+binary printed for the golden captures (tests/golden/*.json, produced by
+tests/golden/make_golden.py), and against the known answers in the reference's docs."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from helpers import GOLDEN_CASES, STATION_LLH, load_golden
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_binary_pairs_match_reference_stdout(case):
+    raws, meta = load_golden(case)
+    ref, tgt = oracle.process_capture_binary(raws)
+    got = [("REF",) + r for r in ref] + [("TGT",) + r for r in tgt]
+    assert len(got) == len(meta["pairs"]) == 6
+    for (kind, delay, corr, _), want in zip(got, meta["pairs"]):
+        assert kind == want["kind"]
+        assert delay == want["delay"], (case, want)
+        # the reference prints %.6f
+        assert abs(corr - want["corr"]) <= 0.51e-6, (case, corr, want)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_binary_preprocess_diagnostics(case):
+    """Initial power / branch of every preprocessSignal call the binary printed."""
+    raws, meta = load_golden(case)
+    sigs = []
+    for kind in ("ref", "tgt"):
+        per = []
+        for raw in raws:
+            d = oracle.unpack_u8(raw)
+            s = oracle.extract_reference(d) if kind == "ref" else oracle.extract_target(d)
+            per.append(s[:1_000_000])
+        for i in range(3):
+            for j in range(i + 1, 3):
+                sigs += [per[i], per[j]]
+    assert len(sigs) == len(meta["initial_power"]) == 12
+    for s, p_want, br_want in zip(sigs, meta["initial_power"], meta["branch"]):
+        p = oracle.signal_power(s)
+        assert abs(p - p_want) <= 0.51e-9 * max(1.0, abs(p_want) / 1e-9 * 1e-9) + 1e-9
+        _, br = oracle.preprocess_binary(s)
+        assert br == br_want
+
+
+def test_baselines_known_answers():
+    # PROJECT_NOTES.md:25-27: 12.29 / 17.02 / 10.02 km
+    want = [12.29, 17.02, 10.02]
+    got = [oracle.baseline(STATION_LLH[i], STATION_LLH[j]) / 1000.0
+           for i in range(3) for j in range(i + 1, 3)]
+    for g, w in zip(got, want):
+        assert abs(g - w) < 0.005
+
+
+def test_microsecond_to_metre_diagnostic():
+    # processor.go:885-889: 10 / 5 / -3 us -> 2997.9 / 1499.0 / -899.4 m
+    for us, m in ((10, 2997.9), (5, 1499.0), (-3, -899.4)):
+        assert abs(us * 1e-6 * 299792458.0 - m) < 0.05
+
+
+def test_source_solver_survey_values():
+    # SURVEY.md 8c cross-check values of the f64 restatement of processor.go:932-1045
+    cases = {
+        (0.0, 0.0, 0.0): (41.262323848, -95.982993948, -681.535),
+        (3.5, 6.0, 2.5): (41.254478374, -95.979774992, 311.680),
+        (10.0, 5.0, -3.0): (41.265694717, -95.943691803, -1108.147),
+        (-3.5, 2.0, 0.0): (41.254686678, -95.998887381, 285.304),
+    }
+    for us, want in cases.items():
+        rd = np.array(us) * 1e-6 * 299792458.0
+        llh, status, _ = oracle.solve_tdoa(STATION_LLH, rd)
+        assert status == 0
+        assert abs(llh[0] - want[0]) < 5e-9 and abs(llh[1] - want[1]) < 5e-9
+        assert abs(llh[2] - want[2]) < 5e-3
+
+
+def test_ecef_round_trip():
+    for llh in STATION_LLH:
+        xyz = oracle.llh_to_ecef(*llh)
+        back = oracle.ecef_to_llh(*xyz)
+        assert np.allclose(back[:2], llh[:2], atol=1e-9) and abs(back[2] - llh[2]) < 1e-3
+
+
+def test_self_correlation_sanity():
+    # correlation_sanity.go:48-63 / simple_corr.go:31-44: crossCorrelate(x, x) > 0.5 at delay 0
+    raws, _ = load_golden("fm_strong")
+    ref = oracle.extract_reference(oracle.unpack_u8(raws[0]))
+    d, c, _ = oracle.cross_correlate_binary(ref, ref)
+    assert d == 0 and c > 0.8
+    d, c = oracle.cross_correlate_source(ref, ref)
+    assert d == 0 and c > 0.5
