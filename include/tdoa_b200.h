@@ -170,6 +170,9 @@ TDOA_API int tdoa_get_stats(tdoa_engine *e, tdoa_stats *out);
 /* Raw CUDA stream of the engine (cudaStream_t as void*), for callers that time or
  * chain work on it. */
 TDOA_API void *tdoa_stream(tdoa_engine *e);
+/* Run on a caller-owned stream instead (cudaStream_t as void*; NULL: a fresh private
+ * stream).  The benchmark uses this so that its CUDA events bracket the engine's work. */
+TDOA_API int tdoa_set_stream(tdoa_engine *e, void *stream);
 /* Block until everything queued on the engine's stream is done. */
 TDOA_API int tdoa_synchronize(tdoa_engine *e);
 

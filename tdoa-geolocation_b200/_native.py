@@ -1,0 +1,321 @@
+"""ctypes binding of libtdoa_b200.so -- the same C ABI a cgo shim binds
+(include/tdoa_b200.h).  No numerics happen in this file: every
+result comes from the CUDA library, and a missing library or GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = _HERE / "libtdoa_b200.so"
+
+MODE_SOURCE, MODE_BINARY, MODE_EXTENDED = 0, 1, 2
+KIND_REF, KIND_TGT = 0, 1
+
+PEAK_RESEARCHED, PEAK_EDGE, PEAK_BRUTE, PEAK_EMPTY = 0x1, 0x2, 0x4, 0x8
+
+ERRORS = {-1: "TDOA_E_INVALID", -2: "TDOA_E_NODEVICE", -3: "TDOA_E_CUDA", -4: "TDOA_E_NOMEM",
+          -5: "TDOA_E_STATE", -6: "TDOA_E_SINGULAR"}
+
+# every symbol include/tdoa_b200.h declares (tests check the library exports them all)
+ABI_SYMBOLS = [
+    "tdoa_default_config", "tdoa_create", "tdoa_destroy", "tdoa_last_error", "tdoa_host_alloc", "tdoa_host_free",
+    "tdoa_load_u8", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device",
+    "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
+    "tdoa_set_stream", "tdoa_synchronize",
+]
+
+
+class TdoaError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {message}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("sample_rate", C.c_double), ("mode", C.c_int32), ("n_stations", C.c_int32),
+        ("chunk_samples", C.c_int32), ("max_lag", C.c_int32), ("block_size", C.c_int32),
+        ("sanity_lag", C.c_int32), ("fast_demod", C.c_int32), ("use_fft", C.c_int32),
+        ("device", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+class PeakStruct(C.Structure):
+    _fields_ = [
+        ("lag", C.c_int32), ("flags", C.c_uint32), ("corr", C.c_double), ("frac", C.c_float),
+        ("margin", C.c_float), ("first_lag", C.c_int32), ("n_blocks", C.c_int32),
+    ]
+
+
+PEAK_DTYPE = np.dtype([("lag", "<i4"), ("flags", "<u4"), ("corr", "<f8"), ("frac", "<f4"), ("margin", "<f4"),
+                       ("first_lag", "<i4"), ("n_blocks", "<i4")])
+assert PEAK_DTYPE.itemsize == C.sizeof(PeakStruct) == 32
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("launches_total", C.c_int64), ("launches_last", C.c_int64), ("ms_preprocess", C.c_float),
+        ("ms_fft", C.c_float), ("ms_exact", C.c_float), ("ms_total", C.c_float), ("fft_launches", C.c_int64),
+        ("ms_fft_seg", C.c_float), ("fft_pair_samples", C.c_int64), ("brute_pairs", C.c_int64),
+    ]
+
+
+@dataclass
+class Peak:
+    lag: int
+    corr: float
+    frac: float
+    flags: int
+    margin: float
+    first_lag: int
+    n_blocks: int
+
+    @property
+    def researched(self) -> bool:
+        return bool(self.flags & PEAK_RESEARCHED)
+
+    @property
+    def branches(self):
+        return (self.flags >> 8) & 3, (self.flags >> 10) & 3
+
+
+_lib = None
+
+
+def library_path() -> Path:
+    return _LIB
+
+
+def load_library():
+    """dlopen libtdoa_b200.so (never builds, never falls back)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB.exists():
+        raise FileNotFoundError(f"{_LIB} is missing: run `python tdoa-geolocation_b200/build.py` "
+                                "(there is no CPU fallback)")
+    L = C.CDLL(str(_LIB))
+    vp, i32, i64, f64p = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double)
+    L.tdoa_default_config.argtypes = [i32, C.POINTER(Config)]
+    L.tdoa_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
+    L.tdoa_destroy.argtypes = [vp]
+    L.tdoa_destroy.restype = None
+    L.tdoa_last_error.argtypes = [vp]
+    L.tdoa_last_error.restype = C.c_char_p
+    L.tdoa_host_alloc.argtypes = [C.c_size_t]
+    L.tdoa_host_alloc.restype = vp
+    L.tdoa_host_free.argtypes = [vp]
+    L.tdoa_host_free.restype = None
+    L.tdoa_load_u8.argtypes = [vp, i32, vp, C.c_size_t]
+    L.tdoa_load_u8_device.argtypes = [vp, i32, vp, C.c_size_t]
+    L.tdoa_unpack.argtypes = [vp, i32, i64, i64, vp]
+    L.tdoa_preprocess.argtypes = [vp, i32, i32, i64, i64, vp, f64p, C.POINTER(i32)]
+    L.tdoa_xcorr.argtypes = [vp, i32, i64, i64, i32, i64, vp]
+    L.tdoa_xcorr_device.argtypes = [vp, i32, i64, i64, i32, i64, vp]
+    L.tdoa_cross_correlate.argtypes = [vp, vp, i64, vp, i64, C.POINTER(PeakStruct)]
+    L.tdoa_baselines.argtypes = [vp, vp, i32, vp]
+    L.tdoa_solve.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
+    L.tdoa_grid.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp]
+    L.tdoa_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.tdoa_stream.argtypes = [vp]
+    L.tdoa_stream.restype = vp
+    L.tdoa_set_stream.argtypes = [vp, vp]
+    L.tdoa_synchronize.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def default_config(mode: int, **overrides) -> Config:
+    cfg = Config()
+    rc = load_library().tdoa_default_config(mode, C.byref(cfg))
+    if rc:
+        raise TdoaError(rc, f"bad mode {mode}")
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+class PinnedBuffer:
+    """Page-locked host memory from tdoa_host_alloc, viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes: int):
+        self._lib = load_library()
+        self.ptr = self._lib.tdoa_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError(f"tdoa_host_alloc({nbytes}) failed")
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.tdoa_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def host_alloc(nbytes: int) -> PinnedBuffer:
+    return PinnedBuffer(nbytes)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One engine = one GPU.  Thin object wrapper over the C ABI."""
+
+    def __init__(self, mode: int = MODE_BINARY, **overrides):
+        self._lib = load_library()
+        self.cfg = default_config(mode, **overrides)
+        h = C.c_void_p()
+        rc = self._lib.tdoa_create(C.byref(h), C.byref(self.cfg))
+        if rc:
+            raise TdoaError(rc, (self._lib.tdoa_last_error(None) or b"").decode())
+        self._h = h
+        self._keep = {}
+
+    # -- plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tdoa_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc:
+            raise TdoaError(rc, (self._lib.tdoa_last_error(self._h) or b"").decode())
+
+    @property
+    def n_stations(self) -> int:
+        return self.cfg.n_stations
+
+    @property
+    def n_pairs(self) -> int:
+        s = self.cfg.n_stations
+        return s * (s - 1) // 2
+
+    @property
+    def stream(self) -> int:
+        return self._lib.tdoa_stream(self._h) or 0
+
+    def set_stream(self, stream_ptr: int):
+        self._check(self._lib.tdoa_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def synchronize(self):
+        self._check(self._lib.tdoa_synchronize(self._h))
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._check(self._lib.tdoa_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in Stats._fields_}
+
+    # -- loadIQData + extract* (processor.go:166-267)
+    def load_u8(self, station: int, iq) -> None:
+        if isinstance(iq, PinnedBuffer):
+            ptr, n = C.c_void_p(iq.ptr), iq.nbytes
+        else:
+            iq = np.ascontiguousarray(iq, dtype=np.uint8)
+            ptr, n = _ptr(iq), iq.size
+        self._check(self._lib.tdoa_load_u8(self._h, station, ptr, n))
+
+    def load_u8_ptr(self, station: int, ptr: int, nbytes: int) -> None:
+        self._check(self._lib.tdoa_load_u8(self._h, station, C.c_void_p(ptr), nbytes))
+
+    def load_u8_device(self, station: int, dev_ptr: int, nbytes: int, keep=None) -> None:
+        self._keep[station] = keep
+        self._check(self._lib.tdoa_load_u8_device(self._h, station, C.c_void_p(dev_ptr), nbytes))
+
+    def unpack(self, station: int, first: int, count: int) -> np.ndarray:
+        out = np.empty(count, np.complex64)
+        self._check(self._lib.tdoa_unpack(self._h, station, first, count, _ptr(out)))
+        return out
+
+    # -- preprocessSignal (processor.go:469-499 / ELF 0x49cd40)
+    def preprocess(self, station: int, kind: int, start: int, length: int):
+        out = np.empty(length, np.complex64)
+        power = C.c_double()
+        branch = C.c_int32()
+        self._check(self._lib.tdoa_preprocess(self._h, station, kind, start, length, _ptr(out),
+                                              C.byref(power), C.byref(branch)))
+        return out, power.value, branch.value
+
+    # -- ProcessTDOA pair loops (processor.go:816-850)
+    def xcorr(self, kind: int, win_start: int = 0, win_len: int = 0, n_windows: int = 1, hop: int = 0) -> np.ndarray:
+        out = np.zeros((n_windows, self.n_pairs), PEAK_DTYPE)
+        self._check(self._lib.tdoa_xcorr(self._h, kind, win_start, win_len, n_windows, hop, _ptr(out)))
+        return out
+
+    def xcorr_device(self, kind: int, dev_out_ptr: int, win_start: int = 0, win_len: int = 0, n_windows: int = 1,
+                     hop: int = 0) -> None:
+        self._check(self._lib.tdoa_xcorr_device(self._h, kind, win_start, win_len, n_windows, hop,
+                                                C.c_void_p(dev_out_ptr)))
+
+    # -- crossCorrelate seam (processor.go:619-643)
+    def cross_correlate(self, sig1, sig2) -> Peak:
+        a = np.ascontiguousarray(sig1, dtype=np.complex64)
+        b = np.ascontiguousarray(sig2, dtype=np.complex64)
+        pk = PeakStruct()
+        self._check(self._lib.tdoa_cross_correlate(self._h, _ptr(a), a.size, _ptr(b), b.size, C.byref(pk)))
+        return Peak(pk.lag, pk.corr, pk.frac, pk.flags, pk.margin, pk.first_lag, pk.n_blocks)
+
+    # -- geodesy / solver (processor.go:125-163, 932-1045)
+    def baselines(self, stations_llh) -> np.ndarray:
+        st = np.ascontiguousarray(stations_llh, dtype=np.float64).reshape(-1, 3)
+        s = st.shape[0]
+        out = np.zeros(s * (s - 1) // 2, np.float64)
+        self._check(self._lib.tdoa_baselines(self._h, _ptr(st), s, _ptr(out)))
+        return out
+
+    def solve(self, stations_llh, range_diffs):
+        st = np.ascontiguousarray(stations_llh, dtype=np.float64).reshape(-1, 3)
+        rd = np.ascontiguousarray(range_diffs, dtype=np.float64)
+        single = rd.ndim == 1
+        rd = rd.reshape(1, -1) if single else rd
+        n, stride = rd.shape
+        out = np.zeros((n, 3), np.float64)
+        status = np.zeros(n, np.int32)
+        iters = np.zeros(n, np.int32)
+        self._check(self._lib.tdoa_solve(self._h, _ptr(st), st.shape[0], _ptr(rd), n, stride, _ptr(out),
+                                         _ptr(status), _ptr(iters)))
+        if single:
+            return out[0], int(status[0]), int(iters[0])
+        return out, status, iters
+
+    def grid(self, stations_llh, grid_desc, range_diffs):
+        st = np.ascontiguousarray(stations_llh, dtype=np.float64).reshape(-1, 3)
+        gd = np.ascontiguousarray(grid_desc, dtype=np.float64)
+        rd = np.ascontiguousarray(range_diffs, dtype=np.float64)
+        single = rd.ndim == 1
+        rd = rd.reshape(1, -1) if single else rd
+        n, stride = rd.shape
+        out = np.zeros((n, 3), np.float64)
+        cost = np.zeros(n, np.float64)
+        idx = np.zeros(n, np.int64)
+        self._check(self._lib.tdoa_grid(self._h, _ptr(st), st.shape[0], _ptr(gd), _ptr(rd), n, stride, _ptr(out),
+                                        _ptr(cost), _ptr(idx)))
+        if single:
+            return out[0], float(cost[0]), int(idx[0])
+        return out, cost, idx

@@ -1,0 +1,1043 @@
+// engine.cu -- the C ABI of libtdoa_b200.so (include/tdoa_b200.h) and the host-side
+// orchestration of the processing stage: which kernels run, on which buffers, in
+// which order.  Mirrors ProcessTDOA's data flow (processor.go:739-929): per station
+// load -> split ref/target -> window -> preprocess once per station-window -> all
+// station pairs i<j -> peak records; then the fix.
+//
+// There is no CPU fallback anywhere in this file: every numeric result is produced
+// by a kernel on the engine's device, and tdoa_create fails without an sm_100 GPU.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tdoa_b200.h"
+#include "kernels.h"
+
+using namespace tdoa;
+
+static_assert(sizeof(tdoa_peak) == 32, "tdoa_peak is a 32-byte wire record");
+static_assert(sizeof(PeakRec) == sizeof(tdoa_peak), "device and ABI peak records must match");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Station {
+    const uint8_t *d_raw = nullptr;
+    uint8_t *owned = nullptr;
+    size_t owned_cap = 0;
+    size_t nbytes = 0;
+    i64 nsamp = 0;
+    bool loaded = false;
+};
+
+// one signal (station-window) moving through preprocessing
+struct Sig {
+    SigSrc src{};
+    i64 n = 0;
+    float *plane[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    float *out_re = nullptr, *out_im = nullptr;  // pre-normalise result (scale in stats)
+    double *stats = nullptr;
+    double *partials = nullptr;
+    unsigned *counter = nullptr;
+    double power0 = 0.0;
+    int branch = 0;
+};
+
+struct Pair {
+    int a, b;  // indices into the Sig array: signal 1, signal 2 (argv order, processor.go:816-817)
+};
+
+constexpr size_t kFrameBytes = 8u << 20;  // descriptor staging per call
+
+}  // namespace
+
+struct tdoa_engine {
+    tdoa_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::vector<Station> stations;
+    std::string error;
+    // descriptor staging
+    uint8_t *h_frame = nullptr, *d_frame = nullptr;
+    size_t frame_used = 0;
+    cudaEvent_t frame_done = nullptr;
+    bool frame_pending = false;
+    // allocations of the current call (stream-ordered)
+    std::vector<void *> call_allocs;
+    // stats
+    tdoa_stats st{};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    int64_t launches_at_call = 0;
+};
+
+namespace {
+
+int fail(tdoa_engine *e, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (e) e->error = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t err__ = (call);                                                                \
+        if (err__ != cudaSuccess)                                                                  \
+            return fail(e, err__ == cudaErrorMemoryAllocation ? TDOA_E_NOMEM : TDOA_E_CUDA,        \
+                        "%s failed: %s", #call, cudaGetErrorString(err__));                        \
+    } while (0)
+
+int begin_call(tdoa_engine *e)
+{
+    CU(cudaSetDevice(e->device));
+    if (e->frame_pending) {
+        CU(cudaEventSynchronize(e->frame_done));
+        e->frame_pending = false;
+    }
+    e->frame_used = 0;
+    e->launches_at_call = e->st.launches_total;
+    return TDOA_OK;
+}
+
+int end_call(tdoa_engine *e, bool sync)
+{
+    for (void *p : e->call_allocs) cudaFreeAsync(p, e->stream);
+    e->call_allocs.clear();
+    CU(cudaEventRecord(e->frame_done, e->stream));
+    e->frame_pending = true;
+    if (sync) {
+        CU(cudaStreamSynchronize(e->stream));
+        e->frame_pending = false;
+    }
+    CU(cudaGetLastError());
+    return TDOA_OK;
+}
+
+// stream-ordered scratch that lives until end_call
+int alloc(tdoa_engine *e, void **out, size_t bytes)
+{
+    *out = nullptr;
+    if (bytes == 0) bytes = 16;
+    CU(cudaMallocAsync(out, bytes, e->stream));
+    e->call_allocs.push_back(*out);
+    return TDOA_OK;
+}
+template <class T>
+int alloc_t(tdoa_engine *e, T **out, size_t count)
+{
+    return alloc(e, reinterpret_cast<void **>(out), count * sizeof(T));
+}
+
+// copy a descriptor array to the device through the pinned frame
+template <class T>
+int upload(tdoa_engine *e, const std::vector<T> &v, const T **d_out)
+{
+    const size_t bytes = v.size() * sizeof(T);
+    const size_t off = (e->frame_used + 255) & ~size_t(255);
+    if (off + bytes > kFrameBytes) return fail(e, TDOA_E_NOMEM, "descriptor frame overflow (%zu bytes)", off + bytes);
+    std::memcpy(e->h_frame + off, v.data(), bytes);
+    CU(cudaMemcpyAsync(e->d_frame + off, e->h_frame + off, bytes, cudaMemcpyHostToDevice, e->stream));
+    e->frame_used = off + bytes;
+    *d_out = reinterpret_cast<const T *>(e->d_frame + off);
+    return TDOA_OK;
+}
+
+inline void count_launch(tdoa_engine *e, int n = 1) { e->st.launches_total += n; }
+
+// ---------------------------------------------------------------- signal views
+
+// processor.go:208-267: block = N/3; REF = blocks 1 and 3 concatenated, TGT = block 2;
+// fewer than 3 samples: the data is returned unchanged.
+i64 signal_length(const Station &s, int kind)
+{
+    const i64 b = s.nsamp / 3;
+    if (b == 0) return s.nsamp;
+    return kind == TDOA_KIND_REF ? 2 * b : b;
+}
+
+SigSrc make_view(const Station &s, int kind, i64 start, i64 len)
+{
+    SigSrc v{};
+    v.raw = s.d_raw;
+    const i64 b = s.nsamp / 3;
+    if (b == 0) {
+        v.run0_start = start; v.run0_len = len; v.run1_start = 0;
+    } else if (kind == TDOA_KIND_TGT) {
+        v.run0_start = b + start; v.run0_len = len; v.run1_start = 0;
+    } else if (start < b) {
+        v.run0_start = start; v.run0_len = std::min(len, b - start); v.run1_start = 2 * b;
+    } else {
+        v.run0_start = 2 * b + (start - b); v.run0_len = len; v.run1_start = 0;
+    }
+    return v;
+}
+
+// processor.go:397-409: window = int(fs / (2 fc)) clamped to [3, 1000]; the reference
+// hard-codes fs = 2e6 in every call site (:440, :488; binary likewise).
+int cutoff_window(double fc)
+{
+    int w = (int)(2000000.0 / (2 * fc));
+    if (w < 3) w = 3;
+    if (w > 1000) w = 1000;
+    return w;
+}
+
+// ---------------------------------------------------------------- preprocessing
+
+struct Step {  // one batched kernel over a set of signals
+    std::vector<SigJob> jobs;
+    i64 max_n = 0;
+};
+
+SigJob base_job(const Sig &s)
+{
+    SigJob j{};
+    j.src = s.src;
+    j.n = s.n;
+    j.stats = s.stats;
+    j.partials = s.partials;
+    j.counter = s.counter;
+    return j;
+}
+
+int ensure_plane(tdoa_engine *e, Sig &s, int idx, bool cplx)
+{
+    if (!s.plane[idx][0]) {
+        int rc = alloc_t(e, &s.plane[idx][0], (size_t)s.n);
+        if (rc) return rc;
+    }
+    if (cplx && !s.plane[idx][1]) {
+        int rc = alloc_t(e, &s.plane[idx][1], (size_t)s.n);
+        if (rc) return rc;
+    }
+    return TDOA_OK;
+}
+
+enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_BOXCAR, K_NOTCH };
+
+// queue of (kernel, jobs) stages; stage k of every signal of a branch is batched
+struct Pipeline {
+    std::vector<Kern> kern;
+    std::vector<Step> steps;
+    void add(size_t stage, Kern k, const SigJob &j)
+    {
+        if (steps.size() <= stage) { steps.resize(stage + 1); kern.resize(stage + 1, k); }
+        kern[stage] = k;
+        steps[stage].jobs.push_back(j);
+        steps[stage].max_n = std::max(steps[stage].max_n, j.n);
+    }
+};
+
+SigJob box_job(const Sig &s, int in, int out, bool cplx, int window, int mode, bool sub_dc, bool power)
+{
+    SigJob j = base_job(s);
+    j.q_re = s.plane[in][0];
+    j.q_im = cplx ? s.plane[in][1] : nullptr;
+    j.p_re = s.plane[out][0];
+    j.p_im = cplx ? s.plane[out][1] : nullptr;
+    j.window = window;
+    j.mode = mode;
+    j.sub_dc = sub_dc;
+    j.want_power = power;
+    return j;
+}
+
+SigJob notch_job(const Sig &s, int in, int band, int out)
+{
+    SigJob j = base_job(s);
+    j.q_re = s.plane[in][0]; j.q_im = s.plane[in][1];
+    j.r_re = s.plane[band][0]; j.r_im = s.plane[band][1];
+    j.p_re = s.plane[out][0]; j.p_im = s.plane[out][1];
+    return j;
+}
+
+int run_pipeline(tdoa_engine *e, Pipeline &pl)
+{
+    for (size_t k = 0; k < pl.steps.size(); k++) {
+        Step &st = pl.steps[k];
+        if (st.jobs.empty()) continue;
+        const SigJob *d_jobs = nullptr;
+        int rc = upload(e, st.jobs, &d_jobs);
+        if (rc) return rc;
+        const int nj = (int)st.jobs.size();
+        switch (pl.kern[k]) {
+            case K_UNPACK: launch_unpack(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
+            case K_DEMOD: launch_demod(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
+            case K_ENVELOPE: launch_envelope(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
+            case K_BOXCAR: launch_boxcar(d_jobs, nj, st.max_n, 0, e->stream); break;
+            case K_NOTCH: launch_notch_combine(d_jobs, nj, st.max_n, e->stream); break;
+        }
+        count_launch(e);
+    }
+    return TDOA_OK;
+}
+
+// Preprocess every signal (preprocessSignal, processor.go:469-499 / ELF 0x49cd40).
+// On return out_re/out_im/stats of each signal are valid on the stream.
+int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
+{
+    if (sigs.empty()) return TDOA_OK;
+    const int ns = (int)sigs.size();
+    i64 max_n = 0;
+    for (auto &s : sigs) max_n = std::max(max_n, s.n);
+    const int gx = stream_grid_x(max_n);
+    const int gmax = std::max(gx, boxcar_grid_x(max_n));
+    double *d_stats = nullptr, *d_partials = nullptr;
+    unsigned *d_counters = nullptr;
+    int rc;
+    if ((rc = alloc_t(e, &d_stats, (size_t)ns * ST_COUNT))) return rc;
+    if ((rc = alloc_t(e, &d_partials, (size_t)ns * 2 * gmax))) return rc;
+    if ((rc = alloc_t(e, &d_counters, (size_t)ns))) return rc;
+    CU(cudaMemsetAsync(d_stats, 0, (size_t)ns * ST_COUNT * sizeof(double), e->stream));
+    CU(cudaMemsetAsync(d_counters, 0, (size_t)ns * sizeof(unsigned), e->stream));
+    for (int i = 0; i < ns; i++) {
+        sigs[i].stats = d_stats + (size_t)i * ST_COUNT;
+        sigs[i].partials = d_partials + (size_t)i * 2 * gmax;
+        sigs[i].counter = d_counters + i;
+    }
+    // ---- initial power (selects the branch)
+    {
+        std::vector<SigJob> jobs;
+        for (auto &s : sigs) jobs.push_back(base_job(s));
+        const SigJob *d_jobs = nullptr;
+        if ((rc = upload(e, jobs, &d_jobs))) return rc;
+        launch_power(d_jobs, ns, max_n, gx, e->stream);
+        count_launch(e);
+        std::vector<double> h_stats((size_t)ns * ST_COUNT);
+        CU(cudaMemcpyAsync(h_stats.data(), d_stats, h_stats.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        for (int i = 0; i < ns; i++) sigs[i].power0 = h_stats[(size_t)i * ST_COUNT + ST_POWER0];
+    }
+    // ---- per-branch pipelines
+    const int mode = e->cfg.mode;
+    Pipeline pl;
+    for (auto &s : sigs) {
+        if (s.n == 0) { s.branch = 0; continue; }
+        if (mode == TDOA_MODE_SOURCE) {
+            const bool weak = s.power0 < 0.001;  // processor.go:476
+            s.branch = weak ? 2 : 0;
+            for (int k = 0; k < (weak ? 4 : 2); k++)
+                if ((rc = ensure_plane(e, s, k, true))) return rc;
+            SigJob u = base_job(s);
+            u.p_re = s.plane[0][0]; u.p_im = s.plane[0][1];
+            size_t g = 0;
+            pl.add(g++, K_UNPACK, u);
+            if (!weak) {
+                // processor.go:485-495  DC -> BP(500, 50k) -> LP(100) -> normalise
+                pl.add(g++, K_BOXCAR, box_job(s, 0, 1, true, cutoff_window(500.0), BOX_HP, true, false));
+                pl.add(g++, K_BOXCAR, box_job(s, 1, 0, true, cutoff_window(50000.0), BOX_LP, false, false));
+                pl.add(g++, K_BOXCAR, box_job(s, 0, 1, true, 100, BOX_LP, false, true));
+                s.out_re = s.plane[1][0]; s.out_im = s.plane[1][1];
+            } else {
+                // processor.go:437-466  enhanceWeakSignal; planes: 0 = scratch T1, 1 = X, 2 = Y, 3 = T2
+                pl.add(g++, K_BOXCAR, box_job(s, 0, 1, true, 1, BOX_LP, true, false));  // X = s - dc
+                // notch 60 Hz / 5 Hz: band = LP(62.5)(HP(57.5)(X)); Y = X - 0.8 band
+                pl.add(g++, K_BOXCAR, box_job(s, 1, 0, true, cutoff_window(57.5), BOX_HP, false, false));
+                pl.add(g++, K_BOXCAR, box_job(s, 0, 3, true, cutoff_window(62.5), BOX_LP, false, false));
+                pl.add(g++, K_NOTCH, notch_job(s, 1, 3, 2));
+                // notch 120 Hz / 5 Hz: X = Y - 0.8 band
+                pl.add(g++, K_BOXCAR, box_job(s, 2, 0, true, cutoff_window(117.5), BOX_HP, false, false));
+                pl.add(g++, K_BOXCAR, box_job(s, 0, 3, true, cutoff_window(122.5), BOX_LP, false, false));
+                pl.add(g++, K_NOTCH, notch_job(s, 2, 3, 1));
+                // notch 1 MHz / 50 kHz: hi clamps to fs/2 so only HP(975 kHz) applies; Y = X - 0.8 band
+                pl.add(g++, K_BOXCAR, box_job(s, 1, 0, true, cutoff_window(975000.0), BOX_HP, false, false));
+                pl.add(g++, K_NOTCH, notch_job(s, 1, 0, 2));
+                // BP(100, 40k): X = LP(40k)(HP(100)(Y))
+                pl.add(g++, K_BOXCAR, box_job(s, 2, 0, true, cutoff_window(100.0), BOX_HP, false, false));
+                pl.add(g++, K_BOXCAR, box_job(s, 0, 1, true, cutoff_window(40000.0), BOX_LP, false, false));
+                // LP(window 50) + power: Y
+                pl.add(g++, K_BOXCAR, box_job(s, 1, 2, true, 50, BOX_LP, false, true));
+                s.out_re = s.plane[2][0]; s.out_im = s.plane[2][1];
+            }
+        } else {
+            // shipped binary (ELF 0x49cd40): > 0.01 strong, > 0.001 moderate, else weak
+            s.branch = s.power0 > 0.01 ? 0 : (s.power0 > 0.001 ? 1 : 2);
+            size_t g = 0;
+            if (s.branch == 0) {
+                const bool cplx = s.n < 2;  // convertToInstantaneousFrequency returns its input for n < 2
+                if ((rc = ensure_plane(e, s, 0, cplx)) || (rc = ensure_plane(e, s, 1, cplx))) return rc;
+                SigJob u = base_job(s);
+                u.p_re = s.plane[0][0]; u.p_im = s.plane[0][1];
+                pl.add(g++, cplx ? K_UNPACK : K_DEMOD, u);
+                pl.add(g++, K_BOXCAR, box_job(s, 0, 1, cplx, 10, BOX_LP, true, true));
+                s.out_re = s.plane[1][0]; s.out_im = s.plane[1][1];
+            } else if (s.branch == 1) {
+                if ((rc = ensure_plane(e, s, 0, false)) || (rc = ensure_plane(e, s, 1, false))) return rc;
+                SigJob u = base_job(s);
+                u.p_re = s.plane[0][0];
+                pl.add(g++, K_ENVELOPE, u);
+                pl.add(g++, K_BOXCAR, box_job(s, 0, 1, false, 1, BOX_LP, true, true));
+                s.out_re = s.plane[1][0]; s.out_im = nullptr;
+            } else {
+                if ((rc = ensure_plane(e, s, 0, true)) || (rc = ensure_plane(e, s, 1, true))) return rc;
+                SigJob u = base_job(s);
+                u.p_re = s.plane[0][0]; u.p_im = s.plane[0][1];
+                pl.add(g++, K_UNPACK, u);
+                // removeDC -> bandpass(100 Hz, 200 kHz) -> normalise
+                pl.add(g++, K_BOXCAR, box_job(s, 0, 1, true, cutoff_window(100.0), BOX_HP, true, false));
+                pl.add(g++, K_BOXCAR, box_job(s, 1, 0, true, cutoff_window(200000.0), BOX_LP, false, true));
+                s.out_re = s.plane[0][0]; s.out_im = s.plane[0][1];
+            }
+        }
+    }
+    return run_pipeline(e, pl);
+}
+
+// ---------------------------------------------------------------- correlation
+
+struct CorrPlan {
+    PairJob job{};
+    PairJob job2{};  // sanity re-search with a different template length (rare)
+    bool need2 = false;
+    PeakJob peak{};
+};
+
+// whole blocks of the reference's loop `for bs = 0; bs < tl - B; bs += B`
+i64 whole_blocks(i64 tl, i64 B)
+{
+    if (B <= 0 || tl <= B) return 0;
+    return (tl - B + B - 1) / B;
+}
+
+int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pair> &pairs, PeakRec *d_out)
+{
+    if (pairs.empty()) return TDOA_OK;
+    const tdoa_config &cfg = e->cfg;
+    const int np = (int)pairs.size();
+    std::vector<CorrPlan> plans(np);
+    i64 max_nb = 0, max_nb2 = 0;
+    int max_lags = 0, max_lags2 = 0;
+    int rc;
+    for (int p = 0; p < np; p++) {
+        const Sig &s1 = sigs[pairs[p].a], &s2 = sigs[pairs[p].b];
+        CorrPlan &pl = plans[p];
+        PairJob &J = pl.job;
+        PeakJob &K = pl.peak;
+        K.out = d_out + p;
+        K.flags = ((uint32_t)s1.branch << 8) | ((uint32_t)s2.branch << 10) | TDOA_PEAK_BRUTE;
+        K.sanity = 0;
+        K.lag_origin = 0;
+        if (s1.n == 0 || s2.n == 0) {  // processor.go:622-625
+            K.flags |= TDOA_PEAK_EMPTY;
+            K.nb = 0; K.n_lags = 0; K.n_lags2 = 0; K.corr = K.corr2 = nullptr;
+            K.variant = CORR_BINARY;
+            continue;
+        }
+        // processor.go:653-661: the shorter input is the template
+        const Sig *tp = &s1, *sg = &s2;
+        if (s1.n > s2.n) { tp = &s2; sg = &s1; }
+        const i64 tl = tp->n, sl = sg->n;
+        J.t_re = tp->out_re; J.t_im = tp->out_im; J.t_stats = tp->stats;
+        J.s_re = sg->out_re; J.s_im = sg->out_im; J.s_stats = sg->stats;
+        J.sl = sl;
+        J.lag0 = 0;
+        J.t_off = 0;
+        if (cfg.mode == TDOA_MODE_EXTENDED) {
+            const i64 W = std::min(tl, sl), L = cfg.max_lag;
+            const i64 n = W - 2 * L;
+            J.variant = CORR_EXTENDED;
+            J.t_off = L;
+            J.n_t = n > 0 ? n : 0;
+            J.block = 8192;
+            J.nb = n > 0 ? (n + J.block - 1) / J.block : 0;
+            J.n_lags = (int)(2 * L + 1);
+            K.lag_origin = (int)-L;
+        } else if (cfg.mode == TDOA_MODE_BINARY) {
+            // ELF 0x49d6a0: equal lengths -> template shortened by maxLag
+            const i64 tl_eff = (sl == tl) ? tl - cfg.max_lag : tl;
+            i64 ml = std::min<i64>(cfg.max_lag, sl - tl_eff);
+            if (ml <= 0) ml = 1;
+            J.variant = CORR_BINARY;
+            J.block = cfg.block_size;
+            J.nb = whole_blocks(tl_eff, J.block);
+            J.n_t = J.nb * J.block;
+            J.n_lags = (int)ml;
+            K.sanity = cfg.sanity_lag;
+            if (K.sanity > 0 && ml > K.sanity + 1) {
+                // ELF 0x49dda7: the re-search template is tl-2000 (hard-coded) for equal lengths
+                const i64 tl2 = (sl == tl) ? tl - 2000 : tl;
+                const i64 nb2 = whole_blocks(tl2, J.block);
+                if (nb2 != J.nb) {
+                    pl.need2 = true;
+                    pl.job2 = J;
+                    pl.job2.nb = nb2;
+                    pl.job2.n_t = nb2 * J.block;
+                    pl.job2.n_lags = K.sanity;
+                }
+            }
+        } else {
+            // processor.go:668-675
+            i64 ml = std::min<i64>(cfg.max_lag, sl - tl);
+            if (ml < 1) ml = 1;
+            J.variant = CORR_SOURCE;
+            J.block = cfg.block_size;
+            J.nb = whole_blocks(tl, J.block);
+            J.n_t = J.nb * J.block;
+            J.n_lags = (int)ml;
+        }
+        if ((rc = alloc_t(e, &J.blocksums, (size_t)std::max<i64>(J.nb, 1) * J.n_lags))) return rc;
+        if ((rc = alloc_t(e, &J.corr, (size_t)J.n_lags))) return rc;
+        K.corr = J.corr; K.corr2 = J.corr;
+        K.n_lags = J.n_lags; K.n_lags2 = J.n_lags;
+        K.nb = (int)J.nb;
+        K.variant = J.variant;
+        max_nb = std::max(max_nb, J.nb);
+        max_lags = std::max(max_lags, J.n_lags);
+        if (pl.need2) {
+            PairJob &J2 = pl.job2;
+            if ((rc = alloc_t(e, &J2.blocksums, (size_t)std::max<i64>(J2.nb, 1) * J2.n_lags))) return rc;
+            if ((rc = alloc_t(e, &J2.corr, (size_t)J2.n_lags))) return rc;
+            K.corr2 = J2.corr; K.n_lags2 = J2.nb > 0 ? J2.n_lags : 0;
+            max_nb2 = std::max(max_nb2, J2.nb);
+            max_lags2 = std::max(max_lags2, J2.n_lags);
+        }
+    }
+    std::vector<PairJob> jobs, jobs2;
+    std::vector<PeakJob> peaks;
+    for (auto &pl : plans) {
+        if (pl.peak.n_lags > 0) jobs.push_back(pl.job);
+        if (pl.need2) jobs2.push_back(pl.job2);
+        peaks.push_back(pl.peak);
+    }
+    if (!jobs.empty()) {
+        const PairJob *d_jobs = nullptr;
+        if ((rc = upload(e, jobs, &d_jobs))) return rc;
+        if (max_nb > 0) { launch_corr_brute(d_jobs, (int)jobs.size(), max_nb, max_lags, e->stream); count_launch(e); }
+        launch_corr_finalize(d_jobs, (int)jobs.size(), max_lags, e->stream);
+        count_launch(e);
+        e->st.brute_pairs += (int64_t)jobs.size();
+    }
+    if (!jobs2.empty()) {
+        const PairJob *d_jobs = nullptr;
+        if ((rc = upload(e, jobs2, &d_jobs))) return rc;
+        if (max_nb2 > 0) { launch_corr_brute(d_jobs, (int)jobs2.size(), max_nb2, max_lags2, e->stream); count_launch(e); }
+        launch_corr_finalize(d_jobs, (int)jobs2.size(), max_lags2, e->stream);
+        count_launch(e);
+    }
+    const PeakJob *d_peaks = nullptr;
+    if ((rc = upload(e, peaks, &d_peaks))) return rc;
+    launch_peak(d_peaks, np, e->stream);
+    count_launch(e);
+    return TDOA_OK;
+}
+
+// ---------------------------------------------------------------- xcorr over windows
+
+int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len, int32_t n_windows, int64_t hop,
+               tdoa_peak *out, bool out_is_device)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (!out) return fail(e, TDOA_E_INVALID, "tdoa_xcorr: out is NULL");
+    if (kind != TDOA_KIND_REF && kind != TDOA_KIND_TGT) return fail(e, TDOA_E_INVALID, "tdoa_xcorr: bad kind %d", kind);
+    if (n_windows < 1 || win_start < 0 || win_len < 0 || (n_windows > 1 && hop <= 0))
+        return fail(e, TDOA_E_INVALID, "tdoa_xcorr: bad window arguments");
+    const int S = e->cfg.n_stations, P = S * (S - 1) / 2;
+    for (int s = 0; s < S; s++)
+        if (!e->stations[s].loaded) return fail(e, TDOA_E_STATE, "tdoa_xcorr: station %d has no capture loaded", s);
+    // window length per station
+    std::vector<i64> len(S);
+    for (int s = 0; s < S; s++) {
+        const i64 n = signal_length(e->stations[s], kind);
+        if (win_len == 0) {
+            // processor.go:772-780: truncate to the test chunk when longer
+            i64 l = n - win_start;
+            if (l < 0) l = 0;
+            if (e->cfg.chunk_samples > 0 && l > e->cfg.chunk_samples) l = e->cfg.chunk_samples;
+            len[s] = l;
+            if (n_windows > 1) return fail(e, TDOA_E_INVALID, "tdoa_xcorr: win_len = 0 needs n_windows = 1");
+        } else {
+            const i64 last = win_start + (i64)(n_windows - 1) * hop + win_len;
+            if (last > n)
+                return fail(e, TDOA_E_INVALID, "tdoa_xcorr: windows end at %lld but station %d has %lld samples",
+                            (long long)last, s, (long long)n);
+            len[s] = win_len;
+        }
+    }
+    PeakRec *d_out = nullptr;
+    if (out_is_device) d_out = reinterpret_cast<PeakRec *>(out);
+    else if ((rc = alloc_t(e, &d_out, (size_t)n_windows * P))) return rc;
+
+    cudaEventRecord(e->ev[0], e->stream);
+    float ms_pre = 0.f, ms_corr = 0.f;
+    // windows are processed in groups that keep the working set bounded
+    i64 per_window_bytes = 0;
+    for (int s = 0; s < S; s++) per_window_bytes += len[s] * 4 * 4;
+    const i64 budget = (i64)24 << 30;
+    int group = (int)std::max<i64>(1, std::min<i64>(n_windows, budget / std::max<i64>(per_window_bytes, 1)));
+    group = std::min(group, 64);
+    for (int w0 = 0; w0 < n_windows; w0 += group) {
+        const int gw = std::min(group, n_windows - w0);
+        std::vector<Sig> sigs((size_t)gw * S);
+        std::vector<Pair> pairs;
+        for (int w = 0; w < gw; w++) {
+            for (int s = 0; s < S; s++) {
+                Sig &sg = sigs[(size_t)w * S + s];
+                sg.n = len[s];
+                sg.src = make_view(e->stations[s], kind, win_start + (i64)(w0 + w) * hop, len[s]);
+            }
+            for (int i = 0; i < S; i++)
+                for (int j = i + 1; j < S; j++) pairs.push_back({w * S + i, w * S + j});
+        }
+        cudaEventRecord(e->ev[1], e->stream);
+        if ((rc = preprocess(e, sigs))) return rc;
+        cudaEventRecord(e->ev[2], e->stream);
+        if ((rc = correlate(e, sigs, pairs, d_out + (size_t)w0 * P))) return rc;
+        cudaEventRecord(e->ev[3], e->stream);
+        // free this group's planes before the next group allocates
+        if (w0 + group < n_windows) {
+            CU(cudaStreamSynchronize(e->stream));
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, e->ev[1], e->ev[2]);
+            cudaEventElapsedTime(&b, e->ev[2], e->ev[3]);
+            ms_pre += a; ms_corr += b;
+            for (void *p : e->call_allocs)
+                if (p != d_out) cudaFreeAsync(p, e->stream);
+            e->call_allocs.clear();
+            if (!out_is_device) e->call_allocs.push_back(d_out);
+        }
+    }
+    cudaEventRecord(e->ev[4], e->stream);
+    if (!out_is_device)
+        CU(cudaMemcpyAsync(out, d_out, (size_t)n_windows * P * sizeof(tdoa_peak), cudaMemcpyDeviceToHost, e->stream));
+    rc = end_call(e, !out_is_device);
+    if (rc) return rc;
+    e->st.launches_last = e->st.launches_total - e->launches_at_call;
+    if (!out_is_device) {
+        float a = 0.f, b = 0.f, t = 0.f;
+        cudaEventElapsedTime(&a, e->ev[1], e->ev[2]);
+        cudaEventElapsedTime(&b, e->ev[2], e->ev[3]);
+        cudaEventElapsedTime(&t, e->ev[0], e->ev[4]);
+        e->st.ms_preprocess = ms_pre + a;
+        e->st.ms_exact = ms_corr + b;
+        e->st.ms_fft = 0.f;
+        e->st.ms_total = t;
+    }
+    return TDOA_OK;
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+
+extern "C" {
+
+int tdoa_default_config(int32_t mode, tdoa_config *cfg)
+{
+    if (!cfg) return TDOA_E_INVALID;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->sample_rate = 2000000.0;  // processor.go:821
+    cfg->mode = mode;
+    cfg->n_stations = 3;
+    cfg->device = 0;
+    switch (mode) {
+        case TDOA_MODE_SOURCE:
+            cfg->chunk_samples = 2000000;  // processor.go:772
+            cfg->max_lag = 20000;          // processor.go:633
+            cfg->block_size = 1000;        // processor.go:682
+            cfg->sanity_lag = 0;
+            cfg->use_fft = 0;
+            break;
+        case TDOA_MODE_BINARY:
+            cfg->chunk_samples = 1000000;
+            cfg->max_lag = 2000;
+            cfg->block_size = 10000;
+            cfg->sanity_lag = 120;
+            cfg->use_fft = 1;
+            break;
+        case TDOA_MODE_EXTENDED:
+            cfg->chunk_samples = 0;
+            cfg->max_lag = 2000;
+            cfg->block_size = 10000;
+            cfg->sanity_lag = 0;
+            cfg->use_fft = 1;
+            break;
+        default:
+            return TDOA_E_INVALID;
+    }
+    return TDOA_OK;
+}
+
+int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
+{
+    tdoa_engine *e = nullptr;  // CU() reports into the thread-local create error
+    if (!out || !cfg) return fail(nullptr, TDOA_E_INVALID, "tdoa_create: NULL argument");
+    *out = nullptr;
+    if (cfg->mode < TDOA_MODE_SOURCE || cfg->mode > TDOA_MODE_EXTENDED)
+        return fail(nullptr, TDOA_E_INVALID, "tdoa_create: bad mode %d", cfg->mode);
+    if (cfg->n_stations < 2 || cfg->n_stations > 64)
+        return fail(nullptr, TDOA_E_INVALID, "tdoa_create: n_stations must be 2..64, got %d", cfg->n_stations);
+    if (cfg->max_lag < 0 || cfg->block_size < 1 || cfg->chunk_samples < 0 || cfg->sanity_lag < 0)
+        return fail(nullptr, TDOA_E_INVALID, "tdoa_create: negative size in config");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, TDOA_E_NODEVICE, "tdoa_create: no CUDA device (this engine has no CPU path)");
+    }
+    if (cfg->device < 0 || cfg->device >= n_dev)
+        return fail(nullptr, TDOA_E_NODEVICE, "tdoa_create: device %d of %d does not exist", cfg->device, n_dev);
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(nullptr, TDOA_E_NODEVICE, "tdoa_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    cfg->device, prop.major, prop.minor);
+    CU(cudaSetDevice(cfg->device));
+    e = new tdoa_engine();
+    e->cfg = *cfg;
+    e->device = cfg->device;
+    e->stations.resize(cfg->n_stations);
+    cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) { e->own_stream = true; err = cudaMallocHost(&e->h_frame, kFrameBytes); }
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_frame, kFrameBytes);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->frame_done, cudaEventDisableTiming);
+    for (int i = 0; i < 6 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev[i]);
+    if (err == cudaSuccess) {
+        // keep freed stream-ordered scratch cached in the pool between calls
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    if (err != cudaSuccess) {
+        g_create_error = std::string("tdoa_create: ") + cudaGetErrorString(err);
+        tdoa_destroy(e);
+        return err == cudaErrorMemoryAllocation ? TDOA_E_NOMEM : TDOA_E_CUDA;
+    }
+    const int bad = unpack_selftest(e->stream);
+    if (bad != 0) {
+        g_create_error = "tdoa_create: device unpack self-test failed (kernel image not runnable on this GPU?)";
+        tdoa_destroy(e);
+        return TDOA_E_CUDA;
+    }
+    e->st.launches_total = 1;
+    *out = e;
+    return TDOA_OK;
+}
+
+void tdoa_destroy(tdoa_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void *p : e->call_allocs) cudaFreeAsync(p, e->stream);
+    for (auto &s : e->stations)
+        if (s.owned) cudaFree(s.owned);
+    if (e->h_frame) cudaFreeHost(e->h_frame);
+    if (e->d_frame) cudaFree(e->d_frame);
+    if (e->frame_done) cudaEventDestroy(e->frame_done);
+    for (auto &ev : e->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->stream && e->own_stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    delete e;
+}
+
+const char *tdoa_last_error(const tdoa_engine *e) { return e ? e->error.c_str() : g_create_error.c_str(); }
+
+void *tdoa_host_alloc(size_t nbytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void tdoa_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int tdoa_set_stream(tdoa_engine *e, void *stream)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
+    if (stream) {
+        e->stream = reinterpret_cast<cudaStream_t>(stream);
+    } else {
+        CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        e->own_stream = true;
+    }
+    return TDOA_OK;
+}
+
+int tdoa_load_u8(tdoa_engine *e, int32_t station, const uint8_t *iq, size_t nbytes)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (station < 0 || station >= e->cfg.n_stations) return fail(e, TDOA_E_INVALID, "tdoa_load_u8: bad station %d", station);
+    if (!iq && nbytes) return fail(e, TDOA_E_INVALID, "tdoa_load_u8: NULL capture");
+    Station &s = e->stations[station];
+    if (s.owned_cap < nbytes || !s.owned) {
+        CU(cudaStreamSynchronize(e->stream));
+        if (s.owned) cudaFree(s.owned);
+        s.owned = nullptr; s.owned_cap = 0;
+        const size_t cap = std::max<size_t>((nbytes + 255) & ~size_t(255), 256);
+        CU(cudaMalloc(&s.owned, cap));
+        s.owned_cap = cap;
+    }
+    if (nbytes) CU(cudaMemcpyAsync(s.owned, iq, nbytes, cudaMemcpyHostToDevice, e->stream));
+    // the caller's buffer may be Go memory: do not return before the copy has left it
+    CU(cudaStreamSynchronize(e->stream));
+    s.d_raw = s.owned;
+    s.nbytes = nbytes;
+    s.nsamp = (i64)(nbytes / 2);  // processor.go:187  numSamples = fileSize / 2
+    s.loaded = true;
+    return TDOA_OK;
+}
+
+int tdoa_load_u8_device(tdoa_engine *e, int32_t station, const uint8_t *d_iq, size_t nbytes)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (station < 0 || station >= e->cfg.n_stations)
+        return fail(e, TDOA_E_INVALID, "tdoa_load_u8_device: bad station %d", station);
+    if (!d_iq && nbytes) return fail(e, TDOA_E_INVALID, "tdoa_load_u8_device: NULL capture");
+    if (reinterpret_cast<uintptr_t>(d_iq) & 15u)
+        return fail(e, TDOA_E_INVALID, "tdoa_load_u8_device: capture must be 16-byte aligned");
+    Station &s = e->stations[station];
+    s.d_raw = d_iq;
+    s.nbytes = nbytes;
+    s.nsamp = (i64)(nbytes / 2);
+    s.loaded = true;
+    return TDOA_OK;
+}
+
+int tdoa_unpack(tdoa_engine *e, int32_t station, int64_t first, int64_t count, float *out_c64)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (station < 0 || station >= e->cfg.n_stations || !e->stations[station].loaded)
+        return fail(e, TDOA_E_STATE, "tdoa_unpack: station %d not loaded", station);
+    const Station &s = e->stations[station];
+    if (first < 0 || count < 0 || first + count > s.nsamp || (!out_c64 && count))
+        return fail(e, TDOA_E_INVALID, "tdoa_unpack: range [%lld,+%lld) outside %lld samples", (long long)first,
+                    (long long)count, (long long)s.nsamp);
+    if (count == 0) return end_call(e, true);
+    std::vector<Sig> sigs(1);
+    Sig &sg = sigs[0];
+    sg.n = count;
+    sg.src.raw = s.d_raw; sg.src.run0_start = first; sg.src.run0_len = count;
+    float *d_c64 = nullptr;
+    if ((rc = ensure_plane(e, sg, 0, true))) return rc;
+    if ((rc = alloc_t(e, &sg.stats, ST_COUNT)) || (rc = alloc_t(e, &sg.partials, (size_t)2 * stream_grid_x(count))) ||
+        (rc = alloc_t(e, &sg.counter, 1)) || (rc = alloc_t(e, &d_c64, (size_t)2 * count)))
+        return rc;
+    CU(cudaMemsetAsync(sg.counter, 0, sizeof(unsigned), e->stream));
+    std::vector<SigJob> jobs(1, base_job(sg));
+    jobs[0].p_re = sg.plane[0][0]; jobs[0].p_im = sg.plane[0][1];
+    const SigJob *d_jobs = nullptr;
+    if ((rc = upload(e, jobs, &d_jobs))) return rc;
+    launch_unpack(d_jobs, 1, count, stream_grid_x(count), e->stream);
+    launch_interleave(sg.plane[0][0], sg.plane[0][1], count, d_c64, e->stream);
+    count_launch(e, 2);
+    CU(cudaMemcpyAsync(out_c64, d_c64, (size_t)2 * count * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    return end_call(e, true);
+}
+
+int tdoa_preprocess(tdoa_engine *e, int32_t station, int32_t kind, int64_t start, int64_t len, float *out_c64,
+                    double *power, int32_t *branch)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (station < 0 || station >= e->cfg.n_stations || !e->stations[station].loaded)
+        return fail(e, TDOA_E_STATE, "tdoa_preprocess: station %d not loaded", station);
+    if (kind != TDOA_KIND_REF && kind != TDOA_KIND_TGT) return fail(e, TDOA_E_INVALID, "tdoa_preprocess: bad kind");
+    const Station &s = e->stations[station];
+    const i64 n = signal_length(s, kind);
+    if (start < 0 || len < 0 || start + len > n || (!out_c64 && len))
+        return fail(e, TDOA_E_INVALID, "tdoa_preprocess: range [%lld,+%lld) outside %lld samples", (long long)start,
+                    (long long)len, (long long)n);
+    std::vector<Sig> sigs(1);
+    sigs[0].n = len;
+    sigs[0].src = make_view(s, kind, start, len);
+    if ((rc = preprocess(e, sigs))) return rc;
+    if (power) *power = sigs[0].power0;
+    if (branch) *branch = sigs[0].branch;
+    if (len > 0) {
+        Sig &sg = sigs[0];
+        float *d_nre = nullptr, *d_nim = nullptr, *d_c64 = nullptr;
+        if ((rc = alloc_t(e, &d_nre, (size_t)len)) || (rc = alloc_t(e, &d_nim, (size_t)len)) ||
+            (rc = alloc_t(e, &d_c64, (size_t)2 * len)))
+            return rc;
+        SigJob j = base_job(sg);
+        j.q_re = sg.out_re; j.q_im = sg.out_im; j.p_re = d_nre; j.p_im = d_nim;
+        std::vector<SigJob> jobs(1, j);
+        const SigJob *d_jobs = nullptr;
+        if ((rc = upload(e, jobs, &d_jobs))) return rc;
+        launch_normalize(d_jobs, 1, len, e->stream);
+        launch_interleave(d_nre, d_nim, len, d_c64, e->stream);
+        count_launch(e, 2);
+        CU(cudaMemcpyAsync(out_c64, d_c64, (size_t)2 * len * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    }
+    return end_call(e, true);
+}
+
+int tdoa_xcorr(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len, int32_t n_windows, int64_t hop,
+               tdoa_peak *out)
+{
+    return xcorr_impl(e, kind, win_start, win_len, n_windows, hop, out, false);
+}
+
+int tdoa_xcorr_device(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len, int32_t n_windows,
+                      int64_t hop, tdoa_peak *d_out)
+{
+    return xcorr_impl(e, kind, win_start, win_len, n_windows, hop, d_out, true);
+}
+
+int tdoa_cross_correlate(tdoa_engine *e, const float *sig1_c64, int64_t n1, const float *sig2_c64, int64_t n2,
+                         tdoa_peak *out)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (!out || n1 < 0 || n2 < 0 || (n1 && !sig1_c64) || (n2 && !sig2_c64))
+        return fail(e, TDOA_E_INVALID, "tdoa_cross_correlate: bad arguments");
+    std::vector<Sig> sigs(2);
+    const float *h[2] = {sig1_c64, sig2_c64};
+    const i64 n[2] = {n1, n2};
+    for (int k = 0; k < 2; k++) {
+        Sig &sg = sigs[k];
+        sg.n = n[k];
+        if (n[k] == 0) continue;
+        float *d_c64 = nullptr, *d_re = nullptr, *d_im = nullptr;
+        if ((rc = alloc_t(e, &d_c64, (size_t)2 * n[k])) || (rc = alloc_t(e, &d_re, (size_t)n[k])) ||
+            (rc = alloc_t(e, &d_im, (size_t)n[k])))
+            return rc;
+        CU(cudaMemcpyAsync(d_c64, h[k], (size_t)2 * n[k] * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        launch_deinterleave(d_c64, n[k], d_re, d_im, e->stream);
+        count_launch(e);
+        sg.src.raw = nullptr; sg.src.re = d_re; sg.src.im = d_im;
+        sg.src.run0_len = n[k];
+    }
+    // the host slices may be Go memory: they have been read once the copies complete,
+    // which preprocess() guarantees (it synchronises after the power pass)
+    PeakRec *d_out = nullptr;
+    if ((rc = alloc_t(e, &d_out, 1))) return rc;
+    if ((rc = preprocess(e, sigs))) return rc;
+    std::vector<Pair> pairs(1, Pair{0, 1});
+    if ((rc = correlate(e, sigs, pairs, d_out))) return rc;
+    CU(cudaMemcpyAsync(out, d_out, sizeof(tdoa_peak), cudaMemcpyDeviceToHost, e->stream));
+    rc = end_call(e, true);
+    e->st.launches_last = e->st.launches_total - e->launches_at_call;
+    return rc;
+}
+
+int tdoa_baselines(tdoa_engine *e, const double *stations_llh, int32_t n_stations, double *baselines)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (!stations_llh || !baselines || n_stations < 2)
+        return fail(e, TDOA_E_INVALID, "tdoa_baselines: bad arguments");
+    const int P = n_stations * (n_stations - 1) / 2;
+    double *d_llh = nullptr, *d_out = nullptr;
+    if ((rc = alloc_t(e, &d_llh, (size_t)3 * n_stations)) || (rc = alloc_t(e, &d_out, (size_t)P))) return rc;
+    CU(cudaMemcpyAsync(d_llh, stations_llh, (size_t)3 * n_stations * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    launch_baselines(d_llh, n_stations, d_out, e->stream);
+    count_launch(e);
+    CU(cudaMemcpyAsync(baselines, d_out, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    return end_call(e, true);
+}
+
+int tdoa_solve(tdoa_engine *e, const double *stations_llh, int32_t n_stations, const double *range_diffs,
+               int32_t n_sets, int32_t rd_stride, double *out_llh, int32_t *status, int32_t *iters)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    // processor.go:933-935 needs at least 3 stations and 2 range differences
+    if (!stations_llh || !range_diffs || !out_llh || !status || n_stations < 3 || n_sets < 0 || rd_stride < 2)
+        return fail(e, TDOA_E_INVALID, "tdoa_solve: bad arguments (need >= 3 stations, rd_stride >= 2)");
+    if (n_sets == 0) return end_call(e, true);
+    double *d_llh = nullptr, *d_rd = nullptr, *d_out = nullptr;
+    int *d_status = nullptr, *d_iters = nullptr;
+    if ((rc = alloc_t(e, &d_llh, (size_t)3 * n_stations)) || (rc = alloc_t(e, &d_rd, (size_t)n_sets * rd_stride)) ||
+        (rc = alloc_t(e, &d_out, (size_t)3 * n_sets)) || (rc = alloc_t(e, &d_status, (size_t)n_sets)) ||
+        (rc = alloc_t(e, &d_iters, (size_t)n_sets)))
+        return rc;
+    CU(cudaMemcpyAsync(d_llh, stations_llh, (size_t)3 * n_stations * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_rd, range_diffs, (size_t)n_sets * rd_stride * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    launch_solve(d_llh, d_rd, n_sets, rd_stride, d_out, d_status, d_iters, e->stream);
+    count_launch(e);
+    std::vector<int> h_status(n_sets);
+    CU(cudaMemcpyAsync(out_llh, d_out, (size_t)3 * n_sets * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(h_status.data(), d_status, (size_t)n_sets * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (iters) CU(cudaMemcpyAsync(iters, d_iters, (size_t)n_sets * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    rc = end_call(e, true);
+    if (rc) return rc;
+    for (int i = 0; i < n_sets; i++) status[i] = h_status[i] ? TDOA_E_SINGULAR : TDOA_OK;
+    return TDOA_OK;
+}
+
+int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_stations, const double *grid_desc,
+              const double *range_diffs, int32_t n_sets, int32_t rd_stride, double *out_llh, double *out_cost,
+              int64_t *out_index)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    const int P = n_stations * (n_stations - 1) / 2;
+    if (!stations_llh || !grid_desc || !range_diffs || !out_llh || n_stations < 2 || n_stations > 16 || n_sets < 0 ||
+        rd_stride < P)
+        return fail(e, TDOA_E_INVALID, "tdoa_grid: bad arguments (2..16 stations, rd_stride >= pairs)");
+    const int nlat = (int)grid_desc[4], nlon = (int)grid_desc[5];
+    if (nlat < 1 || nlon < 1) return fail(e, TDOA_E_INVALID, "tdoa_grid: empty grid");
+    if (n_sets == 0) return end_call(e, true);
+    double *d_llh = nullptr, *d_desc = nullptr, *d_rd = nullptr, *d_cost = nullptr, *d_out = nullptr;
+    i64 *d_idx = nullptr;
+    void *d_scratch = nullptr;
+    if ((rc = alloc_t(e, &d_llh, (size_t)3 * n_stations)) || (rc = alloc_t(e, &d_desc, 8)) ||
+        (rc = alloc_t(e, &d_rd, (size_t)n_sets * rd_stride)) || (rc = alloc_t(e, &d_cost, (size_t)n_sets)) ||
+        (rc = alloc_t(e, &d_idx, (size_t)n_sets)) || (rc = alloc_t(e, &d_out, (size_t)3 * n_sets)) ||
+        (rc = alloc(e, &d_scratch, grid_scratch_bytes(n_stations, nlat, nlon, n_sets))))
+        return rc;
+    CU(cudaMemcpyAsync(d_llh, stations_llh, (size_t)3 * n_stations * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_desc, grid_desc, 7 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_rd, range_diffs, (size_t)n_sets * rd_stride * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    launch_grid_cells(d_llh, n_stations, d_desc, nlat, nlon, d_rd, n_sets, rd_stride, d_cost, d_idx, d_out, d_scratch,
+                      e->stream);
+    count_launch(e, 2);
+    CU(cudaMemcpyAsync(out_llh, d_out, (size_t)3 * n_sets * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (out_cost) CU(cudaMemcpyAsync(out_cost, d_cost, (size_t)n_sets * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (out_index) CU(cudaMemcpyAsync(out_index, d_idx, (size_t)n_sets * sizeof(i64), cudaMemcpyDeviceToHost, e->stream));
+    return end_call(e, true);
+}
+
+int tdoa_get_stats(tdoa_engine *e, tdoa_stats *out)
+{
+    if (!e || !out) return TDOA_E_INVALID;
+    *out = e->st;
+    return TDOA_OK;
+}
+
+void *tdoa_stream(tdoa_engine *e) { return e ? reinterpret_cast<void *>(e->stream) : nullptr; }
+
+int tdoa_synchronize(tdoa_engine *e)
+{
+    if (!e) return TDOA_E_INVALID;
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return TDOA_OK;
+}
+
+}  // extern "C"

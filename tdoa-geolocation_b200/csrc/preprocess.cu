@@ -1,0 +1,328 @@
+// preprocess.cu -- per-signal stage of the path: uint8 IQ unpack, power, DC, the FM
+// discriminator / envelope, the edge-normalised box-car filters and normalisation.
+//
+// Replaces, per signal:  loadIQData (processor.go:193-201), calculateSignalPower
+// (:322-333), removeDCBias (:299-319), applyLowPassFilter (:270-296) and its HP/BP/
+// notch compositions (:354-434), normalizeSignal (:336-351), and the shipped binary's
+// convertToInstantaneousFrequency / envelope (ELF 0x49d120 / 0x49d021).
+//
+// Layout: signals are planar f32 (re[], im[]); im == nullptr means "identically 0",
+// which is what the discriminator and envelope branches produce.
+#include "kernels.h"
+
+namespace tdoa {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBoxTile = 2048;   // outputs per CTA of the box-car kernel
+constexpr int kBoxHalfMax = 500; // processor.go:404 clamps the window to 1000
+
+__device__ __forceinline__ float dc_from_sum(double sum, i64 n)
+{
+    // processor.go:309  dcBias /= complex(float32(len), 0): f32 accumulator divided by
+    // f32(n), correctly rounded.  The accumulator here is the exactly rounded sum.
+    return __fdiv_rn((float)sum, (float)n);
+}
+
+// ---------------------------------------------------------------- power
+__global__ void __launch_bounds__(kThreads) k_power(const SigJob *jobs)
+{
+    __shared__ double scratch[32];
+    const SigJob &J = jobs[blockIdx.y];
+    double acc = 0.0;
+    const i64 stride = (i64)gridDim.x * kThreads;
+    for (i64 i = (i64)blockIdx.x * kThreads + threadIdx.x; i < J.n; i += stride) {
+        const float2 v = load_sample(J.src, i);
+        acc += (double)mag2_f32(v.x, v.y);
+    }
+    double part[1] = {block_sum(acc, scratch)}, total[1];
+    if (grid_sum_last<1>(part, J.partials, J.counter, gridDim.x, blockIdx.x, scratch, total))
+        J.stats[ST_POWER0] = J.n > 0 ? total[0] / (double)J.n : 0.0;
+}
+
+// ---------------------------------------------------------------- unpack to planes (+ DC sums)
+__global__ void __launch_bounds__(kThreads) k_unpack(const SigJob *jobs)
+{
+    __shared__ double scratch[32];
+    const SigJob &J = jobs[blockIdx.y];
+    double sr = 0.0, si = 0.0;
+    const i64 stride = (i64)gridDim.x * kThreads;
+    for (i64 i = (i64)blockIdx.x * kThreads + threadIdx.x; i < J.n; i += stride) {
+        const float2 v = load_sample(J.src, i);
+        J.p_re[i] = v.x;
+        J.p_im[i] = v.y;
+        sr += (double)v.x;
+        si += (double)v.y;
+    }
+    double part[2], total[2];
+    part[0] = block_sum(sr, scratch);
+    part[1] = block_sum(si, scratch);
+    if (grid_sum_last<2>(part, J.partials, J.counter, gridDim.x, blockIdx.x, scratch, total)) {
+        J.stats[ST_SUM_RE] = total[0];
+        J.stats[ST_SUM_IM] = total[1];
+        J.stats[ST_DC_RE] = J.n > 0 ? (double)dc_from_sum(total[0], J.n) : 0.0;
+        J.stats[ST_DC_IM] = J.n > 0 ? (double)dc_from_sum(total[1], J.n) : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------- FM discriminator
+// ELF 0x49d120 (no source): out[i] = atan2(Im p, Re p), p = complex64(s[i]*conj(s[i-1]))
+// (f64 products, one rounding to f32); gates leave 0; out[0] = out[1].
+__device__ __forceinline__ float discriminate(float2 prev, float2 cur)
+{
+    if (prev.x == 0.f && prev.y == 0.f) return 0.f;
+    const double pr = prev.x, pi = prev.y, cr = cur.x, ci = cur.y, npi = -pi;
+    const double re = __dsub_rn(__dmul_rn(pr, cr), __dmul_rn(ci, npi));
+    const double im = __dadd_rn(__dmul_rn(npi, cr), __dmul_rn(ci, pr));
+    const float fre = (float)re, fim = (float)im;
+    if (fre == 0.f && fim == 0.f) return 0.f;
+    const float m = __fadd_rn(__fmul_rn(fre, fre), __fmul_rn(fim, fim));
+    if (!(m > 1e-10f)) return 0.f;
+    return (float)atan2((double)fim, (double)fre);
+}
+
+__global__ void __launch_bounds__(kThreads) k_demod(const SigJob *jobs)
+{
+    __shared__ double scratch[32];
+    const SigJob &J = jobs[blockIdx.y];
+    double sr = 0.0;
+    const i64 stride = (i64)gridDim.x * kThreads;
+    for (i64 i = (i64)blockIdx.x * kThreads + threadIdx.x; i < J.n; i += stride) {
+        const i64 k = i == 0 ? 1 : i;  // out[0] = out[1]
+        const float y = discriminate(load_sample(J.src, k - 1), load_sample(J.src, k));
+        J.p_re[i] = y;
+        sr += (double)y;
+    }
+    double part[1] = {block_sum(sr, scratch)}, total[1];
+    if (grid_sum_last<1>(part, J.partials, J.counter, gridDim.x, blockIdx.x, scratch, total)) {
+        J.stats[ST_SUM_RE] = total[0];
+        J.stats[ST_SUM_IM] = 0.0;
+        J.stats[ST_DC_RE] = J.n > 0 ? (double)dc_from_sum(total[0], J.n) : 0.0;
+        J.stats[ST_DC_IM] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------- envelope (ELF 0x49d021)
+__global__ void __launch_bounds__(kThreads) k_envelope(const SigJob *jobs)
+{
+    __shared__ double scratch[32];
+    const SigJob &J = jobs[blockIdx.y];
+    double sr = 0.0;
+    const i64 stride = (i64)gridDim.x * kThreads;
+    for (i64 i = (i64)blockIdx.x * kThreads + threadIdx.x; i < J.n; i += stride) {
+        const float2 v = load_sample(J.src, i);
+        const float y = __fsqrt_rn(mag2_f32(v.x, v.y));
+        J.p_re[i] = y;
+        sr += (double)y;
+    }
+    double part[1] = {block_sum(sr, scratch)}, total[1];
+    if (grid_sum_last<1>(part, J.partials, J.counter, gridDim.x, blockIdx.x, scratch, total)) {
+        J.stats[ST_SUM_RE] = total[0];
+        J.stats[ST_SUM_IM] = 0.0;
+        J.stats[ST_DC_RE] = J.n > 0 ? (double)dc_from_sum(total[0], J.n) : 0.0;
+        J.stats[ST_DC_IM] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------- box-car
+// processor.go:270-296: out[i] = (sum_{j=i-h..i+h, in range} in[j]) / count, the sum
+// taken in ascending j from a zero f32 accumulator (so every output is an independent
+// sequential sum and the result is bit-identical to the reference's).
+// mode BOX_HP gives in[i] - LP(in)[i] (processor.go:384-394).  sub_dc folds
+// removeDCBias (in[j] - dc) into the tile load.  window <= 1 is the identity (:271).
+__global__ void __launch_bounds__(kThreads) k_boxcar(const SigJob *jobs)
+{
+    __shared__ float s_re[kBoxTile + 2 * kBoxHalfMax];
+    __shared__ float s_im[kBoxTile + 2 * kBoxHalfMax];
+    __shared__ double scratch[32];
+    const SigJob &J = jobs[blockIdx.y];
+    const i64 n = J.n;
+    const bool has_im = J.q_im != nullptr;
+    const int h = J.window <= 1 ? 0 : J.window / 2;
+    const i64 i0 = (i64)blockIdx.x * kBoxTile;
+    double pacc = 0.0;
+    if (i0 < n) {
+        const i64 lo = max((i64)0, i0 - h);
+        const i64 hi = min(n, i0 + kBoxTile + h);  // exclusive
+        const float dcr = J.sub_dc ? (float)J.stats[ST_DC_RE] : 0.f;
+        const float dci = J.sub_dc ? (float)J.stats[ST_DC_IM] : 0.f;
+        for (i64 j = lo + threadIdx.x; j < hi; j += kThreads) {
+            float vr = J.q_re[j];
+            if (J.sub_dc) vr = __fsub_rn(vr, dcr);
+            s_re[j - lo] = vr;
+            if (has_im) {
+                float vi = J.q_im[j];
+                if (J.sub_dc) vi = __fsub_rn(vi, dci);
+                s_im[j - lo] = vi;
+            }
+        }
+        __syncthreads();
+        const i64 iend = min(n, i0 + kBoxTile);
+        for (i64 i = i0 + threadIdx.x; i < iend; i += kThreads) {
+            float outr, outi = 0.f;
+            if (h == 0) {
+                outr = s_re[i - lo];
+                if (has_im) outi = s_im[i - lo];
+            } else {
+                const i64 a = max((i64)0, i - h), b = min(n - 1, i + h);
+                const int ja = (int)(a - lo), cnt = (int)(b - a + 1);
+                const float fc = (float)cnt;
+                float ar = 0.f;
+#pragma unroll 4
+                for (int j = 0; j < cnt; j++) ar = __fadd_rn(ar, s_re[ja + j]);
+                outr = __fdiv_rn(ar, fc);
+                if (J.mode == BOX_HP) outr = __fsub_rn(s_re[i - lo], outr);
+                if (has_im) {
+                    float ai = 0.f;
+#pragma unroll 4
+                    for (int j = 0; j < cnt; j++) ai = __fadd_rn(ai, s_im[ja + j]);
+                    outi = __fdiv_rn(ai, fc);
+                    if (J.mode == BOX_HP) outi = __fsub_rn(s_im[i - lo], outi);
+                }
+            }
+            J.p_re[i] = outr;
+            if (has_im) J.p_im[i] = outi;
+            pacc += (double)mag2_f32(outr, outi);
+        }
+    }
+    if (J.want_power) {
+        double part[1] = {block_sum(pacc, scratch)}, total[1];
+        if (grid_sum_last<1>(part, J.partials, J.counter, gridDim.x, blockIdx.x, scratch, total)) {
+            const double p = n > 0 ? total[0] / (double)n : 0.0;
+            J.stats[ST_POWER1] = p;
+            // processor.go:343-345  scale = f32(1/sqrt(power)); power <= 0 leaves the signal alone
+            J.stats[ST_SCALE] = p > 0.0 ? (double)(float)(1.0 / sqrt(p)) : 1.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- notch combine
+// processor.go:428-431  out = s - 0.8 * band  (complex64 constant: one f32 rounding)
+__global__ void __launch_bounds__(kThreads) k_notch_combine(const SigJob *jobs)
+{
+    const SigJob &J = jobs[blockIdx.y];
+    const i64 stride = (i64)gridDim.x * kThreads;
+    for (i64 i = (i64)blockIdx.x * kThreads + threadIdx.x; i < J.n; i += stride) {
+        J.p_re[i] = __fsub_rn(J.q_re[i], __fmul_rn(J.r_re[i], 0.8f));
+        if (J.q_im) J.p_im[i] = __fsub_rn(J.q_im[i], __fmul_rn(J.r_im[i], 0.8f));
+    }
+}
+
+// ---------------------------------------------------------------- normalise (materialised)
+// processor.go:347-349  out = in * scale.  The correlators fold this multiply into
+// their loads; this kernel only serves the tdoa_preprocess probe.
+__global__ void __launch_bounds__(kThreads) k_normalize(const SigJob *jobs)
+{
+    const SigJob &J = jobs[blockIdx.y];
+    const float sc = (float)J.stats[ST_SCALE];
+    const i64 stride = (i64)gridDim.x * kThreads;
+    for (i64 i = (i64)blockIdx.x * kThreads + threadIdx.x; i < J.n; i += stride) {
+        J.p_re[i] = __fmul_rn(J.q_re[i], sc);
+        if (J.p_im) J.p_im[i] = J.q_im ? __fmul_rn(J.q_im[i], sc) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_interleave(const float *re, const float *im, i64 n, float2 *out)
+{
+    const i64 stride = (i64)gridDim.x * kThreads;
+    for (i64 i = (i64)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+        out[i] = make_float2(re[i], im ? im[i] : 0.f);
+}
+
+__global__ void __launch_bounds__(kThreads) k_deinterleave(const float2 *in, i64 n, float *re, float *im)
+{
+    const i64 stride = (i64)gridDim.x * kThreads;
+    for (i64 i = (i64)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        const float2 v = in[i];
+        re[i] = v.x;
+        im[i] = v.y;
+    }
+}
+
+__global__ void k_unpack_selftest(const float *lut, int *bad)
+{
+    const unsigned b = threadIdx.x;
+    if (unpack_byte(b) != lut[b]) atomicAdd(bad, 1);
+}
+
+}  // namespace
+
+int stream_grid_x(i64 n)
+{
+    const i64 want = (n + kThreads * 4 - 1) / (kThreads * 4);
+    const i64 cap = 148 * 8;
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+int boxcar_grid_x(i64 n)
+{
+    const i64 g = (n + kBoxTile - 1) / kBoxTile;
+    return (int)(g < 1 ? 1 : g);
+}
+
+void launch_power(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cudaStream_t st)
+{
+    (void)max_n;
+    k_power<<<dim3(grid_x, n_jobs), kThreads, 0, st>>>(d_jobs);
+}
+void launch_unpack(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cudaStream_t st)
+{
+    (void)max_n;
+    k_unpack<<<dim3(grid_x, n_jobs), kThreads, 0, st>>>(d_jobs);
+}
+void launch_demod(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cudaStream_t st)
+{
+    (void)max_n;
+    k_demod<<<dim3(grid_x, n_jobs), kThreads, 0, st>>>(d_jobs);
+}
+void launch_envelope(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cudaStream_t st)
+{
+    (void)max_n;
+    k_envelope<<<dim3(grid_x, n_jobs), kThreads, 0, st>>>(d_jobs);
+}
+void launch_boxcar(const SigJob *d_jobs, int n_jobs, i64 max_n, int max_window, cudaStream_t st)
+{
+    (void)max_window;
+    k_boxcar<<<dim3(boxcar_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
+}
+void launch_notch_combine(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)
+{
+    k_notch_combine<<<dim3(stream_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
+}
+void launch_normalize(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)
+{
+    k_normalize<<<dim3(stream_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
+}
+void launch_interleave(const float *re, const float *im, i64 n, float *out_c64, cudaStream_t st)
+{
+    k_interleave<<<stream_grid_x(n), kThreads, 0, st>>>(re, im, n, reinterpret_cast<float2 *>(out_c64));
+}
+void launch_deinterleave(const float *c64, i64 n, float *re, float *im, cudaStream_t st)
+{
+    k_deinterleave<<<stream_grid_x(n), kThreads, 0, st>>>(reinterpret_cast<const float2 *>(c64), n, re, im);
+}
+
+int unpack_selftest(cudaStream_t st)
+{
+    float h_lut[256];
+    for (int b = 0; b < 256; b++) {
+        volatile float x = (float)b - 127.5f;  // processor.go:198, host IEEE arithmetic
+        volatile float y = x / 127.5f;
+        h_lut[b] = y;
+    }
+    float *d_lut = nullptr;
+    int *d_bad = nullptr, h_bad = -1;
+    if (cudaMalloc(&d_lut, sizeof(h_lut)) != cudaSuccess) return -1;
+    if (cudaMalloc(&d_bad, sizeof(int)) != cudaSuccess) { cudaFree(d_lut); return -1; }
+    cudaMemcpyAsync(d_lut, h_lut, sizeof(h_lut), cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+    k_unpack_selftest<<<1, 256, 0, st>>>(d_lut, d_bad);
+    cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t err = cudaStreamSynchronize(st);
+    cudaFree(d_lut);
+    cudaFree(d_bad);
+    return err == cudaSuccess ? h_bad : -1;
+}
+
+}  // namespace tdoa

@@ -1,0 +1,262 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden
+vectors of the reference's shipped binary.  Tolerances (BASELINE.json north_star):
+integer lag of every correlation peak bit-exact; sub-sample TDOA within 1e-3 samples;
+position within 1 m.  Float intermediates: the f32 DC bias is computed from an exactly
+rounded sum instead of the reference's sequential f32 accumulator, so preprocessed
+samples may differ in the last bits (<= 2e-6 abs on unit-power signals) and printed
+correlations by <= 1e-6."""
+import io
+
+import numpy as np
+import pytest
+
+import tdoa_b200 as T
+from oracle import oracle
+from helpers import GOLDEN, GOLDEN_CASES, STATION_LLH, fm_capture, load_golden, quantise
+
+pytestmark = pytest.mark.gpu
+
+CORR_TOL = 1e-6
+SAMPLE_TOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def eng_binary():
+    with T.Engine(T.MODE_BINARY) as e:
+        yield e
+
+
+@pytest.fixture(scope="module")
+def eng_source():
+    with T.Engine(T.MODE_SOURCE) as e:
+        yield e
+
+
+def split(raw):
+    d = oracle.unpack_u8(raw)
+    return oracle.extract_reference(d), oracle.extract_target(d)
+
+
+def load_all(e, raws):
+    for k, r in enumerate(raws):
+        e.load_u8(k, r)
+
+
+# ------------------------------------------------------------------ K1 unpack
+def test_unpack_bit_exact(eng_binary):
+    raw = np.arange(512, dtype=np.uint8)  # every code in I and Q
+    raw = np.concatenate([raw, np.random.default_rng(0).integers(0, 256, 100000, dtype=np.uint8)])
+    eng_binary.load_u8(0, raw)
+    got = eng_binary.unpack(0, 0, raw.size // 2)
+    want = oracle.unpack_u8(raw)
+    assert got.view(np.uint32).tolist() == want.view(np.uint32).tolist()
+    part = eng_binary.unpack(0, 17, 1000)
+    assert np.array_equal(part.view(np.uint32), want[17:1017].view(np.uint32))
+
+
+# ------------------------------------------------------------------ preprocessing
+@pytest.mark.parametrize("case,branch", [("fm_strong", 0), ("fm_delays", 0), ("moderate", 1),
+                                         ("weak_noise", 2), ("weak_tones", 2)])
+def test_preprocess_binary_branches(eng_binary, case, branch):
+    raws, meta = load_golden(case)
+    load_all(eng_binary, raws)
+    for st in range(3):
+        ref, tgt = split(raws[st])
+        for kind, sig in ((T.KIND_REF, ref), (T.KIND_TGT, tgt)):
+            got, power, br = eng_binary.preprocess(st, kind, 0, sig.size)
+            want, wbr = oracle.preprocess_binary(sig)
+            assert br == wbr == branch
+            assert power == pytest.approx(oracle.signal_power(sig), rel=1e-12)
+            assert np.max(np.abs(got - want)) <= SAMPLE_TOL
+
+
+def test_preprocess_window_and_joint(eng_binary):
+    """A window that straddles the block-1/block-3 joint of the reference signal."""
+    raws, _ = load_golden("fm_strong")
+    eng_binary.load_u8(0, raws[0])
+    ref, _ = split(raws[0])
+    b = ref.size // 2
+    start, ln = b - 3000, 9000
+    got, _, br = eng_binary.preprocess(0, T.KIND_REF, start, ln)
+    want, _ = oracle.preprocess_binary(ref[start:start + ln])
+    assert br == 0 and np.max(np.abs(got - want)) <= SAMPLE_TOL
+
+
+@pytest.mark.parametrize("amp", [0.5, 0.01])
+def test_preprocess_source_branches(eng_source, amp):
+    rng = np.random.default_rng(5)
+    n = 60000
+    x = amp * np.exp(1j * np.cumsum(rng.standard_normal(n) * 0.1)) + 0.2 * amp * (
+        rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    raw = quantise(np.concatenate([x, x[::-1], x]))
+    eng_source.load_u8(0, raw)
+    _, tgt = split(raw)
+    got, power, br = eng_source.preprocess(0, T.KIND_TGT, 0, tgt.size)
+    want, wbr = oracle.preprocess_source(tgt)
+    assert (br != 0) == bool(wbr) == (amp < 0.03)
+    assert np.max(np.abs(got - want)) <= 5e-6
+
+
+# ------------------------------------------------------------------ golden pairs (shipped binary)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_golden_pairs_binary_mode(eng_binary, case):
+    raws, meta = load_golden(case)
+    load_all(eng_binary, raws)
+    want_ref, want_tgt = oracle.process_capture_binary(raws)
+    got = list(eng_binary.xcorr(T.KIND_REF)[0]) + list(eng_binary.xcorr(T.KIND_TGT)[0])
+    for pk, gold, orc in zip(got, meta["pairs"], want_ref + want_tgt):
+        assert int(pk["lag"]) == gold["delay"] == orc[0], (case, gold)       # bit-exact lag
+        assert abs(float(pk["corr"]) - gold["corr"]) <= 0.5e-6 + CORR_TOL   # reference prints %.6f
+        assert abs(float(pk["corr"]) - orc[1]) <= CORR_TOL
+        assert bool(pk["flags"] & 1) == orc[2]                               # sanity re-search taken
+
+
+def test_cross_correlate_seam_binary(eng_binary):
+    raws, _ = load_golden("fm_delays")
+    t0, t1 = split(raws[0])[1], split(raws[2])[1]
+    pk = eng_binary.cross_correlate(t0, t1)
+    d, c, r = oracle.cross_correlate_binary(t0, t1)
+    assert (pk.lag, pk.researched) == (d, r) and abs(pk.corr - c) <= CORR_TOL
+    # unequal lengths: the shorter input is the template (processor.go:653-661)
+    pk = eng_binary.cross_correlate(t0[:30000], t1)
+    d, c, r = oracle.cross_correlate_binary(t0[:30000], t1)
+    assert (pk.lag, pk.researched) == (d, r) and abs(pk.corr - c) <= CORR_TOL
+    pk = eng_binary.cross_correlate(t1, t0[:30000])
+    d, c, r = oracle.cross_correlate_binary(t1, t0[:30000])
+    assert (pk.lag, pk.researched) == (d, r) and abs(pk.corr - c) <= CORR_TOL
+
+
+def test_empty_and_tiny_inputs(eng_binary):
+    z = np.zeros(0, np.complex64)
+    x = (np.random.default_rng(1).standard_normal(5000) * 0.3).astype(np.complex64)
+    pk = eng_binary.cross_correlate(z, x)
+    assert (pk.lag, pk.corr) == (0, 0.0) and pk.flags & 0x8  # processor.go:622-625
+    # shorter than one block: no whole block -> (0, 0.0) like the reference loop
+    pk = eng_binary.cross_correlate(x, x)
+    d, c, _ = oracle.cross_correlate_binary(x, x)
+    assert (pk.lag, pk.corr) == (d, c) == (0, 0.0)
+
+
+def test_ragged_station_lengths(eng_binary):
+    raws = fm_capture(30000, (0, 4, 9), (0, 12, 30), seed=3)
+    raws[1] = raws[1][: 2 * 3 * 27000]  # a shorter capture: block 27000
+    load_all(eng_binary, raws)
+    want_ref, want_tgt = oracle.process_capture_binary(raws)
+    got = list(eng_binary.xcorr(T.KIND_REF)[0]) + list(eng_binary.xcorr(T.KIND_TGT)[0])
+    for pk, orc in zip(got, want_ref + want_tgt):
+        assert int(pk["lag"]) == orc[0] and abs(float(pk["corr"]) - orc[1]) <= CORR_TOL
+
+
+# ------------------------------------------------------------------ source mode (processor.go as committed)
+def test_source_mode_pairs(eng_source):
+    raws, _ = load_golden("fm_strong")
+    load_all(eng_source, raws)
+    want_ref, want_tgt = oracle.process_capture_source(raws)
+    got = list(eng_source.xcorr(T.KIND_REF)[0]) + list(eng_source.xcorr(T.KIND_TGT)[0])
+    for pk, orc in zip(got, want_ref + want_tgt):
+        # equal lengths: the source evaluates lag 0 only (SURVEY.md finding 3)
+        assert int(pk["lag"]) == orc[0] == 0
+        assert abs(float(pk["corr"]) - orc[1]) <= 2e-4 * max(1.0, abs(orc[1]))
+
+
+def test_source_mode_unequal_lengths(eng_source):
+    raws, _ = load_golden("fm_delays")
+    t0, t1 = split(raws[0])[1], split(raws[1])[1]
+    a, b = t0[:20000], t1[:26000]
+    pk = eng_source.cross_correlate(a, b)
+    d, c = oracle.cross_correlate_source(a, b)
+    assert pk.lag == d
+    assert abs(pk.corr - c) <= 2e-4 * max(1.0, abs(c))
+
+
+# ------------------------------------------------------------------ windows
+def test_windows_equal_single_calls(eng_binary):
+    raws = fm_capture(120000, (0, 3, 8), (0, 20, 41), seed=7)
+    load_all(eng_binary, raws)
+    W, hop, nw = 30000, 25000, 4
+    multi = eng_binary.xcorr(T.KIND_TGT, 1000, W, nw, hop)
+    for w in range(nw):
+        one = eng_binary.xcorr(T.KIND_TGT, 1000 + w * hop, W, 1, 0)[0]
+        assert np.array_equal(multi[w]["lag"], one["lag"])
+        assert np.array_equal(multi[w]["corr"], one["corr"])
+        for p, (i, j) in enumerate([(0, 1), (0, 2), (1, 2)]):
+            ti = split(raws[i])[1][1000 + w * hop:1000 + w * hop + W]
+            tj = split(raws[j])[1][1000 + w * hop:1000 + w * hop + W]
+            d, c, _ = oracle.cross_correlate_binary(ti, tj)
+            assert int(multi[w][p]["lag"]) == d and abs(float(multi[w][p]["corr"]) - c) <= CORR_TOL
+    with pytest.raises(T.TdoaError):
+        eng_binary.xcorr(T.KIND_TGT, 0, 100000, 3, 50000)  # runs past the block
+
+
+# ------------------------------------------------------------------ extended mode (engine-defined)
+def test_extended_two_sided_subsample():
+    L, W = 300, 40000
+    raws = fm_capture(60000, (40, 0, 17), (25, 60, 0), seed=11)  # negative true lags appear
+    with T.Engine(T.MODE_EXTENDED, max_lag=L) as e:
+        load_all(e, raws)
+        got = e.xcorr(T.KIND_TGT, 500, W, 1, 0)[0]
+        for p, (i, j) in enumerate([(0, 1), (0, 2), (1, 2)]):
+            yi, _ = oracle.preprocess_binary(split(raws[i])[1][500:500 + W])
+            yj, _ = oracle.preprocess_binary(split(raws[j])[1][500:500 + W])
+            c = oracle.xcorr_two_sided(yi, yj, L)
+            idx, frac, val = oracle.peak_parabolic(c)
+            assert int(got[p]["lag"]) == idx - L
+            assert abs(float(got[p]["frac"]) - frac) <= 1e-3          # north_star: 1e-3 samples
+            assert abs(float(got[p]["corr"]) - val) <= CORR_TOL
+    assert [int(g["lag"]) for g in got] == [35, -25, -60]
+
+
+# ------------------------------------------------------------------ geodesy + solvers
+def test_baselines_and_solver(eng_binary):
+    base = eng_binary.baselines(STATION_LLH)
+    want = [oracle.baseline(STATION_LLH[i], STATION_LLH[j]) for i in range(3) for j in range(i + 1, 3)]
+    assert np.max(np.abs(base - want)) < 1e-6
+    rng = np.random.default_rng(2)
+    rds = np.concatenate([np.array([[0, 0, 0], [3.5, 6.0, 2.5], [10, 5, -3], [-3.5, 2, 0]]) * 1e-6 * 299792458.0,
+                          rng.uniform(-8000, 8000, (60, 3))])
+    out, status, iters = eng_binary.solve(STATION_LLH, rds)
+    for k in range(len(rds)):
+        w, ws, wi = oracle.solve_tdoa(STATION_LLH, rds[k])
+        assert (status[k] != 0) == (ws != 0) and iters[k] == wi
+        if ws == 0:
+            ga, wa = oracle.llh_to_ecef(*out[k]), oracle.llh_to_ecef(*w)
+            assert np.linalg.norm(ga - wa) < 1e-3  # north_star: position within 1 m
+
+
+def test_grid_multilateration(eng_binary):
+    rng = np.random.default_rng(4)
+    st = np.vstack([STATION_LLH, STATION_LLH[:2] + rng.uniform(-0.1, 0.1, (2, 3)) * [1, 1, 100]])
+    tx = np.array([41.25, -96.0, 350.0])
+    r = [np.linalg.norm(oracle.llh_to_ecef(*tx) - oracle.llh_to_ecef(*s)) for s in st]
+    rd = np.array([r[j] - r[i] for i in range(5) for j in range(i + 1, 5)])
+    rds = np.stack([rd, rd + rng.normal(0, 15, rd.size), rd + rng.normal(0, 40, rd.size)])
+    desc = [41.20, -96.06, 0.002, 0.002, 60, 70, 350.0]
+    out, cost, idx = eng_binary.grid(st, desc, rds)
+    for k in range(3):
+        wi, wc, wl = oracle.grid_solve(st, rds[k], *desc[:4], int(desc[4]), int(desc[5]), desc[6])
+        assert idx[k] == wi
+        assert cost[k] == pytest.approx(wc, rel=1e-9)
+        assert np.allclose(out[k], wl, atol=1e-12)
+
+
+# ------------------------------------------------------------------ the reference-interface mirror
+def test_processor_mirror_stdout(tmp_path):
+    raws, meta = load_golden("fm_delays")
+    files = []
+    for name, raw in zip(["kx0u", "n3pay", "kf0mtl"], raws):
+        f = tmp_path / f"sim-{name}-1.dat"
+        raw.tofile(f)
+        files.append(str(f))
+    buf = io.StringIO()
+    p = T.TDOAProcessor(162400000.0, 92300000.0, str(GOLDEN / "stations.csv"), out=buf)
+    res = p.process_tdoa(files)
+    p.close()
+    text = buf.getvalue()
+    gold = (GOLDEN / "fm_delays.stdout.txt").read_text()
+    for line in gold.splitlines():
+        if line.startswith(("REF ", "TGT ")) or line.endswith(" km"):
+            assert line in text, line
+    assert "*** CALCULATED TRANSMITTER LOCATION ***" in text
+    rd = np.array(res["range_differences"])
+    want, status, _ = oracle.solve_tdoa(STATION_LLH, rd)
+    assert status == 0 and np.allclose(res["position"], want, atol=1e-9)
