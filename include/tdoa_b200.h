@@ -87,7 +87,13 @@ typedef struct {
     int32_t use_fft;       /* 1: FFT candidate search + exact re-evaluation;
                               0: evaluate every lag in the time domain               */
     int32_t device;        /* CUDA device ordinal                                    */
-    int32_t reserved[7];
+    int32_t seq_dc_limit;  /* removeDCBias (processor.go:299-319): signals of up to this many
+                              samples get the reference's sequential f32 accumulator,
+                              bit for bit; longer ones (which the reference never
+                              processes: it truncates to its chunk) an exactly rounded
+                              sum.  0 = mode default (4194304 SOURCE/BINARY, never in
+                              EXTENDED); -1 = never                                   */
+    int32_t reserved[6];
 } tdoa_config;
 
 /* Fill *cfg with the reference-matching defaults of `mode`. */

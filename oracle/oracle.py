@@ -49,6 +49,7 @@ def lib():
         L.orc_signal_power.argtypes = [_vp, _i64]
         L.orc_signal_power.restype = _f64
         L.orc_remove_dc.argtypes = [_vp, _i64, _vp, _vp]
+        L.orc_set_seq_dc_limit.argtypes = [_i64]
         L.orc_lowpass.argtypes = [_vp, _i64, C.c_int, _vp]
         L.orc_cutoff_window.argtypes = [_f64, _f64]
         L.orc_cutoff_window.restype = C.c_int
@@ -126,6 +127,12 @@ def remove_dc(s):
     dc = np.zeros(1, np.complex64)
     lib().orc_remove_dc(_p(s), s.size, _p(out), _p(dc))
     return out, dc[0]
+
+
+def set_seq_dc_limit(n: int) -> None:
+    """Signals longer than n samples get an exactly rounded DC sum (engine-defined
+    extension, see tdoa_oracle.c); n < 0 restores the reference's arithmetic."""
+    lib().orc_set_seq_dc_limit(int(n))
 
 
 def lowpass(s, window: int):

@@ -89,13 +89,29 @@ static inline float div_f32_via_f64(float a, float c)
     return (float)((double)a / (double)c);
 }
 
+/* Engine-defined extension beyond the reference's reach: the reference only ever
+ * runs removeDCBias on <= 2 000 000 samples (it truncates to its test chunk,
+ * processor.go:772-780).  For signals longer than this limit the engine replaces the
+ * sequential f32 accumulator -- which stagnates once the sum passes ~2^24 |x| -- by
+ * an exactly rounded sum; tests of those lengths set the same limit here.  The default
+ * (no limit) is the reference's arithmetic, and is what the golden vectors pin. */
+static int64_t g_seq_dc_limit = INT64_MAX;
+ORC_API void orc_set_seq_dc_limit(int64_t n) { g_seq_dc_limit = n < 0 ? INT64_MAX : n; }
+
 /* processor.go:299-319  removeDCBias: sequential complex64 sum, divide, subtract. */
 ORC_API void orc_remove_dc(const c64 *in, int64_t n, c64 *out, c64 *dc_out)
 {
     c64 dc = {0.f, 0.f};
     if (n == 0) { if (dc_out) *dc_out = dc; return; }
     float sr = 0.f, si = 0.f;
-    for (int64_t i = 0; i < n; i++) { sr += in[i].re; si += in[i].im; }
+    if (n <= g_seq_dc_limit) {
+        for (int64_t i = 0; i < n; i++) { sr += in[i].re; si += in[i].im; }
+    } else {
+        /* f32 values summed in long double are exact far beyond these lengths */
+        long double ar = 0.0L, ai = 0.0L;
+        for (int64_t i = 0; i < n; i++) { ar += in[i].re; ai += in[i].im; }
+        sr = (float)ar; si = (float)ai;
+    }
     dc.re = div_f32_via_f64(sr, (float)n);
     dc.im = div_f32_via_f64(si, (float)n);
     for (int64_t i = 0; i < n; i++) {

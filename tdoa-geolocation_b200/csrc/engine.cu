@@ -226,18 +226,22 @@ int ensure_plane(tdoa_engine *e, Sig &s, int idx, bool cplx)
     return TDOA_OK;
 }
 
-enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_BOXCAR, K_NOTCH };
+enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_SEQSUM, K_BOXCAR, K_NOTCH };
 
-// queue of (kernel, jobs) stages; stage k of every signal of a branch is batched
+// queue of (stage, kernel) steps: step k of every signal that runs the same kernel at
+// that stage is batched into one launch; stages run in order
 struct Pipeline {
-    std::vector<Kern> kern;
-    std::vector<Step> steps;
+    struct Entry { Kern kern; Step step; };
+    std::vector<std::vector<Entry>> stages;
     void add(size_t stage, Kern k, const SigJob &j)
     {
-        if (steps.size() <= stage) { steps.resize(stage + 1); kern.resize(stage + 1, k); }
-        kern[stage] = k;
-        steps[stage].jobs.push_back(j);
-        steps[stage].max_n = std::max(steps[stage].max_n, j.n);
+        if (stages.size() <= stage) stages.resize(stage + 1);
+        Entry *en = nullptr;
+        for (auto &x : stages[stage])
+            if (x.kern == k) en = &x;
+        if (!en) { stages[stage].push_back(Entry{k, Step{}}); en = &stages[stage].back(); }
+        en->step.jobs.push_back(j);
+        en->step.max_n = std::max(en->step.max_n, j.n);
     }
 };
 
@@ -255,6 +259,22 @@ SigJob box_job(const Sig &s, int in, int out, bool cplx, int window, int mode, b
     return j;
 }
 
+// removeDCBias with the reference's sequential f32 accumulator (see seq_dc_limit)
+SigJob seqsum_job(const Sig &s, int in, bool cplx)
+{
+    SigJob j = base_job(s);
+    j.q_re = s.plane[in][0];
+    j.q_im = cplx ? s.plane[in][1] : nullptr;
+    return j;
+}
+
+bool wants_seq_dc(const tdoa_engine *e, i64 n)
+{
+    i64 lim = e->cfg.seq_dc_limit;
+    if (lim == 0) lim = e->cfg.mode == TDOA_MODE_EXTENDED ? -1 : 4194304;
+    return lim > 0 && n <= lim;
+}
+
 SigJob notch_job(const Sig &s, int in, int band, int out)
 {
     SigJob j = base_job(s);
@@ -266,21 +286,24 @@ SigJob notch_job(const Sig &s, int in, int band, int out)
 
 int run_pipeline(tdoa_engine *e, Pipeline &pl)
 {
-    for (size_t k = 0; k < pl.steps.size(); k++) {
-        Step &st = pl.steps[k];
-        if (st.jobs.empty()) continue;
-        const SigJob *d_jobs = nullptr;
-        int rc = upload(e, st.jobs, &d_jobs);
-        if (rc) return rc;
-        const int nj = (int)st.jobs.size();
-        switch (pl.kern[k]) {
-            case K_UNPACK: launch_unpack(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
-            case K_DEMOD: launch_demod(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
-            case K_ENVELOPE: launch_envelope(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
-            case K_BOXCAR: launch_boxcar(d_jobs, nj, st.max_n, 0, e->stream); break;
-            case K_NOTCH: launch_notch_combine(d_jobs, nj, st.max_n, e->stream); break;
+    for (auto &stage : pl.stages) {
+        for (auto &en : stage) {
+            Step &st = en.step;
+            if (st.jobs.empty()) continue;
+            const SigJob *d_jobs = nullptr;
+            int rc = upload(e, st.jobs, &d_jobs);
+            if (rc) return rc;
+            const int nj = (int)st.jobs.size();
+            switch (en.kern) {
+                case K_UNPACK: launch_unpack(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
+                case K_DEMOD: launch_demod(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
+                case K_ENVELOPE: launch_envelope(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
+                case K_SEQSUM: launch_seqsum(d_jobs, nj, e->stream); break;
+                case K_BOXCAR: launch_boxcar(d_jobs, nj, st.max_n, 0, e->stream); break;
+                case K_NOTCH: launch_notch_combine(d_jobs, nj, st.max_n, e->stream); break;
+            }
+            count_launch(e);
         }
-        count_launch(e);
     }
     return TDOA_OK;
 }
@@ -335,6 +358,8 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
             u.p_re = s.plane[0][0]; u.p_im = s.plane[0][1];
             size_t g = 0;
             pl.add(g++, K_UNPACK, u);
+            if (wants_seq_dc(e, s.n)) pl.add(g, K_SEQSUM, seqsum_job(s, 0, true));
+            g++;
             if (!weak) {
                 // processor.go:485-495  DC -> BP(500, 50k) -> LP(100) -> normalise
                 pl.add(g++, K_BOXCAR, box_job(s, 0, 1, true, cutoff_window(500.0), BOX_HP, true, false));
@@ -372,6 +397,8 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
                 SigJob u = base_job(s);
                 u.p_re = s.plane[0][0]; u.p_im = s.plane[0][1];
                 pl.add(g++, cplx ? K_UNPACK : K_DEMOD, u);
+                if (wants_seq_dc(e, s.n)) pl.add(g, K_SEQSUM, seqsum_job(s, 0, cplx));
+                g++;
                 pl.add(g++, K_BOXCAR, box_job(s, 0, 1, cplx, 10, BOX_LP, true, true));
                 s.out_re = s.plane[1][0]; s.out_im = s.plane[1][1];
             } else if (s.branch == 1) {
@@ -379,6 +406,8 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
                 SigJob u = base_job(s);
                 u.p_re = s.plane[0][0];
                 pl.add(g++, K_ENVELOPE, u);
+                if (wants_seq_dc(e, s.n)) pl.add(g, K_SEQSUM, seqsum_job(s, 0, false));
+                g++;
                 pl.add(g++, K_BOXCAR, box_job(s, 0, 1, false, 1, BOX_LP, true, true));
                 s.out_re = s.plane[1][0]; s.out_im = nullptr;
             } else {
@@ -386,6 +415,8 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
                 SigJob u = base_job(s);
                 u.p_re = s.plane[0][0]; u.p_im = s.plane[0][1];
                 pl.add(g++, K_UNPACK, u);
+                if (wants_seq_dc(e, s.n)) pl.add(g, K_SEQSUM, seqsum_job(s, 0, true));
+                g++;
                 // removeDC -> bandpass(100 Hz, 200 kHz) -> normalise
                 pl.add(g++, K_BOXCAR, box_job(s, 0, 1, true, cutoff_window(100.0), BOX_HP, true, false));
                 pl.add(g++, K_BOXCAR, box_job(s, 1, 0, true, cutoff_window(200000.0), BOX_LP, false, true));

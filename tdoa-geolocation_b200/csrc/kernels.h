@@ -93,6 +93,7 @@ void launch_power(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cudaS
 void launch_unpack(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cudaStream_t st);
 void launch_demod(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cudaStream_t st);
 void launch_envelope(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cudaStream_t st);
+void launch_seqsum(const SigJob *d_jobs, int n_jobs, cudaStream_t st);
 void launch_boxcar(const SigJob *d_jobs, int n_jobs, i64 max_n, int max_window, cudaStream_t st);
 void launch_notch_combine(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
 void launch_normalize(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);

@@ -125,6 +125,57 @@ __global__ void __launch_bounds__(kThreads) k_envelope(const SigJob *jobs)
     }
 }
 
+// ---------------------------------------------------------------- sequential f32 DC sum
+// processor.go:304-309 accumulates the DC bias in a complex64, i.e. two sequential f32
+// chains; their rounding error is far from negligible on DC-heavy signals (the
+// envelope branch), so parity of the printed correlation needs the same chain.  One
+// warp per (signal, component): lanes fetch 32 consecutive samples at a time (next
+// batch prefetched), every lane then walks the same 32 dependent adds.
+__global__ void __launch_bounds__(32) k_seqsum(const SigJob *jobs)
+{
+    const SigJob &J = jobs[blockIdx.x];
+    const float *x = blockIdx.y == 0 ? J.q_re : J.q_im;
+    const int lane = threadIdx.x;
+    if (!x) {
+        if (lane == 0) J.stats[blockIdx.y == 0 ? ST_DC_RE : ST_DC_IM] = 0.0;
+        return;
+    }
+    const i64 n = J.n;
+    float s = 0.f;
+    constexpr int U = 4;
+    float cur[U], nxt[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const i64 i = (i64)u * 32 + lane;
+        cur[u] = i < n ? x[i] : 0.f;
+    }
+    for (i64 base = 0; base < n; base += 32 * U) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const i64 i = base + 32 * U + (i64)u * 32 + lane;
+            nxt[u] = i < n ? x[i] : 0.f;
+        }
+        const i64 left = n - base;
+        if (left >= 32 * U) {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int k = 0; k < 32; k++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, cur[u], k));
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int k = 0; k < 32; k++) {
+                    const float v = __shfl_sync(0xffffffffu, cur[u], k);
+                    if ((i64)u * 32 + k < left) s = __fadd_rn(s, v);
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) cur[u] = nxt[u];
+    }
+    if (lane == 0) J.stats[blockIdx.y == 0 ? ST_DC_RE : ST_DC_IM] = n > 0 ? (double)__fdiv_rn(s, (float)n) : 0.0;
+}
+
 // ---------------------------------------------------------------- box-car
 // processor.go:270-296: out[i] = (sum_{j=i-h..i+h, in range} in[j]) / count, the sum
 // taken in ascending j from a zero f32 accumulator (so every output is an independent
@@ -280,6 +331,10 @@ void launch_envelope(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cu
 {
     (void)max_n;
     k_envelope<<<dim3(grid_x, n_jobs), kThreads, 0, st>>>(d_jobs);
+}
+void launch_seqsum(const SigJob *d_jobs, int n_jobs, cudaStream_t st)
+{
+    k_seqsum<<<dim3(n_jobs, 2), 32, 0, st>>>(d_jobs);
 }
 void launch_boxcar(const SigJob *d_jobs, int n_jobs, i64 max_n, int max_window, cudaStream_t st)
 {

@@ -192,6 +192,7 @@ def test_windows_equal_single_calls(eng_binary):
 def test_extended_two_sided_subsample():
     L, W = 300, 40000
     raws = fm_capture(60000, (40, 0, 17), (25, 60, 0), seed=11)  # negative true lags appear
+    oracle.set_seq_dc_limit(0)  # EXTENDED mode: exactly rounded DC sum (engine-defined)
     with T.Engine(T.MODE_EXTENDED, max_lag=L) as e:
         load_all(e, raws)
         got = e.xcorr(T.KIND_TGT, 500, W, 1, 0)[0]
@@ -203,6 +204,7 @@ def test_extended_two_sided_subsample():
             assert int(got[p]["lag"]) == idx - L
             assert abs(float(got[p]["frac"]) - frac) <= 1e-3          # north_star: 1e-3 samples
             assert abs(float(got[p]["corr"]) - val) <= CORR_TOL
+    oracle.set_seq_dc_limit(-1)
     assert [int(g["lag"]) for g in got] == [35, -25, -60]
 
 
@@ -241,7 +243,7 @@ def test_grid_multilateration(eng_binary):
 
 # ------------------------------------------------------------------ the reference-interface mirror
 def test_processor_mirror_stdout(tmp_path):
-    raws, meta = load_golden("fm_delays")
+    raws, meta = load_golden("fm_strong")
     files = []
     for name, raw in zip(["kx0u", "n3pay", "kf0mtl"], raws):
         f = tmp_path / f"sim-{name}-1.dat"
@@ -252,7 +254,7 @@ def test_processor_mirror_stdout(tmp_path):
     res = p.process_tdoa(files)
     p.close()
     text = buf.getvalue()
-    gold = (GOLDEN / "fm_delays.stdout.txt").read_text()
+    gold = (GOLDEN / "fm_strong.stdout.txt").read_text()
     for line in gold.splitlines():
         if line.startswith(("REF ", "TGT ")) or line.endswith(" km"):
             assert line in text, line
