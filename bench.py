@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- station-pair cross-correlation throughput of the B200 TDOA engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): 3 stations x 100 s x 2 Msps dual-frequency uint8 IQ
+captures (200 000 000 samples = 400 MB per station, blocks ref/target/ref), simulator.go
+layout with FM content and integer sample delays (SURVEY.md 8d "Mode B"); every step runs
+the full-length path: unpack -> FM discriminator -> DC -> box-car -> normalise per
+station signal, all 3 station pairs of the reference signal (133 333 332 samples) and of
+the target signal (66 666 666 samples) over lags 0..1999 with the reference binary's
+block arithmetic, peak records, then the 2-D fix.
+
+One step = one pass over one such capture set.  Metric: pair-Msamples/s =
+sum over pairs and kinds of the signal length / step time.
+`value` is timed with the captures already resident in HBM; `e2e` is the same step
+through the C ABI with HOST (pinned) buffers: host->device copy of the three captures
+and device->host read of the peak records and the fix inside the timed region.
+
+N > 1 (torchrun): every rank processes its own capture set (weak scaling, no data-path
+collective); the peak records are gathered with one NCCL all_gather.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+FS = 2e6
+C_LIGHT = 299792458.0
+STATION_LLH = np.array([
+    [41.18660274289527, -95.96064116595667, 355.69],   # kx0u    (lat-lon-table.csv)
+    [41.24669616513154, -96.08366304481238, 329.0],    # n3pay
+    [41.32916620016985, -96.03513381562004, 373.18],   # kf0mtl
+])
+TX_LLH = np.array([41.20, -96.00, 400.0])              # simulator.go:229 usage example
+STATION_NAMES = ["kx0u", "n3pay", "kf0mtl"]
+
+
+def llh_to_ecef(lat, lon, h):
+    a, f = 6378137.0, 1 / 298.257223563
+    e2 = 2 * f - f * f
+    la, lo = np.radians(lat), np.radians(lon)
+    n = a / np.sqrt(1 - e2 * np.sin(la) ** 2)
+    return np.array([(n + h) * np.cos(la) * np.cos(lo), (n + h) * np.cos(la) * np.sin(lo),
+                     (n * (1 - e2) + h) * np.sin(la)])
+
+
+def true_delays():
+    tx = llh_to_ecef(*TX_LLH)
+    d = np.array([np.linalg.norm(tx - llh_to_ecef(*s)) for s in STATION_LLH])
+    k = np.rint(d / C_LIGHT * FS).astype(int)
+    return k - k.min()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": sorted(reasons),
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+# ----------------------------------------------------------------------------- synthetic captures
+def synth_captures_gpu(torch, device, block: int, seed: int):
+    """Mode-B captures generated on the GPU (setup only, never timed): FM of box-car
+    filtered Gaussian audio, amplitude 0.5, integer delays from the station geometry,
+    AWGN sigma 0.02, quantised as simulator.go:150-160.  Returns uint8 tensors [3][6*block]."""
+    g = torch.Generator(device=device)
+    delays = true_delays()
+    pad = int(delays.max()) + 64
+
+    def fm(n, sd, dev):
+        g.manual_seed(sd)
+        a = torch.randn(n + 64, device=device, generator=g)
+        cs = torch.cumsum(a, 0)
+        a = (cs[64:] - cs[:-64]) / 64.0          # 64-tap box-car audio
+        a = a / a.abs().max()
+        ph = torch.cumsum(a.double(), 0) * (2 * np.pi * dev / FS)
+        ph = torch.remainder(ph, 2 * np.pi).float()
+        return 0.5 * torch.cos(ph), 0.5 * torch.sin(ph)
+
+    ref_i, ref_q = fm(block + pad, 10 + seed, 75e3)
+    tgt_i, tgt_q = fm(block + pad, 11 + seed, 60e3)
+    caps = []
+    for k in range(3):
+        g.manual_seed(200 + k + 7 * seed)
+        d = int(delays[k])
+        raw = torch.empty(6 * block, dtype=torch.uint8, device=device)
+        for b, (si, sq) in enumerate(((ref_i, ref_q), (tgt_i, tgt_q), (ref_i, ref_q))):
+            for comp, src in ((0, si), (1, sq)):
+                x = src[pad - d:pad - d + block] + 0.02 * torch.randn(block, device=device, generator=g)
+                q = torch.clamp(x * 127.5 + 127.5, 0, 255).to(torch.uint8)  # truncating cast
+                raw[2 * b * block + comp:2 * (b + 1) * block:2] = q
+        caps.append(raw)
+    return caps, delays
+
+
+def synth_captures_cpu(block: int, seed: int = 0):
+    from helpers import fm_capture
+    delays = true_delays()
+    return fm_capture(block, tuple(delays), tuple(delays), seed=seed), delays
+
+
+# ----------------------------------------------------------------------------- reference arm / cpu baseline
+def run_reference_once(paths, csv, n_proc):
+    """n_proc concurrent runs of the reference's shipped ELF (it is single-threaded);
+    returns wall seconds of the slowest."""
+    from oracle import oracle
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([str(oracle.REF_BINARY), "162400000", "92300000", str(csv), *map(str, paths)],
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for _ in range(n_proc)]
+    outs = [p.communicate()[0] for p in procs]
+    wall = time.perf_counter() - t0
+    return wall, outs[0]
+
+
+def reference_sample(block: int):
+    """Bounded sample of the workload for the CPU arms: the same Mode-B content with
+    `block`-sample blocks, written as .dat files the reference binary reads."""
+    raws, delays = synth_captures_cpu(block)
+    td = tempfile.mkdtemp(prefix="tdoa_ref_")
+    paths = []
+    for name, raw in zip(STATION_NAMES, raws):
+        p = Path(td) / f"sim-{name}-1.dat"
+        raw.tofile(p)
+        paths.append(p)
+    return paths, raws, delays
+
+
+def cpu_baseline(block: int = 250_000, n_proc: int = 1):
+    """Times the reference on this host: oracle/_ref/processor (the reference's own
+    binary, kind "reference") if staged, else the C restatement (kind "port")."""
+    from oracle import oracle
+    paths, raws, _ = reference_sample(block)
+    pair_samples = 3 * (2 * block + block)
+    csv = ROOT / "tests" / "golden" / "stations.csv"
+    if oracle.REF_BINARY.exists():
+        wall, out = run_reference_once(paths, csv, n_proc)
+        kind = "reference"
+        ok = out.count("correlation=") >= 6
+    else:
+        t0 = time.perf_counter()
+        oracle.process_capture_binary(raws)
+        wall = time.perf_counter() - t0
+        kind, n_proc, ok = "port", 1, True
+    return {"value": n_proc * pair_samples / wall / 1e6, "unit": "pair-Msamples/s", "cores": n_proc, "kind": kind,
+            "sample": f"3 stations x {3 * block} samples (blocks of {block}), 3 REF + 3 TGT pair correlations x 2000 lags, "
+                      f"{n_proc} concurrent single-threaded run(s) of the reference's processor binary; wall {wall:.2f} s",
+            "ok": ok}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_proc = max(1, min(os.cpu_count() or 1, 32))
+    block = 250_000
+    walls = []
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(block, n_proc)
+        if i >= args.warmup:
+            walls.append(3 * 3 * block * n_proc / (cb["value"] * 1e6))
+    t = float(np.mean(walls))
+    value = n_proc * 9 * block / t / 1e6
+    line = {
+        "impl": "reference", "metric": "station-pair xcorr throughput", "value": value, "unit": "pair-Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": WORKLOAD_CONFIG,
+        "cpu_baseline": {"value": value, "unit": "pair-Msamples/s", "cores": n_proc, "kind": cb["kind"],
+                         "sample": cb["sample"]},
+        "e2e": {"value": value, "unit": "pair-Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "fixes_per_s": 0.0, "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+WORKLOAD_CONFIG = {
+    "workload": "configs[1]: 3-station 100 s 2 Msps dual-frequency capture (3 x 200e6 samples, 400 MB each), "
+                "full-length FM-demod correlation of 3 REF + 3 TGT pairs over lags 0..1999, single fix",
+    "mode": "BINARY (reference binary arithmetic), chunk = whole signal",
+    "stations": 3, "pairs": 3, "samples_per_station": 200_000_000, "max_lag": 2000, "block_size": 10000,
+    "l2": "inputs (1.2 GB of captures per step) exceed the 126 MB L2; no explicit flush",
+}
+
+
+# ----------------------------------------------------------------------------- our arm
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tdoa_b200 as T
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    block = args.block
+    n_samp = 3 * block
+    caps, delays = synth_captures_gpu(torch, device, block, seed=rank)
+    nbytes = caps[0].numel()
+    # host (pinned) copies for the end-to-end leg
+    pinned = [T.host_alloc(nbytes) for _ in range(3)]
+    for k in range(3):
+        pinned[k].array[:] = caps[k].cpu().numpy()
+
+    eng = T.Engine(T.MODE_BINARY, chunk_samples=0, device=local, use_fft=1)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    pair_samples = 3 * (2 * block + block)
+    pairs = [(0, 1), (0, 2), (1, 2)]
+
+    stage = {"ms_preprocess": 0.0, "ms_fft": 0.0, "ms_exact": 0.0, "ms_fft_seg": 0.0, "fft_launches": 0,
+             "fft_pair_samples": 0}
+    collecting = [False]
+
+    def collect():
+        if collecting[0]:
+            st = eng.stats()
+            for k in stage:
+                stage[k] += st[k]
+
+    def step_resident():
+        ref = eng.xcorr(T.KIND_REF)[0]
+        collect()
+        tgt = eng.xcorr(T.KIND_TGT)[0]
+        collect()
+        # processor.go:899-903: range differences from the target time differences
+        rd = tgt["lag"].astype(np.float64) / FS * C_LIGHT
+        pos, status, _ = eng.solve(STATION_LLH, rd)
+        return ref, tgt, pos, status
+
+    def step_e2e():
+        for k in range(3):
+            eng.load_u8(k, pinned[k])
+        return step_resident()
+
+    for k in range(3):
+        eng.load_u8_device(k, caps[k].data_ptr(), nbytes, keep=caps[k])
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # correctness of the benchmarked path on this very input (not timed)
+    ref, tgt, pos, status = step_resident()
+    want = [int(delays[j] - delays[i]) for i, j in pairs]
+    got_r, got_t = [int(x) for x in ref["lag"]], [int(x) for x in tgt["lag"]]
+    clamp = [max(w, 0) for w in want]  # the reference searches non-negative lags only
+    lags_ok = got_r == clamp and got_t == clamp
+
+    def timed(fn, steps, warmup, collect_stats=False):
+        for _ in range(warmup):
+            fn()
+        sync_all()
+        l0 = eng.stats()["launches_total"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        collecting[0] = collect_stats
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        collecting[0] = False
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), eng.stats()["launches_total"] - l0
+
+    with ClockSampler(local) as clocks:
+        ms_res, launches = timed(step_resident, args.steps, args.warmup, collect_stats=True)
+    ms_e2e, _ = timed(step_e2e, max(1, args.steps), max(3, args.warmup) if args.warmup else 0)
+
+    # one NCCL gather of the peak records -- outside the timed steps' data path
+    if world > 1:
+        rec = torch.from_numpy(np.concatenate([ref, tgt]).view(np.uint8).copy()).to(device)
+        out = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(out, rec)
+
+    t_step = ms_res / args.steps / 1e3
+    t_e2e = ms_e2e / max(1, args.steps) / 1e3
+    value = world * pair_samples / t_step / 1e6
+    e2e_value = world * pair_samples / t_e2e / 1e6
+
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = json.loads(peaks_path.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    line = None
+    if rank == 0:
+        st = eng.stats()
+        # dominant kernel: the segmented-FFT cross-spectrum kernel when the FFT path ran,
+        # else the exact time-domain correlator
+        if stage["fft_launches"] > 0 and stage["ms_fft_seg"] > 0:
+            alg_bytes = 8.0 * stage["fft_pair_samples"] / stage["fft_launches"]
+            k_ms = stage["ms_fft_seg"] / stage["fft_launches"]
+            kname = "k_xcorr_fft_segments"
+        else:
+            alg_bytes = 8.0 * pair_samples
+            k_ms = stage["ms_exact"] / max(1, args.steps)
+            kname = "k_corr_brute (REF + TGT launches of one step)"
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        traffic = None
+        tpath = ROOT / "profiles" / "traffic.json"
+        if tpath.exists():
+            traffic = json.loads(tpath.read_text()).get(kname)
+        cb = cpu_baseline() if world == 1 else None
+        line = {
+            "metric": "station-pair xcorr throughput", "value": value, "unit": "pair-Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(WORKLOAD_CONFIG, samples_per_station=n_samp),
+            "fixes_per_s": world / t_step,
+            "e2e": {"value": e2e_value, "unit": "pair-Msamples/s", "h2d_bytes_per_step": 3 * nbytes,
+                    "d2h_bytes_per_step": 2 * 3 * 32 + 3 * 8 + 4 + 4, "ms_per_step": t_e2e * 1e3,
+                    "fixes_per_s": world / t_e2e},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": k_ms},
+            "stage_ms_per_step": {k: stage[k] / args.steps for k in ("ms_preprocess", "ms_fft", "ms_exact")},
+            "parity_check": {"lags_match_injected_delays": bool(lags_ok), "ref_lags": got_r, "tgt_lags": got_t,
+                             "injected": want, "n_candidates": [int(x) >> 16 & 255 for x in list(ref["flags"]) + list(tgt["flags"])], "fix_llh": [float(x) for x in pos], "fix_status": int(status)},
+            "cpu_baseline": {k: v for k, v in cb.items() if k != "ok"} if cb else None,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+    eng.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--block", type=int, default=66_666_666, help="samples per block (default: 100 s capture)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -56,6 +56,7 @@ extern "C" {
 #define TDOA_PEAK_EDGE 0x2u       /* peak on the edge of the lag range (frac = 0)    */
 #define TDOA_PEAK_BRUTE 0x4u      /* every lag was evaluated in the time domain      */
 #define TDOA_PEAK_EMPTY 0x8u      /* empty input: (0, 0.0) as processor.go:622-625   */
+#define TDOA_PEAK_NCAND(f) (((f) >> 16) & 0xffu)   /* lags re-evaluated exactly (FFT path)   */
 #define TDOA_PEAK_BRANCH1(f) (((f) >> 8) & 3u)  /* preprocess branch of signal 1      */
 #define TDOA_PEAK_BRANCH2(f) (((f) >> 10) & 3u) /* 0 strong/std, 1 moderate, 2 weak   */
 

@@ -18,6 +18,7 @@
 
 #include "../../include/tdoa_b200.h"
 #include "kernels.h"
+#include "xcorr_fft.h"
 
 using namespace tdoa;
 
@@ -77,6 +78,9 @@ struct tdoa_engine {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     int64_t launches_at_call = 0;
+    float2 *d_tw = nullptr;  // FFT twiddle table
+    cudaEvent_t ev_fft[2] = {nullptr, nullptr};
+    int sm_count = 148;
 };
 
 namespace {
@@ -443,28 +447,158 @@ i64 whole_blocks(i64 tl, i64 B)
     return (tl - B + B - 1) / B;
 }
 
+// exact time-domain evaluation of every lag (reference order), then the peak scan
+int run_brute(tdoa_engine *e, std::vector<CorrPlan *> &plans)
+{
+    if (plans.empty()) return TDOA_OK;
+    int rc;
+    std::vector<PairJob> jobs, jobs2;
+    std::vector<PeakJob> peaks;
+    i64 max_nb = 0, max_nb2 = 0;
+    int max_lags = 0, max_lags2 = 0;
+    for (CorrPlan *pl : plans) {
+        PairJob &J = pl->job;
+        PeakJob &K = pl->peak;
+        K.flags |= TDOA_PEAK_BRUTE;
+        if (K.n_lags > 0) {
+            if ((rc = alloc_t(e, &J.blocksums, (size_t)std::max<i64>(J.nb, 1) * J.n_lags))) return rc;
+            if ((rc = alloc_t(e, &J.corr, (size_t)J.n_lags))) return rc;
+            K.corr = J.corr; K.corr2 = J.corr;
+            K.n_lags2 = J.n_lags;
+            max_nb = std::max(max_nb, J.nb);
+            max_lags = std::max(max_lags, J.n_lags);
+            if (pl->need2) {
+                PairJob &J2 = pl->job2;
+                if ((rc = alloc_t(e, &J2.blocksums, (size_t)std::max<i64>(J2.nb, 1) * J2.n_lags))) return rc;
+                if ((rc = alloc_t(e, &J2.corr, (size_t)J2.n_lags))) return rc;
+                K.corr2 = J2.corr; K.n_lags2 = J2.nb > 0 ? J2.n_lags : 0;
+                max_nb2 = std::max(max_nb2, J2.nb);
+                max_lags2 = std::max(max_lags2, J2.n_lags);
+                jobs2.push_back(J2);
+            }
+            jobs.push_back(J);
+        }
+        peaks.push_back(K);
+    }
+    if (!jobs.empty()) {
+        const PairJob *d_jobs = nullptr;
+        if ((rc = upload(e, jobs, &d_jobs))) return rc;
+        if (max_nb > 0) { launch_corr_brute(d_jobs, (int)jobs.size(), max_nb, max_lags, e->stream); count_launch(e); }
+        launch_corr_finalize(d_jobs, (int)jobs.size(), max_lags, e->stream);
+        count_launch(e);
+        e->st.brute_pairs += (int64_t)jobs.size();
+    }
+    if (!jobs2.empty()) {
+        const PairJob *d_jobs = nullptr;
+        if ((rc = upload(e, jobs2, &d_jobs))) return rc;
+        if (max_nb2 > 0) { launch_corr_brute(d_jobs, (int)jobs2.size(), max_nb2, max_lags2, e->stream); count_launch(e); }
+        launch_corr_finalize(d_jobs, (int)jobs2.size(), max_lags2, e->stream);
+        count_launch(e);
+    }
+    const PeakJob *d_peaks = nullptr;
+    if ((rc = upload(e, peaks, &d_peaks))) return rc;
+    launch_peak(d_peaks, (int)peaks.size(), e->stream);
+    count_launch(e);
+    return TDOA_OK;
+}
+
+// FFT candidate search + exact evaluation of the candidates (xcorr_fft.cu)
+int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
+{
+    if (plans.empty()) return TDOA_OK;
+    int rc;
+    const int np = (int)plans.size();
+    std::vector<FftJob> fjobs;
+    std::vector<SelJob> sjobs(np);
+    std::vector<CandJob> cjobs(np);
+    std::vector<PairJob> pjobs(np);
+    std::vector<PeakJob> kjobs(np);
+    // lag chunks
+    int n_fft_jobs = 0;
+    for (CorrPlan *pl : plans) n_fft_jobs += (pl->job.n_lags + kLagW - 1) / kLagW;
+    const int cta_budget = std::max(1, 2 * e->sm_count / std::max(1, n_fft_jobs));
+    int max_cta = 0;
+    i64 max_nb = 0;
+    for (int p = 0; p < np; p++) {
+        CorrPlan *pl = plans[p];
+        PairJob &J = pl->job;
+        PeakJob &K = pl->peak;
+        float *d_approx = nullptr, *d_amax = nullptr;
+        int *d_cand = nullptr, *d_ncand = nullptr;
+        if ((rc = alloc_t(e, &d_approx, (size_t)J.n_lags)) || (rc = alloc_t(e, &d_amax, 1)) ||
+            (rc = alloc_t(e, &d_cand, (size_t)kMaxCand)) || (rc = alloc_t(e, &d_ncand, 1)) ||
+            (rc = alloc_t(e, &J.blocksums, (size_t)kMaxCand * std::max<i64>(J.nb, 1))))
+            return rc;
+        for (int c0 = 0; c0 < J.n_lags; c0 += kLagW) {
+            FftJob F{};
+            F.t = J.t_re; F.s = J.s_re; F.t_stats = J.t_stats; F.s_stats = J.s_stats;
+            F.t_off = J.t_off; F.n_t = J.n_t; F.sl = J.sl;
+            F.s_off = (i64)J.lag0 + c0;
+            F.n_lags = std::min(kLagW, J.n_lags - c0);
+            F.n_seg = (int)((J.n_t + kSeg - 1) / kSeg);
+            F.n_cta = std::max(1, std::min(F.n_seg, cta_budget));
+            if ((rc = alloc(e, reinterpret_cast<void **>(&F.partials), fft_partials_bytes(F.n_cta))) ||
+                (rc = alloc_t(e, &F.spectrum, (size_t)kFftBins)))
+                return rc;
+            F.approx = d_approx + c0;
+            max_cta = std::max(max_cta, F.n_cta);
+            fjobs.push_back(F);
+            e->st.fft_pair_samples += J.n_t;
+        }
+        SelJob &S = sjobs[p];
+        S.approx = d_approx; S.n_lags = J.n_lags; S.sanity = K.sanity;
+        S.neighbours = J.variant == CORR_EXTENDED; S.max_cand = kMaxCand;
+        S.tol = 2e-5f;
+        S.cand = d_cand; S.n_cand = d_ncand; S.approx_max = d_amax;
+        CandJob &C = cjobs[p];
+        C.cand = d_cand; C.n_cand = d_ncand; C.max_cand = kMaxCand; C.approx = d_approx; C.blocksums = J.blocksums;
+        pjobs[p] = J;
+        kjobs[p] = K;
+        max_nb = std::max(max_nb, J.nb);
+    }
+    const FftJob *d_f = nullptr;
+    const SelJob *d_s = nullptr;
+    const CandJob *d_c = nullptr;
+    const PairJob *d_p = nullptr;
+    const PeakJob *d_k = nullptr;
+    if ((rc = upload(e, fjobs, &d_f)) || (rc = upload(e, sjobs, &d_s)) || (rc = upload(e, cjobs, &d_c)) ||
+        (rc = upload(e, pjobs, &d_p)) || (rc = upload(e, kjobs, &d_k)))
+        return rc;
+    cudaEventRecord(e->ev_fft[0], e->stream);
+    launch_fft_segments(d_f, (int)fjobs.size(), max_cta, e->d_tw, e->stream);
+    cudaEventRecord(e->ev_fft[1], e->stream);
+    launch_fft_reduce(d_f, (int)fjobs.size(), e->stream);
+    launch_fft_finish(d_f, (int)fjobs.size(), e->d_tw, e->stream);
+    launch_select_candidates(d_s, np, e->stream);
+    cudaEventRecord(e->ev[5], e->stream);
+    launch_corr_candidates(d_p, d_c, np, max_nb, e->stream);
+    launch_peak_candidates(d_p, d_c, d_k, np, e->stream);
+    count_launch(e, 6);
+    e->st.fft_launches += 1;
+    return TDOA_OK;
+}
+
 int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pair> &pairs, PeakRec *d_out)
 {
     if (pairs.empty()) return TDOA_OK;
     const tdoa_config &cfg = e->cfg;
     const int np = (int)pairs.size();
     std::vector<CorrPlan> plans(np);
-    i64 max_nb = 0, max_nb2 = 0;
-    int max_lags = 0, max_lags2 = 0;
-    int rc;
+    std::vector<CorrPlan *> brute, viafft;
     for (int p = 0; p < np; p++) {
         const Sig &s1 = sigs[pairs[p].a], &s2 = sigs[pairs[p].b];
         CorrPlan &pl = plans[p];
         PairJob &J = pl.job;
         PeakJob &K = pl.peak;
         K.out = d_out + p;
-        K.flags = ((uint32_t)s1.branch << 8) | ((uint32_t)s2.branch << 10) | TDOA_PEAK_BRUTE;
+        K.flags = ((uint32_t)s1.branch << 8) | ((uint32_t)s2.branch << 10);
         K.sanity = 0;
         K.lag_origin = 0;
         if (s1.n == 0 || s2.n == 0) {  // processor.go:622-625
             K.flags |= TDOA_PEAK_EMPTY;
             K.nb = 0; K.n_lags = 0; K.n_lags2 = 0; K.corr = K.corr2 = nullptr;
             K.variant = CORR_BINARY;
+            brute.push_back(&pl);
             continue;
         }
         // processor.go:653-661: the shorter input is the template
@@ -519,49 +653,30 @@ int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pa
             J.n_t = J.nb * J.block;
             J.n_lags = (int)ml;
         }
-        if ((rc = alloc_t(e, &J.blocksums, (size_t)std::max<i64>(J.nb, 1) * J.n_lags))) return rc;
-        if ((rc = alloc_t(e, &J.corr, (size_t)J.n_lags))) return rc;
-        K.corr = J.corr; K.corr2 = J.corr;
-        K.n_lags = J.n_lags; K.n_lags2 = J.n_lags;
+        K.n_lags = J.n_lags;
+        K.n_lags2 = J.n_lags;
         K.nb = (int)J.nb;
         K.variant = J.variant;
-        max_nb = std::max(max_nb, J.nb);
-        max_lags = std::max(max_lags, J.n_lags);
-        if (pl.need2) {
-            PairJob &J2 = pl.job2;
-            if ((rc = alloc_t(e, &J2.blocksums, (size_t)std::max<i64>(J2.nb, 1) * J2.n_lags))) return rc;
-            if ((rc = alloc_t(e, &J2.corr, (size_t)J2.n_lags))) return rc;
-            K.corr2 = J2.corr; K.n_lags2 = J2.nb > 0 ? J2.n_lags : 0;
-            max_nb2 = std::max(max_nb2, J2.nb);
-            max_lags2 = std::max(max_lags2, J2.n_lags);
-        }
+        // the FFT path serves the real-valued correlators; a handful of lags is cheaper exactly
+        const bool fft_ok = cfg.use_fft && J.variant != CORR_SOURCE && J.nb > 0 && J.n_lags > 8 && !pl.need2;
+        (fft_ok ? viafft : brute).push_back(&pl);
     }
-    std::vector<PairJob> jobs, jobs2;
-    std::vector<PeakJob> peaks;
-    for (auto &pl : plans) {
-        if (pl.peak.n_lags > 0) jobs.push_back(pl.job);
-        if (pl.need2) jobs2.push_back(pl.job2);
-        peaks.push_back(pl.peak);
+    int rc;
+    if ((rc = run_brute(e, brute))) return rc;
+    if (!viafft.empty()) {
+        if ((rc = run_fft(e, viafft))) return rc;
+        // candidate overflow (a flat correlation surface): redo those pairs lag by lag
+        std::vector<PeakRec> h(np);
+        CU(cudaMemcpyAsync(h.data(), d_out, (size_t)np * sizeof(PeakRec), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e->ev_fft[0], e->ev_fft[1]) == cudaSuccess) e->st.ms_fft_seg += ms;
+        if (cudaEventElapsedTime(&ms, e->ev_fft[0], e->ev[5]) == cudaSuccess) e->st.ms_fft += ms;
+        std::vector<CorrPlan *> redo;
+        for (CorrPlan *pl : viafft)
+            if (h[pl->peak.out - d_out].flags & 0x10u) redo.push_back(pl);
+        if ((rc = run_brute(e, redo))) return rc;
     }
-    if (!jobs.empty()) {
-        const PairJob *d_jobs = nullptr;
-        if ((rc = upload(e, jobs, &d_jobs))) return rc;
-        if (max_nb > 0) { launch_corr_brute(d_jobs, (int)jobs.size(), max_nb, max_lags, e->stream); count_launch(e); }
-        launch_corr_finalize(d_jobs, (int)jobs.size(), max_lags, e->stream);
-        count_launch(e);
-        e->st.brute_pairs += (int64_t)jobs.size();
-    }
-    if (!jobs2.empty()) {
-        const PairJob *d_jobs = nullptr;
-        if ((rc = upload(e, jobs2, &d_jobs))) return rc;
-        if (max_nb2 > 0) { launch_corr_brute(d_jobs, (int)jobs2.size(), max_nb2, max_lags2, e->stream); count_launch(e); }
-        launch_corr_finalize(d_jobs, (int)jobs2.size(), max_lags2, e->stream);
-        count_launch(e);
-    }
-    const PeakJob *d_peaks = nullptr;
-    if ((rc = upload(e, peaks, &d_peaks))) return rc;
-    launch_peak(d_peaks, np, e->stream);
-    count_launch(e);
     return TDOA_OK;
 }
 
@@ -603,6 +718,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
     if (out_is_device) d_out = reinterpret_cast<PeakRec *>(out);
     else if ((rc = alloc_t(e, &d_out, (size_t)n_windows * P))) return rc;
 
+    e->st.ms_fft = 0.f; e->st.ms_fft_seg = 0.f; e->st.fft_launches = 0; e->st.fft_pair_samples = 0;
     cudaEventRecord(e->ev[0], e->stream);
     float ms_pre = 0.f, ms_corr = 0.f;
     // windows are processed in groups that keep the working set bounded
@@ -639,6 +755,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
             for (void *p : e->call_allocs)
                 if (p != d_out) cudaFreeAsync(p, e->stream);
             e->call_allocs.clear();
+            e->frame_used = 0;  // the stream is idle: descriptor staging can be reused
             if (!out_is_device) e->call_allocs.push_back(d_out);
         }
     }
@@ -654,8 +771,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
         cudaEventElapsedTime(&b, e->ev[2], e->ev[3]);
         cudaEventElapsedTime(&t, e->ev[0], e->ev[4]);
         e->st.ms_preprocess = ms_pre + a;
-        e->st.ms_exact = ms_corr + b;
-        e->st.ms_fft = 0.f;
+        e->st.ms_exact = ms_corr + b - e->st.ms_fft;
         e->st.ms_total = t;
     }
     return TDOA_OK;
@@ -749,6 +865,14 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
         tdoa_destroy(e);
         return err == cudaErrorMemoryAllocation ? TDOA_E_NOMEM : TDOA_E_CUDA;
     }
+    for (int i = 0; i < 2 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev_fft[i]);
+    e->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    if (err == cudaSuccess && fft_setup(e->stream, &e->d_tw) != 0) err = cudaErrorUnknown;
+    if (err != cudaSuccess) {
+        g_create_error = std::string("tdoa_create: ") + cudaGetErrorString(err);
+        tdoa_destroy(e);
+        return TDOA_E_CUDA;
+    }
     const int bad = unpack_selftest(e->stream);
     if (bad != 0) {
         g_create_error = "tdoa_create: device unpack self-test failed (kernel image not runnable on this GPU?)";
@@ -770,6 +894,9 @@ void tdoa_destroy(tdoa_engine *e)
         if (s.owned) cudaFree(s.owned);
     if (e->h_frame) cudaFreeHost(e->h_frame);
     if (e->d_frame) cudaFree(e->d_frame);
+    if (e->d_tw) cudaFree(e->d_tw);
+    for (auto &ev : e->ev_fft)
+        if (ev) cudaEventDestroy(ev);
     if (e->frame_done) cudaEventDestroy(e->frame_done);
     for (auto &ev : e->ev)
         if (ev) cudaEventDestroy(ev);

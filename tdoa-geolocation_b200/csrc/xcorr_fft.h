@@ -1,0 +1,59 @@
+// xcorr_fft.h -- job descriptors and launchers of the FFT correlation path (xcorr_fft.cu).
+#pragma once
+#include "kernels.h"
+
+namespace tdoa {
+
+constexpr int kFftN = 8192;               // complex FFT size held in one CTA's shared memory
+constexpr int kLagW = 2048;               // lags served by one FFT job
+constexpr int kSeg = kFftN - kLagW;       // template samples per segment (6144 = 24 * 256)
+constexpr int kMaxCand = 64;              // candidate lags re-evaluated exactly per pair
+constexpr int kFftBins = kFftN / 2 + 1;
+
+// One (pair, lag chunk): approx[d] ~ corr(lag0 + d), d in [0, n_lags), n_lags <= kLagW.
+struct FftJob {
+    const float *t, *s;              // real planes, pre-normalise
+    const double *t_stats, *s_stats; // ST_SCALE applied in the finish kernel
+    i64 t_off;                       // template starts at t + t_off
+    i64 n_t;                         // template samples that take part
+    i64 sl;                          // signal length
+    i64 s_off;                       // signal index matched with template index 0 at lag index 0
+    int n_lags;
+    int n_seg;                       // ceil(n_t / kSeg)
+    int n_cta;                       // CTAs (= partial spectra) of this job
+    float2 *partials;                // [n_cta][kFftBins]
+    float2 *spectrum;                // [kFftBins] sum of the partials
+    float *approx;                   // [n_lags] correlation-coefficient units
+};
+
+struct SelJob {
+    const float *approx;  // [n_lags] all lag chunks of the pair
+    int n_lags;
+    int sanity;           // re-search range [0, sanity), 0 = none
+    int neighbours;       // also select lag +-1 of every candidate (parabolic vertex)
+    int max_cand;
+    float tol;
+    int *cand;            // [max_cand] ascending lag indices
+    int *n_cand;          // candidates found (may exceed max_cand: overflow)
+    float *approx_max;
+};
+
+struct CandJob {
+    const int *cand;
+    const int *n_cand;
+    int max_cand;
+    const float *approx;
+    double *blocksums;    // [max_cand][nb]
+};
+
+int fft_setup(cudaStream_t st, float2 **d_tw);
+size_t fft_partials_bytes(int n_cta);
+void launch_fft_segments(const FftJob *d_jobs, int n_jobs, int max_cta, const float2 *d_tw, cudaStream_t st);
+void launch_fft_reduce(const FftJob *d_jobs, int n_jobs, cudaStream_t st);
+void launch_fft_finish(const FftJob *d_jobs, int n_jobs, const float2 *d_tw, cudaStream_t st);
+void launch_select_candidates(const SelJob *d_jobs, int n_jobs, cudaStream_t st);
+void launch_corr_candidates(const PairJob *d_jobs, const CandJob *d_cjobs, int n_jobs, i64 max_nb, cudaStream_t st);
+void launch_peak_candidates(const PairJob *d_jobs, const CandJob *d_cjobs, const PeakJob *d_pjobs, int n_jobs,
+                            cudaStream_t st);
+
+}  // namespace tdoa

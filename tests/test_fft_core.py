@@ -1,0 +1,22 @@
+"""CPU check of the shared-memory FFT's per-thread phases (csrc/fft_core.cuh): the
+host emulation in tests/native/fft_emul.cu runs the same __host__ __device__ code one
+"thread" at a time and compares the 8192-point result with a direct DFT."""
+import shutil
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="needs nvcc (host compile only)")
+def test_fft_phases_match_direct_dft(tmp_path):
+    exe = tmp_path / "fft_emul"
+    subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I",
+                    str(ROOT / "tdoa-geolocation_b200" / "csrc"), "-o", str(exe),
+                    str(ROOT / "tests" / "native" / "fft_emul.cu")], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    rel = float(res.stdout.split()[1])
+    assert rel < 1e-6

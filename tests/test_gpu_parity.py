@@ -147,6 +147,24 @@ def test_ragged_station_lengths(eng_binary):
         assert int(pk["lag"]) == orc[0] and abs(float(pk["corr"]) - orc[1]) <= CORR_TOL
 
 
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_fft_path_equals_every_lag_path(case):
+    """use_fft=1 (candidate search + exact re-evaluation) must pick the same peak as the
+    exhaustive time-domain evaluation of every lag."""
+    raws, _ = load_golden(case)
+    res = []
+    for use_fft in (0, 1):
+        with T.Engine(T.MODE_BINARY, use_fft=use_fft) as e:
+            load_all(e, raws)
+            res.append(np.concatenate([e.xcorr(T.KIND_REF)[0], e.xcorr(T.KIND_TGT)[0]]))
+    brute, fft = res
+    assert np.all(brute["flags"] & 4) and not np.any(fft["flags"] & 4), "paths not exercised"
+    assert np.array_equal(brute["lag"], fft["lag"])
+    assert np.array_equal(brute["first_lag"], fft["first_lag"])
+    assert np.array_equal(brute["flags"] & 1, fft["flags"] & 1)
+    assert np.max(np.abs(brute["corr"] - fft["corr"])) <= 1e-12
+
+
 # ------------------------------------------------------------------ source mode (processor.go as committed)
 def test_source_mode_pairs(eng_source):
     raws, _ = load_golden("fm_strong")
