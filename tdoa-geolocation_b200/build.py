@@ -23,6 +23,7 @@ OBJ = HERE / "build"
 # (source, extra flags)
 UNITS = [
     ("preprocess.cu", ["-fmad=false"]),
+    ("preprocess_fast.cu", []),
     ("xcorr_exact.cu", ["-fmad=false"]),
     ("solve.cu", ["-fmad=false"]),
     ("xcorr_fft.cu", []),

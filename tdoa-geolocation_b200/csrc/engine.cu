@@ -49,6 +49,8 @@ struct Sig {
     unsigned *counter = nullptr;
     double power0 = 0.0;
     int branch = 0;
+    int memo = -1;        // slot of the branch memo (station * 2 + kind), -1: none
+    bool fused = false;   // stage 0 ran the fused power + discriminator kernel
 };
 
 struct Pair {
@@ -79,6 +81,7 @@ struct tdoa_engine {
     bool ev_valid = false;
     int64_t launches_at_call = 0;
     float2 *d_tw = nullptr;  // FFT twiddle table
+    std::vector<int8_t> branch_memo;  // last preprocess branch per (station, kind); -1 unknown
     cudaEvent_t ev_fft[2] = {nullptr, nullptr};
     int sm_count = 148;
 };
@@ -230,7 +233,7 @@ int ensure_plane(tdoa_engine *e, Sig &s, int idx, bool cplx)
     return TDOA_OK;
 }
 
-enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_SEQSUM, K_BOXCAR, K_NOTCH };
+enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_SEQSUM, K_BOXCAR, K_BOXCAR_SMALL, K_NOTCH };
 
 // queue of (stage, kernel) steps: step k of every signal that runs the same kernel at
 // that stage is batched into one launch; stages run in order
@@ -304,6 +307,7 @@ int run_pipeline(tdoa_engine *e, Pipeline &pl)
                 case K_ENVELOPE: launch_envelope(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
                 case K_SEQSUM: launch_seqsum(d_jobs, nj, e->stream); break;
                 case K_BOXCAR: launch_boxcar(d_jobs, nj, st.max_n, 0, e->stream); break;
+                case K_BOXCAR_SMALL: launch_boxcar_small(d_jobs, nj, st.max_n, e->stream); break;
                 case K_NOTCH: launch_notch_combine(d_jobs, nj, st.max_n, e->stream); break;
             }
             count_launch(e);
@@ -321,7 +325,7 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
     i64 max_n = 0;
     for (auto &s : sigs) max_n = std::max(max_n, s.n);
     const int gx = stream_grid_x(max_n);
-    const int gmax = std::max(gx, boxcar_grid_x(max_n));
+    const int gmax = std::max(std::max(gx, boxcar_grid_x(max_n)), fast_grid_x(max_n));
     double *d_stats = nullptr, *d_partials = nullptr;
     unsigned *d_counters = nullptr;
     int rc;
@@ -335,14 +339,39 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
         sigs[i].partials = d_partials + (size_t)i * 2 * gmax;
         sigs[i].counter = d_counters + i;
     }
-    // ---- initial power (selects the branch)
+    // ---- initial power (selects the branch).  In the shipped binary's modes a capture
+    // that was "strong FM" last time is assumed to be so again: its power pass is fused
+    // with the discriminator (one read of the raw bytes); a wrong guess only costs the
+    // discarded demod output.
+    const int gmax2 = std::max(gmax, fast_grid_x(max_n));
+    (void)gmax2;
     {
-        std::vector<SigJob> jobs;
-        for (auto &s : sigs) jobs.push_back(base_job(s));
-        const SigJob *d_jobs = nullptr;
-        if ((rc = upload(e, jobs, &d_jobs))) return rc;
-        launch_power(d_jobs, ns, max_n, gx, e->stream);
-        count_launch(e);
+        std::vector<SigJob> pjobs, fjobs;
+        for (auto &s : sigs) {
+            const bool spec = e->cfg.mode != TDOA_MODE_SOURCE && s.src.raw && s.n >= 2 &&
+                              (s.memo < 0 || e->branch_memo[s.memo] <= 0);
+            s.fused = spec;
+            if (spec) {
+                if ((rc = ensure_plane(e, s, 0, false))) return rc;
+                SigJob j = base_job(s);
+                j.p_re = s.plane[0][0];
+                fjobs.push_back(j);
+            } else {
+                pjobs.push_back(base_job(s));
+            }
+        }
+        if (!pjobs.empty()) {
+            const SigJob *d_jobs = nullptr;
+            if ((rc = upload(e, pjobs, &d_jobs))) return rc;
+            launch_power(d_jobs, (int)pjobs.size(), max_n, gx, e->stream);
+            count_launch(e);
+        }
+        if (!fjobs.empty()) {
+            const SigJob *d_jobs = nullptr;
+            if ((rc = upload(e, fjobs, &d_jobs))) return rc;
+            launch_demod_fused(d_jobs, (int)fjobs.size(), max_n, e->cfg.fast_demod, e->stream);
+            count_launch(e);
+        }
         std::vector<double> h_stats((size_t)ns * ST_COUNT);
         CU(cudaMemcpyAsync(h_stats.data(), d_stats, h_stats.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
         CU(cudaStreamSynchronize(e->stream));
@@ -395,15 +424,19 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
             // shipped binary (ELF 0x49cd40): > 0.01 strong, > 0.001 moderate, else weak
             s.branch = s.power0 > 0.01 ? 0 : (s.power0 > 0.001 ? 1 : 2);
             size_t g = 0;
+            if (s.memo >= 0) e->branch_memo[s.memo] = (int8_t)s.branch;
             if (s.branch == 0) {
                 const bool cplx = s.n < 2;  // convertToInstantaneousFrequency returns its input for n < 2
                 if ((rc = ensure_plane(e, s, 0, cplx)) || (rc = ensure_plane(e, s, 1, cplx))) return rc;
-                SigJob u = base_job(s);
-                u.p_re = s.plane[0][0]; u.p_im = s.plane[0][1];
-                pl.add(g++, cplx ? K_UNPACK : K_DEMOD, u);
+                if (!s.fused) {
+                    SigJob u = base_job(s);
+                    u.p_re = s.plane[0][0]; u.p_im = s.plane[0][1];
+                    pl.add(g, cplx ? K_UNPACK : K_DEMOD, u);
+                }
+                g++;
                 if (wants_seq_dc(e, s.n)) pl.add(g, K_SEQSUM, seqsum_job(s, 0, cplx));
                 g++;
-                pl.add(g++, K_BOXCAR, box_job(s, 0, 1, cplx, 10, BOX_LP, true, true));
+                pl.add(g++, cplx ? K_BOXCAR : K_BOXCAR_SMALL, box_job(s, 0, 1, cplx, 10, BOX_LP, true, true));
                 s.out_re = s.plane[1][0]; s.out_im = s.plane[1][1];
             } else if (s.branch == 1) {
                 if ((rc = ensure_plane(e, s, 0, false)) || (rc = ensure_plane(e, s, 1, false))) return rc;
@@ -736,6 +769,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
                 Sig &sg = sigs[(size_t)w * S + s];
                 sg.n = len[s];
                 sg.src = make_view(e->stations[s], kind, win_start + (i64)(w0 + w) * hop, len[s]);
+                sg.memo = s * 2 + kind;
             }
             for (int i = 0; i < S; i++)
                 for (int j = i + 1; j < S; j++) pairs.push_back({w * S + i, w * S + j});
@@ -847,6 +881,7 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
     e->cfg = *cfg;
     e->device = cfg->device;
     e->stations.resize(cfg->n_stations);
+    e->branch_memo.assign((size_t)cfg->n_stations * 2, (int8_t)-1);
     cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) { e->own_stream = true; err = cudaMallocHost(&e->h_frame, kFrameBytes); }
     if (err == cudaSuccess) err = cudaMalloc(&e->d_frame, kFrameBytes);

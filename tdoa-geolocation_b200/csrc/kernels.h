@@ -103,6 +103,12 @@ int boxcar_grid_x(i64 n);
 int stream_grid_x(i64 n);
 int unpack_selftest(cudaStream_t st);  // 0 ok: arithmetic unpack == host LUT for all 256 codes
 
+// ---- preprocess_fast.cu
+void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, cudaStream_t st);
+void launch_boxcar_small(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
+int boxcar_small_max_half();
+int fast_grid_x(i64 n);
+
 // ---- xcorr_exact.cu
 void launch_corr_brute(const PairJob *d_jobs, int n_jobs, i64 max_nb, int max_lags, cudaStream_t st);
 void launch_corr_finalize(const PairJob *d_jobs, int n_jobs, int max_lags, cudaStream_t st);

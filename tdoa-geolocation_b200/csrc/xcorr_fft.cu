@@ -304,6 +304,47 @@ __global__ void __launch_bounds__(kCandThreads) k_corr_candidates(const PairJob 
         double acc[kCandGroup];
 #pragma unroll
         for (int c = 0; c < kCandGroup; c++) acc[c] = 0.0;
+        const i64 s_first = blk_start + J.lag0 + dmin;
+        if (ng <= 2 && s_first >= 0 && s_first + blk_len + span <= J.sl) {
+            // sharp peak (the common case): stream both signals straight from global
+            // memory, 4 independent strides in flight per thread, no staging, no barriers
+            const float *__restrict__ tp = J.t_re + J.t_off + blk_start;
+            const float *__restrict__ sp = J.s_re + s_first;
+            const int o1 = off[1];
+            const int len = (int)blk_len;
+            int i = tid;
+            for (; i + 3 * kCandThreads < len; i += 4 * kCandThreads) {
+                float tv[4], s0[4], s1[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    tv[u] = tp[i + u * kCandThreads];
+                    s0[u] = sp[i + u * kCandThreads];
+                    s1[u] = ng == 2 ? sp[i + u * kCandThreads + o1] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float t = __fmul_rn(tv[u], sc_t), a = __fmul_rn(s0[u], sc_s), bb = __fmul_rn(s1[u], sc_s);
+                    if (exact_f64) {
+                        acc[0] = __dadd_rn(acc[0], __dmul_rn((double)t, (double)a));
+                        if (ng == 2) acc[1] = __dadd_rn(acc[1], __dmul_rn((double)t, (double)bb));
+                    } else {
+                        acc[0] = __dadd_rn(acc[0], (double)__fmul_rn(t, a));
+                        if (ng == 2) acc[1] = __dadd_rn(acc[1], (double)__fmul_rn(t, bb));
+                    }
+                }
+            }
+            for (; i < len; i += kCandThreads) {
+                const float t = __fmul_rn(tp[i], sc_t), a = __fmul_rn(sp[i], sc_s);
+                const float bb = ng == 2 ? __fmul_rn(sp[i + o1], sc_s) : 0.f;
+                if (exact_f64) {
+                    acc[0] = __dadd_rn(acc[0], __dmul_rn((double)t, (double)a));
+                    if (ng == 2) acc[1] = __dadd_rn(acc[1], __dmul_rn((double)t, (double)bb));
+                } else {
+                    acc[0] = __dadd_rn(acc[0], (double)__fmul_rn(t, a));
+                    if (ng == 2) acc[1] = __dadd_rn(acc[1], (double)__fmul_rn(t, bb));
+                }
+            }
+        } else
         for (i64 c0 = 0; c0 < blk_len; c0 += kCandChunk) {
             const int clen = (int)min((i64)kCandChunk, blk_len - c0);
             __syncthreads();

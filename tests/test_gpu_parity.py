@@ -280,3 +280,29 @@ def test_processor_mirror_stdout(tmp_path):
     rd = np.array(res["range_differences"])
     want, status, _ = oracle.solve_tdoa(STATION_LLH, rd)
     assert status == 0 and np.allclose(res["position"], want, atol=1e-9)
+
+
+# ------------------------------------------------------------------ discriminator bit parity
+def test_discriminator_bits_match_oracle(eng_binary):
+    """Strong-FM branch, sample by sample: the custom f64 arctangent rounds to the same
+    f32 as the reference's math.Atan2 (up to the ~1e-8/sample chance that two correct
+    f64 implementations straddle an f32 rounding boundary)."""
+    raws, _ = load_golden("fm_delays")
+    eng_binary.load_u8(0, raws[0])
+    ref, tgt = split(raws[0])
+    for kind, sig in ((T.KIND_REF, ref), (T.KIND_TGT, tgt)):
+        got, _, br = eng_binary.preprocess(0, kind, 0, sig.size)
+        want, _ = oracle.preprocess_binary(sig)
+        assert br == 0
+        mism = int(np.count_nonzero(got.view(np.uint32) != want.view(np.uint32)))
+        assert mism <= 2, f"{mism} of {sig.size} samples differ"
+
+
+def test_fast_demod_keeps_the_lags():
+    raws, meta = load_golden("fm_delays")
+    with T.Engine(T.MODE_BINARY, fast_demod=1) as e:
+        load_all(e, raws)
+        got = list(e.xcorr(T.KIND_REF)[0]) + list(e.xcorr(T.KIND_TGT)[0])
+    for pk, gold in zip(got, meta["pairs"]):
+        assert int(pk["lag"]) == gold["delay"]
+        assert abs(float(pk["corr"]) - gold["corr"]) <= 5e-6
