@@ -174,6 +174,11 @@ typedef struct {
 } tdoa_stats;
 TDOA_API int tdoa_get_stats(tdoa_engine *e, tdoa_stats *out);
 
+/* Device self-tests of arithmetic shortcuts the kernels rely on.  which = 0: the
+ * box-car's constant-divisor division equals a correctly rounded f32 divide for every
+ * float input (exhaustive, ~10 ms).  *mismatches = 0 means proven. */
+TDOA_API int tdoa_selftest(tdoa_engine *e, int32_t which, int64_t *mismatches);
+
 /* Raw CUDA stream of the engine (cudaStream_t as void*), for callers that time or
  * chain work on it. */
 TDOA_API void *tdoa_stream(tdoa_engine *e);

@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "tdoa_default_config", "tdoa_create", "tdoa_destroy", "tdoa_last_error", "tdoa_host_alloc", "tdoa_host_free",
     "tdoa_load_u8", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device",
     "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
-    "tdoa_set_stream", "tdoa_synchronize",
+    "tdoa_set_stream", "tdoa_synchronize", "tdoa_selftest",
 ]
 
 
@@ -125,6 +125,7 @@ def load_library():
     L.tdoa_stream.restype = vp
     L.tdoa_set_stream.argtypes = [vp, vp]
     L.tdoa_synchronize.argtypes = [vp]
+    L.tdoa_selftest.argtypes = [vp, i32, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -226,6 +227,11 @@ class Engine:
 
     def synchronize(self):
         self._check(self._lib.tdoa_synchronize(self._h))
+
+    def selftest(self, which: int = 0) -> int:
+        bad = C.c_int64(-1)
+        self._check(self._lib.tdoa_selftest(self._h, which, C.byref(bad)))
+        return bad.value
 
     def stats(self) -> dict:
         st = Stats()

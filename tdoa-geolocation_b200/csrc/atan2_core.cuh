@@ -35,33 +35,67 @@ __host__ __device__ constexpr double atan_k8(int k)
     return t[k];
 }
 
-// y, x: finite, not both zero.  `table` points at the 9 atan(k/8) values (shared memory on
-// the device; nullptr on the host selects the constexpr table).
-TDOA_A2_HD double atan2_octant(double y, double x, const double *table)
+#ifdef __CUDACC__
+// polynomial of atan(z) = z + z w P(w), w = z^2: -1/3, 1/5, -1/7, 1/9, -1/11, 1/13
+// (constant-bank operands: no immediate moves in the inner loop)
+__constant__ double kAtanPoly[6] = {-1.0 / 3.0, 1.0 / 5.0, -1.0 / 7.0, 1.0 / 9.0, -1.0 / 11.0, 1.0 / 13.0};
+#endif
+
+// num / den for den in [1e-6, 4]: MUFU.RCP64H seed (>= 20 bits), two Newton steps and one
+// residual correction -- branch-free, error < 1 ulp.  The host build divides.
+TDOA_A2_HD double div_pos(double num, double den)
+{
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    const double q = num * r;
+    return fma(r, fma(-den, q, num), q);
+#else
+    return num / den;
+#endif
+}
+
+// y, x: finite, not both zero; yf, xf: the same values in f32 (only used to pick the
+// table entry).  `table` points at the 9 atan(k/8) values (shared memory on the device;
+// nullptr on the host selects the constexpr table).
+TDOA_A2_HD double atan2_octant(double y, double x, float yf, float xf, const double *table)
 {
     const double ax = fabs(x), ay = fabs(y);
     const double mx = fmax(ax, ay), mn = fmin(ax, ay);
     // k = round(8 mn/mx): an f32 estimate is plenty, the polynomial absorbs the slack
-    const float qf = (float)mn / (float)mx;
+    const float axf = fabsf(xf), ayf = fabsf(yf);
+#ifdef __CUDA_ARCH__
+    const float qf = __fdividef(fminf(axf, ayf), fmaxf(axf, ayf));
+#else
+    const float qf = fminf(axf, ayf) / fmaxf(axf, ayf);
+#endif
     int k = (int)(qf * 8.0f + 0.5f);
     k = k < 0 ? 0 : (k > 8 ? 8 : k);
     const double c = (double)k * 0.125;
     const double num = fma(-c, mx, mn);  // mn - c mx
     const double den = fma(c, mn, mx);   // mx + c mn
-    const double z = num / den;
+    const double z = div_pos(num, den);
     const double w = z * z;
+#ifdef __CUDA_ARCH__
+    double p = kAtanPoly[5];
+    p = fma(p, w, kAtanPoly[4]);
+    p = fma(p, w, kAtanPoly[3]);
+    p = fma(p, w, kAtanPoly[2]);
+    p = fma(p, w, kAtanPoly[1]);
+    p = fma(p, w, kAtanPoly[0]);
+    const double base = table[k];
+#else
     double p = 1.0 / 13.0;
     p = fma(p, w, -1.0 / 11.0);
     p = fma(p, w, 1.0 / 9.0);
     p = fma(p, w, -1.0 / 7.0);
     p = fma(p, w, 1.0 / 5.0);
     p = fma(p, w, -1.0 / 3.0);
-    const double az = fma(z * w, p, z);  // atan(z)
-#ifdef __CUDA_ARCH__
-    const double base = table[k];
-#else
     const double base = table ? table[k] : atan_k8(k);
 #endif
+    const double az = fma(z * w, p, z);  // atan(z)
     double r = base + az;                               // atan(mn/mx) in [0, pi/4]
     if (ay > ax) r = 1.57079632679489661923 - r;         // pi/2 - r
     if (x < 0.0) r = 3.14159265358979323846 - r;         // pi - r

@@ -1223,6 +1223,18 @@ int tdoa_get_stats(tdoa_engine *e, tdoa_stats *out)
     return TDOA_OK;
 }
 
+int tdoa_selftest(tdoa_engine *e, int32_t which, int64_t *mismatches)
+{
+    if (!e || !mismatches) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (which != 0) return fail(e, TDOA_E_INVALID, "tdoa_selftest: unknown test %d", which);
+    const long long bad = div_selftest(e->stream);
+    if (bad < 0) return fail(e, TDOA_E_CUDA, "tdoa_selftest: kernel failed");
+    *mismatches = bad;
+    return TDOA_OK;
+}
+
 void *tdoa_stream(tdoa_engine *e) { return e ? reinterpret_cast<void *>(e->stream) : nullptr; }
 
 int tdoa_synchronize(tdoa_engine *e)

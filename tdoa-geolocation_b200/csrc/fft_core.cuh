@@ -160,6 +160,19 @@ TDOA_HD void pass2_store(float2 (&u)[16], int j, const float2 *tw, float2 *sm)
     for (int r = 0; r < 16; r++) sm[pad(j0 + 32 * r)] = u[r];
 }
 
+// pass 2 with the twiddles W_512^(r k) pre-tabulated per lane: tab[r * 32 + k], k = j % 32
+// (k is the lane id for both butterflies of a thread, so the reads are conflict free)
+TDOA_HD void pass2_store_tab(float2 (&u)[16], int j, const float2 *tab, float2 *sm)
+{
+    const int k = j & 31;
+#pragma unroll
+    for (int r = 1; r < 16; r++) u[r] = cmul(u[r], tab[r * 32 + k]);
+    dft<16>(u);
+    const int j0 = (j >> 5) * 512 + k;
+#pragma unroll
+    for (int r = 0; r < 16; r++) sm[pad(j0 + 32 * r)] = u[r];
+}
+
 // pass 3: radix 16, Ns = 512: twiddle W_8192^(r j); result u[r] = X[j + 512 r]
 TDOA_HD void pass3_compute(float2 (&u)[16], int j, const float2 *tw)
 {

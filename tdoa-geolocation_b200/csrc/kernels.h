@@ -107,6 +107,7 @@ int unpack_selftest(cudaStream_t st);  // 0 ok: arithmetic unpack == host LUT fo
 void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, cudaStream_t st);
 void launch_boxcar_small(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
 int boxcar_small_max_half();
+long long div_selftest(cudaStream_t st);  // mismatches of the constant-divisor division, 0 = proven
 int fast_grid_x(i64 n);
 
 // ---- xcorr_exact.cu

@@ -39,67 +39,88 @@ __device__ __forceinline__ float atan2_fast(float y, float x, const float *table
     return y < 0.f ? -r : r;
 }
 
+struct DemodLuts {
+    double lut[256];   // unpacked sample value, widened (exact)
+    float lutf[256];
+    double atan_d[9];
+    float atan_f[9];
+};
+
+// one discriminator output from the raw bytes of samples i-1 (prv) and i (cur)
+template <bool FAST>
+__device__ __forceinline__ float demod_one(const DemodLuts &L, uchar2 prv, uchar2 cur)
+{
+    if (FAST) {
+        const float pr = L.lutf[prv.x], pi = L.lutf[prv.y], cr = L.lutf[cur.x], ci = L.lutf[cur.y];
+        const float fre = fmaf(pr, cr, pi * ci), fim = fmaf(ci, pr, -(pi * cr));
+        const float m = fre * fre + fim * fim;
+        const float y = atan2_fast(fim, fre, L.atan_f);
+        return m > 1e-10f ? y : 0.f;
+    } else {
+        const double pr = L.lut[prv.x], pi = L.lut[prv.y], cr = L.lut[cur.x], ci = L.lut[cur.y];
+        // products of f32 values are exact in f64, so one fused rounding equals the
+        // reference's  pr*cr - ci*(-pi)  and  (-pi)*cr + ci*pr
+        const double re = fma(pr, cr, __dmul_rn(ci, pi));
+        const double im = fma(ci, pr, -__dmul_rn(pi, cr));
+        const float fre = (float)re, fim = (float)im;
+        // gates of the reference (p == 0, |p|^2 <= 1e-10f) as a select: no divergence
+        const float m = __fadd_rn(__fmul_rn(fre, fre), __fmul_rn(fim, fim));
+        const float y = (float)atan2_octant((double)fim, (double)fre, fim, fre, L.atan_d);
+        return m > 1e-10f ? y : 0.f;
+    }
+}
+
 template <bool FAST>
 __global__ void __launch_bounds__(kThreads) k_demod_fused(const SigJob *jobs)
 {
-    __shared__ double s_lut[256];   // unpacked sample value, widened (exact)
-    __shared__ float s_lutf[256];
-    __shared__ double s_atan[9];
-    __shared__ float s_atanf[9];
+    __shared__ DemodLuts L;
     __shared__ double scratch[32];
     const SigJob &J = jobs[blockIdx.y];
     const int tid = threadIdx.x;
     {
         const float v = unpack_byte((unsigned)tid);
-        s_lutf[tid] = v;
-        s_lut[tid] = (double)v;
-        if (tid < 9) { s_atan[tid] = atan_k8(tid); s_atanf[tid] = (float)atan_k8(tid); }
+        L.lutf[tid] = v;
+        L.lut[tid] = (double)v;
+        if (tid < 9) { L.atan_d[tid] = atan_k8(tid); L.atan_f[tid] = (float)atan_k8(tid); }
     }
     __syncthreads();
     const i64 n = J.n;
-    const uchar2 *raw = reinterpret_cast<const uchar2 *>(J.src.raw);
+    const uchar2 *__restrict__ raw = reinterpret_cast<const uchar2 *>(J.src.raw);
+    float *__restrict__ out = J.p_re;
+    const i64 run0 = J.src.run0_len;
     double pw = 0.0, sr = 0.0;
     for (i64 i0 = (i64)blockIdx.x * kTile; i0 < n; i0 += (i64)gridDim.x * kTile) {
-        uchar2 cur[8], prv[8];
+        // whole tile (and the sample before it) inside one run of the capture: plain
+        // 32-bit indexing from one base pointer, no per-sample bounds or run tests
+        const bool one_run = i0 > 0 && i0 + kTile <= n && (i0 - 1 >= run0 || i0 + kTile <= run0);
+        if (one_run) {
+            const uchar2 *__restrict__ base = raw + raw_index(J.src, i0) + tid;
+            float *__restrict__ o = out + i0 + tid;
+            uchar2 cur[8], prv[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const i64 i = i0 + tid + 256 * u;
-            const i64 k = i == 0 ? 1 : i;  // out[0] = out[1]
-            cur[u] = make_uchar2(128, 128);
-            prv[u] = cur[u];
-            if (i < n) {
-                cur[u] = raw[raw_index(J.src, k)];
-                prv[u] = raw[raw_index(J.src, k - 1)];
+            for (int u = 0; u < 8; u++) {
+                cur[u] = base[256 * u];
+                prv[u] = base[256 * u - 1];
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const i64 i = i0 + tid + 256 * u;
-            if (i >= n) continue;
-            // initial power of sample i (f32 re*re + im*im, widened)
-            const uchar2 me = i == 0 ? prv[u] : cur[u];
-            pw += (double)mag2_f32(s_lutf[me.x], s_lutf[me.y]);
-            float y;
-            if (FAST) {
-                const float pr = s_lutf[prv[u].x], pi = s_lutf[prv[u].y], cr = s_lutf[cur[u].x], ci = s_lutf[cur[u].y];
-                const float fre = fmaf(pr, cr, pi * ci), fim = fmaf(ci, pr, -(pi * cr));
-                const float m = fre * fre + fim * fim;
-                y = m > 1e-10f ? atan2_fast(fim, fre, s_atanf) : 0.f;
-            } else {
-                const double pr = s_lut[prv[u].x], pi = s_lut[prv[u].y], cr = s_lut[cur[u].x], ci = s_lut[cur[u].y];
-                // products of f32 values are exact in f64, so one fused rounding equals the
-                // reference's  pr*cr - ci*(-pi)  and  (-pi)*cr + ci*pr
-                const double re = fma(pr, cr, __dmul_rn(ci, pi));
-                const double im = fma(ci, pr, -__dmul_rn(pi, cr));
-                const float fre = (float)re, fim = (float)im;
-                y = 0.f;
-                if (!(fre == 0.f && fim == 0.f)) {
-                    const float m = __fadd_rn(__fmul_rn(fre, fre), __fmul_rn(fim, fim));
-                    if (m > 1e-10f) y = (float)atan2_octant((double)fim, (double)fre, s_atan);
-                }
+            for (int u = 0; u < 8; u++) {
+                pw += (double)mag2_f32(L.lutf[cur[u].x], L.lutf[cur[u].y]);
+                const float y = demod_one<FAST>(L, prv[u], cur[u]);
+                o[256 * u] = y;
+                sr += (double)y;
             }
-            J.p_re[i] = y;
-            sr += (double)y;
+        } else {
+            for (int u = 0; u < 8; u++) {
+                const i64 i = i0 + tid + 256 * u;
+                if (i >= n) break;
+                const i64 k = i == 0 ? 1 : i;  // out[0] = out[1]
+                const uchar2 cur = raw[raw_index(J.src, k)], prv = raw[raw_index(J.src, k - 1)];
+                const uchar2 me = i == 0 ? prv : cur;  // initial power is of sample i itself
+                pw += (double)mag2_f32(L.lutf[me.x], L.lutf[me.y]);
+                const float y = demod_one<FAST>(L, prv, cur);
+                out[i] = y;
+                sr += (double)y;
+            }
         }
     }
     double part[2], total[2];
@@ -118,17 +139,55 @@ __global__ void __launch_bounds__(kThreads) k_demod_fused(const SigJob *jobs)
 constexpr int kHalo = 16;   // staged halo each side (multiple of 4 for float4 staging)
 constexpr int kHalfMax = 8; // window / 2 served by this kernel
 
+// x / d for a small odd integer d, correctly rounded: q = x * RN(1/d), one FMA residual,
+// one FMA correction (Markstein).  Exhaustively checked against __fdiv_rn over all 2^32
+// float inputs for every d this file uses (tdoa_selftest / tests/test_gpu_parity.py).
+template <int D>
+__device__ __forceinline__ float div_small(float x)
+{
+    constexpr float r = 1.0f / (float)D;
+    const float q = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-q, (float)D, x);
+    return __fmaf_rn(e, r, q);
+}
+
 // Leading / trailing out-of-range taps are staged as 0.f: 0.f + x == x and acc + 0.f == acc
 // exactly, so the tap sum equals the reference's sum over the in-range taps only.
-template <int H>
-__device__ __forceinline__ void box_outputs(const float (&w)[24], float (&out)[8])
+// INTERIOR: every output has all 2H+1 taps in range -> constant divisor.
+template <int H, bool INTERIOR>
+__device__ __forceinline__ void box_outputs(const float (&w)[24], float (&out)[8], i64 ib, i64 n)
 {
 #pragma unroll
     for (int o = 0; o < 8; o++) {
         float acc = w[8 + o - H];
 #pragma unroll
         for (int j = 1; j <= 2 * H; j++) acc = __fadd_rn(acc, w[8 + o - H + j]);
-        out[o] = acc;
+        if (INTERIOR) {
+            out[o] = div_small<2 * H + 1>(acc);
+        } else {
+            const i64 i = ib + o;
+            const i64 a = max((i64)0, i - H), b = min(n - 1, i + H);
+            out[o] = __fdiv_rn(acc, (float)(int)(b - a + 1));  // processor.go:289 divides by the tap count
+        }
+    }
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ void box_dispatch(int h, const float (&w)[24], float (&out)[8], i64 ib, i64 n)
+{
+    switch (h) {
+        case 0:
+#pragma unroll
+            for (int o = 0; o < 8; o++) out[o] = w[8 + o];
+            break;
+        case 1: box_outputs<1, INTERIOR>(w, out, ib, n); break;
+        case 2: box_outputs<2, INTERIOR>(w, out, ib, n); break;
+        case 3: box_outputs<3, INTERIOR>(w, out, ib, n); break;
+        case 4: box_outputs<4, INTERIOR>(w, out, ib, n); break;
+        case 5: box_outputs<5, INTERIOR>(w, out, ib, n); break;
+        case 6: box_outputs<6, INTERIOR>(w, out, ib, n); break;
+        case 7: box_outputs<7, INTERIOR>(w, out, ib, n); break;
+        default: box_outputs<8, INTERIOR>(w, out, ib, n); break;
     }
 }
 
@@ -142,23 +201,24 @@ __global__ void __launch_bounds__(kThreads) k_boxcar_small(const SigJob *jobs)
     const int h = J.window <= 1 ? 0 : J.window / 2;
     const float dc = J.sub_dc ? (float)J.stats[ST_DC_RE] : 0.f;
     const float *__restrict__ q = J.q_re;
+    float *__restrict__ p = J.p_re;
     double pacc = 0.0;
     for (i64 i0 = (i64)blockIdx.x * kTile; i0 < n; i0 += (i64)gridDim.x * kTile) {
+        const bool interior = i0 >= kHalo && i0 + kTile + kHalo <= n;
         __syncthreads();
-        // stage [i0 - kHalo, i0 + kTile + kHalo) minus dc; float4 where whole and aligned
-        for (int j4 = tid; j4 < (kTile + 2 * kHalo) / 4; j4 += kThreads) {
-            const i64 g = i0 - kHalo + 4 * (i64)j4;
-            float4 v;
-            if (g >= 0 && g + 3 < n) {
-                v = *reinterpret_cast<const float4 *>(q + g);
+        // stage [i0 - kHalo, i0 + kTile + kHalo) minus dc
+        if (interior) {
+            const float4 *__restrict__ src = reinterpret_cast<const float4 *>(q + (i0 - kHalo));
+            for (int j4 = tid; j4 < (kTile + 2 * kHalo) / 4; j4 += kThreads) {
+                float4 v = src[j4];
                 v.x = __fsub_rn(v.x, dc); v.y = __fsub_rn(v.y, dc); v.z = __fsub_rn(v.z, dc); v.w = __fsub_rn(v.w, dc);
-            } else {
-                v.x = (g >= 0 && g < n) ? __fsub_rn(q[g], dc) : 0.f;
-                v.y = (g + 1 >= 0 && g + 1 < n) ? __fsub_rn(q[g + 1], dc) : 0.f;
-                v.z = (g + 2 >= 0 && g + 2 < n) ? __fsub_rn(q[g + 2], dc) : 0.f;
-                v.w = (g + 3 >= 0 && g + 3 < n) ? __fsub_rn(q[g + 3], dc) : 0.f;
+                *reinterpret_cast<float4 *>(s_x + 4 * j4) = v;
             }
-            *reinterpret_cast<float4 *>(s_x + 4 * j4) = v;
+        } else {
+            for (int j = tid; j < kTile + 2 * kHalo; j += kThreads) {
+                const i64 g = i0 - kHalo + j;
+                s_x[j] = (g >= 0 && g < n) ? __fsub_rn(q[g], dc) : 0.f;
+            }
         }
         __syncthreads();
         const i64 ib = i0 + 8 * tid;  // first output of this thread
@@ -172,47 +232,52 @@ __global__ void __launch_bounds__(kThreads) k_boxcar_small(const SigJob *jobs)
                 w[4 * v4] = v.x; w[4 * v4 + 1] = v.y; w[4 * v4 + 2] = v.z; w[4 * v4 + 3] = v.w;
             }
             float out[8];
-            switch (h) {
-                case 0:
-#pragma unroll
-                    for (int o = 0; o < 8; o++) out[o] = w[8 + o];
-                    break;
-                case 1: box_outputs<1>(w, out); break;
-                case 2: box_outputs<2>(w, out); break;
-                case 3: box_outputs<3>(w, out); break;
-                case 4: box_outputs<4>(w, out); break;
-                case 5: box_outputs<5>(w, out); break;
-                case 6: box_outputs<6>(w, out); break;
-                case 7: box_outputs<7>(w, out); break;
-                default: box_outputs<8>(w, out); break;
-            }
-#pragma unroll
-            for (int o = 0; o < 8; o++) {
-                const i64 i = ib + o;
-                if (h > 0) {
-                    const i64 a = max((i64)0, i - h), b = min(n - 1, i + h);
-                    out[o] = __fdiv_rn(out[o], (float)(int)(b - a + 1));
-                }
-                if (i < n) pacc += (double)__fmul_rn(out[o], out[o]);
-            }
+            if (interior) box_dispatch<true>(h, w, out, ib, n);
+            else box_dispatch<false>(h, w, out, ib, n);
             if (ib + 7 < n) {
-                *reinterpret_cast<float4 *>(J.p_re + ib) = make_float4(out[0], out[1], out[2], out[3]);
-                *reinterpret_cast<float4 *>(J.p_re + ib + 4) = make_float4(out[4], out[5], out[6], out[7]);
+#pragma unroll
+                for (int o = 0; o < 8; o++) pacc += (double)__fmul_rn(out[o], out[o]);
+                *reinterpret_cast<float4 *>(p + ib) = make_float4(out[0], out[1], out[2], out[3]);
+                *reinterpret_cast<float4 *>(p + ib + 4) = make_float4(out[4], out[5], out[6], out[7]);
             } else {
 #pragma unroll
                 for (int o = 0; o < 8; o++)
-                    if (ib + o < n) J.p_re[ib + o] = out[o];
+                    if (ib + o < n) {
+                        pacc += (double)__fmul_rn(out[o], out[o]);
+                        p[ib + o] = out[o];
+                    }
             }
         }
     }
     if (J.want_power) {
         double part[1] = {block_sum(pacc, scratch)}, total[1];
         if (grid_sum_last<1>(part, J.partials, J.counter, gridDim.x, blockIdx.x, scratch, total)) {
-            const double p = n > 0 ? total[0] / (double)n : 0.0;
-            J.stats[ST_POWER1] = p;
-            J.stats[ST_SCALE] = p > 0.0 ? (double)(float)(1.0 / sqrt(p)) : 1.0;
+            const double pw = n > 0 ? total[0] / (double)n : 0.0;
+            J.stats[ST_POWER1] = pw;
+            J.stats[ST_SCALE] = pw > 0.0 ? (double)(float)(1.0 / sqrt(pw)) : 1.0;
         }
     }
+}
+
+// exhaustive check of div_small<D> against __fdiv_rn over every float bit pattern
+template <int D>
+__device__ __forceinline__ unsigned div_mismatch(float x)
+{
+    const float a = div_small<D>(x), b = __fdiv_rn(x, (float)D);
+    return (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_div_selftest(unsigned long long *bad)
+{
+    unsigned cnt = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * 256 + threadIdx.x; v < (1ull << 32); v += stride) {
+        const float x = __uint_as_float((unsigned)v);
+        if (fabsf(x) < 1e-35f || fabsf(x) > 1e35f) continue;  // box-car sums live far inside this range
+        cnt += div_mismatch<3>(x) + div_mismatch<5>(x) + div_mismatch<7>(x) + div_mismatch<9>(x) + div_mismatch<11>(x) +
+               div_mismatch<13>(x) + div_mismatch<15>(x) + div_mismatch<17>(x);
+    }
+    if (cnt) atomicAdd(bad, (unsigned long long)cnt);
 }
 
 }  // namespace
@@ -237,5 +302,17 @@ void launch_boxcar_small(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream
 }
 
 int boxcar_small_max_half() { return kHalfMax; }
+
+long long div_selftest(cudaStream_t st)
+{
+    unsigned long long *d_bad = nullptr, h_bad = ~0ull;
+    if (cudaMalloc(&d_bad, sizeof(*d_bad)) != cudaSuccess) return -1;
+    cudaMemsetAsync(d_bad, 0, sizeof(*d_bad), st);
+    k_div_selftest<<<148 * 16, 256, 0, st>>>(d_bad);
+    cudaMemcpyAsync(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, st);
+    const cudaError_t err = cudaStreamSynchronize(st);
+    cudaFree(d_bad);
+    return err == cudaSuccess ? (long long)h_bad : -1;
+}
 
 }  // namespace tdoa

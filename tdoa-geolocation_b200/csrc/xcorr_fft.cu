@@ -25,7 +25,8 @@ using namespace fft;
 namespace {
 
 constexpr int kBins = kN / 2 + 1;          // 4097 cross-spectrum bins kept (Hermitian)
-constexpr int kSmemBytes = kPad * (int)sizeof(float2);
+constexpr int kTabLen = 16 * 32;                                // pass-2 twiddles per lane
+constexpr int kSmemBytes = (kPad + kTabLen) * (int)sizeof(float2);
 
 // ---------------------------------------------------------------- segment accumulate
 __global__ void __launch_bounds__(kThreads, 2) k_fft_segments(const FftJob *jobs, const float2 *__restrict__ tw)
@@ -37,6 +38,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_fft_segments(const FftJob *jobs
     const int tid = threadIdx.x;
     const float *__restrict__ tp = J.t + J.t_off;
     const float *__restrict__ sp = J.s;
+    float2 *tab = sm + kPad;
+    for (int idx = tid; idx < kTabLen; idx += kThreads) tab[idx] = tw[(16 * (idx & 31) * (idx >> 5)) & (kN - 1)];
+    // (the first barrier inside the segment loop orders these writes before their use)
 
     float acc_re[16], acc_im[16];
     float acc_nyq = 0.f;
@@ -49,14 +53,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_fft_segments(const FftJob *jobs
         const i64 t_left = J.n_t - t0;        // template samples left (>= 1)
         {
             float2 v[32];
+            if (t_left >= kSeg && s0 >= 0 && s0 + kN <= J.sl) {
+                // interior segment: one base pointer each, immediate offsets, no bounds tests
+                const float *__restrict__ tq = tp + t0 + tid;
+                const float *__restrict__ sq = sp + s0 + tid;
 #pragma unroll
-            for (int r = 0; r < 32; r++) {
-                const int m = tid + 256 * r;
-                float a = 0.f, b = 0.f;
-                if (r < kSeg / 256 && m < t_left) a = tp[t0 + m];
-                const i64 g = s0 + m;
-                if (g >= 0 && g < J.sl) b = sp[g];
-                v[r] = make_float2(a, b);
+                for (int r = 0; r < 32; r++) v[r] = make_float2(r < kSeg / 256 ? tq[256 * r] : 0.f, sq[256 * r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    const int m = tid + 256 * r;
+                    float a = 0.f, b = 0.f;
+                    if (r < kSeg / 256 && m < t_left) a = tp[t0 + m];
+                    const i64 g = s0 + m;
+                    if (g >= 0 && g < J.sl) b = sp[g];
+                    v[r] = make_float2(a, b);
+                }
             }
             pass1_store(v, tid, sm);
         }
@@ -65,8 +77,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_fft_segments(const FftJob *jobs
         pass_load16(sm, tid, u0);
         pass_load16(sm, tid + 256, u1);
         __syncthreads();
-        pass2_store(u0, tid, tw, sm);
-        pass2_store(u1, tid + 256, tw, sm);
+        pass2_store_tab(u0, tid, tab, sm);
+        pass2_store_tab(u1, tid + 256, tab, sm);
         __syncthreads();
         pass_load16(sm, tid, u0);
         pass_load16(sm, tid + 256, u1);

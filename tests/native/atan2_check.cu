@@ -21,7 +21,7 @@ int main()
         if (it % 13 == 0) x = -y;
         if (x == 0.f && y == 0.f) continue;
         const double want = atan2((double)y, (double)x);
-        const double got = tdoa::atan2_octant((double)y, (double)x, nullptr);
+        const double got = tdoa::atan2_octant((double)y, (double)x, y, x, nullptr);
         const double ulp = want == 0.0 ? (got == 0.0 ? 0.0 : 1e9) : fabs(got - want) / (fabs(want) * 2.220446049250313e-16);
         if (ulp > max_ulp) max_ulp = ulp;
         if ((float)want != (float)got) mism32++;

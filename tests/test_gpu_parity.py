@@ -306,3 +306,9 @@ def test_fast_demod_keeps_the_lags():
     for pk, gold in zip(got, meta["pairs"]):
         assert int(pk["lag"]) == gold["delay"]
         assert abs(float(pk["corr"]) - gold["corr"]) <= 5e-6
+
+
+def test_constant_divisor_division_is_exact(eng_binary):
+    """The small box-car divides by its tap count with a reciprocal + FMA correction; the
+    device checks it against a correctly rounded divide for every float bit pattern."""
+    assert eng_binary.selftest(0) == 0
