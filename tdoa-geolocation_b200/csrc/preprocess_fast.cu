@@ -191,7 +191,7 @@ __device__ __forceinline__ void box_dispatch(int h, const float (&w)[24], float 
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_boxcar_small(const SigJob *jobs)
+__global__ void __launch_bounds__(kThreads, 4) k_boxcar_small(const SigJob *jobs)
 {
     __shared__ __align__(16) float s_x[kTile + 2 * kHalo];
     __shared__ double scratch[32];
@@ -203,16 +203,36 @@ __global__ void __launch_bounds__(kThreads) k_boxcar_small(const SigJob *jobs)
     const float *__restrict__ q = J.q_re;
     float *__restrict__ p = J.p_re;
     double pacc = 0.0;
+    // software pipeline: the next tile's global loads are issued before this tile's taps
+    // are summed, so their latency hides behind the arithmetic (3 float4 per thread)
+    constexpr int kStage4 = (kTile + 2 * kHalo) / 4;          // 520 float4 per tile
+    constexpr int kPer = (kStage4 + kThreads - 1) / kThreads;  // 3
+    float4 pf[kPer];
+    auto tile_interior = [&](i64 t0) { return t0 >= kHalo && t0 + kTile + kHalo <= n; };
+    auto prefetch = [&](i64 t0) {
+        if (t0 < n && tile_interior(t0)) {
+            const float4 *__restrict__ src = reinterpret_cast<const float4 *>(q + (t0 - kHalo));
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+                const int j4 = tid + k * kThreads;
+                if (j4 < kStage4) pf[k] = src[j4];
+            }
+        }
+    };
+    prefetch((i64)blockIdx.x * kTile);
     for (i64 i0 = (i64)blockIdx.x * kTile; i0 < n; i0 += (i64)gridDim.x * kTile) {
-        const bool interior = i0 >= kHalo && i0 + kTile + kHalo <= n;
+        const bool interior = tile_interior(i0);
         __syncthreads();
         // stage [i0 - kHalo, i0 + kTile + kHalo) minus dc
         if (interior) {
-            const float4 *__restrict__ src = reinterpret_cast<const float4 *>(q + (i0 - kHalo));
-            for (int j4 = tid; j4 < (kTile + 2 * kHalo) / 4; j4 += kThreads) {
-                float4 v = src[j4];
-                v.x = __fsub_rn(v.x, dc); v.y = __fsub_rn(v.y, dc); v.z = __fsub_rn(v.z, dc); v.w = __fsub_rn(v.w, dc);
-                *reinterpret_cast<float4 *>(s_x + 4 * j4) = v;
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+                const int j4 = tid + k * kThreads;
+                if (j4 < kStage4) {
+                    float4 v = pf[k];
+                    v.x = __fsub_rn(v.x, dc); v.y = __fsub_rn(v.y, dc); v.z = __fsub_rn(v.z, dc); v.w = __fsub_rn(v.w, dc);
+                    *reinterpret_cast<float4 *>(s_x + 4 * j4) = v;
+                }
             }
         } else {
             for (int j = tid; j < kTile + 2 * kHalo; j += kThreads) {
@@ -220,6 +240,7 @@ __global__ void __launch_bounds__(kThreads) k_boxcar_small(const SigJob *jobs)
                 s_x[j] = (g >= 0 && g < n) ? __fsub_rn(q[g], dc) : 0.f;
             }
         }
+        prefetch(i0 + (i64)gridDim.x * kTile);
         __syncthreads();
         const i64 ib = i0 + 8 * tid;  // first output of this thread
         if (ib < n) {

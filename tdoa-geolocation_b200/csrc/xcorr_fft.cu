@@ -53,6 +53,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_fft_segments(const FftJob *jobs
         const i64 t_left = J.n_t - t0;        // template samples left (>= 1)
         {
             float2 v[32];
+            {
+                // pull the next segment of this CTA towards L2 while this one is transformed:
+                // 448 lines of 128 B per segment, two per thread
+                const i64 nt0 = t0 + (i64)J.n_cta * kSeg, ns0 = s0 + (i64)J.n_cta * kSeg;
+                const i64 pt = nt0 + 32 * tid, ps = ns0 + 32 * tid;
+                if (tid < kSeg / 32 && pt < J.n_t) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + pt));
+                if (ps >= 0 && ps < J.sl) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + ps));
+            }
             if (t_left >= kSeg && s0 >= 0 && s0 + kN <= J.sl) {
                 // interior segment: one base pointer each, immediate offsets, no bounds tests
                 const float *__restrict__ tq = tp + t0 + tid;
