@@ -176,7 +176,9 @@ TDOA_API int tdoa_get_stats(tdoa_engine *e, tdoa_stats *out);
 
 /* Device self-tests of arithmetic shortcuts the kernels rely on.  which = 0: the
  * box-car's constant-divisor division equals a correctly rounded f32 divide for every
- * float input (exhaustive, ~10 ms).  *mismatches = 0 means proven. */
+ * float input (exhaustive, ~10 ms); *mismatches = 0 means proven.  which = 1: the
+ * production FM discriminator against the reference statement of it over all 2^32
+ * (previous, current) byte quads; the differing quads are listed in tdoa_last_error. */
 TDOA_API int tdoa_selftest(tdoa_engine *e, int32_t which, int64_t *mismatches);
 
 /* Raw CUDA stream of the engine (cudaStream_t as void*), for callers that time or

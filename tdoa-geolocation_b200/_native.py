@@ -233,6 +233,9 @@ class Engine:
         self._check(self._lib.tdoa_selftest(self._h, which, C.byref(bad)))
         return bad.value
 
+    def last_error(self) -> str:
+        return (self._lib.tdoa_last_error(self._h) or b"").decode()
+
     def stats(self) -> dict:
         st = Stats()
         self._check(self._lib.tdoa_get_stats(self._h, C.byref(st)))

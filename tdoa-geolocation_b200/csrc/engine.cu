@@ -903,6 +903,7 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
     for (int i = 0; i < 2 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev_fft[i]);
     e->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if (err == cudaSuccess && fft_setup(e->stream, &e->d_tw) != 0) err = cudaErrorUnknown;
+    if (err == cudaSuccess && demod_setup(e->stream) != 0) err = cudaErrorUnknown;
     if (err != cudaSuccess) {
         g_create_error = std::string("tdoa_create: ") + cudaGetErrorString(err);
         tdoa_destroy(e);
@@ -1228,8 +1229,16 @@ int tdoa_selftest(tdoa_engine *e, int32_t which, int64_t *mismatches)
     if (!e || !mismatches) return TDOA_E_INVALID;
     int rc = begin_call(e);
     if (rc) return rc;
-    if (which != 0) return fail(e, TDOA_E_INVALID, "tdoa_selftest: unknown test %d", which);
-    const long long bad = div_selftest(e->stream);
+    if (which != 0 && which != 1) return fail(e, TDOA_E_INVALID, "tdoa_selftest: unknown test %d", which);
+    unsigned first_bad[64] = {0};
+    const long long bad = which == 0 ? div_selftest(e->stream) : demod_selftest(e->stream, first_bad);
+    if (which == 1 && bad > 0) {
+        char buf[400];
+        int off = snprintf(buf, sizeof(buf), "demod selftest: %lld differing quads, first:", bad);
+        for (unsigned k = 0; k < first_bad[0] && k < 12 && off < (int)sizeof(buf) - 12; k++)
+            off += snprintf(buf + off, sizeof(buf) - off, " %08x", first_bad[1 + k]);
+        e->error = buf;
+    }
     if (bad < 0) return fail(e, TDOA_E_CUDA, "tdoa_selftest: kernel failed");
     *mismatches = bad;
     return TDOA_OK;

@@ -108,6 +108,10 @@ void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, c
 void launch_boxcar_small(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
 int boxcar_small_max_half();
 long long div_selftest(cudaStream_t st);  // mismatches of the constant-divisor division, 0 = proven
+int demod_setup(cudaStream_t st);         // tables + shared-memory opt-in of the lean discriminator; 0 ok
+// lean discriminator against the reference statement over all 2^32 (previous, current) byte quads;
+// first_bad: [0] = count stored, [1..63] = offending quads (prev I, prev Q, cur I, cur Q from the low byte up)
+long long demod_selftest(cudaStream_t st, unsigned *first_bad);
 int fast_grid_x(i64 n);
 
 // ---- xcorr_exact.cu

@@ -135,6 +135,280 @@ __global__ void __launch_bounds__(kThreads) k_demod_fused(const SigJob *jobs)
     }
 }
 
+// ---------------------------------------------------------------- lean discriminator
+// The same arithmetic as demod_one<false> -- f64 products, one rounding to f32, f64
+// arctangent, one rounding to f32 -- laid out for the B200's issue/pipe budget.  Measured
+// on this part (tools/fp64_rates.cu): FP64 runs at half the FP32 rate (64/clk/SM), and
+// every f32<->f64 conversion costs 8 cycles of the 16-lane XU pipe per warp, so the
+// conversions are what the first version of this kernel was bound by.  Here:
+//   - a thread owns 8 consecutive samples (one 16-byte span of the capture), so each
+//     sample is unpacked once and reused as the "previous" of the next;
+//   - bytes index a 256 x 16-slot table of {value widened to f64, f32 square}; slot =
+//     lane % 16 makes every 128-bit load conflict free, and the address is one PRMT
+//     (byte << 8 | slot << 4) with the table base folded into the LDS as a uniform register;
+//   - "round the f64 product to f32" is integer arithmetic on the bit pattern (rn24);
+//   - arctangent: octant by select, atan(q) = atan(k/64) + atan(z) with k from a
+//     magic-number add (no int<->float conversion), one RCP64H + one Newton step + one
+//     residual correction for the quotient, |z| <= 1/127 so three odd terms suffice
+//     (truncation < 2^-59 relative); the octant fix-ups pi/2 - a, pi - a are folded
+//     into the table (one entry per octant case and k) and a sign flip of atan(z);
+//   - the |p|^2 <= 1e-10 gate of the reference can never fire for uint8 samples (the
+//     smallest product magnitude is 9.46e-10), so it is not evaluated.
+// tdoa_selftest(1) runs this function and demod_one<false> over all 2^32 byte quads.
+constexpr int kLeanThreads = 512;
+constexpr int kLeanPer = 8;                           // consecutive samples per thread
+constexpr int kLeanTile = kLeanThreads * kLeanPer;    // 4096 samples per CTA step
+constexpr int kAtanK = 64;
+constexpr int kOctStride = 128;                       // table entries per octant case
+
+struct __align__(16) LeanEntry {
+    double v;   // unpacked sample value (processor.go:198-199), widened: exact
+    float sq;   // RN_f32(v * v)
+    float vf;   // v
+};
+
+struct LeanSmem {
+    LeanEntry tab[256][16];         // 64 KB
+    double oct[4][kOctStride];      // B(case) + sigma(case) * atan(k / 64)
+    double scratch[32];
+    int last;
+};
+
+__device__ __forceinline__ void lean_fill(LeanSmem &S, const double *__restrict__ atab_g)
+{
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+        const float v = unpack_byte((unsigned)(i >> 4));
+        LeanEntry e;
+        e.v = (double)v; e.sq = __fmul_rn(v, v); e.vf = v;
+        S.tab[i >> 4][i & 15] = e;
+    }
+    // case = swap + 2 * (x < 0):  a, pi/2 - a, pi - a, pi/2 + a
+    for (int i = threadIdx.x; i < 4 * kOctStride; i += blockDim.x) {
+        const int oc = i / kOctStride, k = i % kOctStride;
+        const double a = atab_g[k <= kAtanK ? k : kAtanK];
+        const double pio2 = 1.57079632679489661923, pi = 3.14159265358979323846;
+        S.oct[oc][k] = oc == 0 ? a : (oc == 1 ? pio2 - a : (oc == 2 ? pi - a : pio2 + a));
+    }
+}
+
+__device__ __forceinline__ double hilo(unsigned hi, unsigned lo) { return __hiloint2double((int)hi, (int)lo); }
+
+// x rounded to f32 precision, ties to even, returned as f64 (x finite, in f32's normal range or 0)
+__device__ __forceinline__ double rn24(double x)
+{
+    unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    u += 0x0FFFFFFFull + ((u >> 29) & 1ull);
+    return __longlong_as_double((long long)(u & ~0x1FFFFFFFull));
+}
+
+__device__ __forceinline__ double rcp_seed(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+
+__device__ __forceinline__ double lds_f64(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// f64 arctangent of (y, x), both f32-representable, not both zero, y != -0.  <= 1 ulp.
+// oct_base: shared-window address of LeanSmem::oct.
+__device__ __forceinline__ double atan2_lean(double y, double x, unsigned oct_base)
+{
+    const unsigned xh = (unsigned)__double2hiint(x), yh = (unsigned)__double2hiint(y);
+    const double ax = hilo(xh & 0x7fffffffu, (unsigned)__double2loint(x));
+    const double ay = hilo(yh & 0x7fffffffu, (unsigned)__double2loint(y));
+    const bool swap = ay > ax;
+    const double mx = swap ? ay : ax, mn = swap ? ax : ay;
+    // k = round(64 mn / mx) from the low mantissa bits of q + 1.5 * 2^46 (ulp 2^-6)
+    const double kMagic = 105553116266496.0;
+    const double t = __dadd_rn(__dmul_rn(mn, rcp_seed(mx)), kMagic);
+    const unsigned k = (unsigned)__double2loint(t);
+    const double c = __dadd_rn(t, -kMagic);          // k / 64, exact
+    const double num = fma(-c, mx, mn);              // mn - c mx
+    const double den = fma(c, mn, mx);               // mx + c mn  in [mx, 2 mx]
+    double r = rcp_seed(den);
+    r = fma(r, fma(-den, r, 1.0), r);
+    const double z0 = num * r;
+    const double z = fma(r, fma(-den, z0, num), z0);
+    const double w = z * z;
+    double p = fma(w, -1.0 / 7.0, 1.0 / 5.0);
+    p = fma(w, p, -1.0 / 3.0);
+    const double az = fma(z * w, p, z);              // atan(z), |z| <= 1/127
+    const unsigned sw = swap ? 1u : 0u, xn = xh >> 31;
+    const double base = lds_f64(oct_base + ((xn * 2u + sw) * (unsigned)kOctStride + k) * 8u);
+    // atan(z) enters with a minus sign when exactly one of {swap, x < 0} holds
+    const unsigned flip = (sw ^ xn) << 31;
+    const double a = base + hilo((unsigned)__double2hiint(az) ^ flip, (unsigned)__double2loint(az));
+    return hilo((unsigned)__double2hiint(a) | (yh & 0x80000000u), (unsigned)__double2loint(a));
+}
+
+// discriminator output for the sample (cr, ci) given the previous sample (pr, pi)
+__device__ __forceinline__ float lean_one(double pr, double pi, double cr, double ci, unsigned oct_base)
+{
+    const double re = rn24(fma(pr, cr, __dmul_rn(pi, ci)));
+    const double im = rn24(fma(ci, pr, -__dmul_rn(pi, cr)));
+    return (float)atan2_lean(im, re, oct_base);
+}
+
+__device__ __forceinline__ void lean_lookup(unsigned addr, double &v, float &sq)
+{
+    unsigned r0, r1, r2, r3;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+    v = hilo(r1, r0);
+    sq = __uint_as_float(r2);
+}
+
+// grid_sum_last with the "am I last" flag in caller-provided shared memory
+template <int K>
+__device__ __forceinline__ bool grid_sum_last_dyn(const double (&part)[K], double *partials, unsigned *counter,
+                                                  int n_cta, int cta, double *scratch, int *s_last, double (&total)[K])
+{
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) partials[(size_t)k * n_cta + cta] = part[k];
+        __threadfence();
+        const unsigned t = atomicAdd(counter, 1u);
+        *s_last = (t == (unsigned)n_cta - 1u);
+    }
+    __syncthreads();
+    if (!*s_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < n_cta; i += blockDim.x) v += __ldcg(partials + (size_t)k * n_cta + i);
+        v = block_sum(v, scratch);
+        total[k] = v;
+    }
+    if (threadIdx.x == 0) {
+        *counter = 0u;
+        return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean(const SigJob *jobs, const double *__restrict__ atab_g)
+{
+    extern __shared__ __align__(16) unsigned char lean_raw[];
+    LeanSmem &S = *reinterpret_cast<LeanSmem *>(lean_raw);
+    const SigJob &J = jobs[blockIdx.y];
+    const int tid = threadIdx.x;
+    lean_fill(S, atab_g);
+    __syncthreads();
+    const i64 n = J.n;
+    const uint8_t *__restrict__ rawb = J.src.raw;
+    float *__restrict__ out = J.p_re;
+    const i64 run0 = J.src.run0_len;
+    const unsigned slot16 = (unsigned)(tid & 15) * 16u;
+    const unsigned tab_base = (unsigned)__cvta_generic_to_shared(&S.tab[0][0]);
+    const unsigned oct_base = (unsigned)__cvta_generic_to_shared(&S.oct[0][0]);
+    double pw = 0.0, sr = 0.0;
+    for (i64 i0 = (i64)blockIdx.x * kLeanTile; i0 < n; i0 += (i64)gridDim.x * kLeanTile) {
+        // whole tile, the sample before it and one 32-bit word after it inside one run
+        const bool in0 = i0 + kLeanTile + 2 <= run0, in1 = i0 - 1 >= run0 && i0 + kLeanTile + 2 <= n;
+        if (i0 > 0 && (in0 || in1)) {
+            // byte address of this thread's first sample; only 2-byte alignment is known
+            const uint8_t *ap = rawb + 2 * (raw_index(J.src, i0) + (i64)kLeanPer * tid);
+            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(ap) & 2u) * 8u;
+            const unsigned *__restrict__ wp = reinterpret_cast<const unsigned *>(ap - (sh >> 3));
+            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+            const unsigned pv = *reinterpret_cast<const unsigned short *>(ap - 2);
+            unsigned w[4];
+            w[0] = __funnelshift_r(w0, w1, sh); w[1] = __funnelshift_r(w1, w2, sh);
+            w[2] = __funnelshift_r(w2, w3, sh); w[3] = __funnelshift_r(w3, w4, sh);
+            // table address of byte b of a word: (b << 8) | slot * 16
+            double pr, pi;
+            float sq_i, sq_q;
+            lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5504), pr, sq_i);
+            lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5514), pi, sq_q);
+            float o[kLeanPer];
+#pragma unroll
+            for (int s = 0; s < kLeanPer; s++) {
+                const unsigned ww = w[s >> 1];
+                double cr, ci;
+                lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5524 : 0x5504), cr, sq_i);
+                lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5534 : 0x5514), ci, sq_q);
+                pw += (double)__fadd_rn(sq_i, sq_q);   // processor.go:328, f32 re*re + im*im
+                o[s] = lean_one(pr, pi, cr, ci, oct_base);
+                sr += (double)o[s];
+                pr = cr; pi = ci;
+            }
+            float4 *op = reinterpret_cast<float4 *>(out + i0 + (i64)kLeanPer * tid);
+            op[0] = make_float4(o[0], o[1], o[2], o[3]);
+            op[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+            // edges (signal start, the block-1/block-3 joint, the tail): the reference's
+            // own statement of the discriminator, sample by sample, gates included
+            for (int u = 0; u < kLeanPer; u++) {
+                const i64 i = i0 + tid + (i64)kLeanThreads * u;
+                if (i >= n) break;
+                const i64 k = i == 0 ? 1 : i;  // out[0] = out[1]
+                const uchar2 cur = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k)];
+                const uchar2 prv = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k - 1)];
+                const uchar2 me = i == 0 ? prv : cur;  // initial power is of sample i itself
+                pw += (double)__fadd_rn(S.tab[me.x][0].sq, S.tab[me.y][0].sq);
+                const double pr = S.tab[prv.x][0].v, pi = S.tab[prv.y][0].v, cr = S.tab[cur.x][0].v, ci = S.tab[cur.y][0].v;
+                const double re = fma(pr, cr, __dmul_rn(ci, pi)), im = fma(ci, pr, -__dmul_rn(pi, cr));
+                const float fre = (float)re, fim = (float)im;
+                const float m = __fadd_rn(__fmul_rn(fre, fre), __fmul_rn(fim, fim));
+                float y = 0.f;
+                if (m > 1e-10f) y = (float)atan2_lean((double)fim, (double)fre, oct_base);
+                out[i] = y;
+                sr += (double)y;
+            }
+        }
+    }
+    double part[2], total[2];
+    part[0] = block_sum(pw, S.scratch);
+    part[1] = block_sum(sr, S.scratch);
+    if (grid_sum_last_dyn<2>(part, J.partials, J.counter, gridDim.x, blockIdx.x, S.scratch, &S.last, total)) {
+        J.stats[ST_POWER0] = n > 0 ? total[0] / (double)n : 0.0;
+        J.stats[ST_SUM_RE] = total[1];
+        J.stats[ST_SUM_IM] = 0.0;
+        J.stats[ST_DC_RE] = n > 0 ? (double)dc_from_sum(total[1], n) : 0.0;
+        J.stats[ST_DC_IM] = 0.0;
+    }
+}
+
+// every (previous, current) byte quad: lean_one against demod_one<false>
+__global__ void __launch_bounds__(256) k_demod_selftest(const double *__restrict__ atab_g, unsigned long long *bad,
+                                                        unsigned *first_bad)
+{
+    extern __shared__ __align__(16) unsigned char lean_raw[];
+    LeanSmem &S = *reinterpret_cast<LeanSmem *>(lean_raw);
+    __shared__ DemodLuts L;
+    lean_fill(S, atab_g);
+    {
+        const float v = unpack_byte((unsigned)threadIdx.x);
+        L.lutf[threadIdx.x] = v;
+        L.lut[threadIdx.x] = (double)v;
+        if (threadIdx.x < 9) { L.atan_d[threadIdx.x] = atan_k8(threadIdx.x); L.atan_f[threadIdx.x] = (float)atan_k8(threadIdx.x); }
+    }
+    __syncthreads();
+    const unsigned oct_base = (unsigned)__cvta_generic_to_shared(&S.oct[0][0]);
+    const int slot = threadIdx.x & 15;
+    unsigned cnt = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * 256 + threadIdx.x; q < (1ull << 32); q += stride) {
+        const uchar2 prv = make_uchar2((unsigned char)(q & 255), (unsigned char)(q >> 8 & 255));
+        const uchar2 cur = make_uchar2((unsigned char)(q >> 16 & 255), (unsigned char)(q >> 24 & 255));
+        const float want = demod_one<false>(L, prv, cur);
+        const float got = lean_one(S.tab[prv.x][slot].v, S.tab[prv.y][slot].v, S.tab[cur.x][slot].v, S.tab[cur.y][slot].v,
+                                   oct_base);
+        if (__float_as_uint(want) != __float_as_uint(got)) {
+            cnt++;
+            const unsigned at = atomicAdd(first_bad, 1u);
+            if (at < 63) first_bad[1 + at] = (unsigned)q;
+        }
+    }
+    if (cnt) atomicAdd(bad, (unsigned long long)cnt);
+}
+
 // ---------------------------------------------------------------- small box-car, real signal
 constexpr int kHalo = 16;   // staged halo each side (multiple of 4 for float4 staging)
 constexpr int kHalfMax = 8; // window / 2 served by this kernel
@@ -310,11 +584,57 @@ int fast_grid_x(i64 n)
     return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
 }
 
+// atan(k / 64) for the lean discriminator, correctly rounded by the host's libm
+static double *g_atab = nullptr;
+
+int demod_setup(cudaStream_t st)
+{
+    if (g_atab) return 0;
+    double h[kAtanK + 2];
+    for (int k = 0; k <= kAtanK + 1; k++) h[k] = atan((double)k / (double)kAtanK);
+    if (cudaMalloc(&g_atab, sizeof(h)) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(g_atab, h, sizeof(h), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_demod_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) != cudaSuccess)
+        return -1;
+    if (cudaFuncSetAttribute(k_demod_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) !=
+        cudaSuccess)
+        return -1;
+    return 0;
+}
+
+int lean_grid_x(i64 n, int n_jobs)
+{
+    const i64 tiles = (n + kLeanTile - 1) / kLeanTile;
+    i64 cap = (2 * 148) / (n_jobs > 0 ? n_jobs : 1);  // all jobs together: one resident wave, 2 CTAs per SM
+    if (cap < 1) cap = 1;
+    return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
+}
+
 void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, cudaStream_t st)
 {
-    const dim3 grid(fast_grid_x(max_n), n_jobs);
-    if (fast) k_demod_fused<true><<<grid, kThreads, 0, st>>>(d_jobs);
-    else k_demod_fused<false><<<grid, kThreads, 0, st>>>(d_jobs);
+    if (fast) {
+        k_demod_fused<true><<<dim3(fast_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
+    } else {
+        k_demod_lean<<<dim3(lean_grid_x(max_n, n_jobs), n_jobs), kLeanThreads, sizeof(LeanSmem), st>>>(d_jobs, g_atab);
+    }
+}
+
+long long demod_selftest(cudaStream_t st, unsigned *first_bad_out)
+{
+    unsigned long long *d_bad = nullptr, h_bad = ~0ull;
+    unsigned *d_first = nullptr;
+    if (cudaMalloc(&d_bad, sizeof(*d_bad)) != cudaSuccess) return -1;
+    if (cudaMalloc(&d_first, 64 * sizeof(unsigned)) != cudaSuccess) { cudaFree(d_bad); return -1; }
+    cudaMemsetAsync(d_bad, 0, sizeof(*d_bad), st);
+    cudaMemsetAsync(d_first, 0, 64 * sizeof(unsigned), st);
+    k_demod_selftest<<<148 * 2, 256, sizeof(LeanSmem), st>>>(g_atab, d_bad, d_first);
+    cudaMemcpyAsync(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, st);
+    if (first_bad_out) cudaMemcpyAsync(first_bad_out, d_first, 64 * sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+    const cudaError_t err = cudaStreamSynchronize(st);
+    cudaFree(d_bad);
+    cudaFree(d_first);
+    return err == cudaSuccess ? (long long)h_bad : -1;
 }
 
 void launch_boxcar_small(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)

@@ -312,3 +312,15 @@ def test_constant_divisor_division_is_exact(eng_binary):
     """The small box-car divides by its tap count with a reciprocal + FMA correction; the
     device checks it against a correctly rounded divide for every float bit pattern."""
     assert eng_binary.selftest(0) == 0
+
+
+def test_lean_discriminator_all_byte_quads(eng_binary):
+    """The production discriminator (integer rounding of the f64 products, table-driven
+    f64 arctangent) against the reference statement (F2F conversions, gates, the older
+    arctangent) over every (previous, current) byte quad -- the discriminator is a function
+    of four bytes, so this is exhaustive.  Two <= 1 ulp f64 arctangents may round to
+    different f32 values only when the true value sits within ~1e-16 relative of an f32
+    rounding boundary: a handful of the 2^32 inputs, each 1 f32 ulp apart."""
+    bad = eng_binary.selftest(1)
+    print("lean discriminator: differing byte quads =", bad, eng_binary.last_error() if bad else "")
+    assert 0 <= bad <= 256
