@@ -27,6 +27,7 @@ UNITS = [
     ("xcorr_exact.cu", ["-fmad=false"]),
     ("solve.cu", ["-fmad=false"]),
     ("xcorr_fft.cu", []),
+    ("xcorr_tile.cu", []),
     ("engine.cu", []),
 ]
 

@@ -55,6 +55,7 @@ struct Sig {
 
 struct Pair {
     int a, b;  // indices into the Sig array: signal 1, signal 2 (argv order, processor.go:816-817)
+    int group = 0;  // window the pair belongs to
 };
 
 constexpr size_t kFrameBytes = 8u << 20;  // descriptor staging per call
@@ -467,6 +468,7 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
 // ---------------------------------------------------------------- correlation
 
 struct CorrPlan {
+    int group = 0;   // pairs of one group (window) may share transforms in a tile
     PairJob job{};
     PairJob job2{};  // sanity re-search with a different template length (rare)
     bool need2 = false;
@@ -546,12 +548,74 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     std::vector<CandJob> cjobs(np);
     std::vector<PairJob> pjobs(np);
     std::vector<PeakJob> kjobs(np);
+    // ---- tiles: pairs of one group with identical geometry share transforms.  Rows are
+    // the distinct template planes, columns the distinct signal planes; rows and columns
+    // are taken two at a time, and a tile carries the (<= 4) pairs that exist among them.
+    struct Tile { int plan[4]; const float *t[2]; const float *s[2]; };
+    std::vector<Tile> tiles;
+    const bool tiled = e->cfg.use_fft != 2;
+    {
+        std::vector<char> done(np, 0);
+        for (int p0 = 0; p0 < np; p0++) {
+            if (done[p0]) continue;
+            const PairJob &K0 = plans[p0]->job;
+            std::vector<int> grp;  // plans with the geometry of p0
+            for (int p = p0; p < np; p++) {
+                const PairJob &K = plans[p]->job;
+                if (!done[p] && plans[p]->group == plans[p0]->group && K.t_off == K0.t_off && K.n_t == K0.n_t &&
+                    K.sl == K0.sl && K.lag0 == K0.lag0 && K.n_lags == K0.n_lags) {
+                    grp.push_back(p);
+                    done[p] = 1;
+                }
+            }
+            if (!tiled) {
+                for (int p : grp) tiles.push_back(Tile{{p, -1, -1, -1}, {plans[p]->job.t_re, plans[p]->job.t_re},
+                                                       {plans[p]->job.s_re, plans[p]->job.s_re}});
+                continue;
+            }
+            std::vector<const float *> rows;
+            for (int p : grp)
+                if (std::find(rows.begin(), rows.end(), plans[p]->job.t_re) == rows.end()) rows.push_back(plans[p]->job.t_re);
+            for (size_t r = 0; r < rows.size(); r += 2) {
+                const float *tr[2] = {rows[r], r + 1 < rows.size() ? rows[r + 1] : rows[r]};
+                std::vector<const float *> cols;
+                for (int p : grp) {
+                    const PairJob &K = plans[p]->job;
+                    if ((K.t_re == tr[0] || K.t_re == tr[1]) && std::find(cols.begin(), cols.end(), K.s_re) == cols.end())
+                        cols.push_back(K.s_re);
+                }
+                for (size_t c = 0; c < cols.size(); c += 2) {
+                    Tile T{{-1, -1, -1, -1}, {tr[0], tr[1]}, {cols[c], c + 1 < cols.size() ? cols[c + 1] : cols[c]}};
+                    bool any = false;
+                    for (int p : grp) {
+                        const PairJob &K = plans[p]->job;
+                        for (int a = 0; a < 2; a++)
+                            for (int b = 0; b < 2; b++)
+                                if (K.t_re == T.t[a] && K.s_re == T.s[b] && T.plan[2 * a + b] < 0 &&
+                                    !(a == 1 && T.t[1] == T.t[0]) && !(b == 1 && T.s[1] == T.s[0])) {
+                                    T.plan[2 * a + b] = p;
+                                    any = true;
+                                }
+                    }
+                    if (any) tiles.push_back(T);
+                }
+            }
+        }
+    }
     // lag chunks
-    int n_fft_jobs = 0;
+    int n_fft_jobs = 0, n_tile_jobs = 0;
     for (CorrPlan *pl : plans) n_fft_jobs += (pl->job.n_lags + kLagW - 1) / kLagW;
-    const int cta_budget = std::max(1, 2 * e->sm_count / std::max(1, n_fft_jobs));
+    for (const Tile &T : tiles) {
+        int p = -1;
+        for (int q = 0; q < 4; q++) if (T.plan[q] >= 0) p = T.plan[q];
+        n_tile_jobs += (plans[p]->job.n_lags + kLagW - 1) / kLagW;
+    }
+    // per-pair kernel: 2 CTAs per SM; tile kernel: 1 CTA (512 threads) per SM
+    const int cta_budget = tiled ? std::max(1, e->sm_count / std::max(1, n_tile_jobs))
+                                 : std::max(1, 2 * e->sm_count / std::max(1, n_fft_jobs));
     int max_cta = 0;
     i64 max_nb = 0;
+    std::vector<int> first_job(np, 0);  // index into fjobs of the plan's first lag chunk
     for (int p = 0; p < np; p++) {
         CorrPlan *pl = plans[p];
         PairJob &J = pl->job;
@@ -562,6 +626,7 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
             (rc = alloc_t(e, &d_cand, (size_t)kMaxCand)) || (rc = alloc_t(e, &d_ncand, 1)) ||
             (rc = alloc_t(e, &J.blocksums, (size_t)kMaxCand * std::max<i64>(J.nb, 1))))
             return rc;
+        first_job[p] = (int)fjobs.size();
         for (int c0 = 0; c0 < J.n_lags; c0 += kLagW) {
             FftJob F{};
             F.t = J.t_re; F.s = J.s_re; F.t_stats = J.t_stats; F.s_stats = J.s_stats;
@@ -589,6 +654,24 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
         kjobs[p] = K;
         max_nb = std::max(max_nb, J.nb);
     }
+    std::vector<TileJob> tjobs;
+    if (tiled) {
+        for (const Tile &T : tiles) {
+            int lead = -1;
+            for (int q = 0; q < 4; q++) if (T.plan[q] >= 0) lead = T.plan[q];
+            const PairJob &K = plans[lead]->job;
+            const int n_chunks = (K.n_lags + kLagW - 1) / kLagW;
+            for (int ci = 0; ci < n_chunks; ci++) {
+                const FftJob &F0 = fjobs[first_job[lead] + ci];
+                TileJob TJ{};
+                TJ.t0 = T.t[0]; TJ.t1 = T.t[1]; TJ.s0 = T.s[0]; TJ.s1 = T.s[1];
+                TJ.t_off = F0.t_off; TJ.n_t = F0.n_t; TJ.sl = F0.sl; TJ.s_off = F0.s_off;
+                TJ.n_seg = F0.n_seg; TJ.n_cta = F0.n_cta;
+                for (int q = 0; q < 4; q++) TJ.partials[q] = T.plan[q] >= 0 ? fjobs[first_job[T.plan[q]] + ci].partials : nullptr;
+                tjobs.push_back(TJ);
+            }
+        }
+    }
     const FftJob *d_f = nullptr;
     const SelJob *d_s = nullptr;
     const CandJob *d_c = nullptr;
@@ -597,8 +680,11 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     if ((rc = upload(e, fjobs, &d_f)) || (rc = upload(e, sjobs, &d_s)) || (rc = upload(e, cjobs, &d_c)) ||
         (rc = upload(e, pjobs, &d_p)) || (rc = upload(e, kjobs, &d_k)))
         return rc;
+    const TileJob *d_t = nullptr;
+    if (tiled && (rc = upload(e, tjobs, &d_t))) return rc;
     cudaEventRecord(e->ev_fft[0], e->stream);
-    launch_fft_segments(d_f, (int)fjobs.size(), max_cta, e->d_tw, e->stream);
+    if (tiled) launch_fft_tiles(d_t, (int)tjobs.size(), max_cta, e->d_tw, e->stream);
+    else launch_fft_segments(d_f, (int)fjobs.size(), max_cta, e->d_tw, e->stream);
     cudaEventRecord(e->ev_fft[1], e->stream);
     launch_fft_reduce(d_f, (int)fjobs.size(), e->stream);
     launch_fft_finish(d_f, (int)fjobs.size(), e->d_tw, e->stream);
@@ -621,6 +707,7 @@ int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pa
     for (int p = 0; p < np; p++) {
         const Sig &s1 = sigs[pairs[p].a], &s2 = sigs[pairs[p].b];
         CorrPlan &pl = plans[p];
+        pl.group = pairs[p].group;
         PairJob &J = pl.job;
         PeakJob &K = pl.peak;
         K.out = d_out + p;
@@ -772,7 +859,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
                 sg.memo = s * 2 + kind;
             }
             for (int i = 0; i < S; i++)
-                for (int j = i + 1; j < S; j++) pairs.push_back({w * S + i, w * S + j});
+                for (int j = i + 1; j < S; j++) pairs.push_back({w * S + i, w * S + j, w});
         }
         cudaEventRecord(e->ev[1], e->stream);
         if ((rc = preprocess(e, sigs))) return rc;
@@ -904,6 +991,7 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
     e->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if (err == cudaSuccess && fft_setup(e->stream, &e->d_tw) != 0) err = cudaErrorUnknown;
     if (err == cudaSuccess && demod_setup(e->stream) != 0) err = cudaErrorUnknown;
+    if (err == cudaSuccess && fft_tile_setup() != 0) err = cudaErrorUnknown;
     if (err != cudaSuccess) {
         g_create_error = std::string("tdoa_create: ") + cudaGetErrorString(err);
         tdoa_destroy(e);
@@ -1128,7 +1216,7 @@ int tdoa_cross_correlate(tdoa_engine *e, const float *sig1_c64, int64_t n1, cons
     PeakRec *d_out = nullptr;
     if ((rc = alloc_t(e, &d_out, 1))) return rc;
     if ((rc = preprocess(e, sigs))) return rc;
-    std::vector<Pair> pairs(1, Pair{0, 1});
+    std::vector<Pair> pairs(1, Pair{0, 1, 0});
     if ((rc = correlate(e, sigs, pairs, d_out))) return rc;
     CU(cudaMemcpyAsync(out, d_out, sizeof(tdoa_peak), cudaMemcpyDeviceToHost, e->stream));
     rc = end_call(e, true);

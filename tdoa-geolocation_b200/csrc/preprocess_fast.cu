@@ -167,9 +167,12 @@ struct __align__(16) LeanEntry {
     float vf;   // v
 };
 
+constexpr int kLeanWords = 6;  // 32-bit words of the capture a thread needs: 1 before + 4 + 1 after
+
 struct LeanSmem {
     LeanEntry tab[256][16];         // 64 KB
     double oct[4][kOctStride];      // B(case) + sigma(case) * atan(k / 64)
+    unsigned stage[2][kLeanWords][kLeanThreads];  // cp.async landing zone, double buffered
     double scratch[32];
     int last;
 };
@@ -308,24 +311,46 @@ __global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean(const SigJob *jo
     const unsigned tab_base = (unsigned)__cvta_generic_to_shared(&S.tab[0][0]);
     const unsigned oct_base = (unsigned)__cvta_generic_to_shared(&S.oct[0][0]);
     double pw = 0.0, sr = 0.0;
-    for (i64 i0 = (i64)blockIdx.x * kLeanTile; i0 < n; i0 += (i64)gridDim.x * kLeanTile) {
-        // whole tile, the sample before it and one 32-bit word after it inside one run
-        const bool in0 = i0 + kLeanTile + 2 <= run0, in1 = i0 - 1 >= run0 && i0 + kLeanTile + 2 <= n;
-        if (i0 > 0 && (in0 || in1)) {
-            // byte address of this thread's first sample; only 2-byte alignment is known
-            const uint8_t *ap = rawb + 2 * (raw_index(J.src, i0) + (i64)kLeanPer * tid);
-            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(ap) & 2u) * 8u;
-            const unsigned *__restrict__ wp = reinterpret_cast<const unsigned *>(ap - (sh >> 3));
-            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-            const unsigned pv = *reinterpret_cast<const unsigned short *>(ap - 2);
+    // A tile takes the fast path when it, the sample before it and one 32-bit word after
+    // it lie inside one run of the capture.  Its bytes are fetched one tile ahead with
+    // cp.async (4-byte granules: only 2-byte alignment of a signal start is known), each
+    // thread staging and later reading only its own six words, so no barrier is needed.
+    auto fast_tile = [&](i64 t0) {
+        const bool in0 = t0 + kLeanTile + 2 <= run0, in1 = t0 - 1 >= run0 && t0 + kLeanTile + 2 <= n;
+        return t0 > 0 && t0 < n && (in0 || in1);
+    };
+    auto tile_addr = [&](i64 t0) { return rawb + 2 * (raw_index(J.src, t0) + (i64)kLeanPer * tid); };
+    auto stage_tile = [&](i64 t0, int buf) {
+        if (fast_tile(t0)) {
+            const uint8_t *ap = tile_addr(t0);
+            const unsigned *wp = reinterpret_cast<const unsigned *>(ap - (reinterpret_cast<uintptr_t>(ap) & 2u)) - 1;
+#pragma unroll
+            for (int k = 0; k < kLeanWords; k++) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&S.stage[buf][k][tid]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(wp + k) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const i64 step = (i64)gridDim.x * kLeanTile;
+    int buf = 0;
+    stage_tile((i64)blockIdx.x * kLeanTile, 0);
+    for (i64 i0 = (i64)blockIdx.x * kLeanTile; i0 < n; i0 += step, buf ^= 1) {
+        stage_tile(i0 + step, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (fast_tile(i0)) {
+            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(tile_addr(i0)) & 2u) * 8u;
+            const unsigned wm = S.stage[buf][0][tid], w0 = S.stage[buf][1][tid], w1 = S.stage[buf][2][tid],
+                           w2 = S.stage[buf][3][tid], w3 = S.stage[buf][4][tid], w4 = S.stage[buf][5][tid];
+            const unsigned pv = __funnelshift_r(wm, w0, sh);   // bytes [ap - 4, ap): previous sample in the top half
             unsigned w[4];
             w[0] = __funnelshift_r(w0, w1, sh); w[1] = __funnelshift_r(w1, w2, sh);
             w[2] = __funnelshift_r(w2, w3, sh); w[3] = __funnelshift_r(w3, w4, sh);
             // table address of byte b of a word: (b << 8) | slot * 16
             double pr, pi;
             float sq_i, sq_q;
-            lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5504), pr, sq_i);
-            lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5514), pi, sq_q);
+            lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5524), pr, sq_i);
+            lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5534), pi, sq_q);
             float o[kLeanPer];
 #pragma unroll
             for (int s = 0; s < kLeanPer; s++) {

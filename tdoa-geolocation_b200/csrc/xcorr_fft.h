@@ -26,6 +26,17 @@ struct FftJob {
     float *approx;                   // [n_lags] correlation-coefficient units
 };
 
+// A tile of one window's pairs: up to two template signals x two signal-role signals that
+// share offsets and lengths.  Product p = 2 a + b is conj(T_a) S_b; partials[p] == nullptr
+// where the tile has no such pair.  (xcorr_tile.cu)
+struct TileJob {
+    const float *t0, *t1;   // template planes (t1 == t0 when the tile has one template)
+    const float *s0, *s1;   // signal planes
+    i64 t_off, n_t, sl, s_off;
+    int n_seg, n_cta;
+    float2 *partials[4];    // [n_cta][kFftBins] each
+};
+
 struct SelJob {
     const float *approx;  // [n_lags] all lag chunks of the pair
     int n_lags;
@@ -49,6 +60,8 @@ struct CandJob {
 int fft_setup(cudaStream_t st, float2 **d_tw);
 size_t fft_partials_bytes(int n_cta);
 void launch_fft_segments(const FftJob *d_jobs, int n_jobs, int max_cta, const float2 *d_tw, cudaStream_t st);
+int fft_tile_setup();
+void launch_fft_tiles(const TileJob *d_jobs, int n_jobs, int max_cta, const float2 *d_tw, cudaStream_t st);
 void launch_fft_reduce(const FftJob *d_jobs, int n_jobs, cudaStream_t st);
 void launch_fft_finish(const FftJob *d_jobs, int n_jobs, const float2 *d_tw, cudaStream_t st);
 void launch_select_candidates(const SelJob *d_jobs, int n_jobs, cudaStream_t st);

@@ -1,0 +1,243 @@
+// xcorr_tile.cu -- segmented-FFT cross-spectra of a TILE of station pairs in one pass.
+//
+// The per-pair kernel (xcorr_fft.cu, k_fft_segments) spends one 8192-point complex
+// transform per pair and segment: z = t + i s.  Pairs of one window share stations, so a
+// tile of up to 2 template stations x 2 signal stations needs only TWO transforms per
+// segment -- A = FFT(t0 + i t1), B = FFT(s0 + i s1) -- for up to four cross-spectra
+// conj(T_a) S_b (three for the reference's 3-station case: (0,1), (0,2), (1,2)).
+//
+// One CTA of 512 threads per SM: threads 0..255 run transform A, threads 256..511
+// transform B, concurrently, each in its own shared-memory buffer with its own named
+// barrier (fft_tile_core.cuh).  The accumulated cross-spectra -- 4 products x 4097 bins
+// x (re, im) = 128 KB per CTA, 64 floats per thread -- do not fit in the register file
+// next to a 32-point-per-thread transform, and shared memory is taken by the two
+// buffers; they live in the SM's TENSOR MEMORY (256 KB, otherwise idle on this path):
+// each thread owns 72 columns of its TMEM lane and does tcgen05.ld -> FMA -> tcgen05.st
+// around the bins it is responsible for (measured: a full read-modify-write of all
+// 128 KB takes ~400 cycles, tools/micro/tmem_rw.cu).  No tensor-core instruction is
+// involved: the FFT is not a dense contraction.
+//
+// The next segment's samples are loaded into registers before the cross phase, so the
+// HBM latency hides behind it.
+#include "fft_tile_core.cuh"
+#include "kernels.h"
+#include "xcorr_fft.h"
+
+namespace tdoa {
+
+using namespace fft2;
+
+namespace {
+
+constexpr int kBins = kN / 2 + 1;
+constexpr int kTileThreads = 2 * kT;
+constexpr int kTileSmem = (2 * kBuf + kTab) * (int)sizeof(float2);   // 143 360 B: one CTA per SM
+constexpr int kTmemCols = 512;
+
+static_assert(kSeg == 6144 && kFftN == kN, "tile kernel is written for 6144-sample segments of an 8192-point transform");
+
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float *v)
+{
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const float *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                    "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                    "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+                    "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                    "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+                    "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float *v)
+{
+    unsigned r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const float *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                    "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                    "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// barrier over the 256 threads of transform g (ids 1 and 2; 0 is __syncthreads)
+__device__ __forceinline__ void bar_transform(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
+
+// samples m = t + 256 r of one segment as complex points (x0[m], x1[m]); CNT rows carry data
+template <int CNT>
+__device__ __forceinline__ void load_rows(const float *__restrict__ x0, const float *__restrict__ x1, i64 base, i64 lo,
+                                          i64 hi, int t, float2 (&v)[32])
+{
+    if (lo <= 0 && hi >= 256 * CNT) {
+        const float *__restrict__ p0 = x0 + base + t;
+        const float *__restrict__ p1 = x1 + base + t;
+#pragma unroll
+        for (int r = 0; r < 32; r++) v[r] = r < CNT ? make_float2(p0[256 * r], p1[256 * r]) : make_float2(0.f, 0.f);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const i64 m = t + 256 * r;
+            const bool ok = r < CNT && m >= lo && m < hi;
+            v[r] = ok ? make_float2(x0[base + m], x1[base + m]) : make_float2(0.f, 0.f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads, 1) k_fft_tiles(const TileJob *jobs, const float2 *__restrict__ tw)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    __shared__ unsigned s_tmem;
+    const TileJob &J = jobs[blockIdx.y];
+    const int cta = blockIdx.x;
+    if (cta >= J.n_cta) return;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int g = tid >> 8, t = tid & (kT - 1);
+    float2 *buf = sm + g * kBuf;
+    float2 *tab = sm + 2 * kBuf;
+    for (int idx = tid; idx < kTab; idx += kTileThreads) tab[idx] = tw[(16 * (idx & 31) * (idx >> 5)) & (kN - 1)];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(&s_tmem)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const unsigned tmem_base = s_tmem;
+    // this thread's accumulators: lane 32 (warp % 4) + lane id, columns 128 (warp / 4) + [0, 72)
+    const unsigned tmem = tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(128 * (warp >> 2));
+    {
+        float z[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) z[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 5; c++) tmem_st16(tmem + 16 * c, z);
+        tmem_wait_st();
+    }
+    const float2 w1a = tw[t], w1b = tw[t + 256];
+    const float *__restrict__ x0 = g ? J.s0 : J.t0;
+    const float *__restrict__ x1 = g ? J.s1 : J.t1;
+
+    auto load_segment = [&](int seg, float2 (&v)[32]) {
+        const i64 first = (i64)seg * kSeg;
+        if (g == 0) {
+            load_rows<kSeg / 256>(x0, x1, J.t_off + first, 0, J.n_t - first, t, v);
+        } else {
+            const i64 base = J.s_off + first;
+            load_rows<32>(x0, x1, base, -base, J.sl - base, t, v);
+        }
+    };
+
+    float2 v[32];
+    int seg = cta;
+    load_segment(seg, v);
+    const float2 *ZA = sm, *ZB = sm + kBuf;
+    for (; seg < J.n_seg; seg += J.n_cta) {
+        pass1_store(v, t, buf);
+        bar_transform(g);
+        float2 u0[16], u1[16];
+        pass_load(buf, t, u0);
+        pass_load(buf, t + 256, u1);
+        bar_transform(g);
+        pass2_twiddle(u0, u1, t, tab);
+        pass2_store(u0, t, buf);
+        pass2_store(u1, t + 256, buf);
+        bar_transform(g);
+        pass_load(buf, t, u0);
+        pass_load(buf, t + 256, u1);
+        bar_transform(g);
+        pass3_compute(u0, w1a);
+        pass3_compute(u1, w1b);
+        // spectrum in natural order into the (free again) buffer: Z[t + 512 r], Z[t + 256 + 512 r]
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            buf[t + 512 * r] = u0[r];
+            buf[t + 256 + 512 * r] = u1[r];
+        }
+        // the next segment's samples travel while the cross-spectra are formed
+        if (seg + J.n_cta < J.n_seg) load_segment(seg + J.n_cta, v);
+        __syncthreads();
+        // bins k = t + 256 w, w = 8 g .. 8 g + 7: two bins x four products per 16-column chunk
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float acc[16];
+            tmem_ld16(tmem + 16 * c, acc);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int k = t + 256 * (8 * g + 2 * c + h);
+                const int nk = (kN - k) & (kN - 1);
+                cross_accumulate(ZA[k], ZA[nk], ZB[k], ZB[nk], acc + 8 * h);
+            }
+            tmem_st16(tmem + 16 * c, acc);
+        }
+        if (warp == 8) {  // Nyquist bin: thread 0 of transform B; the whole warp moves its columns
+            float acc[8];
+            tmem_ld8(tmem + 64, acc);
+            if (t == 0) cross_accumulate(ZA[kN / 2], ZA[kN / 2], ZB[kN / 2], ZB[kN / 2], acc);
+            tmem_st8(tmem + 64, acc);
+        }
+        tmem_wait_st();
+        __syncthreads();
+    }
+    // partial cross-spectra of this CTA, in the convention k_fft_reduce expects (re / 2, im / 4 applied there)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        float acc[16];
+        tmem_ld16(tmem + 16 * c, acc);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int k = t + 256 * (8 * g + 2 * c + h);
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (J.partials[p]) J.partials[p][(size_t)cta * kBins + k] = make_float2(0.5f * acc[8 * h + 2 * p], acc[8 * h + 2 * p + 1]);
+        }
+    }
+    if (warp == 8) {
+        float acc[8];
+        tmem_ld8(tmem + 64, acc);
+        if (t == 0) {
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (J.partials[p]) J.partials[p][(size_t)cta * kBins + kN / 2] = make_float2(0.5f * acc[2 * p], acc[2 * p + 1]);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+}
+
+}  // namespace
+
+int fft_tile_setup()
+{
+    return cudaFuncSetAttribute(k_fft_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem) == cudaSuccess ? 0 : -1;
+}
+
+void launch_fft_tiles(const TileJob *d_jobs, int n_jobs, int max_cta, const float2 *d_tw, cudaStream_t st)
+{
+    if (n_jobs <= 0 || max_cta <= 0) return;
+    k_fft_tiles<<<dim3(max_cta, n_jobs), kTileThreads, kTileSmem, st>>>(d_jobs, d_tw);
+}
+
+}  // namespace tdoa
