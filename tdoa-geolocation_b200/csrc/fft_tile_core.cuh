@@ -157,32 +157,38 @@ TDOA_HD2 void pass1_store(float2 (&v)[32], int t, float2 *buf)
     for (int r = 0; r < 16; r++) row[r] = make_float4(v[2 * r].x, v[2 * r].y, v[2 * r + 1].x, v[2 * r + 1].y);
 }
 
-// passes 2 and 3 read in[j + 512 r], r = 0..15, for the butterflies j = t and t + 256
-TDOA_HD2 void pass_load(const float2 *buf, int j, float2 (&u)[16])
+// passes 2 and 3: a thread owns the ADJACENT butterflies j = 2t and 2t + 1, so every
+// shared-memory access moves two complex points (128 bits).  Inputs in[j + 512 r], r = 0..15.
+TDOA_HD2 void pass_load(const float2 *buf, int t, float2 (&u0)[16], float2 (&u1)[16])
 {
-    const float2 *p = buf + pad2(j);
+    const float4 *p = reinterpret_cast<const float4 *>(buf + pad2(2 * t));
 #pragma unroll
-    for (int r = 0; r < 16; r++) u[r] = p[(512 + 32) * r];
-}
-
-// pass 2: radix 16 with twiddles W_512^(r k), k = j % 32 (= lane), from tab[r * 32 + k];
-// out[(j / 32) * 512 + k + 32 r].  Both butterflies of a thread share k.
-TDOA_HD2 void pass2_twiddle(float2 (&u0)[16], float2 (&u1)[16], int t, const float2 *tab)
-{
-    const float2 *p = tab + (t & 31);
-#pragma unroll
-    for (int r = 1; r < 16; r++) {
-        const float2 w = p[32 * r];
-        u0[r] = cmul(u0[r], w);
-        u1[r] = cmul(u1[r], w);
+    for (int r = 0; r < 16; r++) {
+        const float4 q = p[((512 + 32) / 2) * r];
+        u0[r] = make_float2(q.x, q.y);
+        u1[r] = make_float2(q.z, q.w);
     }
 }
-TDOA_HD2 void pass2_store(float2 (&u)[16], int j, float2 *buf)
+
+// pass 2: radix 16 with twiddles W_512^(r k), k = j % 32, from tab[r * 32 + k];
+// out[(j / 32) * 512 + k + 32 r]
+TDOA_HD2 void pass2_twiddle(float2 (&u0)[16], float2 (&u1)[16], int t, const float2 *tab)
 {
-    dft<16>(u);
-    float2 *p = buf + (j >> 5) * (16 * kRow) + (j & 31);
+    const float4 *p = reinterpret_cast<const float4 *>(tab + ((2 * t) & 31));
 #pragma unroll
-    for (int r = 0; r < 16; r++) p[kRow * r] = u[r];
+    for (int r = 1; r < 16; r++) {
+        const float4 w = p[16 * r];
+        u0[r] = cmul(u0[r], make_float2(w.x, w.y));
+        u1[r] = cmul(u1[r], make_float2(w.z, w.w));
+    }
+}
+TDOA_HD2 void pass2_store(float2 (&u0)[16], float2 (&u1)[16], int t, float2 *buf)
+{
+    dft<16>(u0);
+    dft<16>(u1);
+    float4 *p = reinterpret_cast<float4 *>(buf + ((2 * t) >> 5) * (16 * kRow) + ((2 * t) & 31));
+#pragma unroll
+    for (int r = 0; r < 16; r++) p[(kRow / 2) * r] = make_float4(u0[r].x, u0[r].y, u1[r].x, u1[r].y);
 }
 
 // pass 3: radix 16 with twiddles W_8192^(r j), w1 = W_8192^j; result u[r] = X[j + 512 r]
@@ -190,6 +196,13 @@ TDOA_HD2 void pass3_compute(float2 (&u)[16], float2 w1)
 {
     twiddle16(u, w1);
     dft<16>(u);
+}
+// spectrum in natural order: X[2t + 512 r], X[2t + 1 + 512 r]
+TDOA_HD2 void spectrum_store(const float2 (&u0)[16], const float2 (&u1)[16], int t, float2 *buf)
+{
+    float4 *p = reinterpret_cast<float4 *>(buf) + t;
+#pragma unroll
+    for (int r = 0; r < 16; r++) p[256 * r] = make_float4(u0[r].x, u0[r].y, u1[r].x, u1[r].y);
 }
 
 // ---- cross-spectra of a 2 x 2 tile.  A = FFT(t0 + i t1), B = FFT(s0 + i s1) with real

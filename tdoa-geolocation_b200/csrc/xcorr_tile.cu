@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_fft_tiles(const TileJob *jo
         for (int c = 0; c < 5; c++) tmem_st16(tmem + 16 * c, z);
         tmem_wait_st();
     }
-    const float2 w1a = tw[t], w1b = tw[t + 256];
+    const float2 w1a = tw[2 * t], w1b = tw[2 * t + 1];
     const float *__restrict__ x0 = g ? J.s0 : J.t0;
     const float *__restrict__ x1 = g ? J.s1 : J.t1;
 
@@ -157,40 +157,33 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_fft_tiles(const TileJob *jo
     for (; seg < J.n_seg; seg += J.n_cta) {
         pass1_store(v, t, buf);
         bar_transform(g);
-        float2 u0[16], u1[16];
-        pass_load(buf, t, u0);
-        pass_load(buf, t + 256, u1);
-        bar_transform(g);
-        pass2_twiddle(u0, u1, t, tab);
-        pass2_store(u0, t, buf);
-        pass2_store(u1, t + 256, buf);
-        bar_transform(g);
-        pass_load(buf, t, u0);
-        pass_load(buf, t + 256, u1);
-        bar_transform(g);
-        pass3_compute(u0, w1a);
-        pass3_compute(u1, w1b);
-        // spectrum in natural order into the (free again) buffer: Z[t + 512 r], Z[t + 256 + 512 r]
-#pragma unroll
-        for (int r = 0; r < 16; r++) {
-            buf[t + 512 * r] = u0[r];
-            buf[t + 256 + 512 * r] = u1[r];
+        {
+            float2 u0[16], u1[16];
+            pass_load(buf, t, u0, u1);
+            bar_transform(g);
+            pass2_twiddle(u0, u1, t, tab);
+            pass2_store(u0, u1, t, buf);
+            bar_transform(g);
+            pass_load(buf, t, u0, u1);
+            bar_transform(g);
+            pass3_compute(u0, w1a);
+            pass3_compute(u1, w1b);
+            spectrum_store(u0, u1, t, buf);  // natural order, into the (free again) buffer
         }
-        // the next segment's samples travel while the cross-spectra are formed
+        // the next segment's samples travel while the cross-spectra are formed (the fence
+        // keeps the loads from being hoisted into the transform, where registers are full)
+        asm volatile("" ::: "memory");
         if (seg + J.n_cta < J.n_seg) load_segment(seg + J.n_cta, v);
         __syncthreads();
-        // bins k = t + 256 w, w = 8 g .. 8 g + 7: two bins x four products per 16-column chunk
+        // bins k = t + 256 w, w = 8 g .. 8 g + 7: four products per 8-column chunk
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            float acc[16];
-            tmem_ld16(tmem + 16 * c, acc);
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int k = t + 256 * (8 * g + 2 * c + h);
-                const int nk = (kN - k) & (kN - 1);
-                cross_accumulate(ZA[k], ZA[nk], ZB[k], ZB[nk], acc + 8 * h);
-            }
-            tmem_st16(tmem + 16 * c, acc);
+        for (int c = 0; c < 8; c++) {
+            float acc[8];
+            tmem_ld8(tmem + 8 * c, acc);
+            const int k = t + 256 * (8 * g + c);
+            const int nk = (kN - k) & (kN - 1);
+            cross_accumulate(ZA[k], ZA[nk], ZB[k], ZB[nk], acc);
+            tmem_st8(tmem + 8 * c, acc);
         }
         if (warp == 8) {  // Nyquist bin: thread 0 of transform B; the whole warp moves its columns
             float acc[8];
@@ -203,16 +196,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_fft_tiles(const TileJob *jo
     }
     // partial cross-spectra of this CTA, in the convention k_fft_reduce expects (re / 2, im / 4 applied there)
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        float acc[16];
-        tmem_ld16(tmem + 16 * c, acc);
+    for (int c = 0; c < 8; c++) {
+        float acc[8];
+        tmem_ld8(tmem + 8 * c, acc);
+        const int k = t + 256 * (8 * g + c);
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int k = t + 256 * (8 * g + 2 * c + h);
-#pragma unroll
-            for (int p = 0; p < 4; p++)
-                if (J.partials[p]) J.partials[p][(size_t)cta * kBins + k] = make_float2(0.5f * acc[8 * h + 2 * p], acc[8 * h + 2 * p + 1]);
-        }
+        for (int p = 0; p < 4; p++)
+            if (J.partials[p]) J.partials[p][(size_t)cta * kBins + k] = make_float2(0.5f * acc[2 * p], acc[2 * p + 1]);
     }
     if (warp == 8) {
         float acc[8];

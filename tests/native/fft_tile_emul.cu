@@ -25,26 +25,29 @@ static void transform(const std::vector<float2> &x, std::vector<float2> &X)
     std::vector<float2> regs(kT * 32);
     for (int t = 0; t < kT; t++) {
         float2 u0[16], u1[16];
-        pass_load(buf.data(), t, u0);
-        pass_load(buf.data(), t + 256, u1);
+        pass_load(buf.data(), t, u0, u1);
         pass2_twiddle(u0, u1, t, g_tab.data());
         for (int r = 0; r < 16; r++) { regs[(t * 2) * 16 + r] = u0[r]; regs[(t * 2 + 1) * 16 + r] = u1[r]; }
     }
-    for (int t = 0; t < kT; t++)
-        for (int b = 0; b < 2; b++) {
-            float2 u[16];
-            for (int r = 0; r < 16; r++) u[r] = regs[(t * 2 + b) * 16 + r];
-            pass2_store(u, t + 256 * b, buf.data());
-        }
+    for (int t = 0; t < kT; t++) {
+        float2 u0[16], u1[16];
+        for (int r = 0; r < 16; r++) { u0[r] = regs[(t * 2) * 16 + r]; u1[r] = regs[(t * 2 + 1) * 16 + r]; }
+        pass2_store(u0, u1, t, buf.data());
+    }
+    for (int t = 0; t < kT; t++) {
+        float2 u0[16], u1[16];
+        pass_load(buf.data(), t, u0, u1);
+        for (int r = 0; r < 16; r++) { regs[(t * 2) * 16 + r] = u0[r]; regs[(t * 2 + 1) * 16 + r] = u1[r]; }
+    }
+    X.assign(kBuf, make_float2(0.f, 0.f));
+    for (int t = 0; t < kT; t++) {
+        float2 u0[16], u1[16];
+        for (int r = 0; r < 16; r++) { u0[r] = regs[(t * 2) * 16 + r]; u1[r] = regs[(t * 2 + 1) * 16 + r]; }
+        pass3_compute(u0, g_tw[2 * t]);
+        pass3_compute(u1, g_tw[2 * t + 1]);
+        spectrum_store(u0, u1, t, X.data());
+    }
     X.resize(kN);
-    for (int t = 0; t < kT; t++)
-        for (int b = 0; b < 2; b++) {
-            float2 u[16];
-            const int j = t + 256 * b;
-            pass_load(buf.data(), j, u);
-            pass3_compute(u, g_tw[j]);
-            for (int r = 0; r < 16; r++) X[j + 512 * r] = u[r];
-        }
 }
 
 static void direct(const std::vector<double> &xr, const std::vector<double> &xi, std::vector<double> &Xr, std::vector<double> &Xi)
