@@ -158,6 +158,21 @@ TDOA_API int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_sta
                        const double *grid_desc, const double *range_diffs, int32_t n_sets,
                        int32_t rd_stride, double *out_llh, double *out_cost, int64_t *out_index);
 
+/* What the reference prints while it works on a pair (shipped binary: "Initial signal
+ * power", "Removed DC bias", "Normalized signal power", "Time domain correlation ... at
+ * delay" before the sanity re-search; processor.go:474-497 prints the same quantities).
+ * Values of window 0 of the last tdoa_xcorr(kind) call; signals in station order,
+ * first_corr in pair order. */
+typedef struct {
+    double power0;        /* calculateSignalPower of the raw signal (processor.go:322)   */
+    double dc_re, dc_im;  /* removeDCBias mean (processor.go:309)                         */
+    double power1;        /* power entering normalizeSignal (processor.go:336)            */
+    int32_t branch;       /* 0 strong FM / standard, 1 moderate (envelope), 2 weak        */
+    int32_t reserved;
+    int64_t n;            /* samples of the signal                                        */
+} tdoa_signal_info;
+TDOA_API int tdoa_xcorr_info(tdoa_engine *e, int32_t kind, tdoa_signal_info *signals, double *first_corr);
+
 /* Introspection for the benchmark: kernels launched and device time of the last
  * tdoa_xcorr call, per stage (CUDA events on the engine's stream). */
 typedef struct {

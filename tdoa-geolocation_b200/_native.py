@@ -23,7 +23,7 @@ ERRORS = {-1: "TDOA_E_INVALID", -2: "TDOA_E_NODEVICE", -3: "TDOA_E_CUDA", -4: "T
 # every symbol include/tdoa_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "tdoa_default_config", "tdoa_create", "tdoa_destroy", "tdoa_last_error", "tdoa_host_alloc", "tdoa_host_free",
-    "tdoa_load_u8", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device",
+    "tdoa_load_u8", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_xcorr_info",
     "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
     "tdoa_set_stream", "tdoa_synchronize", "tdoa_selftest",
 ]
@@ -54,6 +54,11 @@ class PeakStruct(C.Structure):
 PEAK_DTYPE = np.dtype([("lag", "<i4"), ("flags", "<u4"), ("corr", "<f8"), ("frac", "<f4"), ("margin", "<f4"),
                        ("first_lag", "<i4"), ("n_blocks", "<i4")])
 assert PEAK_DTYPE.itemsize == C.sizeof(PeakStruct) == 32
+
+
+class SignalInfo(C.Structure):
+    _fields_ = [("power0", C.c_double), ("dc_re", C.c_double), ("dc_im", C.c_double), ("power1", C.c_double),
+                ("branch", C.c_int32), ("reserved", C.c_int32), ("n", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -115,6 +120,7 @@ def load_library():
     L.tdoa_unpack.argtypes = [vp, i32, i64, i64, vp]
     L.tdoa_preprocess.argtypes = [vp, i32, i32, i64, i64, vp, f64p, C.POINTER(i32)]
     L.tdoa_xcorr.argtypes = [vp, i32, i64, i64, i32, i64, vp]
+    L.tdoa_xcorr_info.argtypes = [vp, i32, vp, vp]
     L.tdoa_xcorr_device.argtypes = [vp, i32, i64, i64, i32, i64, vp]
     L.tdoa_cross_correlate.argtypes = [vp, vp, i64, vp, i64, C.POINTER(PeakStruct)]
     L.tdoa_baselines.argtypes = [vp, vp, i32, vp]
@@ -276,6 +282,15 @@ class Engine:
         out = np.zeros((n_windows, self.n_pairs), PEAK_DTYPE)
         self._check(self._lib.tdoa_xcorr(self._h, kind, win_start, win_len, n_windows, hop, _ptr(out)))
         return out
+
+    def xcorr_info(self, kind: int):
+        """(signals, first_corr) of window 0 of the last xcorr(kind): what the reference prints while it
+        works on a pair -- initial power, branch, DC bias, power before normalisation per station signal,
+        and the first-pass peak correlation per pair."""
+        sig = (SignalInfo * self.n_stations)()
+        first = np.zeros(self.n_pairs, np.float64)
+        self._check(self._lib.tdoa_xcorr_info(self._h, kind, C.cast(sig, C.c_void_p), _ptr(first)))
+        return [{k: getattr(x, k) for k, _ in SignalInfo._fields_ if k != "reserved"} for x in sig], first
 
     def xcorr_device(self, kind: int, dev_out_ptr: int, win_start: int = 0, win_len: int = 0, n_windows: int = 1,
                      hop: int = 0) -> None:

@@ -83,6 +83,8 @@ struct tdoa_engine {
     int64_t launches_at_call = 0;
     float2 *d_tw = nullptr;  // FFT twiddle table
     std::vector<int8_t> branch_memo;  // last preprocess branch per (station, kind); -1 unknown
+    std::vector<tdoa_signal_info> info_sig[2];  // window 0 of the last xcorr per kind
+    std::vector<double> info_first[2];
     cudaEvent_t ev_fft[2] = {nullptr, nullptr};
     int sm_count = 148;
 };
@@ -697,7 +699,8 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     return TDOA_OK;
 }
 
-int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pair> &pairs, PeakRec *d_out)
+int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pair> &pairs, PeakRec *d_out,
+              double *d_first = nullptr)
 {
     if (pairs.empty()) return TDOA_OK;
     const tdoa_config &cfg = e->cfg;
@@ -711,6 +714,7 @@ int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pa
         PairJob &J = pl.job;
         PeakJob &K = pl.peak;
         K.out = d_out + p;
+        K.first_corr = d_first ? d_first + p : nullptr;
         K.flags = ((uint32_t)s1.branch << 8) | ((uint32_t)s2.branch << 10);
         K.sanity = 0;
         K.lag_origin = 0;
@@ -864,8 +868,25 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
         cudaEventRecord(e->ev[1], e->stream);
         if ((rc = preprocess(e, sigs))) return rc;
         cudaEventRecord(e->ev[2], e->stream);
-        if ((rc = correlate(e, sigs, pairs, d_out + (size_t)w0 * P))) return rc;
+        double *d_first = nullptr;
+        if (w0 == 0 && (rc = alloc_t(e, &d_first, pairs.size()))) return rc;
+        if ((rc = correlate(e, sigs, pairs, d_out + (size_t)w0 * P, d_first))) return rc;
         cudaEventRecord(e->ev[3], e->stream);
+        if (w0 == 0) {
+            // what the reference prints about window 0 (tdoa_xcorr_info)
+            std::vector<double> h((size_t)S * ST_COUNT);
+            e->info_first[kind].assign(P, 0.0);
+            CU(cudaMemcpyAsync(h.data(), sigs[0].stats, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaMemcpyAsync(e->info_first[kind].data(), d_first, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaStreamSynchronize(e->stream));
+            e->info_sig[kind].assign(S, tdoa_signal_info{});
+            for (int s = 0; s < S; s++) {
+                tdoa_signal_info &I = e->info_sig[kind][s];
+                const double *st = h.data() + (size_t)s * ST_COUNT;
+                I.power0 = st[ST_POWER0]; I.dc_re = st[ST_DC_RE]; I.dc_im = st[ST_DC_IM]; I.power1 = st[ST_POWER1];
+                I.branch = sigs[s].branch; I.n = sigs[s].n;
+            }
+        }
         // free this group's planes before the next group allocates
         if (w0 + group < n_windows) {
             CU(cudaStreamSynchronize(e->stream));
@@ -1303,6 +1324,16 @@ int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_stations, co
     if (out_cost) CU(cudaMemcpyAsync(out_cost, d_cost, (size_t)n_sets * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     if (out_index) CU(cudaMemcpyAsync(out_index, d_idx, (size_t)n_sets * sizeof(i64), cudaMemcpyDeviceToHost, e->stream));
     return end_call(e, true);
+}
+
+int tdoa_xcorr_info(tdoa_engine *e, int32_t kind, tdoa_signal_info *signals, double *first_corr)
+{
+    if (!e) return TDOA_E_INVALID;
+    if (kind != TDOA_KIND_REF && kind != TDOA_KIND_TGT) return fail(e, TDOA_E_INVALID, "tdoa_xcorr_info: bad kind %d", kind);
+    if (e->info_sig[kind].empty()) return fail(e, TDOA_E_STATE, "tdoa_xcorr_info: no tdoa_xcorr call of this kind yet");
+    if (signals) std::copy(e->info_sig[kind].begin(), e->info_sig[kind].end(), signals);
+    if (first_corr) std::copy(e->info_first[kind].begin(), e->info_first[kind].end(), first_corr);
+    return TDOA_OK;
 }
 
 int tdoa_get_stats(tdoa_engine *e, tdoa_stats *out)

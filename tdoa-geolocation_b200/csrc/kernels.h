@@ -86,6 +86,7 @@ struct PeakJob {
     int nb;               // blocks of the first pass (0: nothing evaluated)
     uint32_t flags;       // flags or-ed into the record
     PeakRec *out;
+    double *first_corr;   // optional: correlation of the first-pass peak (before the sanity re-search)
 };
 
 // ---- preprocess.cu

@@ -172,8 +172,10 @@ __global__ void __launch_bounds__(32) k_peak(const PeakJob *jobs)
     const PeakJob &J = jobs[blockIdx.x];
     PeakRec r;
     r.lag = 0; r.flags = J.flags; r.corr = 0.0; r.frac = 0.f; r.margin = 0.f; r.first_lag = 0; r.n_blocks = J.nb;
+    double first = 0.0;
     if (J.nb > 0 && J.n_lags > 0) {
         const Best b = warp_argmax_abs(J.corr, J.n_lags);
+        first = b.v;
         const double second = warp_second_abs(J.corr, J.n_lags, b.idx);
         r.lag = b.idx + J.lag_origin;
         r.first_lag = r.lag;
@@ -199,7 +201,10 @@ __global__ void __launch_bounds__(32) k_peak(const PeakJob *jobs)
             }
         }
     }
-    if ((threadIdx.x & 31) == 0) *J.out = r;
+    if ((threadIdx.x & 31) == 0) {
+        *J.out = r;
+        if (J.first_corr) *J.first_corr = first;
+    }
 }
 
 }  // namespace

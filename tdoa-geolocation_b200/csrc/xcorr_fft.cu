@@ -483,6 +483,7 @@ __global__ void __launch_bounds__(256) k_peak_candidates(const PairJob *jobs, co
         }
     }
     *K.out = r;
+    if (K.first_corr) *K.first_corr = (K.nb > 0 && best >= 0) ? bv : 0.0;
 }
 
 }  // namespace

@@ -129,11 +129,51 @@ class TDOAProcessor:
             raise RuntimeError("singular Jacobian matrix")  # :997-999
         return float(out[0]), float(out[1]), float(out[2])
 
-    # -- processor.go:739-929
+    # -- stdout of the shipped binary while it works on one pair (ELF 0x49cd40, 0x49d6a0)
+    _BRANCH_TEXT = ("Strong FM signal - using instantaneous frequency correlation approach",
+                    "Moderate signal - envelope correlation approach",
+                    "Weak signal - standard processing with timing preservation")
+
+    def _print_pair_binary(self, sig1, sig2, pk, first_corr, fs, max_lag, block, sanity):
+        P = self._print
+        P("=== Cross-Correlation Analysis ===")
+        P("\n--- Signal Preprocessing ---")
+        for k, sg in ((1, sig1), (2, sig2)):
+            P("Preprocessing Signal %d signal (%d samples)" % (k, sg["n"]))
+            P("Initial signal power: %.9f" % sg["power0"])
+            P(self._BRANCH_TEXT[sg["branch"]])
+            P("Removed DC bias: %.6f + %.6fi" % (sg["dc_re"], sg["dc_im"]))
+            if sg["branch"] == 2:
+                P("Bandpass filter: %.1f - %.1f Hz (at %.0f Hz sample rate)" % (100.0, 200000.0, 2000000.0))
+            P("Normalized signal power: %.6f → %.6f" % (sg["power1"], 1.0 if sg["power1"] > 0 else 0.0))
+        P("\n--- Time Domain Correlation ---")
+        P("Performing time domain correlation")
+        tl, sl = min(sig1["n"], sig2["n"]), max(sig1["n"], sig2["n"])
+        P("Template: %d samples, Signal: %d samples" % (tl, sl))
+        if tl == sl:
+            P("Reduced template to %d samples to allow %d sample delay search" % (tl - max_lag, max_lag))
+        P("Using coherent integration with %d-sample blocks" % block)
+        n_lags = max_lag if tl == sl else max(1, min(max_lag, sl - tl))
+        P("Time domain progress: 0/%d (coherent blocks: %d)" % (n_lags, pk["n_blocks"]))
+        first_lag = int(pk["first_lag"])
+        P("Time domain correlation: %.6f at delay %d samples" % (first_corr, first_lag))
+        if sanity > 0 and first_lag > sanity:
+            P("WARNING: Delay %d samples (%.1f μs) exceeds reasonable range for baseline distances"
+              % (first_lag, first_lag / fs * 1e6))
+            P("Maximum expected delay: 56.7 μs for 17 km baseline")
+            P("This suggests correlation algorithm found wrong peak")
+            if int(pk["flags"]) & 1:
+                P("Found better peak within reasonable range: delay=%d samples (%.1f μs), correlation=%.6f"
+                  % (pk["lag"], pk["lag"] / fs * 1e6, pk["corr"]))
+        P("\n--- Result: Time Domain with Preprocessing ---")
+        P("Correlation: %.6f at delay %d samples" % (pk["corr"], pk["lag"]))
+
+    # -- processor.go:739-929; in MODE_BINARY every stdout line of the shipped binary
     def process_tdoa(self, dat_files: List[str]):
         if len(dat_files) < 3:
             raise RuntimeError(f"need at least 3 collector stations, got {len(dat_files)}")
         P = self._print
+        binary = self.mode == N.MODE_BINARY
         P("Processing TDOA for target frequency %.3f MHz" % (self.target_freq / 1e6))
         r = self.ref_station
         P("Reference: %s at %.6f°, %.6f°, %.1fm" % (r.name, r.latitude, r.longitude, r.elevation))
@@ -146,9 +186,18 @@ class TDOAProcessor:
             except RuntimeError as exc:
                 raise RuntimeError(f"failed to identify station for {fn}: {exc}") from exc
             try:
-                self.load_iq_data(slot, fn, S)
+                n = self.load_iq_data(slot, fn, S)
             except RuntimeError as exc:
                 raise RuntimeError(f"failed to load data from {fn}: {exc}") from exc
+            if binary:
+                b = n // 3  # processor.go:211-236, :244-265
+                P("Extracting reference signal from dual-frequency data")
+                P("Total samples: %d, block size: %d" % (n, b))
+                P("Extracted %d reference samples from blocks 1 and 3" % (2 * b))
+                P("Extracting target signal from dual-frequency data")
+                P("Total samples: %d, block size: %d" % (n, b))
+                P("Extracted %d target samples from block 2" % b)
+                P("Coherent integration time: 500 ms (expecting ~10.0 dB processing gain)")
             stations.append(st)
             P("Loaded collector: %s at %.6f°, %.6f°, %.1fm" % (st.name, st.latitude, st.longitude, st.elevation))
         llh = np.array([s.llh for s in stations], np.float64)
@@ -162,26 +211,74 @@ class TDOAProcessor:
         for kind, label in ((N.KIND_REF, "REF"), (N.KIND_TGT, "TGT")):
             if kind == N.KIND_REF:
                 P("\n=== REFERENCE SIGNAL CORRELATION TEST ===")
+                if binary:
+                    P("Testing weak %.1f MHz NOAA weather signal:" % (self.reference_freq / 1e6))
             else:
                 P("\n=== TARGET SIGNAL CORRELATION TEST ===")
+                if binary:
+                    P("Testing strong %.1f MHz FM broadcast signal:" % (self.target_freq / 1e6))
             peaks = eng.xcorr(kind)[0]
+            info, first = eng.xcorr_info(kind) if binary else (None, None)
             tds = []
-            for (i, j), pk in zip(pairs, peaks):
+            for p_idx, ((i, j), pk) in enumerate(zip(pairs, peaks)):
                 td = float(pk["lag"]) / fs
                 tds.append(td)
+                if binary:
+                    self._print_pair_binary(info[i], info[j], pk, float(first[p_idx]), fs, eng.cfg.max_lag,
+                                            eng.cfg.block_size, eng.cfg.sanity_lag)
                 P("%s %s - %s: delay=%d samples (%.3f μs), correlation=%.6f"
                   % (label, stations[i].name, stations[j].name, pk["lag"], td * 1e6, pk["corr"]))
             results[label] = (peaks, tds)
         ref_td, tgt_td = results["REF"][1], results["TGT"][1]
-        if self.mode == N.MODE_SOURCE:
+        if not binary:
             tds = tgt_td  # processor.go:853: target differences only
         else:
-            # shipped binary: "REFERENCE SIGNAL SYNCHRONIZATION" corrected = tgt - ref
+            # shipped binary: corrected = target - reference, pair by pair
+            P("\n=== REFERENCE SIGNAL SYNCHRONIZATION ===")
+            P("Using reference signal to synchronize collector timing...")
+            for k, t in enumerate(ref_td):
+                P("Reference timing offset %d: %.3f μs" % (k, t * 1e6))
+            P("\n=== APPLYING TIMING CORRECTIONS TO TARGET SIGNAL ===")
             tds = [t - r_ for t, r_ in zip(tgt_td, ref_td)]
+            for k, (t, r_, c) in enumerate(zip(tgt_td, ref_td, tds)):
+                P("Target delay %d: %.3f μs (raw) - %.3f μs (ref offset) = %.3f μs (corrected)"
+                  % (k, t * 1e6, r_ * 1e6, c * 1e6))
+            P("\n=== CORRELATION COMPARISON ===")
+            P("Reference signal (%.1f MHz): Used for timing synchronization" % (self.reference_freq / 1e6))
+            P("Target signal (%.1f MHz): Corrected with reference timing offsets" % (self.target_freq / 1e6))
+            P("Using corrected target signal for TDOA calculation")
         rds = [td * SPEED_OF_LIGHT for td in tds]  # :899-903
+        if binary:
+            P("\nTDOA triangulation:")
+            P("Corrected time differences: " + ", ".join("%.3f μs" % (td * 1e6) for td in tds))
+            P("Corrected distance differences: " + ", ".join("%.1f m" % rd for rd in rds))
+            P("\nDiagnostic test with example delays:")  # processor.go:885-889
+            P("Simulating 10 μs, 5 μs, -3 μs delays...")
+            for k, us in enumerate((10.0, 5.0, -3.0)):
+                P("Test delay %d: %.1f μs → %.1f m" % (k + 1, us, us * 1e-6 * SPEED_OF_LIGHT))
         P("\n=== TDOA GEOLOCATION ===")
         P("Time differences (μs): " + "".join("%.3f " % (td * 1e6) for td in tds))
         P("Range differences (m): " + "".join("%.1f " % rd for rd in rds))
+        if binary:
+            # shipped binary: measurements beyond 1.2 x 17 km are dropped before its solver
+            # (which then aborts on every input, SURVEY.md finding 4; the fix below is
+            # processor.go's solveTDOA on the unfiltered differences)
+            P("Validating range differences against baseline distances...")
+            limit, valid = 20400.0, 0
+            for k, rd in enumerate(rds):
+                if abs(rd) <= limit:
+                    P("VALID: Range difference %d: %.1fm (within ±%.1fm limit)" % (k, rd, limit))
+                    valid += 1
+                else:
+                    P("FILTERING OUT: Range difference %d: %.1fm exceeds expected maximum %.1fm" % (k, rd, limit))
+                    P("This measurement is unreliable and will be excluded")
+            if valid == len(rds):
+                P("Using %d of %d range difference measurements" % (valid, len(rds)))
+                e0, e1, e2 = (ecef(*s.llh) for s in stations[:3])
+                area = 0.5 * abs((e1[0] - e0[0]) * (e2[1] - e0[1]) - (e2[0] - e0[0]) * (e1[1] - e0[1]))
+                P("Station geometry triangle area: %.1f m²" % area)
+                m = llh[:3].mean(axis=0)
+                P("Initial guess: %.6f°, %.6f°, %.1fm" % (m[0], m[1], m[2]))
         try:
             lat, lon, elev = self.solve_tdoa(stations, rds)
         except RuntimeError as exc:
@@ -192,6 +289,17 @@ class TDOAProcessor:
         P("Elevation: %.1f m" % elev)
         return {"ref": results["REF"][0], "tgt": results["TGT"][0], "time_differences": tds,
                 "range_differences": rds, "position": (lat, lon, elev)}
+
+
+def ecef(lat, lon, h):
+    """processor.go:125-148 latLonToECEF (WGS-84), host copy used only for the printed triangle area."""
+    import math
+    a, f = 6378137.0, 1.0 / 298.257223563
+    e2 = 2 * f - f * f
+    la, lo = math.radians(lat), math.radians(lon)
+    n = a / math.sqrt(1 - e2 * math.sin(la) ** 2)
+    return ((n + h) * math.cos(la) * math.cos(lo), (n + h) * math.cos(la) * math.sin(lo),
+            (n * (1 - e2) + h) * math.sin(la))
 
 
 def main(argv=None) -> int:
