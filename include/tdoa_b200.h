@@ -158,6 +158,24 @@ TDOA_API int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_sta
                        const double *grid_desc, const double *range_diffs, int32_t n_sets,
                        int32_t rd_stride, double *out_llh, double *out_cost, int64_t *out_index);
 
+/* Per-capture signal quality (fast_analyzer.go:15-24 FastAnalysis, analyzer.go:18-42
+ * SignalAnalysis): the numbers the reference's analyzers print and base their gain
+ * recommendations on.  fast != 0 follows fast_analyzer.go (first 32768 samples of each
+ * block, 8192-point Hanning spectrum, top 10 % vs bottom 40 %); fast == 0 follows
+ * analyzer.go (whole blocks, dead-zone scan, 16384-point DC-corrected Blackman-Harris
+ * spectrum, top 10 % vs lowest 50 %).  ref = blocks 1 + 3, tgt = block 2 of `station`. */
+typedef struct {
+    int64_t total_samples;
+    double i_avg, q_avg, i_std, q_std;
+    int32_t i_min, i_max, q_min, q_max;
+    double snr_db, power_db;
+    double dc_offset, iq_imbalance;            /* analyzer.go only */
+    int32_t has_clipping, has_overload;
+    int32_t has_dead_zones, has_noise;         /* analyzer.go only */
+} tdoa_signal_quality;
+TDOA_API int tdoa_analyze(tdoa_engine *e, int32_t station, int32_t fast, tdoa_signal_quality *ref,
+                          tdoa_signal_quality *tgt);
+
 /* What the reference prints while it works on a pair (shipped binary: "Initial signal
  * power", "Removed DC bias", "Normalized signal power", "Time domain correlation ... at
  * delay" before the sanity re-search; processor.go:474-497 prints the same quantities).

@@ -349,3 +349,38 @@ def run_reference_binary(dat_paths, csv_path, ref_hz="162400000", tgt_hz="923000
     res = subprocess.run([str(REF_BINARY), ref_hz, tgt_hz, str(csv_path), *map(str, dat_paths)],
                          capture_output=True, text=True, timeout=timeout)
     return res.stdout, res.stderr, res.returncode
+
+
+# ---- fast_analyzer.go / analyzer.go
+class Quality(C.Structure):
+    _fields_ = [("total_samples", C.c_int64), ("i_avg", C.c_double), ("q_avg", C.c_double), ("i_std", C.c_double),
+                ("q_std", C.c_double), ("i_min", C.c_int32), ("i_max", C.c_int32), ("q_min", C.c_int32),
+                ("q_max", C.c_int32), ("snr_db", C.c_double), ("power_db", C.c_double), ("dc_offset", C.c_double),
+                ("iq_imbalance", C.c_double), ("has_clipping", C.c_int32), ("has_overload", C.c_int32),
+                ("has_dead_zones", C.c_int32), ("has_noise", C.c_int32)]
+
+
+def analyze_samples(sig_bytes: np.ndarray, fast: bool) -> dict:
+    """fastAnalyzeSamples (fast_analyzer.go:113) / analyzeSamples (analyzer.go:130) of one
+    signal's interleaved uint8 bytes."""
+    b = np.ascontiguousarray(sig_bytes, np.uint8)
+    q = Quality()
+    L = lib()
+    L.orc_analyze_samples.argtypes = [_vp, _i64, C.c_int, _vp]
+    L.orc_analyze_samples(b.ctypes.data, b.size // 2, 1 if fast else 0, C.cast(C.byref(q), _vp))
+    return {k: getattr(q, k) for k, _ in Quality._fields_}
+
+
+def analyze_capture(raw: np.ndarray, fast: bool):
+    """(ref, tgt) as fastAnalyzeDualFrequencyFile (fast_analyzer.go:54) / analyzeDualFrequencyFile (analyzer.go:85)."""
+    raw = np.ascontiguousarray(raw, np.uint8)
+    total = raw.size // 2
+    block = total // 3
+    if fast:
+        a = min(32768, block)
+        ref = np.concatenate([raw[0:2 * a], raw[4 * block:4 * block + 2 * a]])
+        tgt = raw[2 * block:2 * block + 2 * a]
+    else:
+        ref = np.concatenate([raw[0:2 * block], raw[4 * block:2 * total]])[:4 * block]
+        tgt = raw[2 * block:4 * block]
+    return analyze_samples(ref, fast), analyze_samples(tgt, fast)

@@ -627,3 +627,158 @@ ORC_API void orc_grid_solve(const double *st_llh, int n_st, const double *rd,
     }
     free(s); free(r);
 }
+
+/* ======================================================================================
+ * Per-file signal quality analysis: fast_analyzer.go and analyzer.go.
+ * `s` is the signal's interleaved uint8 I,Q bytes (the reference concatenates blocks 1
+ * and 3 for REF before analysing), n its sample count.  Every step in the reference's
+ * order and in float64; the DFTs are the reference's O(M^2) loops.
+ * ==================================================================================== */
+typedef struct {
+    int64_t total_samples;
+    double i_avg, q_avg, i_std, q_std;
+    int32_t i_min, i_max, q_min, q_max;
+    double snr_db, power_db, dc_offset, iq_imbalance;
+    int32_t has_clipping, has_overload, has_dead_zones, has_noise;
+} orc_quality;
+
+static int cmp_f64(const void *a, const void *b)
+{
+    const double x = *(const double *)a, y = *(const double *)b;
+    return (x > y) - (x < y);
+}
+
+/* fast_analyzer.go:155-227 fastSNRCalculation: 8192 samples from the middle, (b-127.5)/127.5,
+ * Hanning, DFT with a twiddle table indexed (k*i) % n, top 10 % vs bottom 40 % of the PSD */
+static double orc_fast_snr(const uint8_t *s, int64_t total)
+{
+    int64_t m = 8192;
+    if (total < m) m = total;
+    if (m <= 0) return -20.0;
+    const int64_t start = (total - m) / 2;
+    double *re = malloc(sizeof(double) * m), *im = malloc(sizeof(double) * m);
+    double *twr = malloc(sizeof(double) * m), *twi = malloc(sizeof(double) * m);
+    double *psd = malloc(sizeof(double) * m), *sorted = malloc(sizeof(double) * m);
+    for (int64_t i = 0; i < m; i++) {
+        const double iv = ((double)s[2 * (start + i)] - 127.5) / 127.5, qv = ((double)s[2 * (start + i) + 1] - 127.5) / 127.5;
+        const double w = 0.5 - 0.5 * cos(2 * M_PI * (double)i / (double)(m - 1));
+        re[i] = w * iv; im[i] = w * qv;
+    }
+    for (int64_t k = 0; k < m; k++) {
+        const double a = -2 * M_PI * (double)k / (double)m;
+        twr[k] = cos(a); twi[k] = sin(a);
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < m; k++) {
+        double sr = 0, si = 0;
+        for (int64_t i = 0; i < m; i++) {
+            const int64_t idx = (k * i) % m;
+            sr += re[i] * twr[idx] - im[i] * twi[idx];
+            si += re[i] * twi[idx] + im[i] * twr[idx];
+        }
+        const double a = hypot(sr, si);  /* cmplx.Abs */
+        psd[k] = a * a;
+    }
+    memcpy(sorted, psd, sizeof(double) * m);
+    qsort(sorted, m, sizeof(double), cmp_f64);
+    const double sig_thr = sorted[(int64_t)(0.9 * (double)m)], noise_thr = sorted[(int64_t)(0.4 * (double)m)];
+    double sp = 0, np_ = 0;
+    int64_t sc = 0, nc = 0;
+    for (int64_t k = 0; k < m; k++) {
+        if (psd[k] >= sig_thr) { sp += psd[k]; sc++; }
+        else if (psd[k] <= noise_thr) { np_ += psd[k]; nc++; }
+    }
+    if (sc > 0) sp /= (double)sc;
+    if (nc > 0) np_ /= (double)nc;
+    free(re); free(im); free(twr); free(twi); free(psd); free(sorted);
+    if (np_ > 0 && sp > np_) return 10 * log10(sp / np_);
+    return -20.0;
+}
+
+/* analyzer.go:210-271 calculateProperSNR: 16384 samples from the middle, DC-corrected,
+ * Blackman-Harris, DFT, top 10 % mean vs mean of the lowest 50 % */
+static double orc_proper_snr(const uint8_t *s, int64_t total)
+{
+    int64_t m = 16384;
+    if (total < m) m = total;
+    if (m <= 0) return -20.0;
+    const int64_t start = (total - m) / 2;
+    double *re = malloc(sizeof(double) * m), *im = malloc(sizeof(double) * m);
+    double *psd = malloc(sizeof(double) * m), *sorted = malloc(sizeof(double) * m);
+    double isum = 0, qsum = 0;
+    for (int64_t i = 0; i < m; i++) { isum += (double)s[2 * (start + i)]; qsum += (double)s[2 * (start + i) + 1]; }
+    const double idc = isum / (double)m, qdc = qsum / (double)m;
+    for (int64_t i = 0; i < m; i++) {
+        const double iv = ((double)s[2 * (start + i)] - idc) / 127.5, qv = ((double)s[2 * (start + i) + 1] - qdc) / 127.5;
+        const double x = (double)i / (double)(m - 1);
+        const double w = 0.35875 - 0.48829 * cos(2 * M_PI * x) + 0.14128 * cos(4 * M_PI * x) - 0.01168 * cos(6 * M_PI * x);
+        re[i] = w * iv; im[i] = w * qv;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < m; k++) {
+        double sr = 0, si = 0;
+        for (int64_t i = 0; i < m; i++) {
+            const double a = -2 * M_PI * (double)k * (double)i / (double)m;
+            const double c = cos(a), sn = sin(a);
+            sr += re[i] * c - im[i] * sn;
+            si += re[i] * sn + im[i] * c;
+        }
+        const double a = hypot(sr, si);
+        psd[k] = a * a;
+    }
+    memcpy(sorted, psd, sizeof(double) * m);
+    qsort(sorted, m, sizeof(double), cmp_f64);
+    const double thr = sorted[(int64_t)(0.9 * (double)m)];
+    double sp = 0, np_ = 0;
+    int64_t sc = 0;
+    for (int64_t k = 0; k < m; k++) if (psd[k] >= thr) { sp += psd[k]; sc++; }
+    if (sc > 0) sp /= (double)sc;
+    const int64_t ne = (int64_t)(0.5 * (double)m);
+    for (int64_t k = 0; k < ne; k++) np_ += sorted[k];
+    np_ /= (double)ne;
+    free(re); free(im); free(psd); free(sorted);
+    if (np_ > 0 && sp > np_) return 10 * log10(sp / np_);
+    return -20.0;
+}
+
+/* fast != 0: fast_analyzer.go:113-153 fastAnalyzeSamples; else analyzer.go:130-192 analyzeSamples */
+ORC_API void orc_analyze_samples(const uint8_t *s, int64_t n, int fast, orc_quality *out)
+{
+    memset(out, 0, sizeof(*out));
+    out->total_samples = n;
+    double isum = 0, qsum = 0, isq = 0, qsq = 0;
+    int imin = 255, imax = 0, qmin = 255, qmax = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int iv = s[2 * i], qv = s[2 * i + 1];
+        isum += iv; qsum += qv; isq += (double)iv * iv; qsq += (double)qv * qv;
+        if (iv < imin) imin = iv;
+        if (iv > imax) imax = iv;
+        if (qv < qmin) qmin = qv;
+        if (qv > qmax) qmax = qv;
+    }
+    const double dn = (double)n;
+    out->i_avg = isum / dn; out->q_avg = qsum / dn;
+    out->i_std = sqrt(isq / dn - out->i_avg * out->i_avg);
+    out->q_std = sqrt(qsq / dn - out->q_avg * out->q_avg);
+    out->i_min = imin; out->i_max = imax; out->q_min = qmin; out->q_max = qmax;
+    const double mag = sqrt(out->i_std * out->i_std + out->q_std * out->q_std);
+    if (fast) out->power_db = mag <= 1e-10 ? -100.0 : 20 * log10(mag);
+    else out->power_db = 20 * log10(mag);
+    out->has_clipping = imin == 0 || imax == 255 || qmin == 0 || qmax == 255;
+    out->has_overload = out->i_std < 2 || out->q_std < 2;
+    if (fast) {
+        out->snr_db = orc_fast_snr(s, n);
+        return;
+    }
+    out->dc_offset = sqrt(pow(out->i_avg - 127.5, 2) + pow(out->q_avg - 127.5, 2));
+    out->iq_imbalance = fabs(out->i_std - out->q_std) / fmax(out->i_std, out->q_std);
+    /* analyzer.go:194-208 checkForDeadZones: longest run of zero BYTES > 1000 (a run still open at the end is not counted) */
+    int64_t run = 0, longest = 0;
+    for (int64_t i = 0; i < 2 * n; i++) {
+        if (s[i] == 0) run++;
+        else { if (run > longest) longest = run; run = 0; }
+    }
+    out->has_dead_zones = longest > 1000;
+    out->has_noise = out->i_std > 60 || out->q_std > 60;
+    out->snr_db = orc_proper_snr(s, n);
+}

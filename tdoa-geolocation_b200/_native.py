@@ -23,7 +23,7 @@ ERRORS = {-1: "TDOA_E_INVALID", -2: "TDOA_E_NODEVICE", -3: "TDOA_E_CUDA", -4: "T
 # every symbol include/tdoa_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "tdoa_default_config", "tdoa_create", "tdoa_destroy", "tdoa_last_error", "tdoa_host_alloc", "tdoa_host_free",
-    "tdoa_load_u8", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_xcorr_info",
+    "tdoa_load_u8", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_xcorr_info", "tdoa_analyze",
     "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
     "tdoa_set_stream", "tdoa_synchronize", "tdoa_selftest",
 ]
@@ -59,6 +59,17 @@ assert PEAK_DTYPE.itemsize == C.sizeof(PeakStruct) == 32
 class SignalInfo(C.Structure):
     _fields_ = [("power0", C.c_double), ("dc_re", C.c_double), ("dc_im", C.c_double), ("power1", C.c_double),
                 ("branch", C.c_int32), ("reserved", C.c_int32), ("n", C.c_int64)]
+
+
+class SignalQuality(C.Structure):
+    _fields_ = [("total_samples", C.c_int64), ("i_avg", C.c_double), ("q_avg", C.c_double), ("i_std", C.c_double),
+                ("q_std", C.c_double), ("i_min", C.c_int32), ("i_max", C.c_int32), ("q_min", C.c_int32),
+                ("q_max", C.c_int32), ("snr_db", C.c_double), ("power_db", C.c_double), ("dc_offset", C.c_double),
+                ("iq_imbalance", C.c_double), ("has_clipping", C.c_int32), ("has_overload", C.c_int32),
+                ("has_dead_zones", C.c_int32), ("has_noise", C.c_int32)]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class Stats(C.Structure):
@@ -121,6 +132,7 @@ def load_library():
     L.tdoa_preprocess.argtypes = [vp, i32, i32, i64, i64, vp, f64p, C.POINTER(i32)]
     L.tdoa_xcorr.argtypes = [vp, i32, i64, i64, i32, i64, vp]
     L.tdoa_xcorr_info.argtypes = [vp, i32, vp, vp]
+    L.tdoa_analyze.argtypes = [vp, i32, i32, vp, vp]
     L.tdoa_xcorr_device.argtypes = [vp, i32, i64, i64, i32, i64, vp]
     L.tdoa_cross_correlate.argtypes = [vp, vp, i64, vp, i64, C.POINTER(PeakStruct)]
     L.tdoa_baselines.argtypes = [vp, vp, i32, vp]
@@ -291,6 +303,13 @@ class Engine:
         first = np.zeros(self.n_pairs, np.float64)
         self._check(self._lib.tdoa_xcorr_info(self._h, kind, C.cast(sig, C.c_void_p), _ptr(first)))
         return [{k: getattr(x, k) for k, _ in SignalInfo._fields_ if k != "reserved"} for x in sig], first
+
+    def analyze(self, station: int, fast: bool = True):
+        """Signal quality of a loaded capture, (ref, tgt) dicts: fast_analyzer.go (fast=True) or
+        analyzer.go (fast=False) numbers."""
+        ref, tgt = SignalQuality(), SignalQuality()
+        self._check(self._lib.tdoa_analyze(self._h, station, 1 if fast else 0, C.byref(ref), C.byref(tgt)))
+        return ref.as_dict(), tgt.as_dict()
 
     def xcorr_device(self, kind: int, dev_out_ptr: int, win_start: int = 0, win_len: int = 0, n_windows: int = 1,
                      hop: int = 0) -> None:

@@ -26,6 +26,7 @@ UNITS = [
     ("preprocess_fast.cu", []),
     ("xcorr_exact.cu", ["-fmad=false"]),
     ("solve.cu", ["-fmad=false"]),
+    ("analyze.cu", ["-fmad=false"]),
     ("xcorr_fft.cu", []),
     ("xcorr_tile.cu", []),
     ("engine.cu", []),

@@ -1013,6 +1013,7 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
     if (err == cudaSuccess && fft_setup(e->stream, &e->d_tw) != 0) err = cudaErrorUnknown;
     if (err == cudaSuccess && demod_setup(e->stream) != 0) err = cudaErrorUnknown;
     if (err == cudaSuccess && fft_tile_setup() != 0) err = cudaErrorUnknown;
+    if (err == cudaSuccess && quality_setup() != 0) err = cudaErrorUnknown;
     if (err != cudaSuccess) {
         g_create_error = std::string("tdoa_create: ") + cudaGetErrorString(err);
         tdoa_destroy(e);
@@ -1324,6 +1325,59 @@ int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_stations, co
     if (out_cost) CU(cudaMemcpyAsync(out_cost, d_cost, (size_t)n_sets * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     if (out_index) CU(cudaMemcpyAsync(out_index, d_idx, (size_t)n_sets * sizeof(i64), cudaMemcpyDeviceToHost, e->stream));
     return end_call(e, true);
+}
+
+int tdoa_analyze(tdoa_engine *e, int32_t station, int32_t fast, tdoa_signal_quality *ref, tdoa_signal_quality *tgt)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (station < 0 || station >= e->cfg.n_stations || !e->stations[station].loaded)
+        return fail(e, TDOA_E_STATE, "tdoa_analyze: station %d not loaded", station);
+    if (!ref || !tgt) return fail(e, TDOA_E_INVALID, "tdoa_analyze: NULL output");
+    const Station &s = e->stations[station];
+    const i64 block = s.nsamp / 3;
+    // fast_analyzer.go:71-73
+    if (block == 0) return fail(e, TDOA_E_INVALID, "file too small for dual-frequency analysis");
+    std::vector<QualJob> jobs(2);
+    const int n_cta = 4 * e->sm_count;
+    tdoa_signal_quality *d_out = nullptr;
+    if ((rc = alloc_t(e, &d_out, 2))) return rc;
+    int max_m = 0;
+    for (int k = 0; k < 2; k++) {
+        QualJob &J = jobs[k];
+        J.fast = fast ? 1 : 0;
+        if (fast) {
+            // fast_analyzer.go:76-103: the first min(32768, block) samples of each block
+            const i64 a = std::min<i64>(32768, block);
+            if (k == 0) { J.src.raw = s.d_raw; J.src.run0_start = 0; J.src.run0_len = a; J.src.run1_start = 2 * block; J.n = 2 * a; }
+            else { J.src.raw = s.d_raw; J.src.run0_start = block; J.src.run0_len = a; J.src.run1_start = 0; J.n = a; }
+        } else {
+            // analyzer.go:111-121: whole blocks
+            J.n = k == 0 ? 2 * block : block;
+            J.src = make_view(s, k == 0 ? TDOA_KIND_REF : TDOA_KIND_TGT, 0, J.n);
+        }
+        const i64 msz = fast ? 8192 : 16384;
+        J.m = (int)std::min<i64>(msz, J.n);
+        max_m = std::max(max_m, J.m);
+        J.out = d_out + k;
+        if ((rc = alloc(e, &J.parts, quality_part_bytes() * (size_t)n_cta)) ||
+            (rc = alloc(e, &J.fft_a, sizeof(double) * 2 * (size_t)std::max(J.m, 1))) ||
+            (rc = alloc(e, &J.fft_b, sizeof(double) * 2 * (size_t)std::max(J.m, 1))) ||
+            (rc = alloc_t(e, &J.psd, (size_t)std::max(J.m, 1))))
+            return rc;
+    }
+    const QualJob *d_jobs = nullptr;
+    if ((rc = upload(e, jobs, &d_jobs))) return rc;
+    launch_quality(d_jobs, 2, n_cta, max_m, e->stream);
+    count_launch(e, 2);
+    tdoa_signal_quality h[2];
+    CU(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+    rc = end_call(e, true);
+    if (rc) return rc;
+    *ref = h[0];
+    *tgt = h[1];
+    return TDOA_OK;
 }
 
 int tdoa_xcorr_info(tdoa_engine *e, int32_t kind, tdoa_signal_info *signals, double *first_corr)

@@ -6,6 +6,7 @@
 // the same bits every time.
 #pragma once
 #include "common.cuh"
+#include "../../include/tdoa_b200.h"
 
 namespace tdoa {
 
@@ -119,6 +120,21 @@ int fast_grid_x(i64 n);
 void launch_corr_brute(const PairJob *d_jobs, int n_jobs, i64 max_nb, int max_lags, cudaStream_t st);
 void launch_corr_finalize(const PairJob *d_jobs, int n_jobs, int max_lags, cudaStream_t st);
 void launch_peak(const PeakJob *d_jobs, int n_jobs, cudaStream_t st);
+
+// ---- analyze.cu (fast_analyzer.go / analyzer.go)
+struct QualJob {
+    SigSrc src;      // the signal's bytes (REF: first run in block 1, second in block 3)
+    i64 n;           // samples
+    int fast;        // 1: fast_analyzer.go, 0: analyzer.go
+    int m;           // analysed samples of the spectrum (8192 / 16384, or n when shorter)
+    void *parts;     // per-CTA partial statistics (quality_part_bytes() each)
+    void *out;       // tdoa_signal_quality on the device
+    void *fft_a, *fft_b;  // m double2 each
+    double *psd;     // m doubles
+};
+size_t quality_part_bytes();
+int quality_setup();
+void launch_quality(const QualJob *d_jobs, int n_jobs, int n_stat_cta, int max_m, cudaStream_t st);
 
 // ---- solve.cu
 void launch_baselines(const double *d_llh, int n_st, double *d_out, cudaStream_t st);

@@ -20,3 +20,18 @@ def test_fft_phases_match_direct_dft(tmp_path):
     assert res.returncode == 0, res.stdout
     rel = float(res.stdout.split()[1])
     assert rel < 1e-6
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="needs nvcc (host compile only)")
+def test_tile_fft_phases_and_cross_spectra(tmp_path):
+    """csrc/fft_tile_core.cuh (the tile kernel's transform: DIT-FMA butterflies, adjacent
+    butterflies per thread, 128-bit row layout) and the 2 x 2 tile cross-spectrum formulas,
+    emulated thread by thread on the host against direct DFTs in double precision."""
+    exe = tmp_path / "fft_tile_emul"
+    subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I",
+                    str(ROOT / "tdoa-geolocation_b200" / "csrc"), "-o", str(exe),
+                    str(ROOT / "tests" / "native" / "fft_tile_emul.cu")], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    vals = {l.split()[0]: float(l.split()[1]) for l in res.stdout.splitlines()}
+    assert vals["rel_rms_err"] < 1e-6 and vals["cross_rel_rms_err"] < 2e-6
