@@ -264,8 +264,9 @@ def main_ours(args):
     pairs = [(0, 1), (0, 2), (1, 2)]
     gather_out = [torch.empty(6 * 32, dtype=torch.uint8, device=device) for _ in range(world)]
 
-    stage = {"ms_preprocess": 0.0, "ms_fft": 0.0, "ms_exact": 0.0, "ms_fft_seg": 0.0, "fft_launches": 0,
-             "fft_pair_samples": 0}
+    stage = {k: 0.0 for k in ("ms_preprocess", "ms_fft", "ms_exact", "ms_fft_seg", "fft_launches", "fft_pair_samples",
+                              "ms_demod", "ms_boxcar", "ms_cand", "demod_launches", "demod_samples",
+                              "boxcar_launches", "boxcar_samples", "cand_launches", "cand_pair_samples")}
     collecting = [False]
 
     def collect():
@@ -345,21 +346,39 @@ def main_ours(args):
     line = None
     if rank == 0:
         st = eng.stats()
-        # dominant kernel: the segmented-FFT cross-spectrum kernel when the FFT path ran,
-        # else the exact time-domain correlator
-        if stage["fft_launches"] > 0 and stage["ms_fft_seg"] > 0:
-            alg_bytes = 8.0 * stage["fft_pair_samples"] / stage["fft_launches"]
-            k_ms = stage["ms_fft_seg"] / stage["fft_launches"]
-            kname = "k_xcorr_fft_segments"
-        else:
-            alg_bytes = 8.0 * pair_samples
-            k_ms = stage["ms_exact"] / max(1, args.steps)
-            kname = "k_corr_brute (REF + TGT launches of one step)"
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        traffic = None
+        # per-kernel roofline: ALGORITHMIC bytes per launch (distinct input +
+        # output bytes per unit x units of the launch) / device time of the launch (CUDA
+        # events recorded by the engine around the launch, on its own stream)
+        traffic_db = {}
         tpath = ROOT / "profiles" / "traffic.json"
         if tpath.exists():
-            traffic = json.loads(tpath.read_text()).get(kname)
+            traffic_db = json.loads(tpath.read_text())
+
+        def kernel_line(name, bytes_per_unit, units_key, ms_key, n_key):
+            n = stage[n_key]
+            if n <= 0 or stage[ms_key] <= 0:
+                return None
+            alg = bytes_per_unit * stage[units_key] / n
+            ms = stage[ms_key] / n
+            ach = alg / (ms * 1e-3) / 1e9
+            return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic_db.get(name), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                    "kernel_ms_per_launch": ms, "share_of_step": stage[ms_key] / (ms_res if ms_res > 0 else 1.0)}
+
+        kernels = [k for k in (
+            kernel_line("k_demod_lean", 6.0, "demod_samples", "ms_demod", "demod_launches"),
+            kernel_line("k_boxcar_small", 8.0, "boxcar_samples", "ms_boxcar", "boxcar_launches"),
+            kernel_line("k_fft_tiles", 8.0, "fft_pair_samples", "ms_fft_seg", "fft_launches"),
+            kernel_line("k_corr_candidates", 8.0, "cand_pair_samples", "ms_cand", "cand_launches"),
+        ) if k]
+        if not kernels:  # FFT path disabled: the exact every-lag correlator carries the step
+            k_ms = stage["ms_exact"] / max(1, args.steps)
+            ach = 8.0 * pair_samples / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+            kernels = [{"bound": "hbm", "kernel": "k_corr_brute", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": 8.0 * pair_samples, "kernel_ms_per_launch": k_ms,
+                        "share_of_step": 1.0}]
+        dominant = max(kernels, key=lambda k: k["share_of_step"])
         cb = cpu_baseline() if world == 1 else None
         line = {
             "metric": "station-pair xcorr throughput", "value": value, "unit": "pair-Msamples/s", "n_gpus": world,
@@ -374,9 +393,8 @@ def main_ours(args):
                     "fixes_per_s": world / t_e2e},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": k_ms},
+            "roofline": dominant,
+            "roofline_kernels": kernels,
             "stage_ms_per_step": {k: stage[k] / args.steps for k in ("ms_preprocess", "ms_fft", "ms_exact")},
             "parity_check": {"lags_match_injected_delays": bool(lags_ok), "ref_lags": got_r, "tgt_lags": got_t,
                              "injected": want, "n_candidates": [int(x) >> 16 & 255 for x in list(ref["flags"]) + list(tgt["flags"])], "fix_llh": [float(x) for x in pos], "fix_status": int(status)},
@@ -394,7 +412,7 @@ def main_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--block", type=int, default=66_666_666, help="samples per block (default: 100 s capture)")

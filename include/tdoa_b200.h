@@ -204,6 +204,15 @@ typedef struct {
     float ms_fft_seg;         /* device time of those launches                    */
     int64_t fft_pair_samples; /* template samples they covered                    */
     int64_t brute_pairs;      /* pair-windows that fell back to every-lag search  */
+    /* per-kernel device time of the last call (CUDA events around each launch) and the
+     * units each kernel covered -- what the benchmark's per-kernel roofline is made of */
+    float ms_demod;           /* fused unpack + power + FM discriminator launches */
+    float ms_boxcar;          /* small box-car (DC subtract + low-pass + power)   */
+    float ms_cand;            /* exact re-evaluation of the candidate lags        */
+    float reserved0;
+    int64_t demod_launches, demod_samples;
+    int64_t boxcar_launches, boxcar_samples;
+    int64_t cand_launches, cand_pair_samples;
 } tdoa_stats;
 TDOA_API int tdoa_get_stats(tdoa_engine *e, tdoa_stats *out);
 

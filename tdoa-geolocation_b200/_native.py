@@ -77,6 +77,10 @@ class Stats(C.Structure):
         ("launches_total", C.c_int64), ("launches_last", C.c_int64), ("ms_preprocess", C.c_float),
         ("ms_fft", C.c_float), ("ms_exact", C.c_float), ("ms_total", C.c_float), ("fft_launches", C.c_int64),
         ("ms_fft_seg", C.c_float), ("fft_pair_samples", C.c_int64), ("brute_pairs", C.c_int64),
+        ("ms_demod", C.c_float), ("ms_boxcar", C.c_float), ("ms_cand", C.c_float), ("reserved0", C.c_float),
+        ("demod_launches", C.c_int64), ("demod_samples", C.c_int64),
+        ("boxcar_launches", C.c_int64), ("boxcar_samples", C.c_int64),
+        ("cand_launches", C.c_int64), ("cand_pair_samples", C.c_int64),
     ]
 
 

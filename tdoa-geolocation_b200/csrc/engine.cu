@@ -87,6 +87,10 @@ struct tdoa_engine {
     std::vector<double> info_first[2];
     cudaEvent_t ev_fft[2] = {nullptr, nullptr};
     int sm_count = 148;
+    // per-kernel timing spans of the current call (events are created once and reused)
+    struct Span { cudaEvent_t a = nullptr, b = nullptr; int tag = 0; };
+    std::vector<Span> spans;
+    size_t spans_used = 0;
 };
 
 namespace {
@@ -118,6 +122,7 @@ int begin_call(tdoa_engine *e)
         e->frame_pending = false;
     }
     e->frame_used = 0;
+    e->spans_used = 0;
     e->launches_at_call = e->st.launches_total;
     return TDOA_OK;
 }
@@ -166,6 +171,42 @@ int upload(tdoa_engine *e, const std::vector<T> &v, const T **d_out)
 }
 
 inline void count_launch(tdoa_engine *e, int n = 1) { e->st.launches_total += n; }
+
+// ---- per-kernel device time: an event pair around a launch, read back at the call's sync
+enum { SPAN_DEMOD = 0, SPAN_BOXCAR = 1, SPAN_CAND = 2 };
+
+int span_begin(tdoa_engine *e, int tag)
+{
+    if (e->spans_used == e->spans.size()) {
+        tdoa_engine::Span sp;
+        if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return -1;
+        e->spans.push_back(sp);
+    }
+    const int idx = (int)e->spans_used++;
+    e->spans[idx].tag = tag;
+    cudaEventRecord(e->spans[idx].a, e->stream);
+    return idx;
+}
+
+void span_end(tdoa_engine *e, int idx)
+{
+    if (idx >= 0) cudaEventRecord(e->spans[idx].b, e->stream);
+}
+
+// the stream must be idle
+void spans_collect(tdoa_engine *e)
+{
+    for (size_t i = 0; i < e->spans_used; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e->spans[i].a, e->spans[i].b) != cudaSuccess) { cudaGetLastError(); continue; }
+        switch (e->spans[i].tag) {
+            case SPAN_DEMOD: e->st.ms_demod += ms; e->st.demod_launches++; break;
+            case SPAN_BOXCAR: e->st.ms_boxcar += ms; e->st.boxcar_launches++; break;
+            case SPAN_CAND: e->st.ms_cand += ms; e->st.cand_launches++; break;
+        }
+    }
+    e->spans_used = 0;
+}
 
 // ---------------------------------------------------------------- signal views
 
@@ -310,7 +351,13 @@ int run_pipeline(tdoa_engine *e, Pipeline &pl)
                 case K_ENVELOPE: launch_envelope(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
                 case K_SEQSUM: launch_seqsum(d_jobs, nj, e->stream); break;
                 case K_BOXCAR: launch_boxcar(d_jobs, nj, st.max_n, 0, e->stream); break;
-                case K_BOXCAR_SMALL: launch_boxcar_small(d_jobs, nj, st.max_n, e->stream); break;
+                case K_BOXCAR_SMALL: {
+                    const int sp = span_begin(e, SPAN_BOXCAR);
+                    launch_boxcar_small(d_jobs, nj, st.max_n, e->stream);
+                    span_end(e, sp);
+                    for (const SigJob &j : st.jobs) e->st.boxcar_samples += j.n;
+                    break;
+                }
                 case K_NOTCH: launch_notch_combine(d_jobs, nj, st.max_n, e->stream); break;
             }
             count_launch(e);
@@ -372,7 +419,10 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
         if (!fjobs.empty()) {
             const SigJob *d_jobs = nullptr;
             if ((rc = upload(e, fjobs, &d_jobs))) return rc;
+            const int sp = span_begin(e, SPAN_DEMOD);
             launch_demod_fused(d_jobs, (int)fjobs.size(), max_n, e->cfg.fast_demod, e->stream);
+            span_end(e, sp);
+            for (const SigJob &j : fjobs) e->st.demod_samples += j.n;
             count_launch(e);
         }
         std::vector<double> h_stats((size_t)ns * ST_COUNT);
@@ -692,7 +742,12 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     launch_fft_finish(d_f, (int)fjobs.size(), e->d_tw, e->stream);
     launch_select_candidates(d_s, np, e->stream);
     cudaEventRecord(e->ev[5], e->stream);
-    launch_corr_candidates(d_p, d_c, np, max_nb, e->stream);
+    {
+        const int sp = span_begin(e, SPAN_CAND);
+        launch_corr_candidates(d_p, d_c, np, max_nb, e->stream);
+        span_end(e, sp);
+        for (const PairJob &J : pjobs) e->st.cand_pair_samples += J.n_t;
+    }
     launch_peak_candidates(d_p, d_c, d_k, np, e->stream);
     count_launch(e, 6);
     e->st.fft_launches += 1;
@@ -843,6 +898,10 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
     else if ((rc = alloc_t(e, &d_out, (size_t)n_windows * P))) return rc;
 
     e->st.ms_fft = 0.f; e->st.ms_fft_seg = 0.f; e->st.fft_launches = 0; e->st.fft_pair_samples = 0;
+    e->st.ms_demod = e->st.ms_boxcar = e->st.ms_cand = 0.f;
+    e->st.demod_launches = e->st.demod_samples = e->st.boxcar_launches = e->st.boxcar_samples = 0;
+    e->st.cand_launches = e->st.cand_pair_samples = 0;
+    e->spans_used = 0;
     cudaEventRecord(e->ev[0], e->stream);
     float ms_pre = 0.f, ms_corr = 0.f;
     // windows are processed in groups that keep the working set bounded
@@ -894,6 +953,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
             cudaEventElapsedTime(&a, e->ev[1], e->ev[2]);
             cudaEventElapsedTime(&b, e->ev[2], e->ev[3]);
             ms_pre += a; ms_corr += b;
+            spans_collect(e);
             for (void *p : e->call_allocs)
                 if (p != d_out) cudaFreeAsync(p, e->stream);
             e->call_allocs.clear();
@@ -909,6 +969,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
     e->st.launches_last = e->st.launches_total - e->launches_at_call;
     if (!out_is_device) {
         float a = 0.f, b = 0.f, t = 0.f;
+        spans_collect(e);
         cudaEventElapsedTime(&a, e->ev[1], e->ev[2]);
         cudaEventElapsedTime(&b, e->ev[2], e->ev[3]);
         cudaEventElapsedTime(&t, e->ev[0], e->ev[4]);
@@ -1043,6 +1104,7 @@ void tdoa_destroy(tdoa_engine *e)
     if (e->d_tw) cudaFree(e->d_tw);
     for (auto &ev : e->ev_fft)
         if (ev) cudaEventDestroy(ev);
+    for (auto &sp : e->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     if (e->frame_done) cudaEventDestroy(e->frame_done);
     for (auto &ev : e->ev)
         if (ev) cudaEventDestroy(ev);

@@ -295,14 +295,18 @@ __device__ __forceinline__ void cand_sweep_ng(int ng, const float *s_t, const fl
 // f32 product, widened, f64 accumulate (processor.go:703-705); per-thread partial sums in
 // ascending i, then a fixed reduction tree -- deterministic, not the reference's order
 // (differences ~1e-16 relative; the brute-force kernel keeps the reference's order).
-__global__ void __launch_bounds__(kCandThreads) k_corr_candidates(const PairJob *jobs, const CandJob *cjobs)
+__global__ void __launch_bounds__(kCandThreads) k_corr_candidates(const PairJob *jobs, const CandJob *cjobs, int n_jobs)
 {
     __shared__ float s_t[kCandChunk];
     __shared__ float s_s[kCandChunk + kCandSpan];
     __shared__ double s_red[kCandGroup][kCandThreads / 32];
-    const PairJob &J = jobs[blockIdx.y];
-    const CandJob &C = cjobs[blockIdx.y];
-    const i64 b = blockIdx.x;
+    // pair fastest: the CTAs that work on block b of every pair of a window are launched
+    // side by side, so the planes the pairs share (3 stations: each plane serves 2 pairs)
+    // come out of L2 for all but the first reader
+    const int pair = (int)(blockIdx.x % (unsigned)n_jobs);
+    const PairJob &J = jobs[pair];
+    const CandJob &C = cjobs[pair];
+    const i64 b = blockIdx.x / (unsigned)n_jobs;
     if (b >= J.nb) return;
     const int n_cand = min(*C.n_cand, C.max_cand);
     if (n_cand <= 0) return;
@@ -533,7 +537,7 @@ void launch_select_candidates(const SelJob *d_jobs, int n_jobs, cudaStream_t st)
 void launch_corr_candidates(const PairJob *d_jobs, const CandJob *d_cjobs, int n_jobs, i64 max_nb, cudaStream_t st)
 {
     if (n_jobs <= 0 || max_nb <= 0) return;
-    k_corr_candidates<<<dim3((unsigned)max_nb, n_jobs), kCandThreads, 0, st>>>(d_jobs, d_cjobs);
+    k_corr_candidates<<<(unsigned)(max_nb * n_jobs), kCandThreads, 0, st>>>(d_jobs, d_cjobs, n_jobs);
 }
 
 void launch_peak_candidates(const PairJob *d_jobs, const CandJob *d_cjobs, const PeakJob *d_pjobs, int n_jobs,
