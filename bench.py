@@ -290,8 +290,11 @@ def main_ours(args):
         return ref, tgt, pos, status
 
     def step_e2e():
+        # host buffers in: the three captures sit in pinned host memory (tdoa_host_alloc);
+        # tdoa_load_u8_pinned queues their copies (REF blocks of all stations first) and the
+        # discriminator follows them chunk by chunk; records and fix come back to the host
         for k in range(3):
-            eng.load_u8(k, pinned[k])
+            eng.load_u8_pinned(k, pinned[k])
         return step_resident()
 
     for k in range(3):
@@ -328,9 +331,11 @@ def main_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), eng.stats()["launches_total"] - l0
 
+    # clocks are sampled over both timed regions (nvidia-smi answers in ~100 ms, the
+    # resident region alone is shorter than that at the default step count)
     with ClockSampler(local) as clocks:
         ms_res, launches = timed(step_resident, args.steps, args.warmup, collect_stats=True)
-    ms_e2e, _ = timed(step_e2e, max(1, args.steps), max(3, args.warmup) if args.warmup else 0)
+        ms_e2e, _ = timed(step_e2e, max(1, args.steps), max(3, args.warmup) if args.warmup else 0)
 
     t_step = ms_res / args.steps / 1e3
     t_e2e = ms_e2e / max(1, args.steps) / 1e3

@@ -94,7 +94,9 @@ typedef struct {
                               processes: it truncates to its chunk) an exactly rounded
                               sum.  0 = mode default (4194304 SOURCE/BINARY, never in
                               EXTENDED); -1 = never                                   */
-    int32_t reserved[6];
+    int32_t copy_chunk;    /* tdoa_load_u8_pinned: samples per host->device copy chunk
+                              (multiple of 4096); 0 = 16777216 (32 MB of capture)    */
+    int32_t reserved[5];
 } tdoa_config;
 
 /* Fill *cfg with the reference-matching defaults of `mode`. */
@@ -112,6 +114,14 @@ TDOA_API void tdoa_host_free(void *p);
  * hands one station's whole .dat capture (interleaved uint8 I,Q) to the engine.
  * The bytes are copied to the device before the call returns. */
 TDOA_API int tdoa_load_u8(tdoa_engine *e, int32_t station, const uint8_t *iq, size_t nbytes);
+/* Same for a capture in memory obtained from tdoa_host_alloc (C memory, outside the Go
+ * heap, so the cgo pointer rules do not apply): returns at once.  The host -> device
+ * copies are queued by the next call that needs the capture -- the blocks of the signal
+ * kind that call asks for first, across all stations, then the rest -- and the FM
+ * discriminator follows them chunk by chunk, so preprocessing overlaps the PCIe
+ * transfer.  The buffer must stay unchanged until tdoa_synchronize() returns or both
+ * kinds have been correlated.  Captures under 384 KiB are copied synchronously. */
+TDOA_API int tdoa_load_u8_pinned(tdoa_engine *e, int32_t station, const uint8_t *pinned_iq, size_t nbytes);
 /* Same, capture already resident in device memory; not copied, caller keeps it alive. */
 TDOA_API int tdoa_load_u8_device(tdoa_engine *e, int32_t station, const uint8_t *d_iq, size_t nbytes);
 

@@ -23,7 +23,7 @@ ERRORS = {-1: "TDOA_E_INVALID", -2: "TDOA_E_NODEVICE", -3: "TDOA_E_CUDA", -4: "T
 # every symbol include/tdoa_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "tdoa_default_config", "tdoa_create", "tdoa_destroy", "tdoa_last_error", "tdoa_host_alloc", "tdoa_host_free",
-    "tdoa_load_u8", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_xcorr_info", "tdoa_analyze",
+    "tdoa_load_u8", "tdoa_load_u8_pinned", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_xcorr_info", "tdoa_analyze",
     "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
     "tdoa_set_stream", "tdoa_synchronize", "tdoa_selftest",
 ]
@@ -40,7 +40,7 @@ class Config(C.Structure):
         ("sample_rate", C.c_double), ("mode", C.c_int32), ("n_stations", C.c_int32),
         ("chunk_samples", C.c_int32), ("max_lag", C.c_int32), ("block_size", C.c_int32),
         ("sanity_lag", C.c_int32), ("fast_demod", C.c_int32), ("use_fft", C.c_int32),
-        ("device", C.c_int32), ("seq_dc_limit", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("device", C.c_int32), ("seq_dc_limit", C.c_int32), ("copy_chunk", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -131,6 +131,7 @@ def load_library():
     L.tdoa_host_free.argtypes = [vp]
     L.tdoa_host_free.restype = None
     L.tdoa_load_u8.argtypes = [vp, i32, vp, C.c_size_t]
+    L.tdoa_load_u8_pinned.argtypes = [vp, i32, vp, C.c_size_t]
     L.tdoa_load_u8_device.argtypes = [vp, i32, vp, C.c_size_t]
     L.tdoa_unpack.argtypes = [vp, i32, i64, i64, vp]
     L.tdoa_preprocess.argtypes = [vp, i32, i32, i64, i64, vp, f64p, C.POINTER(i32)]
@@ -271,6 +272,13 @@ class Engine:
             iq = np.ascontiguousarray(iq, dtype=np.uint8)
             ptr, n = _ptr(iq), iq.size
         self._check(self._lib.tdoa_load_u8(self._h, station, ptr, n))
+
+    def load_u8_pinned(self, station: int, buf: "PinnedBuffer") -> None:
+        """Lazy load from tdoa_host_alloc memory: returns at once; the copies are queued by the next
+        call that needs the capture and the discriminator follows them chunk by chunk.  `buf` must
+        stay unchanged until synchronize() or until both signal kinds were correlated."""
+        self._keep[("pinned", station)] = buf
+        self._check(self._lib.tdoa_load_u8_pinned(self._h, station, C.c_void_p(buf.ptr), buf.nbytes))
 
     def load_u8_ptr(self, station: int, ptr: int, nbytes: int) -> None:
         self._check(self._lib.tdoa_load_u8(self._h, station, C.c_void_p(ptr), nbytes))

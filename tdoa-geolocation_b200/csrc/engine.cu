@@ -29,6 +29,13 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// one piece of a capture on its way to the device (tdoa_load_u8_pinned): samples
+// [q_begin, q_end) of the REF or TGT signal; `landed` is recorded on the copy stream
+struct CopyChunk {
+    i64 q_begin = 0, q_end = 0;
+    cudaEvent_t landed = nullptr;
+};
+
 struct Station {
     const uint8_t *d_raw = nullptr;
     uint8_t *owned = nullptr;
@@ -36,7 +43,16 @@ struct Station {
     size_t nbytes = 0;
     i64 nsamp = 0;
     bool loaded = false;
+    // lazy load from pinned host memory: the copies are queued by the first call that
+    // needs the capture, the needed signal kind first, in chunks the discriminator follows
+    const uint8_t *h_lazy = nullptr;
+    bool lazy_queued = false;
+    std::vector<CopyChunk> chunks[2];
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
 };
+
+constexpr i64 kCopyChunkDefault = (i64)16 << 20;  // samples per copy chunk (32 MB of capture)
 
 // one signal (station-window) moving through preprocessing
 struct Sig {
@@ -50,7 +66,11 @@ struct Sig {
     double power0 = 0.0;
     int branch = 0;
     int memo = -1;        // slot of the branch memo (station * 2 + kind), -1: none
+    int station = -1;     // station and kind the view was cut from (-1: not a capture view)
+    int kind = 0;
+    i64 q0 = 0;           // first sample of the view within that station's REF / TGT signal
     bool fused = false;   // stage 0 ran the fused power + discriminator kernel
+    bool deferred = false;  // branch 0 was assumed without reading the power back; the caller verifies
 };
 
 struct Pair {
@@ -67,10 +87,13 @@ struct tdoa_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // host -> device copies of lazily loaded captures
+    cudaEvent_t ev_reload = nullptr;
     std::vector<Station> stations;
     std::string error;
     // descriptor staging
     uint8_t *h_frame = nullptr, *d_frame = nullptr;
+    const uint8_t *h_frame_dev = nullptr;  // device-side address of the pinned frame
     size_t frame_used = 0;
     cudaEvent_t frame_done = nullptr;
     bool frame_pending = false;
@@ -156,6 +179,15 @@ int alloc_t(tdoa_engine *e, T **out, size_t count)
     return alloc(e, reinterpret_cast<void **>(out), count * sizeof(T));
 }
 
+// Descriptors travel host -> device inside a kernel that reads the pinned (mapped) frame,
+// not through the copy engine: while a lazily loaded capture is arriving, the engine's
+// host -> device queue holds hundreds of MB of bulk copies, and a cudaMemcpyAsync of a
+// few hundred bytes on the compute stream would wait behind all of them.
+__global__ void k_fetch_descriptors(uint4 *__restrict__ dst, const uint4 *__restrict__ src, int n16)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 // copy a descriptor array to the device through the pinned frame
 template <class T>
 int upload(tdoa_engine *e, const std::vector<T> &v, const T **d_out)
@@ -164,7 +196,12 @@ int upload(tdoa_engine *e, const std::vector<T> &v, const T **d_out)
     const size_t off = (e->frame_used + 255) & ~size_t(255);
     if (off + bytes > kFrameBytes) return fail(e, TDOA_E_NOMEM, "descriptor frame overflow (%zu bytes)", off + bytes);
     std::memcpy(e->h_frame + off, v.data(), bytes);
-    CU(cudaMemcpyAsync(e->d_frame + off, e->h_frame + off, bytes, cudaMemcpyHostToDevice, e->stream));
+    const int n16 = (int)((bytes + 15) / 16);
+    if (n16 > 0) {
+        k_fetch_descriptors<<<std::min(32, (n16 + 255) / 256), 256, 0, e->stream>>>(
+            reinterpret_cast<uint4 *>(e->d_frame + off), reinterpret_cast<const uint4 *>(e->h_frame_dev + off), n16);
+        CU(cudaGetLastError());
+    }
     e->frame_used = off + bytes;
     *d_out = reinterpret_cast<const T *>(e->d_frame + off);
     return TDOA_OK;
@@ -244,6 +281,76 @@ int cutoff_window(double fc)
     if (w < 3) w = 3;
     if (w > 1000) w = 1000;
     return w;
+}
+
+// ---------------------------------------------------------------- lazy loads
+
+// Queue the host -> device copies of every lazily loaded capture that is not on its way
+// yet: first the chunks of `first_kind` of all stations, then the other kind, so the
+// pipeline of the signal that was asked for first starts as early as PCIe allows.
+int queue_lazy_copies(tdoa_engine *e, int first_kind)
+{
+    bool any = false;
+    for (auto &s : e->stations) any |= s.h_lazy && !s.lazy_queued;
+    if (!any) return TDOA_OK;
+    // the device buffers may still be read by kernels queued earlier on the compute stream
+    CU(cudaEventRecord(e->ev_reload, e->stream));
+    CU(cudaStreamWaitEvent(e->copy_stream, e->ev_reload, 0));
+    for (int pass = 0; pass < 2; pass++) {
+        const int kind = pass == 0 ? first_kind : 1 - first_kind;
+        for (auto &s : e->stations) {
+            if (!s.h_lazy || s.lazy_queued) continue;
+            const i64 b = s.nsamp / 3;
+            const i64 L = kind == TDOA_KIND_REF ? 2 * b : b;
+            s.chunks[kind].clear();
+            const i64 chunk = e->cfg.copy_chunk > 0 ? std::max<i64>(4096, (i64)e->cfg.copy_chunk / 4096 * 4096) : kCopyChunkDefault;
+            for (i64 q0 = 0; q0 < L; q0 += chunk) {
+                const i64 q1 = std::min(L, q0 + chunk);
+                // raw sample ranges of [q0, q1): REF = blocks 1 and 3, TGT = block 2
+                i64 r0[2], r1[2];
+                int nr = 0;
+                if (kind == TDOA_KIND_TGT) { r0[0] = b + q0; r1[0] = b + q1; nr = 1; }
+                else {
+                    if (q0 < b) { r0[nr] = q0; r1[nr] = std::min(q1, b); nr++; }
+                    if (q1 > b) { r0[nr] = 2 * b + std::max<i64>(q0, b) - b; r1[nr] = 2 * b + q1 - b; nr++; }
+                }
+                for (int k = 0; k < nr; k++) {
+                    size_t off = (size_t)r0[k] * 2, len = (size_t)(r1[k] - r0[k]) * 2;
+                    // the 0..2 samples after block 3 (N not a multiple of 3) travel with its last chunk
+                    if (kind == TDOA_KIND_REF && r1[k] == 3 * b) len = s.nbytes - off;
+                    CU(cudaMemcpyAsync(s.owned + off, s.h_lazy + off, len, cudaMemcpyHostToDevice, e->copy_stream));
+                }
+                if (s.events_used == s.event_pool.size()) {
+                    cudaEvent_t ev = nullptr;
+                    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                    s.event_pool.push_back(ev);
+                }
+                CopyChunk c;
+                c.q_begin = q0; c.q_end = q1; c.landed = s.event_pool[s.events_used++];
+                CU(cudaEventRecord(c.landed, e->copy_stream));
+                s.chunks[kind].push_back(c);
+            }
+        }
+    }
+    for (auto &s : e->stations)
+        if (s.h_lazy) s.lazy_queued = true;
+    return TDOA_OK;
+}
+
+// the compute stream waits until `kind` of the station has landed completely
+int wait_kind(tdoa_engine *e, Station &s, int kind)
+{
+    if (!s.chunks[kind].empty()) CU(cudaStreamWaitEvent(e->stream, s.chunks[kind].back().landed, 0));
+    return TDOA_OK;
+}
+
+// for entry points that read a capture outside the chunk-following discriminator
+int capture_ready(tdoa_engine *e, Station &s)
+{
+    int rc = queue_lazy_copies(e, TDOA_KIND_REF);
+    if (rc) return rc;
+    if ((rc = wait_kind(e, s, TDOA_KIND_REF))) return rc;
+    return wait_kind(e, s, TDOA_KIND_TGT);
 }
 
 // ---------------------------------------------------------------- preprocessing
@@ -366,9 +473,16 @@ int run_pipeline(tdoa_engine *e, Pipeline &pl)
     return TDOA_OK;
 }
 
+// shipped binary (ELF 0x49cd40): > 0.01 strong, > 0.001 moderate, else weak
+inline int binary_branch(double power0) { return power0 > 0.01 ? 0 : (power0 > 0.001 ? 1 : 2); }
+
 // Preprocess every signal (preprocessSignal, processor.go:469-499 / ELF 0x49cd40).
 // On return out_re/out_im/stats of each signal are valid on the stream.
-int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
+// allow_defer: when every signal runs the speculative fused kernel, do not wait for the
+// powers at all -- assume the "strong FM" branch, queue the whole pipeline, and leave
+// the check to the caller (verify_deferred), which reads the statistics back at the
+// call's final synchronisation and redoes the group if a guess was wrong.
+int preprocess(tdoa_engine *e, std::vector<Sig> &sigs, bool allow_defer = false)
 {
     if (sigs.empty()) return TDOA_OK;
     const int ns = (int)sigs.size();
@@ -397,17 +511,68 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
     (void)gmax2;
     {
         std::vector<SigJob> pjobs, fjobs;
-        for (auto &s : sigs) {
+        // signals whose capture is still arriving (tdoa_load_u8_pinned): the discriminator
+        // follows the copy chunk by chunk, every launch waiting for one chunk only
+        struct Follow { SigJob job; cudaEvent_t wait; i64 len; int sig; bool last; int n_sub; double *sums; };
+        std::vector<Follow> follow;
+        for (size_t si = 0; si < sigs.size(); si++) {
+            Sig &s = sigs[si];
             const bool spec = e->cfg.mode != TDOA_MODE_SOURCE && s.src.raw && s.n >= 2 &&
                               (s.memo < 0 || e->branch_memo[s.memo] <= 0);
             s.fused = spec;
+            Station *stn = s.station >= 0 ? &e->stations[s.station] : nullptr;
+            const bool arriving = stn && !stn->chunks[s.kind].empty();
             if (spec) {
                 if ((rc = ensure_plane(e, s, 0, false))) return rc;
                 SigJob j = base_job(s);
                 j.p_re = s.plane[0][0];
-                fjobs.push_back(j);
+                if (arriving && !e->cfg.fast_demod) {
+                    const auto &ch = stn->chunks[s.kind];
+                    double *sums = nullptr;
+                    if ((rc = alloc_t(e, &sums, 2 * ch.size()))) return rc;
+                    i64 done = 0;
+                    int n_sub = 0;
+                    const size_t first = follow.size();
+                    for (const CopyChunk &c : ch) {
+                        const i64 avail = std::max<i64>(0, std::min<i64>(s.n, c.q_end - s.q0));
+                        // a tile reads one 32-bit word past its end: stay 8 samples behind the copy
+                        const i64 upto = avail == s.n ? s.n : std::max<i64>(0, (avail - 8) / 4096 * 4096);
+                        if (upto <= done) continue;
+                        Follow f{j, c.landed, upto - done, (int)si, false, 0, sums};
+                        f.job.i_begin = done; f.job.i_end = upto; f.job.chunk_out = sums + 2 * n_sub;
+                        follow.push_back(f);
+                        done = upto;
+                        n_sub++;
+                        if (done == s.n) break;
+                    }
+                    follow.back().last = true;
+                    for (size_t k = first; k < follow.size(); k++) follow[k].n_sub = n_sub;
+                } else {
+                    if (arriving && (rc = wait_kind(e, *stn, s.kind))) return rc;
+                    fjobs.push_back(j);
+                }
             } else {
+                if (arriving && (rc = wait_kind(e, *stn, s.kind))) return rc;
                 pjobs.push_back(base_job(s));
+            }
+        }
+        if (!follow.empty()) {
+            std::vector<SigJob> jobs;
+            for (const Follow &f : follow) jobs.push_back(f.job);
+            const SigJob *d_jobs = nullptr;
+            if ((rc = upload(e, jobs, &d_jobs))) return rc;
+            for (size_t k = 0; k < follow.size(); k++) {
+                const Follow &f = follow[k];
+                CU(cudaStreamWaitEvent(e->stream, f.wait, 0));
+                const int sp = span_begin(e, SPAN_DEMOD);
+                launch_demod_fused(d_jobs + k, 1, f.len, 0, e->stream);
+                span_end(e, sp);
+                e->st.demod_samples += f.len;
+                count_launch(e);
+                if (f.last) {
+                    launch_demod_finish(f.sums, f.n_sub, sigs[f.sig].n, sigs[f.sig].stats, e->stream);
+                    count_launch(e);
+                }
             }
         }
         if (!pjobs.empty()) {
@@ -425,10 +590,16 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
             for (const SigJob &j : fjobs) e->st.demod_samples += j.n;
             count_launch(e);
         }
-        std::vector<double> h_stats((size_t)ns * ST_COUNT);
-        CU(cudaMemcpyAsync(h_stats.data(), d_stats, h_stats.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
-        for (int i = 0; i < ns; i++) sigs[i].power0 = h_stats[(size_t)i * ST_COUNT + ST_POWER0];
+        const bool defer = allow_defer && pjobs.empty();
+        (void)follow;
+        if (defer) {
+            for (auto &s : sigs) s.deferred = true;
+        } else {
+            std::vector<double> h_stats((size_t)ns * ST_COUNT);
+            CU(cudaMemcpyAsync(h_stats.data(), d_stats, h_stats.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaStreamSynchronize(e->stream));
+            for (int i = 0; i < ns; i++) sigs[i].power0 = h_stats[(size_t)i * ST_COUNT + ST_POWER0];
+        }
     }
     // ---- per-branch pipelines
     const int mode = e->cfg.mode;
@@ -475,9 +646,9 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs)
             }
         } else {
             // shipped binary (ELF 0x49cd40): > 0.01 strong, > 0.001 moderate, else weak
-            s.branch = s.power0 > 0.01 ? 0 : (s.power0 > 0.001 ? 1 : 2);
+            s.branch = s.deferred ? 0 : binary_branch(s.power0);
             size_t g = 0;
-            if (s.memo >= 0) e->branch_memo[s.memo] = (int8_t)s.branch;
+            if (s.memo >= 0 && !s.deferred) e->branch_memo[s.memo] = (int8_t)s.branch;
             if (s.branch == 0) {
                 const bool cplx = s.n < 2;  // convertToInstantaneousFrequency returns its input for n < 2
                 if ((rc = ensure_plane(e, s, 0, cplx)) || (rc = ensure_plane(e, s, 1, cplx))) return rc;
@@ -893,6 +1064,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
             len[s] = win_len;
         }
     }
+    if ((rc = queue_lazy_copies(e, kind))) return rc;
     PeakRec *d_out = nullptr;
     if (out_is_device) d_out = reinterpret_cast<PeakRec *>(out);
     else if ((rc = alloc_t(e, &d_out, (size_t)n_windows * P))) return rc;
@@ -920,28 +1092,64 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
                 sg.n = len[s];
                 sg.src = make_view(e->stations[s], kind, win_start + (i64)(w0 + w) * hop, len[s]);
                 sg.memo = s * 2 + kind;
+                sg.station = s; sg.kind = kind; sg.q0 = win_start + (i64)(w0 + w) * hop;
             }
             for (int i = 0; i < S; i++)
                 for (int j = i + 1; j < S; j++) pairs.push_back({w * S + i, w * S + j, w});
         }
-        cudaEventRecord(e->ev[1], e->stream);
-        if ((rc = preprocess(e, sigs))) return rc;
-        cudaEventRecord(e->ev[2], e->stream);
         double *d_first = nullptr;
-        if (w0 == 0 && (rc = alloc_t(e, &d_first, pairs.size()))) return rc;
-        if ((rc = correlate(e, sigs, pairs, d_out + (size_t)w0 * P, d_first))) return rc;
-        cudaEventRecord(e->ev[3], e->stream);
+        std::vector<double> h_stats;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            cudaEventRecord(e->ev[1], e->stream);
+            if ((rc = preprocess(e, sigs, attempt == 0))) return rc;
+            cudaEventRecord(e->ev[2], e->stream);
+            d_first = nullptr;
+            if (w0 == 0 && (rc = alloc_t(e, &d_first, pairs.size()))) return rc;
+            if ((rc = correlate(e, sigs, pairs, d_out + (size_t)w0 * P, d_first))) return rc;
+            cudaEventRecord(e->ev[3], e->stream);
+            bool any_deferred = false;
+            for (auto &sg : sigs) any_deferred |= sg.deferred;
+            if (!any_deferred && w0 != 0) break;
+            // statistics of the group: the branch check of the speculated signals and
+            // (window 0) what the reference prints.  One read-back; it waits for the stream.
+            h_stats.resize(sigs.size() * ST_COUNT);
+            CU(cudaMemcpyAsync(h_stats.data(), sigs[0].stats, h_stats.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                               e->stream));
+            CU(cudaStreamSynchronize(e->stream));
+            bool wrong = false;
+            for (size_t i = 0; i < sigs.size(); i++) {
+                Sig &sg = sigs[i];
+                if (!sg.deferred) continue;
+                sg.power0 = h_stats[i * ST_COUNT + ST_POWER0];
+                const int actual = sg.n == 0 ? 0 : binary_branch(sg.power0);
+                if (sg.memo >= 0) e->branch_memo[sg.memo] = (int8_t)actual;
+                wrong |= actual != 0;
+            }
+            if (!wrong) break;
+            // a guess was wrong (the capture is not "strong FM"): drop the group's scratch and
+            // redo it with the powers read first; the memo now keeps those signals off the fused path
+            spans_collect(e);
+            for (void *p : e->call_allocs)
+                if (p != d_out) cudaFreeAsync(p, e->stream);
+            e->call_allocs.clear();
+            e->frame_used = 0;
+            if (!out_is_device) e->call_allocs.push_back(d_out);
+            for (auto &sg : sigs) {
+                Sig fresh;
+                fresh.n = sg.n; fresh.src = sg.src; fresh.memo = sg.memo;
+                fresh.station = sg.station; fresh.kind = sg.kind; fresh.q0 = sg.q0;
+                sg = fresh;
+            }
+        }
         if (w0 == 0) {
             // what the reference prints about window 0 (tdoa_xcorr_info)
-            std::vector<double> h((size_t)S * ST_COUNT);
             e->info_first[kind].assign(P, 0.0);
-            CU(cudaMemcpyAsync(h.data(), sigs[0].stats, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
             CU(cudaMemcpyAsync(e->info_first[kind].data(), d_first, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
             CU(cudaStreamSynchronize(e->stream));
             e->info_sig[kind].assign(S, tdoa_signal_info{});
             for (int s = 0; s < S; s++) {
                 tdoa_signal_info &I = e->info_sig[kind][s];
-                const double *st = h.data() + (size_t)s * ST_COUNT;
+                const double *st = h_stats.data() + (size_t)s * ST_COUNT;
                 I.power0 = st[ST_POWER0]; I.dc_re = st[ST_DC_RE]; I.dc_im = st[ST_DC_IM]; I.power1 = st[ST_POWER1];
                 I.branch = sigs[s].branch; I.n = sigs[s].n;
             }
@@ -1053,6 +1261,13 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
     e->branch_memo.assign((size_t)cfg->n_stations * 2, (int8_t)-1);
     cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) { e->own_stream = true; err = cudaMallocHost(&e->h_frame, kFrameBytes); }
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_reload, cudaEventDisableTiming);
+    if (err == cudaSuccess) {
+        void *dp = nullptr;
+        err = cudaHostGetDevicePointer(&dp, e->h_frame, 0);
+        e->h_frame_dev = static_cast<const uint8_t *>(dp);
+    }
     if (err == cudaSuccess) err = cudaMalloc(&e->d_frame, kFrameBytes);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->frame_done, cudaEventDisableTiming);
     for (int i = 0; i < 6 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev[i]);
@@ -1095,10 +1310,15 @@ void tdoa_destroy(tdoa_engine *e)
 {
     if (!e) return;
     cudaSetDevice(e->device);
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void *p : e->call_allocs) cudaFreeAsync(p, e->stream);
-    for (auto &s : e->stations)
+    for (auto &s : e->stations) {
         if (s.owned) cudaFree(s.owned);
+        for (cudaEvent_t ev : s.event_pool) cudaEventDestroy(ev);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->ev_reload) cudaEventDestroy(e->ev_reload);
     if (e->h_frame) cudaFreeHost(e->h_frame);
     if (e->d_frame) cudaFree(e->d_frame);
     if (e->d_tw) cudaFree(e->d_tw);
@@ -1142,14 +1362,15 @@ int tdoa_set_stream(tdoa_engine *e, void *stream)
     return TDOA_OK;
 }
 
-int tdoa_load_u8(tdoa_engine *e, int32_t station, const uint8_t *iq, size_t nbytes)
+// device buffer of a station for a capture of nbytes; forgets any lazy load in progress
+static int station_buffer(tdoa_engine *e, Station &s, size_t nbytes)
 {
-    if (!e) return TDOA_E_INVALID;
-    int rc = begin_call(e);
-    if (rc) return rc;
-    if (station < 0 || station >= e->cfg.n_stations) return fail(e, TDOA_E_INVALID, "tdoa_load_u8: bad station %d", station);
-    if (!iq && nbytes) return fail(e, TDOA_E_INVALID, "tdoa_load_u8: NULL capture");
-    Station &s = e->stations[station];
+    if (s.h_lazy || !s.chunks[0].empty() || !s.chunks[1].empty()) {
+        CU(cudaStreamSynchronize(e->copy_stream));  // copies of the previous capture still target this buffer
+        s.h_lazy = nullptr; s.lazy_queued = false;
+        s.chunks[0].clear(); s.chunks[1].clear();
+        s.events_used = 0;
+    }
     if (s.owned_cap < nbytes || !s.owned) {
         CU(cudaStreamSynchronize(e->stream));
         if (s.owned) cudaFree(s.owned);
@@ -1158,6 +1379,44 @@ int tdoa_load_u8(tdoa_engine *e, int32_t station, const uint8_t *iq, size_t nbyt
         CU(cudaMalloc(&s.owned, cap));
         s.owned_cap = cap;
     }
+    return TDOA_OK;
+}
+
+int tdoa_load_u8_pinned(tdoa_engine *e, int32_t station, const uint8_t *pinned_iq, size_t nbytes)
+{
+    if (!e) return TDOA_E_INVALID;
+    // small captures gain nothing from following the copy
+    if (nbytes < (size_t)12 * 4096 * 8) return tdoa_load_u8(e, station, pinned_iq, nbytes);
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (station < 0 || station >= e->cfg.n_stations)
+        return fail(e, TDOA_E_INVALID, "tdoa_load_u8_pinned: bad station %d", station);
+    if (!pinned_iq) return fail(e, TDOA_E_INVALID, "tdoa_load_u8_pinned: NULL capture");
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, pinned_iq) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        return fail(e, TDOA_E_INVALID, "tdoa_load_u8_pinned: the capture must live in tdoa_host_alloc memory");
+    }
+    Station &s = e->stations[station];
+    if ((rc = station_buffer(e, s, nbytes))) return rc;
+    s.h_lazy = pinned_iq;
+    s.lazy_queued = false;
+    s.d_raw = s.owned;
+    s.nbytes = nbytes;
+    s.nsamp = (i64)(nbytes / 2);
+    s.loaded = true;
+    return TDOA_OK;
+}
+
+int tdoa_load_u8(tdoa_engine *e, int32_t station, const uint8_t *iq, size_t nbytes)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (station < 0 || station >= e->cfg.n_stations) return fail(e, TDOA_E_INVALID, "tdoa_load_u8: bad station %d", station);
+    if (!iq && nbytes) return fail(e, TDOA_E_INVALID, "tdoa_load_u8: NULL capture");
+    Station &s = e->stations[station];
+    if ((rc = station_buffer(e, s, nbytes))) return rc;
     if (nbytes) CU(cudaMemcpyAsync(s.owned, iq, nbytes, cudaMemcpyHostToDevice, e->stream));
     // the caller's buffer may be Go memory: do not return before the copy has left it
     CU(cudaStreamSynchronize(e->stream));
@@ -1179,6 +1438,12 @@ int tdoa_load_u8_device(tdoa_engine *e, int32_t station, const uint8_t *d_iq, si
     if (reinterpret_cast<uintptr_t>(d_iq) & 15u)
         return fail(e, TDOA_E_INVALID, "tdoa_load_u8_device: capture must be 16-byte aligned");
     Station &s = e->stations[station];
+    if (s.h_lazy || !s.chunks[0].empty() || !s.chunks[1].empty()) {
+        CU(cudaStreamSynchronize(e->copy_stream));
+        s.h_lazy = nullptr; s.lazy_queued = false;
+        s.chunks[0].clear(); s.chunks[1].clear();
+        s.events_used = 0;
+    }
     s.d_raw = d_iq;
     s.nbytes = nbytes;
     s.nsamp = (i64)(nbytes / 2);
@@ -1193,7 +1458,8 @@ int tdoa_unpack(tdoa_engine *e, int32_t station, int64_t first, int64_t count, f
     if (rc) return rc;
     if (station < 0 || station >= e->cfg.n_stations || !e->stations[station].loaded)
         return fail(e, TDOA_E_STATE, "tdoa_unpack: station %d not loaded", station);
-    const Station &s = e->stations[station];
+    Station &s = e->stations[station];
+    if ((rc = capture_ready(e, s))) return rc;
     if (first < 0 || count < 0 || first + count > s.nsamp || (!out_c64 && count))
         return fail(e, TDOA_E_INVALID, "tdoa_unpack: range [%lld,+%lld) outside %lld samples", (long long)first,
                     (long long)count, (long long)s.nsamp);
@@ -1236,6 +1502,8 @@ int tdoa_preprocess(tdoa_engine *e, int32_t station, int32_t kind, int64_t start
     std::vector<Sig> sigs(1);
     sigs[0].n = len;
     sigs[0].src = make_view(s, kind, start, len);
+    sigs[0].station = station; sigs[0].kind = kind; sigs[0].q0 = start;
+    if ((rc = queue_lazy_copies(e, kind))) return rc;
     if ((rc = preprocess(e, sigs))) return rc;
     if (power) *power = sigs[0].power0;
     if (branch) *branch = sigs[0].branch;
@@ -1397,7 +1665,8 @@ int tdoa_analyze(tdoa_engine *e, int32_t station, int32_t fast, tdoa_signal_qual
     if (station < 0 || station >= e->cfg.n_stations || !e->stations[station].loaded)
         return fail(e, TDOA_E_STATE, "tdoa_analyze: station %d not loaded", station);
     if (!ref || !tgt) return fail(e, TDOA_E_INVALID, "tdoa_analyze: NULL output");
-    const Station &s = e->stations[station];
+    Station &s = e->stations[station];
+    if ((rc = capture_ready(e, s))) return rc;
     const i64 block = s.nsamp / 3;
     // fast_analyzer.go:71-73
     if (block == 0) return fail(e, TDOA_E_INVALID, "file too small for dual-frequency analysis");
@@ -1485,6 +1754,9 @@ int tdoa_synchronize(tdoa_engine *e)
 {
     if (!e) return TDOA_E_INVALID;
     CU(cudaSetDevice(e->device));
+    int rc = queue_lazy_copies(e, TDOA_KIND_REF);  // a lazily loaded capture is on the device after this call
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(e->copy_stream));
     CU(cudaStreamSynchronize(e->stream));
     return TDOA_OK;
 }

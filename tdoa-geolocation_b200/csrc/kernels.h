@@ -40,6 +40,12 @@ struct SigJob {
     int mode;          // BOX_LP / BOX_HP
     int sub_dc;        // subtract ST_DC_* from the input while loading
     int want_power;    // accumulate ST_POWER1 / ST_SCALE of the output
+    // fused discriminator only: process samples [i_begin, i_end) of the signal (i_end == 0:
+    // all of it; i_begin a multiple of 4096) and, when chunk_out is set, leave the two
+    // partial sums (power, output sum) there instead of finishing the statistics -- the
+    // capture is demodulated chunk by chunk while it is still arriving over PCIe
+    i64 i_begin, i_end;
+    double *chunk_out;
 };
 
 // correlator variants
@@ -107,6 +113,8 @@ int unpack_selftest(cudaStream_t st);  // 0 ok: arithmetic unpack == host LUT fo
 
 // ---- preprocess_fast.cu
 void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, cudaStream_t st);
+// statistics of a signal demodulated in chunks: adds chunk_sums[c][0..1] in chunk order
+void launch_demod_finish(const double *chunk_sums, int n_chunks, i64 n, double *stats, cudaStream_t st);
 void launch_boxcar_small(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
 int boxcar_small_max_half();
 long long div_selftest(cudaStream_t st);  // mismatches of the constant-divisor division, 0 = proven

@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean(const SigJob *jo
     lean_fill(S, atab_g);
     __syncthreads();
     const i64 n = J.n;
+    const i64 i_begin = J.i_begin, i_end = J.i_end > 0 ? J.i_end : n;
     const uint8_t *__restrict__ rawb = J.src.raw;
     float *__restrict__ out = J.p_re;
     const i64 run0 = J.src.run0_len;
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean(const SigJob *jo
     // thread staging and later reading only its own six words, so no barrier is needed.
     auto fast_tile = [&](i64 t0) {
         const bool in0 = t0 + kLeanTile + 2 <= run0, in1 = t0 - 1 >= run0 && t0 + kLeanTile + 2 <= n;
-        return t0 > 0 && t0 < n && (in0 || in1);
+        return t0 > 0 && t0 + kLeanTile <= i_end && (in0 || in1);
     };
     auto tile_addr = [&](i64 t0) { return rawb + 2 * (raw_index(J.src, t0) + (i64)kLeanPer * tid); };
     auto stage_tile = [&](i64 t0, int buf) {
@@ -334,8 +335,8 @@ __global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean(const SigJob *jo
     };
     const i64 step = (i64)gridDim.x * kLeanTile;
     int buf = 0;
-    stage_tile((i64)blockIdx.x * kLeanTile, 0);
-    for (i64 i0 = (i64)blockIdx.x * kLeanTile; i0 < n; i0 += step, buf ^= 1) {
+    stage_tile(i_begin + (i64)blockIdx.x * kLeanTile, 0);
+    for (i64 i0 = i_begin + (i64)blockIdx.x * kLeanTile; i0 < i_end; i0 += step, buf ^= 1) {
         stage_tile(i0 + step, buf ^ 1);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         if (fast_tile(i0)) {
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean(const SigJob *jo
             // own statement of the discriminator, sample by sample, gates included
             for (int u = 0; u < kLeanPer; u++) {
                 const i64 i = i0 + tid + (i64)kLeanThreads * u;
-                if (i >= n) break;
+                if (i >= i_end) break;
                 const i64 k = i == 0 ? 1 : i;  // out[0] = out[1]
                 const uchar2 cur = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k)];
                 const uchar2 prv = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k - 1)];
@@ -392,12 +393,30 @@ __global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean(const SigJob *jo
     part[0] = block_sum(pw, S.scratch);
     part[1] = block_sum(sr, S.scratch);
     if (grid_sum_last_dyn<2>(part, J.partials, J.counter, gridDim.x, blockIdx.x, S.scratch, &S.last, total)) {
+        if (J.chunk_out) {
+            J.chunk_out[0] = total[0];
+            J.chunk_out[1] = total[1];
+            return;
+        }
         J.stats[ST_POWER0] = n > 0 ? total[0] / (double)n : 0.0;
         J.stats[ST_SUM_RE] = total[1];
         J.stats[ST_SUM_IM] = 0.0;
         J.stats[ST_DC_RE] = n > 0 ? (double)dc_from_sum(total[1], n) : 0.0;
         J.stats[ST_DC_IM] = 0.0;
     }
+}
+
+// statistics of a signal whose discriminator ran in chunks (fixed order: chunk 0, 1, ...)
+__global__ void k_demod_finish(const double *__restrict__ chunk_sums, int n_chunks, i64 n, double *stats)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double pw = 0.0, sr = 0.0;
+    for (int c = 0; c < n_chunks; c++) { pw += chunk_sums[2 * c]; sr += chunk_sums[2 * c + 1]; }
+    stats[ST_POWER0] = n > 0 ? pw / (double)n : 0.0;
+    stats[ST_SUM_RE] = sr;
+    stats[ST_SUM_IM] = 0.0;
+    stats[ST_DC_RE] = n > 0 ? (double)dc_from_sum(sr, n) : 0.0;
+    stats[ST_DC_IM] = 0.0;
 }
 
 // every (previous, current) byte quad: lean_one against demod_one<false>
@@ -643,6 +662,11 @@ void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, c
     } else {
         k_demod_lean<<<dim3(lean_grid_x(max_n, n_jobs), n_jobs), kLeanThreads, sizeof(LeanSmem), st>>>(d_jobs, g_atab);
     }
+}
+
+void launch_demod_finish(const double *chunk_sums, int n_chunks, i64 n, double *stats, cudaStream_t st)
+{
+    k_demod_finish<<<1, 32, 0, st>>>(chunk_sums, n_chunks, n, stats);
 }
 
 long long demod_selftest(cudaStream_t st, unsigned *first_bad_out)

@@ -362,3 +362,47 @@ def test_lean_discriminator_all_byte_quads(eng_binary):
     bad = eng_binary.selftest(1)
     print("lean discriminator: differing byte quads =", bad, eng_binary.last_error() if bad else "")
     assert 0 <= bad <= 256
+
+
+# ------------------------------------------------------------------ lazy pinned load (copy-following discriminator)
+@pytest.mark.parametrize("copy_chunk", [0, 65536, 8192])
+def test_pinned_lazy_load_equals_synchronous_load(copy_chunk):
+    """tdoa_load_u8_pinned queues the host->device copies in chunks (REF blocks of every
+    station first when REF is asked for first) and the discriminator follows them; the
+    records must be those of the synchronous tdoa_load_u8 path.  The power / DC sums are
+    added chunk by chunk, i.e. in another (fixed) order: lags identical, correlation to
+    1e-12; and against the oracle as everywhere else."""
+    block = 150000
+    raws = fm_capture(block, (0, 5, 11), (0, 17, 30), seed=21)
+    with T.Engine(T.MODE_BINARY, chunk_samples=0) as a:
+        load_all(a, raws)
+        want = [a.xcorr(T.KIND_REF)[0], a.xcorr(T.KIND_TGT)[0]]
+    bufs = []
+    for r in raws:
+        b = T.host_alloc(r.size)
+        b.array[:] = r
+        bufs.append(b)
+    for order in ((T.KIND_REF, T.KIND_TGT), (T.KIND_TGT, T.KIND_REF)):
+        with T.Engine(T.MODE_BINARY, chunk_samples=0, copy_chunk=copy_chunk) as e:
+            for rep in range(2):  # second round: reload while the chunk events of the first still exist
+                for k, b in enumerate(bufs):
+                    e.load_u8_pinned(k, b)
+                got = {kind: e.xcorr(kind)[0] for kind in order}
+                for kind in (T.KIND_REF, T.KIND_TGT):
+                    assert np.array_equal(got[kind]["lag"], want[kind]["lag"])
+                    assert np.allclose(got[kind]["corr"], want[kind]["corr"], rtol=0, atol=1e-12)
+                    assert np.array_equal(got[kind]["n_blocks"], want[kind]["n_blocks"])
+            # other readers of the capture wait for the copies too
+            for k, b in enumerate(bufs):
+                e.load_u8_pinned(k, b)
+            assert np.array_equal(e.unpack(2, 3 * block - 64, 64), oracle.unpack_u8(raws[2])[3 * block - 64:])
+            sig, p0, br = e.preprocess(1, T.KIND_TGT, 4096, 50000)
+            with T.Engine(T.MODE_BINARY) as s:
+                load_all(s, raws)
+                sig2, p02, br2 = s.preprocess(1, T.KIND_TGT, 4096, 50000)
+            assert br == br2 and abs(p0 - p02) <= 1e-12 and np.allclose(sig, sig2, rtol=0, atol=2e-6)
+    ref, tgt = oracle.process_capture_binary(raws)  # 300 000 / 150 000 samples: under the 1 M chunk
+    for got, w in zip(list(want[0]) + list(want[1]), ref + tgt):
+        assert int(got["lag"]) == w[0] and abs(float(got["corr"]) - w[1]) <= CORR_TOL
+    for b in bufs:
+        b.free()
