@@ -168,6 +168,18 @@ TDOA_API int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_sta
                        const double *grid_desc, const double *range_diffs, int32_t n_sets,
                        int32_t rd_stride, double *out_llh, double *out_cost, int64_t *out_index);
 
+/* Least-squares fix over ALL S(S-1)/2 range differences (no reference
+ * equivalent -- solveTDOA uses two of three measurements, freezes Z and stops after ten
+ * half steps, processor.go:932-1020).  Levenberg-Marquardt in the local east/north/up
+ * frame; dims = 2 keeps the start elevation (what 3 stations support), dims = 3 solves
+ * it too (>= 4 stations).  init_llh[set][3] = start points (e.g. the tdoa_grid arg-min),
+ * NULL: mean of the station coordinates.  out_rms[set] = sqrt(sum f^2 / P) in metres
+ * (may be NULL); status[set] = 0 ok, 1 degenerate geometry. */
+TDOA_API int tdoa_solve_ls(tdoa_engine *e, const double *stations_llh, int32_t n_stations,
+                           const double *range_diffs, int32_t n_sets, int32_t rd_stride,
+                           const double *init_llh, int32_t dims, double *out_llh, double *out_rms,
+                           int32_t *status, int32_t *iters);
+
 /* Per-capture signal quality (fast_analyzer.go:15-24 FastAnalysis, analyzer.go:18-42
  * SignalAnalysis): the numbers the reference's analyzers print and base their gain
  * recommendations on.  fast != 0 follows fast_analyzer.go (first 32768 samples of each

@@ -81,6 +81,8 @@ def lib():
         L.orc_solve_tdoa.restype = C.c_int
         L.orc_grid_solve.argtypes = [_vp, C.c_int, _vp, _f64, _f64, _f64, _f64, C.c_int, C.c_int,
                                      _f64, _vp, _vp, _vp]
+        L.orc_solve_ls.argtypes = [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]
+        L.orc_solve_ls.restype = C.c_int
     return _lib
 
 
@@ -288,6 +290,19 @@ def solve_tdoa(stations_llh, range_diffs):
     it = np.zeros(1, np.int32)
     status = lib().orc_solve_tdoa(_p(st), _p(rd), _p(out), _p(it))
     return out, status, int(it[0])
+
+
+def solve_ls(stations_llh, range_diffs, init_llh=None, dims=2):
+    """Engine-defined least-squares fix (orc_solve_ls; no reference equivalent)."""
+    st = np.ascontiguousarray(stations_llh, np.float64)
+    rd = np.ascontiguousarray(range_diffs, np.float64)
+    init = None if init_llh is None else np.ascontiguousarray(init_llh, np.float64)
+    out = np.zeros(3, np.float64)
+    rms = np.zeros(1, np.float64)
+    it = np.zeros(1, np.int32)
+    status = lib().orc_solve_ls(_p(st), st.shape[0], _p(rd), _p(init) if init is not None else None, dims,
+                                _p(out), _p(rms), _p(it))
+    return out, float(rms[0]), status, int(it[0])
 
 
 def grid_solve(stations_llh, range_diffs, lat0, lon0, dlat, dlon, nlat, nlon, elev):

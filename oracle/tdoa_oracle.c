@@ -628,6 +628,128 @@ ORC_API void orc_grid_solve(const double *st_llh, int n_st, const double *rd,
     free(s); free(r);
 }
 
+/* ------------------------------------------------- least-squares fix
+ * No reference equivalent ("parity unpinned"); the statement the engine's k_solve_ls follows.
+ * All P = S(S-1)/2 range differences rd_p = r_j - r_i (pairs i<j lexicographic).
+ * Levenberg-Marquardt in the east/north/up frame of the current estimate:
+ *   f_p = (|x-s_j| - |x-s_i|) - rd_p ; row_p = g_j - g_i, g_k = ENU components of (x-s_k)/|x-s_k|
+ *   (J'J + lambda diag J'J) d = -J'f over the first `dims` coordinates (2: elevation kept);
+ *   accept a step only if it lowers sum f^2 (lambda/3, floor 1e-12), else lambda*4, <= 8 tries;
+ *   <= 60 iterations; stop when no try succeeds or |d| < 1e-6 m.  init == NULL: station mean.
+ * Returns 0, or 1 when the cost is NaN. */
+static double ls_cost(const double (*s)[3], int n_st, const double *rd, double lat, double lon, double h, double *r)
+{
+    double x[3];
+    orc_llh_to_ecef(lat, lon, h, x);
+    for (int k = 0; k < n_st; k++) {
+        double dx = x[0] - s[k][0], dy = x[1] - s[k][1], dz = x[2] - s[k][2];
+        r[k] = sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    double c = 0.0; int q = 0;
+    for (int i = 0; i < n_st; i++)
+        for (int j = i + 1; j < n_st; j++, q++) { double f = (r[j] - r[i]) - rd[q]; c += f * f; }
+    return c;
+}
+
+static int ls_step(double A[3][3], const double b[3], double lambda, int n, double d[3])
+{
+    double M[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) M[i][j] = A[i][j];
+    for (int i = 0; i < 3; i++) M[i][i] = A[i][i] + lambda * A[i][i];
+    d[0] = d[1] = d[2] = 0.0;
+    if (n == 2) {
+        double det = M[0][0] * M[1][1] - M[0][1] * M[1][0];
+        if (!(fabs(det) > 1e-300)) return 0;
+        d[0] = -(b[0] * M[1][1] - b[1] * M[0][1]) / det;
+        d[1] = -(M[0][0] * b[1] - M[1][0] * b[0]) / det;
+        return 1;
+    }
+    double c00 = M[1][1] * M[2][2] - M[1][2] * M[2][1];
+    double c01 = M[1][2] * M[2][0] - M[1][0] * M[2][2];
+    double c02 = M[1][0] * M[2][1] - M[1][1] * M[2][0];
+    double det = M[0][0] * c00 + M[0][1] * c01 + M[0][2] * c02;
+    if (!(fabs(det) > 1e-300)) return 0;
+    double c10 = M[0][2] * M[2][1] - M[0][1] * M[2][2];
+    double c11 = M[0][0] * M[2][2] - M[0][2] * M[2][0];
+    double c12 = M[0][1] * M[2][0] - M[0][0] * M[2][1];
+    double c20 = M[0][1] * M[1][2] - M[0][2] * M[1][1];
+    double c21 = M[0][2] * M[1][0] - M[0][0] * M[1][2];
+    double c22 = M[0][0] * M[1][1] - M[0][1] * M[1][0];
+    d[0] = -(c00 * b[0] + c10 * b[1] + c20 * b[2]) / det;
+    d[1] = -(c01 * b[0] + c11 * b[1] + c21 * b[2]) / det;
+    d[2] = -(c02 * b[0] + c12 * b[1] + c22 * b[2]) / det;
+    return 1;
+}
+
+ORC_API int orc_solve_ls(const double *st_llh, int n_st, const double *rd, const double *init_llh, int dims,
+                         double *out_llh, double *out_rms, int *iters)
+{
+    const double a = 6378137.0, f = 1.0 / 298.257223563, e2 = 2 * f - f * f;
+    const int P = n_st * (n_st - 1) / 2;
+    double (*s)[3] = malloc(sizeof(double[3]) * (size_t)n_st);
+    double (*g)[3] = malloc(sizeof(double[3]) * (size_t)n_st);
+    double *r = malloc(sizeof(double) * (size_t)n_st), *rc = malloc(sizeof(double) * (size_t)n_st);
+    for (int k = 0; k < n_st; k++) orc_llh_to_ecef(st_llh[3 * k], st_llh[3 * k + 1], st_llh[3 * k + 2], s[k]);
+    double lat, lon, h;
+    if (init_llh) { lat = init_llh[0]; lon = init_llh[1]; h = init_llh[2]; }
+    else {
+        lat = lon = h = 0.0;
+        for (int k = 0; k < n_st; k++) { lat += st_llh[3 * k]; lon += st_llh[3 * k + 1]; h += st_llh[3 * k + 2]; }
+        lat /= n_st; lon /= n_st; h /= n_st;
+    }
+    double lambda = 1e-3;
+    double cost = ls_cost(s, n_st, rd, lat, lon, h, r);
+    int it = 0;
+    for (; it < 60; it++) {
+        double lr = lat * M_PI / 180, lo = lon * M_PI / 180;
+        double sl = sin(lr), cl = cos(lr), so = sin(lo), co = cos(lo);
+        double w = sqrt(1 - e2 * sl * sl);
+        double Nr = a / w, Mr = a * (1 - e2) / (w * w * w);
+        double x[3];
+        orc_llh_to_ecef(lat, lon, h, x);
+        for (int k = 0; k < n_st; k++) {
+            double ux = (x[0] - s[k][0]) / r[k], uy = (x[1] - s[k][1]) / r[k], uz = (x[2] - s[k][2]) / r[k];
+            g[k][0] = -so * ux + co * uy;
+            g[k][1] = -sl * co * ux - sl * so * uy + cl * uz;
+            g[k][2] = cl * co * ux + cl * so * uy + sl * uz;
+        }
+        double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, b[3] = {0, 0, 0};
+        int q = 0;
+        for (int i = 0; i < n_st; i++)
+            for (int j = i + 1; j < n_st; j++, q++) {
+                double fq = (r[j] - r[i]) - rd[q];
+                double row[3] = {g[j][0] - g[i][0], g[j][1] - g[i][1], g[j][2] - g[i][2]};
+                for (int u = 0; u < 3; u++) {
+                    b[u] += row[u] * fq;
+                    for (int v = 0; v < 3; v++) A[u][v] += row[u] * row[v];
+                }
+            }
+        int moved = 0;
+        double d[3] = {0, 0, 0};
+        for (int tr = 0; tr < 8 && !moved; tr++) {
+            if (!ls_step(A, b, lambda, dims, d)) { lambda *= 10.0; continue; }
+            double clat = lat + d[1] / (Mr + h) * 180.0 / M_PI;
+            double clon = lon + d[0] / ((Nr + h) * cl) * 180.0 / M_PI;
+            double ch = dims == 3 ? h + d[2] : h;
+            double cc = ls_cost(s, n_st, rd, clat, clon, ch, rc);
+            if (cc < cost) {
+                lat = clat; lon = clon; h = ch; cost = cc; moved = 1;
+                for (int k = 0; k < n_st; k++) r[k] = rc[k];
+                lambda = fmax(lambda / 3.0, 1e-12);
+            } else {
+                lambda *= 4.0;
+            }
+        }
+        if (!moved) break;
+        if (sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) < 1e-6) { it++; break; }
+    }
+    out_llh[0] = lat; out_llh[1] = lon; out_llh[2] = h;
+    if (out_rms) *out_rms = P > 0 ? sqrt(cost / P) : 0.0;
+    if (iters) *iters = it;
+    free(s); free(g); free(r); free(rc);
+    return cost == cost ? 0 : 1;
+}
+
 /* ======================================================================================
  * Per-file signal quality analysis: fast_analyzer.go and analyzer.go.
  * `s` is the signal's interleaved uint8 I,Q bytes (the reference concatenates blocks 1

@@ -24,7 +24,7 @@ ERRORS = {-1: "TDOA_E_INVALID", -2: "TDOA_E_NODEVICE", -3: "TDOA_E_CUDA", -4: "T
 ABI_SYMBOLS = [
     "tdoa_default_config", "tdoa_create", "tdoa_destroy", "tdoa_last_error", "tdoa_host_alloc", "tdoa_host_free",
     "tdoa_load_u8", "tdoa_load_u8_pinned", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_xcorr_info", "tdoa_analyze",
-    "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
+    "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_solve_ls", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
     "tdoa_set_stream", "tdoa_synchronize", "tdoa_selftest",
 ]
 
@@ -142,6 +142,7 @@ def load_library():
     L.tdoa_cross_correlate.argtypes = [vp, vp, i64, vp, i64, C.POINTER(PeakStruct)]
     L.tdoa_baselines.argtypes = [vp, vp, i32, vp]
     L.tdoa_solve.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
+    L.tdoa_solve_ls.argtypes = [vp, vp, i32, vp, i32, i32, vp, i32, vp, vp, vp, vp]
     L.tdoa_grid.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp]
     L.tdoa_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.tdoa_stream.argtypes = [vp]
@@ -358,6 +359,28 @@ class Engine:
         if single:
             return out[0], int(status[0]), int(iters[0])
         return out, status, iters
+
+    def solve_ls(self, stations_llh, range_diffs, init_llh=None, dims: int = 2):
+        """Levenberg-Marquardt fix over all pair range differences (engine-defined).
+        Returns (llh, rms_m, status, iters); arrays when range_diffs is 2-D."""
+        st = np.ascontiguousarray(stations_llh, dtype=np.float64).reshape(-1, 3)
+        rd = np.ascontiguousarray(range_diffs, dtype=np.float64)
+        single = rd.ndim == 1
+        rd = rd.reshape(1, -1) if single else rd
+        n, stride = rd.shape
+        init = None
+        if init_llh is not None:
+            init = np.ascontiguousarray(np.broadcast_to(np.asarray(init_llh, np.float64).reshape(-1, 3), (n, 3)))
+        out = np.zeros((n, 3), np.float64)
+        rms = np.zeros(n, np.float64)
+        status = np.zeros(n, np.int32)
+        iters = np.zeros(n, np.int32)
+        self._check(self._lib.tdoa_solve_ls(self._h, _ptr(st), st.shape[0], _ptr(rd), n, stride,
+                                            _ptr(init) if init is not None else None, dims, _ptr(out), _ptr(rms),
+                                            _ptr(status), _ptr(iters)))
+        if single:
+            return out[0], float(rms[0]), int(status[0]), int(iters[0])
+        return out, rms, status, iters
 
     def grid(self, stations_llh, grid_desc, range_diffs):
         st = np.ascontiguousarray(stations_llh, dtype=np.float64).reshape(-1, 3)

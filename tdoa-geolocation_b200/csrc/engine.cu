@@ -1657,6 +1657,43 @@ int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_stations, co
     return end_call(e, true);
 }
 
+int tdoa_solve_ls(tdoa_engine *e, const double *stations_llh, int32_t n_stations, const double *range_diffs,
+                  int32_t n_sets, int32_t rd_stride, const double *init_llh, int32_t dims, double *out_llh,
+                  double *out_rms, int32_t *status, int32_t *iters)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    const int P = n_stations * (n_stations - 1) / 2;
+    if (!stations_llh || !range_diffs || !out_llh || !status || n_sets < 0 || rd_stride < P)
+        return fail(e, TDOA_E_INVALID, "tdoa_solve_ls: bad arguments");
+    if (n_stations < 3 || n_stations > solve_ls_max_stations())
+        return fail(e, TDOA_E_INVALID, "tdoa_solve_ls: 3..%d stations, got %d", solve_ls_max_stations(), n_stations);
+    if (dims != 2 && dims != 3) return fail(e, TDOA_E_INVALID, "tdoa_solve_ls: dims must be 2 or 3");
+    if (dims == 3 && n_stations < 4)
+        return fail(e, TDOA_E_INVALID, "tdoa_solve_ls: elevation needs at least 4 stations (3 range differences)");
+    if (n_sets == 0) return end_call(e, true);
+    double *d_llh = nullptr, *d_rd = nullptr, *d_init = nullptr, *d_out = nullptr, *d_rms = nullptr;
+    int *d_status = nullptr, *d_iters = nullptr;
+    if ((rc = alloc_t(e, &d_llh, (size_t)3 * n_stations)) || (rc = alloc_t(e, &d_rd, (size_t)n_sets * rd_stride)) ||
+        (rc = alloc_t(e, &d_out, (size_t)3 * n_sets)) || (rc = alloc_t(e, &d_rms, (size_t)n_sets)) ||
+        (rc = alloc_t(e, &d_status, (size_t)n_sets)) || (rc = alloc_t(e, &d_iters, (size_t)n_sets)))
+        return rc;
+    CU(cudaMemcpyAsync(d_llh, stations_llh, (size_t)3 * n_stations * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_rd, range_diffs, (size_t)n_sets * rd_stride * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (init_llh) {
+        if ((rc = alloc_t(e, &d_init, (size_t)3 * n_sets))) return rc;
+        CU(cudaMemcpyAsync(d_init, init_llh, (size_t)3 * n_sets * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
+    launch_solve_ls(d_llh, n_stations, d_rd, n_sets, rd_stride, d_init, dims, d_out, d_rms, d_status, d_iters, e->stream);
+    count_launch(e);
+    CU(cudaMemcpyAsync(out_llh, d_out, (size_t)3 * n_sets * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (out_rms) CU(cudaMemcpyAsync(out_rms, d_rms, (size_t)n_sets * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(status, d_status, (size_t)n_sets * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (iters) CU(cudaMemcpyAsync(iters, d_iters, (size_t)n_sets * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    return end_call(e, true);
+}
+
 int tdoa_analyze(tdoa_engine *e, int32_t station, int32_t fast, tdoa_signal_quality *ref, tdoa_signal_quality *tgt)
 {
     if (!e) return TDOA_E_INVALID;

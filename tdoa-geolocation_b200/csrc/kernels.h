@@ -148,6 +148,9 @@ void launch_quality(const QualJob *d_jobs, int n_jobs, int n_stat_cta, int max_m
 void launch_baselines(const double *d_llh, int n_st, double *d_out, cudaStream_t st);
 void launch_solve(const double *d_llh, const double *d_rd, int n_sets, int rd_stride, double *d_out_llh,
                   int *d_status, int *d_iters, cudaStream_t st);
+void launch_solve_ls(const double *d_llh, int n_st, const double *d_rd, int n_sets, int rd_stride, const double *d_init,
+                     int dims, double *d_out_llh, double *d_rms, int *d_status, int *d_iters, cudaStream_t st);
+int solve_ls_max_stations();
 void launch_grid_cells(const double *d_llh, int n_st, const double *d_grid_desc, int nlat, int nlon,
                        const double *d_rd, int n_sets, int rd_stride, double *d_best_cost, i64 *d_best_idx,
                        double *d_out_llh, void *d_scratch, cudaStream_t st);

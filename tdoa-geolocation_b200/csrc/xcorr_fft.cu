@@ -291,7 +291,50 @@ __device__ __forceinline__ void cand_sweep_ng(int ng, const float *s_t, const fl
     else cand_sweep<8, STAGED, F64>(s_t, s_s, J, sc_s, sbase, clen, off, acc);
 }
 
-// One CTA: block blockIdx.x of the template (B samples), pair blockIdx.y, every candidate.
+// Single candidate, vector path: the template block is 16-byte aligned, the signal starts A
+// floats past an aligned address.  Each thread takes 4 consecutive samples per step from
+// 128-bit loads (two for the signal, picked apart by the compile-time shift A), 4 steps in
+// flight: 192 bytes of loads per thread instead of 48, which is what this latency-bound
+// sweep needs.  Returns the thread's partial sum over samples [0, 4 * (len / 4)).
+template <int A, bool F64>
+__device__ __forceinline__ double cand_sweep_vec(const float *__restrict__ tp, const float *__restrict__ sp, int len,
+                                                 float sc_t, float sc_s)
+{
+    const float4 *__restrict__ tp4 = reinterpret_cast<const float4 *>(tp);
+    const float4 *__restrict__ sp4 = reinterpret_cast<const float4 *>(sp - A);
+    const int n4 = len >> 2;
+    double acc = 0.0;
+    auto mac = [&](const float4 &t, const float4 &lo, const float4 &hi) {
+        float sv[4];
+        if (A == 0) { sv[0] = lo.x; sv[1] = lo.y; sv[2] = lo.z; sv[3] = lo.w; }
+        else if (A == 1) { sv[0] = lo.y; sv[1] = lo.z; sv[2] = lo.w; sv[3] = hi.x; }
+        else if (A == 2) { sv[0] = lo.z; sv[1] = lo.w; sv[2] = hi.x; sv[3] = hi.y; }
+        else { sv[0] = lo.w; sv[1] = hi.x; sv[2] = hi.y; sv[3] = hi.z; }
+        const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float a = __fmul_rn(tv[k], sc_t), b = __fmul_rn(sv[k], sc_s);
+            if (F64) acc = __dadd_rn(acc, __dmul_rn((double)a, (double)b));
+            else acc = __dadd_rn(acc, (double)__fmul_rn(a, b));
+        }
+    };
+    int j = threadIdx.x;
+    for (; j + 3 * kCandThreads < n4; j += 4 * kCandThreads) {
+        float4 t[4], lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            t[u] = tp4[j + u * kCandThreads];
+            lo[u] = sp4[j + u * kCandThreads];
+            hi[u] = A ? sp4[j + u * kCandThreads + 1] : lo[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) mac(t[u], lo[u], hi[u]);
+    }
+    for (; j < n4; j += kCandThreads) mac(tp4[j], sp4[j], A ? sp4[j + 1] : sp4[j]);
+    return acc;
+}
+
+// One CTA: block b of the template (B samples) of one pair, every candidate.
 // f32 product, widened, f64 accumulate (processor.go:703-705); per-thread partial sums in
 // ascending i, then a fixed reduction tree -- deterministic, not the reference's order
 // (differences ~1e-16 relative; the brute-force kernel keeps the reference's order).
@@ -329,7 +372,26 @@ __global__ void __launch_bounds__(kCandThreads) k_corr_candidates(const PairJob 
 #pragma unroll
         for (int c = 0; c < kCandGroup; c++) acc[c] = 0.0;
         const i64 s_first = blk_start + J.lag0 + dmin;
-        if (ng <= 2 && s_first >= 0 && s_first + blk_len + span <= J.sl) {
+        if (ng == 1 && s_first >= 0 && s_first + blk_len + 4 <= J.sl && ((J.t_off + blk_start) & 3) == 0 &&
+            (reinterpret_cast<uintptr_t>(J.t_re) & 15) == 0 && (reinterpret_cast<uintptr_t>(J.s_re) & 15) == 0) {
+            const float *__restrict__ tp = J.t_re + J.t_off + blk_start;
+            const float *__restrict__ sp = J.s_re + s_first;
+            const int len = (int)blk_len;
+            const int a = (int)(s_first & 3);
+            double v;
+            if (exact_f64) {
+                v = a == 0 ? cand_sweep_vec<0, true>(tp, sp, len, sc_t, sc_s) : a == 1 ? cand_sweep_vec<1, true>(tp, sp, len, sc_t, sc_s)
+                  : a == 2 ? cand_sweep_vec<2, true>(tp, sp, len, sc_t, sc_s) : cand_sweep_vec<3, true>(tp, sp, len, sc_t, sc_s);
+            } else {
+                v = a == 0 ? cand_sweep_vec<0, false>(tp, sp, len, sc_t, sc_s) : a == 1 ? cand_sweep_vec<1, false>(tp, sp, len, sc_t, sc_s)
+                  : a == 2 ? cand_sweep_vec<2, false>(tp, sp, len, sc_t, sc_s) : cand_sweep_vec<3, false>(tp, sp, len, sc_t, sc_s);
+            }
+            for (int i = (len & ~3) + tid; i < len; i += kCandThreads) {  // the block's last len % 4 samples
+                const float t = __fmul_rn(tp[i], sc_t), q = __fmul_rn(sp[i], sc_s);
+                v = exact_f64 ? __dadd_rn(v, __dmul_rn((double)t, (double)q)) : __dadd_rn(v, (double)__fmul_rn(t, q));
+            }
+            acc[0] = v;
+        } else if (ng <= 2 && s_first >= 0 && s_first + blk_len + span <= J.sl) {
             // sharp peak (the common case): stream both signals straight from global
             // memory, 4 independent strides in flight per thread, no staging, no barriers
             const float *__restrict__ tp = J.t_re + J.t_off + blk_start;
@@ -422,11 +484,26 @@ __global__ void __launch_bounds__(256) k_peak_candidates(const PairJob *jobs, co
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_all = *C.n_cand;
     const int n_cand = min(n_all, C.max_cand);
-    for (int c = wid; c < n_cand; c += 8) {
+    // few candidates and many blocks (the sharp-peak, long-signal case): the whole CTA adds
+    // one candidate's blocks -- thread t takes blocks t, t + 256, ...; then the fixed tree
+    __shared__ double s_part[8];
+    const bool wide = n_cand < 8 && J.nb > 1024;
+    for (int c = wide ? 0 : wid; c < n_cand; c += wide ? 1 : 8) {
         double v = 0.0;
-        for (i64 b = lane; b < J.nb; b += 32) v += C.blocksums[(size_t)c * J.nb + b];
-        v = warp_sum(v);
-        if (lane == 0) {
+        if (wide) {
+            for (i64 b = tid; b < J.nb; b += 256) v += C.blocksums[(size_t)c * J.nb + b];
+            v = warp_sum(v);
+            __syncthreads();
+            if (lane == 0) s_part[wid] = v;
+            __syncthreads();
+            v = 0.0;
+            if (tid == 0)
+                for (int w = 0; w < 8; w++) v += s_part[w];
+        } else {
+            for (i64 b = lane; b < J.nb; b += 32) v += C.blocksums[(size_t)c * J.nb + b];
+            v = warp_sum(v);
+        }
+        if (wide ? tid == 0 : lane == 0) {
             if (J.variant == CORR_EXTENDED) v = J.n_t > 0 ? v / (double)J.n_t : 0.0;
             else {
                 v = J.nb > 0 ? v / (double)J.nb : 0.0;

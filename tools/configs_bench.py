@@ -129,7 +129,7 @@ def main():
     # ---- config 4: 16 stations (120 pairs), windowed
     st16 = ring_stations(16)
     d16, _ = delays_for(st16)
-    block = 4_000_000 if args.quick else 16_000_000
+    block = 4_000_000 if args.quick else 66_666_666
     caps = synth(dev, 16, block, d16)
     nw = block // W
     want16 = [int(d16[j] - d16[i]) for i in range(16) for j in range(i + 1, 16)]
