@@ -36,6 +36,7 @@ extern "C" {
 #define TDOA_E_NOMEM (-4)     /* device or pinned-host allocation failed           */
 #define TDOA_E_STATE (-5)     /* call sequence error (e.g. station not loaded)     */
 #define TDOA_E_SINGULAR (-6)  /* solveTDOA: singular Jacobian (processor.go:997)   */
+#define TDOA_E_IO (-7)        /* loadIQData: open / stat / read failed (:170-191)  */
 
 /* processing modes (tdoa_config.mode) */
 #define TDOA_MODE_SOURCE 0   /* processor.go as committed: complex64 box-car path,
@@ -96,7 +97,10 @@ typedef struct {
                               EXTENDED); -1 = never                                   */
     int32_t copy_chunk;    /* tdoa_load_u8_pinned: samples per host->device copy chunk
                               (multiple of 4096); 0 = 16777216 (32 MB of capture)    */
-    int32_t reserved[5];
+    int32_t guard_samples; /* samples dropped at the start of blocks 2 and 3 (the retune
+                              transient, collector.go:85 / rtl_sdr.c:117-135); 0 = the
+                              reference's split (processor.go:208-267)                */
+    int32_t reserved[4];
 } tdoa_config;
 
 /* Fill *cfg with the reference-matching defaults of `mode`. */
@@ -114,6 +118,11 @@ TDOA_API void tdoa_host_free(void *p);
  * hands one station's whole .dat capture (interleaved uint8 I,Q) to the engine.
  * The bytes are copied to the device before the call returns. */
 TDOA_API int tdoa_load_u8(tdoa_engine *e, int32_t station, const uint8_t *iq, size_t nbytes);
+/* loadIQData on a file (processor.go:166-205): streams the .dat capture to the device
+ * through two pinned 32 MB staging buffers (disk read of one piece overlaps the PCIe copy
+ * of the previous).  *n_samples (may be NULL) = file size / 2 (:183).  Errors carry the
+ * reference's messages ("failed to open file: ...", TDOA_E_IO). */
+TDOA_API int tdoa_load_file(tdoa_engine *e, int32_t station, const char *path, int64_t *n_samples);
 /* Same for a capture in memory obtained from tdoa_host_alloc (C memory, outside the Go
  * heap, so the cgo pointer rules do not apply): returns at once.  The host -> device
  * copies are queued by the next call that needs the capture -- the blocks of the signal

@@ -18,12 +18,12 @@ KIND_REF, KIND_TGT = 0, 1
 PEAK_RESEARCHED, PEAK_EDGE, PEAK_BRUTE, PEAK_EMPTY = 0x1, 0x2, 0x4, 0x8
 
 ERRORS = {-1: "TDOA_E_INVALID", -2: "TDOA_E_NODEVICE", -3: "TDOA_E_CUDA", -4: "TDOA_E_NOMEM",
-          -5: "TDOA_E_STATE", -6: "TDOA_E_SINGULAR"}
+          -5: "TDOA_E_STATE", -6: "TDOA_E_SINGULAR", -7: "TDOA_E_IO"}
 
 # every symbol include/tdoa_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "tdoa_default_config", "tdoa_create", "tdoa_destroy", "tdoa_last_error", "tdoa_host_alloc", "tdoa_host_free",
-    "tdoa_load_u8", "tdoa_load_u8_pinned", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_xcorr_info", "tdoa_analyze",
+    "tdoa_load_u8", "tdoa_load_file", "tdoa_load_u8_pinned", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_xcorr_info", "tdoa_analyze",
     "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_solve_ls", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
     "tdoa_set_stream", "tdoa_synchronize", "tdoa_selftest",
 ]
@@ -40,7 +40,7 @@ class Config(C.Structure):
         ("sample_rate", C.c_double), ("mode", C.c_int32), ("n_stations", C.c_int32),
         ("chunk_samples", C.c_int32), ("max_lag", C.c_int32), ("block_size", C.c_int32),
         ("sanity_lag", C.c_int32), ("fast_demod", C.c_int32), ("use_fft", C.c_int32),
-        ("device", C.c_int32), ("seq_dc_limit", C.c_int32), ("copy_chunk", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("device", C.c_int32), ("seq_dc_limit", C.c_int32), ("copy_chunk", C.c_int32), ("guard_samples", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -132,6 +132,7 @@ def load_library():
     L.tdoa_host_free.restype = None
     L.tdoa_load_u8.argtypes = [vp, i32, vp, C.c_size_t]
     L.tdoa_load_u8_pinned.argtypes = [vp, i32, vp, C.c_size_t]
+    L.tdoa_load_file.argtypes = [vp, i32, C.c_char_p, C.POINTER(i64)]
     L.tdoa_load_u8_device.argtypes = [vp, i32, vp, C.c_size_t]
     L.tdoa_unpack.argtypes = [vp, i32, i64, i64, vp]
     L.tdoa_preprocess.argtypes = [vp, i32, i32, i64, i64, vp, f64p, C.POINTER(i32)]
@@ -273,6 +274,12 @@ class Engine:
             iq = np.ascontiguousarray(iq, dtype=np.uint8)
             ptr, n = _ptr(iq), iq.size
         self._check(self._lib.tdoa_load_u8(self._h, station, ptr, n))
+
+    def load_file(self, station: int, path) -> int:
+        """loadIQData (processor.go:166-205): streams a .dat capture to the device; returns the sample count."""
+        n = C.c_int64(0)
+        self._check(self._lib.tdoa_load_file(self._h, station, str(path).encode(), C.byref(n)))
+        return int(n.value)
 
     def load_u8_pinned(self, station: int, buf: "PinnedBuffer") -> None:
         """Lazy load from tdoa_host_alloc memory: returns at once; the copies are queued by the next

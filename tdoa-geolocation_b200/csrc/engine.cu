@@ -7,8 +7,12 @@
 // There is no CPU fallback anywhere in this file: every numeric result is produced
 // by a kernel on the engine's device, and tdoa_create fails without an sm_100 GPU.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -88,6 +92,8 @@ struct tdoa_engine {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;   // host -> device copies of lazily loaded captures
+    void *h_stage[2] = {nullptr, nullptr};        // tdoa_load_file: pinned staging, double buffered
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_reload = nullptr;
     std::vector<Station> stations;
     std::string error;
@@ -249,26 +255,33 @@ void spans_collect(tdoa_engine *e)
 
 // processor.go:208-267: block = N/3; REF = blocks 1 and 3 concatenated, TGT = block 2;
 // fewer than 3 samples: the data is returned unchanged.
-i64 signal_length(const Station &s, int kind)
+// guard = samples dropped at the start of blocks 2 and 3 (0: the reference's split).  The
+// retune of the dual-frequency recorder is issued from the USB callback while up to 15
+// buffers of 262144 bytes are in flight (rtl_sdr.c:117-135, librtlsdr.c:358), so the first
+// samples of a block after a retune still carry the other frequency ("contamination
+// dilution", collector.go:85); an engine-defined option, not reference behaviour.
+i64 signal_length(const Station &s, int kind, i64 guard)
 {
     const i64 b = s.nsamp / 3;
     if (b == 0) return s.nsamp;
-    return kind == TDOA_KIND_REF ? 2 * b : b;
+    const i64 g = std::min(guard, b);
+    return kind == TDOA_KIND_REF ? 2 * b - g : b - g;
 }
 
-SigSrc make_view(const Station &s, int kind, i64 start, i64 len)
+SigSrc make_view(const Station &s, int kind, i64 start, i64 len, i64 guard)
 {
     SigSrc v{};
     v.raw = s.d_raw;
     const i64 b = s.nsamp / 3;
+    const i64 g = std::min(guard, b);
     if (b == 0) {
         v.run0_start = start; v.run0_len = len; v.run1_start = 0;
     } else if (kind == TDOA_KIND_TGT) {
-        v.run0_start = b + start; v.run0_len = len; v.run1_start = 0;
+        v.run0_start = b + g + start; v.run0_len = len; v.run1_start = 0;
     } else if (start < b) {
-        v.run0_start = start; v.run0_len = std::min(len, b - start); v.run1_start = 2 * b;
+        v.run0_start = start; v.run0_len = std::min(len, b - start); v.run1_start = 2 * b + g;
     } else {
-        v.run0_start = 2 * b + (start - b); v.run0_len = len; v.run1_start = 0;
+        v.run0_start = 2 * b + g + (start - b); v.run0_len = len; v.run1_start = 0;
     }
     return v;
 }
@@ -1048,7 +1061,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
     // window length per station
     std::vector<i64> len(S);
     for (int s = 0; s < S; s++) {
-        const i64 n = signal_length(e->stations[s], kind);
+        const i64 n = signal_length(e->stations[s], kind, e->cfg.guard_samples);
         if (win_len == 0) {
             // processor.go:772-780: truncate to the test chunk when longer
             i64 l = n - win_start;
@@ -1090,7 +1103,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
             for (int s = 0; s < S; s++) {
                 Sig &sg = sigs[(size_t)w * S + s];
                 sg.n = len[s];
-                sg.src = make_view(e->stations[s], kind, win_start + (i64)(w0 + w) * hop, len[s]);
+                sg.src = make_view(e->stations[s], kind, win_start + (i64)(w0 + w) * hop, len[s], e->cfg.guard_samples);
                 sg.memo = s * 2 + kind;
                 sg.station = s; sg.kind = kind; sg.q0 = win_start + (i64)(w0 + w) * hop;
             }
@@ -1239,7 +1252,8 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
         return fail(nullptr, TDOA_E_INVALID, "tdoa_create: bad mode %d", cfg->mode);
     if (cfg->n_stations < 2 || cfg->n_stations > 64)
         return fail(nullptr, TDOA_E_INVALID, "tdoa_create: n_stations must be 2..64, got %d", cfg->n_stations);
-    if (cfg->max_lag < 0 || cfg->block_size < 1 || cfg->chunk_samples < 0 || cfg->sanity_lag < 0)
+    if (cfg->max_lag < 0 || cfg->block_size < 1 || cfg->chunk_samples < 0 || cfg->sanity_lag < 0 || cfg->guard_samples < 0 ||
+        cfg->copy_chunk < 0)
         return fail(nullptr, TDOA_E_INVALID, "tdoa_create: negative size in config");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) {
@@ -1318,6 +1332,10 @@ void tdoa_destroy(tdoa_engine *e)
         for (cudaEvent_t ev : s.event_pool) cudaEventDestroy(ev);
     }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int k = 0; k < 2; k++) {
+        if (e->h_stage[k]) cudaFreeHost(e->h_stage[k]);
+        if (e->ev_stage[k]) cudaEventDestroy(e->ev_stage[k]);
+    }
     if (e->ev_reload) cudaEventDestroy(e->ev_reload);
     if (e->h_frame) cudaFreeHost(e->h_frame);
     if (e->d_frame) cudaFree(e->d_frame);
@@ -1386,7 +1404,8 @@ int tdoa_load_u8_pinned(tdoa_engine *e, int32_t station, const uint8_t *pinned_i
 {
     if (!e) return TDOA_E_INVALID;
     // small captures gain nothing from following the copy
-    if (nbytes < (size_t)12 * 4096 * 8) return tdoa_load_u8(e, station, pinned_iq, nbytes);
+    // (and the chunk map below is written for the reference's split: no guard)
+    if (nbytes < (size_t)12 * 4096 * 8 || e->cfg.guard_samples > 0) return tdoa_load_u8(e, station, pinned_iq, nbytes);
     int rc = begin_call(e);
     if (rc) return rc;
     if (station < 0 || station >= e->cfg.n_stations)
@@ -1405,6 +1424,79 @@ int tdoa_load_u8_pinned(tdoa_engine *e, int32_t station, const uint8_t *pinned_i
     s.nbytes = nbytes;
     s.nsamp = (i64)(nbytes / 2);
     s.loaded = true;
+    return TDOA_OK;
+}
+
+// loadIQData for a file (processor.go:166-191): the capture is read in 32 MB pieces into two
+// pinned staging buffers and copied to the device from there, the read of one piece
+// overlapping the PCIe copy of the previous one; nothing of the file stays in host memory.
+int tdoa_load_file(tdoa_engine *e, int32_t station, const char *path, int64_t *n_samples)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (station < 0 || station >= e->cfg.n_stations) return fail(e, TDOA_E_INVALID, "tdoa_load_file: bad station %d", station);
+    if (!path) return fail(e, TDOA_E_INVALID, "tdoa_load_file: NULL path");
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(e, TDOA_E_IO, "failed to open file: %s: %s", path, strerror(errno));  // processor.go:170-172
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) {
+        const int err = errno;
+        close(fd);
+        return fail(e, TDOA_E_IO, "failed to get file size: %s", strerror(err));  // processor.go:177-179
+    }
+    const size_t nbytes = (size_t)sb.st_size;
+    Station &s = e->stations[station];
+    if ((rc = station_buffer(e, s, nbytes))) { close(fd); return rc; }
+    constexpr size_t kPiece = (size_t)32 << 20;
+    for (int k = 0; k < 2; k++) {
+        if (!e->h_stage[k]) {
+            if (cudaMallocHost(&e->h_stage[k], kPiece) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_stage[k], cudaEventDisableTiming) != cudaSuccess) {
+                close(fd);
+                return fail(e, TDOA_E_NOMEM, "tdoa_load_file: pinned staging allocation failed");
+            }
+        }
+    }
+    // kernels queued earlier may still read the station's previous capture
+    cudaEventRecord(e->ev_reload, e->stream);
+    cudaStreamWaitEvent(e->copy_stream, e->ev_reload, 0);
+    size_t off = 0;
+    int piece = 0;
+    bool used[2] = {false, false};
+    while (off < nbytes) {
+        const int k = piece & 1;
+        if (used[k]) cudaEventSynchronize(e->ev_stage[k]);  // the copy out of this buffer has finished
+        const size_t want = std::min(kPiece, nbytes - off);
+        size_t got = 0;
+        while (got < want) {
+            const ssize_t r = read(fd, static_cast<uint8_t *>(e->h_stage[k]) + got, want - got);
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) {
+                const int err = errno;
+                close(fd);
+                cudaStreamSynchronize(e->copy_stream);
+                return fail(e, TDOA_E_IO, "failed to read data: %s", r == 0 ? "unexpected end of file" : strerror(err));  // :189-191
+            }
+            got += (size_t)r;
+        }
+        cudaError_t ce = cudaMemcpyAsync(s.owned + off, e->h_stage[k], want, cudaMemcpyHostToDevice, e->copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_stage[k], e->copy_stream);
+        if (ce != cudaSuccess) {
+            close(fd);
+            return fail(e, TDOA_E_CUDA, "tdoa_load_file: copy failed: %s", cudaGetErrorString(ce));
+        }
+        used[k] = true;
+        off += want;
+        piece++;
+    }
+    close(fd);
+    CU(cudaStreamSynchronize(e->copy_stream));
+    s.d_raw = s.owned;
+    s.nbytes = nbytes;
+    s.nsamp = (i64)(nbytes / 2);  // processor.go:183  numSamples = fileSize / 2
+    s.loaded = true;
+    if (n_samples) *n_samples = s.nsamp;
     return TDOA_OK;
 }
 
@@ -1495,13 +1587,13 @@ int tdoa_preprocess(tdoa_engine *e, int32_t station, int32_t kind, int64_t start
         return fail(e, TDOA_E_STATE, "tdoa_preprocess: station %d not loaded", station);
     if (kind != TDOA_KIND_REF && kind != TDOA_KIND_TGT) return fail(e, TDOA_E_INVALID, "tdoa_preprocess: bad kind");
     const Station &s = e->stations[station];
-    const i64 n = signal_length(s, kind);
+    const i64 n = signal_length(s, kind, e->cfg.guard_samples);
     if (start < 0 || len < 0 || start + len > n || (!out_c64 && len))
         return fail(e, TDOA_E_INVALID, "tdoa_preprocess: range [%lld,+%lld) outside %lld samples", (long long)start,
                     (long long)len, (long long)n);
     std::vector<Sig> sigs(1);
     sigs[0].n = len;
-    sigs[0].src = make_view(s, kind, start, len);
+    sigs[0].src = make_view(s, kind, start, len, e->cfg.guard_samples);
     sigs[0].station = station; sigs[0].kind = kind; sigs[0].q0 = start;
     if ((rc = queue_lazy_copies(e, kind))) return rc;
     if ((rc = preprocess(e, sigs))) return rc;
@@ -1723,7 +1815,7 @@ int tdoa_analyze(tdoa_engine *e, int32_t station, int32_t fast, tdoa_signal_qual
         } else {
             // analyzer.go:111-121: whole blocks
             J.n = k == 0 ? 2 * block : block;
-            J.src = make_view(s, k == 0 ? TDOA_KIND_REF : TDOA_KIND_TGT, 0, J.n);
+            J.src = make_view(s, k == 0 ? TDOA_KIND_REF : TDOA_KIND_TGT, 0, J.n, 0);
         }
         const i64 msz = fast ? 8192 : 16384;
         J.m = (int)std::min<i64>(msz, J.n);

@@ -105,12 +105,11 @@ class TDOAProcessor:
     def load_iq_data(self, slot: int, filename: str, n_stations: int) -> int:
         self._print(f"Loading I/Q data from: {filename}")
         try:
-            raw = np.fromfile(filename, dtype=np.uint8)
-        except OSError as exc:
-            raise RuntimeError(f"failed to open file: {exc}") from exc
-        n = raw.size // 2
-        self._print(f"File size: {raw.size} bytes, samples: {n}")
-        self.engine(n_stations).load_u8(slot, raw)
+            # tdoa_load_file: streamed to the device through pinned staging, never held on the host
+            n = self.engine(n_stations).load_file(slot, filename)
+        except N.TdoaError as exc:
+            raise RuntimeError(str(exc)) from exc   # "failed to open file: ..." as processor.go:170-172
+        self._print(f"File size: {os.path.getsize(filename)} bytes, samples: {n}")
         self._print(f"Successfully loaded {n} complex samples")
         return n
 

@@ -406,3 +406,49 @@ def test_pinned_lazy_load_equals_synchronous_load(copy_chunk):
         assert int(got["lag"]) == w[0] and abs(float(got["corr"]) - w[1]) <= CORR_TOL
     for b in bufs:
         b.free()
+
+
+# ------------------------------------------------------------------ streaming file loader, guard samples
+def test_load_file_streams_the_capture(tmp_path, eng_binary):
+    """tdoa_load_file (loadIQData, processor.go:166-205): same device bytes as tdoa_load_u8,
+    the reference's sample count (:183) and its error text for a missing file (:170-172)."""
+    raws = fm_capture(60001, (0, 4, 9), (0, 11, 25), seed=33)   # odd sizes: N % 3 != 0 and a ragged last piece
+    for k, r in enumerate(raws):
+        p = tmp_path / f"sim-st{k}-1.dat"
+        r.tofile(p)
+        assert eng_binary.load_file(k, p) == r.size // 2
+        n = r.size // 2
+        assert np.array_equal(eng_binary.unpack(k, n - 1000, 1000), oracle.unpack_u8(r)[n - 1000:])
+        assert np.array_equal(eng_binary.unpack(k, 0, 1000), oracle.unpack_u8(r)[:1000])
+    got = eng_binary.xcorr(T.KIND_TGT)[0]
+    load_all(eng_binary, raws)
+    want = eng_binary.xcorr(T.KIND_TGT)[0]
+    assert np.array_equal(got["lag"], want["lag"]) and np.array_equal(got["corr"], want["corr"])
+    with pytest.raises(T.TdoaError) as ei:
+        eng_binary.load_file(0, tmp_path / "absent.dat")
+    assert ei.value.code == -7 and "failed to open file" in str(ei.value)
+    big = np.random.default_rng(5).integers(0, 256, 70_000_000, dtype=np.uint8)   # three 32 MB pieces
+    big.tofile(tmp_path / "big.dat")
+    assert eng_binary.load_file(1, tmp_path / "big.dat") == big.size // 2
+    for first in (0, (32 << 19) - 8, (32 << 20) - 8, big.size // 2 - 16):
+        assert np.array_equal(eng_binary.unpack(1, first, 16), oracle.unpack_u8(big[2 * first:2 * first + 32]))
+
+
+def test_guard_samples_trim_the_retuned_blocks():
+    """guard_samples = G (engine-defined; 0 is the reference's split): REF = block 1 ++ block 3[G:],
+    TGT = block 2[G:]; everything downstream is the reference's arithmetic on those signals."""
+    G = 5000
+    raws = fm_capture(90000, (0, 6, 13), (0, 15, 33), seed=44)
+    with T.Engine(T.MODE_BINARY, guard_samples=G) as e:
+        load_all(e, raws)
+        ref = e.xcorr(T.KIND_REF)[0]
+        tgt = e.xcorr(T.KIND_TGT)[0]
+    sigs = []
+    for r in raws:
+        d = oracle.unpack_u8(r)
+        b = len(d) // 3
+        sigs.append((np.concatenate([d[:b], d[2 * b + G:3 * b]]), d[b + G:2 * b]))
+    for p, (i, j) in enumerate([(0, 1), (0, 2), (1, 2)]):
+        for got, k in ((ref[p], 0), (tgt[p], 1)):
+            d, c, _ = oracle.cross_correlate_binary(sigs[i][k], sigs[j][k])
+            assert int(got["lag"]) == d and abs(float(got["corr"]) - c) <= CORR_TOL
