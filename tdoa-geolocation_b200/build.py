@@ -29,6 +29,7 @@ UNITS = [
     ("analyze.cu", ["-fmad=false"]),
     ("xcorr_fft.cu", []),
     ("xcorr_tile.cu", []),
+    ("xcorr_big.cu", []),
     ("engine.cu", []),
 ]
 

@@ -111,6 +111,7 @@ struct tdoa_engine {
     bool ev_valid = false;
     int64_t launches_at_call = 0;
     float2 *d_tw = nullptr;  // FFT twiddle table
+    float2 *d_tw_fine = nullptr;  // W_N^k, k < 2048, of the 2^21-point transform
     std::vector<int8_t> branch_memo;  // last preprocess branch per (station, kind); -1 unknown
     std::vector<tdoa_signal_info> info_sig[2];  // window 0 of the last xcorr per kind
     std::vector<double> info_first[2];
@@ -838,10 +839,26 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
             }
         }
     }
+    // wide lag ranges go through the 2^21-point transform in global memory (xcorr_big.cu)
+    std::vector<char> big_plan(np, 0), big_tile(tiles.size(), 0);
+    if (tiled && e->cfg.use_fft != 3) {
+        for (size_t ti = 0; ti < tiles.size(); ti++) {
+            int lead = -1;
+            for (int q = 0; q < 4; q++) if (tiles[ti].plan[q] >= 0) lead = tiles[ti].plan[q];
+            const PairJob &K = plans[lead]->job;
+            if (K.n_lags >= kBigMinLags && (i64)K.n_lags <= kBigN / 2) {
+                big_tile[ti] = 1;
+                for (int q = 0; q < 4; q++) if (tiles[ti].plan[q] >= 0) big_plan[tiles[ti].plan[q]] = 1;
+            }
+        }
+    }
     // lag chunks
     int n_fft_jobs = 0, n_tile_jobs = 0;
-    for (CorrPlan *pl : plans) n_fft_jobs += (pl->job.n_lags + kLagW - 1) / kLagW;
-    for (const Tile &T : tiles) {
+    for (int p = 0; p < np; p++)
+        if (!big_plan[p]) n_fft_jobs += (plans[p]->job.n_lags + kLagW - 1) / kLagW;
+    for (size_t ti = 0; ti < tiles.size(); ti++) {
+        if (big_tile[ti]) continue;
+        const Tile &T = tiles[ti];
         int p = -1;
         for (int q = 0; q < 4; q++) if (T.plan[q] >= 0) p = T.plan[q];
         n_tile_jobs += (plans[p]->job.n_lags + kLagW - 1) / kLagW;
@@ -863,7 +880,7 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
             (rc = alloc_t(e, &J.blocksums, (size_t)kMaxCand * std::max<i64>(J.nb, 1))))
             return rc;
         first_job[p] = (int)fjobs.size();
-        for (int c0 = 0; c0 < J.n_lags; c0 += kLagW) {
+        for (int c0 = 0; c0 < J.n_lags && !big_plan[p]; c0 += kLagW) {
             FftJob F{};
             F.t = J.t_re; F.s = J.s_re; F.t_stats = J.t_stats; F.s_stats = J.s_stats;
             F.t_off = J.t_off; F.n_t = J.n_t; F.sl = J.sl;
@@ -892,7 +909,9 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     }
     std::vector<TileJob> tjobs;
     if (tiled) {
-        for (const Tile &T : tiles) {
+        for (size_t ti = 0; ti < tiles.size(); ti++) {
+            if (big_tile[ti]) continue;
+            const Tile &T = tiles[ti];
             int lead = -1;
             for (int q = 0; q < 4; q++) if (T.plan[q] >= 0) lead = T.plan[q];
             const PairJob &K = plans[lead]->job;
@@ -924,6 +943,89 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     cudaEventRecord(e->ev_fft[1], e->stream);
     launch_fft_reduce(d_f, (int)fjobs.size(), e->stream);
     launch_fft_finish(d_f, (int)fjobs.size(), e->d_tw, e->stream);
+    // ---- big tiles, in batches that share four 16 MiB buffers per tile
+    {
+        std::vector<int> bt;
+        for (size_t ti = 0; ti < tiles.size(); ti++) if (big_tile[ti]) bt.push_back((int)ti);
+        const int kBatch = 48;
+        const size_t buf_elems = (size_t)kBigN;
+        float2 *pool = nullptr;
+        if (!bt.empty() && (rc = alloc_t(e, &pool, (size_t)std::min<int>(kBatch, (int)bt.size()) * 4 * buf_elems))) return rc;
+        for (size_t b0 = 0; b0 < bt.size(); b0 += kBatch) {
+            const int nb_t = (int)std::min<size_t>(kBatch, bt.size() - b0);
+            struct Geo { i64 t_off, n_t, sl, lag0, Ts; int n_lags, n_seg; };
+            std::vector<Geo> geo(nb_t);
+            int max_seg = 0;
+            for (int k = 0; k < nb_t; k++) {
+                const Tile &T = tiles[bt[b0 + k]];
+                int lead = -1;
+                for (int q = 0; q < 4; q++) if (T.plan[q] >= 0) lead = T.plan[q];
+                const PairJob &K = plans[lead]->job;
+                Geo &G = geo[k];
+                G.t_off = K.t_off; G.n_t = K.n_t; G.sl = K.sl; G.lag0 = K.lag0; G.n_lags = K.n_lags;
+                G.Ts = (kBigN - K.n_lags) & ~(i64)3;
+                G.n_seg = (int)std::max<i64>(1, (K.n_t + G.Ts - 1) / G.Ts);
+                max_seg = std::max(max_seg, G.n_seg);
+            }
+            auto buf = [&](int k, int which) { return pool + ((size_t)k * 4 + which) * buf_elems; };  // A, B, G0, G1
+            for (int g = 0; g < max_seg; g++) {
+                std::vector<BigColJob> cj;
+                std::vector<BigRowJob> rj;
+                std::vector<BigCrossJob> xj;
+                for (int k = 0; k < nb_t; k++) {
+                    const Geo &G = geo[k];
+                    if (g >= G.n_seg) continue;
+                    const Tile &T = tiles[bt[b0 + k]];
+                    const i64 first = (i64)g * G.Ts;
+                    BigColJob a{};
+                    a.x0 = T.t[0]; a.x1 = T.t[1]; a.base = G.t_off + first; a.lo = 0;
+                    a.hi = std::max<i64>(0, std::min<i64>(G.Ts, G.n_t - first)); a.out = buf(k, 0);
+                    BigColJob b{};
+                    b.x0 = T.s[0]; b.x1 = T.s[1]; b.base = G.lag0 + first;
+                    b.lo = std::max<i64>(0, -b.base); b.hi = std::max<i64>(b.lo, std::min<i64>(kBigN, G.sl - b.base));
+                    b.out = buf(k, 1);
+                    cj.push_back(a); cj.push_back(b);
+                    rj.push_back(BigRowJob{buf(k, 0), 0});
+                    rj.push_back(BigRowJob{buf(k, 1), 0});
+                    xj.push_back(BigCrossJob{buf(k, 0), buf(k, 1), buf(k, 2), buf(k, 3), g > 0 ? 1 : 0});
+                }
+                const BigColJob *d_cj = nullptr;
+                const BigRowJob *d_rj = nullptr;
+                const BigCrossJob *d_xj = nullptr;
+                if ((rc = upload(e, cj, &d_cj)) || (rc = upload(e, rj, &d_rj)) || (rc = upload(e, xj, &d_xj))) return rc;
+                launch_big_cols(d_cj, (int)cj.size(), e->d_tw, e->d_tw_fine, e->stream);
+                launch_big_rows(d_rj, (int)rj.size(), e->d_tw, e->d_tw_fine, e->stream);
+                launch_big_cross(d_xj, (int)xj.size(), e->stream);
+                count_launch(e, 3);
+            }
+            std::vector<BigRowJob> irj;
+            std::vector<BigOutJob> oj;
+            for (int k = 0; k < nb_t; k++) {
+                const Tile &T = tiles[bt[b0 + k]];
+                for (int a = 0; a < 2; a++) {
+                    const int q0 = T.plan[2 * a], q1 = T.plan[2 * a + 1];
+                    if (q0 < 0 && q1 < 0) continue;
+                    const int any = q0 >= 0 ? q0 : q1;
+                    BigOutJob O{};
+                    O.G = buf(k, 2 + a);
+                    O.approx0 = q0 >= 0 ? const_cast<float *>(sjobs[q0].approx) : nullptr;
+                    O.approx1 = q1 >= 0 ? const_cast<float *>(sjobs[q1].approx) : nullptr;
+                    O.t_stats = plans[any]->job.t_stats;
+                    O.s0_stats = q0 >= 0 ? plans[q0]->job.s_stats : plans[any]->job.s_stats;
+                    O.s1_stats = q1 >= 0 ? plans[q1]->job.s_stats : plans[any]->job.s_stats;
+                    O.n_t = geo[k].n_t; O.n_lags = geo[k].n_lags;
+                    irj.push_back(BigRowJob{buf(k, 2 + a), 1});
+                    oj.push_back(O);
+                }
+            }
+            const BigRowJob *d_irj = nullptr;
+            const BigOutJob *d_oj = nullptr;
+            if ((rc = upload(e, irj, &d_irj)) || (rc = upload(e, oj, &d_oj))) return rc;
+            launch_big_rows(d_irj, (int)irj.size(), e->d_tw, e->d_tw_fine, e->stream);
+            launch_big_out(d_oj, (int)oj.size(), e->d_tw, e->stream);
+            count_launch(e, 2);
+        }
+    }
     launch_select_candidates(d_s, np, e->stream);
     cudaEventRecord(e->ev[5], e->stream);
     {
@@ -1303,6 +1405,7 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
     if (err == cudaSuccess && fft_setup(e->stream, &e->d_tw) != 0) err = cudaErrorUnknown;
     if (err == cudaSuccess && demod_setup(e->stream) != 0) err = cudaErrorUnknown;
     if (err == cudaSuccess && fft_tile_setup() != 0) err = cudaErrorUnknown;
+    if (err == cudaSuccess && big_setup(e->stream, &e->d_tw_fine) != 0) err = cudaErrorUnknown;
     if (err == cudaSuccess && quality_setup() != 0) err = cudaErrorUnknown;
     if (err != cudaSuccess) {
         g_create_error = std::string("tdoa_create: ") + cudaGetErrorString(err);
@@ -1340,6 +1443,7 @@ void tdoa_destroy(tdoa_engine *e)
     if (e->h_frame) cudaFreeHost(e->h_frame);
     if (e->d_frame) cudaFree(e->d_frame);
     if (e->d_tw) cudaFree(e->d_tw);
+    if (e->d_tw_fine) cudaFree(e->d_tw_fine);
     for (auto &ev : e->ev_fft)
         if (ev) cudaEventDestroy(ev);
     for (auto &sp : e->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }

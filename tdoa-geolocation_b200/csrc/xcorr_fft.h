@@ -57,6 +57,38 @@ struct CandJob {
     double *blocksums;    // [max_cand][nb]
 };
 
+// ---- wide lag searches through a 2^21-point transform in global memory (xcorr_big.cu)
+constexpr int kBigN1 = 256;
+constexpr i64 kBigN = (i64)kBigN1 * kFftN;     // 2 097 152 complex points
+constexpr int kBigMinLags = 8192;              // narrower searches stay with the segment kernel
+
+struct BigColJob {      // forward column pass of one transform: z[n] = x0[base+n] + i x1[base+n], lo <= n < hi
+    const float *x0, *x1;
+    i64 base, lo, hi;
+    float2 *out;        // [256][8192]
+};
+struct BigRowJob {      // row pass, in place
+    float2 *buf;
+    int inverse;
+};
+struct BigCrossJob {    // G0 = C00 + i C01, G1 = C10 + i C11 with C_ab = 4 conj(T_a) S_b
+    const float2 *A, *B;
+    float2 *G0, *G1;
+    int accumulate;     // add to what G0 / G1 hold (segments after the first)
+};
+struct BigOutJob {      // inverse column pass of one packed pair of correlations
+    const float2 *G;
+    float *approx0, *approx1;                       // [n_lags] each, nullptr: pair absent
+    const double *t_stats, *s0_stats, *s1_stats;    // ST_SCALE of the template and the two signals
+    i64 n_t;
+    int n_lags;
+};
+int big_setup(cudaStream_t st, float2 **d_fine);
+void launch_big_cols(const BigColJob *d_jobs, int n_jobs, const float2 *d_tw, const float2 *d_fine, cudaStream_t st);
+void launch_big_rows(const BigRowJob *d_jobs, int n_jobs, const float2 *d_tw, const float2 *d_fine, cudaStream_t st);
+void launch_big_cross(const BigCrossJob *d_jobs, int n_jobs, cudaStream_t st);
+void launch_big_out(const BigOutJob *d_jobs, int n_jobs, const float2 *d_tw, cudaStream_t st);
+
 int fft_setup(cudaStream_t st, float2 **d_tw);
 size_t fft_partials_bytes(int n_cta);
 void launch_fft_segments(const FftJob *d_jobs, int n_jobs, int max_cta, const float2 *d_tw, cudaStream_t st);

@@ -88,6 +88,25 @@ def test_config3_every_window_recovers_the_delays(gen):
     assert np.array_equal(rev["lag"], pk[5]["lag"]) and np.array_equal(rev["corr"], pk[5]["corr"])
 
 
+def test_wide_lags_long_windows_segmented_big_transform(gen):
+    """Templates longer than one 2^21-point transform: the cross-spectra of the segments are
+    added before the one inverse.  Same records as the 2048-lag chunk path (use_fft=3)."""
+    torch, bench, cb, dev = gen
+    delays, _ = cb.delays_for(bench.STATION_LLH)
+    block, W, L = 12_000_000, 5_000_000, 6_000
+    caps = cb.synth(dev, 3, block, delays)
+    want = [int(delays[j] - delays[i]) for i in range(3) for j in range(i + 1, 3)]
+    out = []
+    for use_fft in (1, 3):
+        with T.Engine(T.MODE_EXTENDED, max_lag=L, use_fft=use_fft) as e:
+            load_dev(e, caps)
+            out.append(e.xcorr(T.KIND_TGT, 1000, W, 2, W))
+    for w in range(2):
+        assert [int(x) for x in out[0][w]["lag"]] == want
+    for name in ("lag", "corr", "frac"):
+        assert np.array_equal(out[0][name], out[1][name]), name
+
+
 def test_config4_sixteen_stations_closure(gen):
     torch, bench, cb, dev = gen
     st = cb.ring_stations(16)

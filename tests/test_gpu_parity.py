@@ -226,6 +226,36 @@ def test_extended_two_sided_subsample():
     assert [int(g["lag"]) for g in got] == [35, -25, -60]
 
 
+def test_extended_wide_lags_use_the_big_transform():
+    """>= 8192 lags: the ranking runs through the 2^21-point four-step transform
+    (xcorr_big.cu) instead of 2048-lag chunks; candidates are still evaluated exactly, so
+    the records must be the oracle's -- and identical to the chunked path's (use_fft=3)."""
+    L, W = 5000, 60000
+    raws = fm_capture(70000, (400, 0, 1700), (2500, 3100, 0), seed=12)
+    oracle.set_seq_dc_limit(0)
+    with T.Engine(T.MODE_EXTENDED, max_lag=L) as e, T.Engine(T.MODE_EXTENDED, max_lag=L, use_fft=3) as e3:
+        load_all(e, raws)
+        load_all(e3, raws)
+        got = e.xcorr(T.KIND_TGT, 500, W, 1, 0)[0]
+        old = e3.xcorr(T.KIND_TGT, 500, W, 1, 0)[0]
+        ref = e.xcorr(T.KIND_REF, 0, 2 * W, 1, 0)[0]   # spans the block-1 / block-3 joint
+        ref3 = e3.xcorr(T.KIND_REF, 0, 2 * W, 1, 0)[0]
+        for name in ("lag", "corr", "frac", "flags"):
+            assert np.array_equal(got[name], old[name]), name
+            assert np.array_equal(ref[name], ref3[name]), name
+        for p, (i, j) in enumerate([(0, 1), (0, 2), (1, 2)]):
+            yi, _ = oracle.preprocess_binary(split(raws[i])[1][500:500 + W])
+            yj, _ = oracle.preprocess_binary(split(raws[j])[1][500:500 + W])
+            c = oracle.xcorr_two_sided(yi, yj, L)
+            idx, frac, val = oracle.peak_parabolic(c)
+            assert int(got[p]["lag"]) == idx - L
+            assert abs(float(got[p]["frac"]) - frac) <= 1e-3
+            assert abs(float(got[p]["corr"]) - val) <= CORR_TOL
+    oracle.set_seq_dc_limit(-1)
+    assert [int(g["lag"]) for g in got] == [-2500 + 3100, -2500, -3100]
+    assert [int(g["lag"]) for g in ref] == [-400, 1300, 1700]
+
+
 # ------------------------------------------------------------------ geodesy + solvers
 def test_baselines_and_solver(eng_binary):
     base = eng_binary.baselines(STATION_LLH)
