@@ -12,9 +12,10 @@
 // With n = 8192 n1 + n2 and k = k1 + 256 k2:
 //   X[k1 + 256 k2] = sum_n2 W_8192^(n2 k2) [ W_N^(n2 k1) sum_n1 x[8192 n1 + n2] W_256^(n1 k1) ]
 //   k_big_cols : 256-point transforms down the columns (two radix-16 stages in shared
-//                memory, 32 columns per CTA, coalesced rows), times W_N^(n2 k1)
-//   k_big_rows : 8192-point transforms along the rows (fft_tile_core.cuh); the spectrum
-//                stays in the [k1][k2] layout -- a pointwise product does not care
+//                memory, 32 columns per CTA, coalesced rows)
+//   k_big_rows : times W_N^(n2 k1) while loading, then 8192-point transforms along the
+//                rows (fft_tile_core.cuh); the spectrum stays in the [k1][k2] layout -- a
+//                pointwise product does not care
 //   k_big_cross: T, S from Z[k], Z[N-k] (the mirror of [k1][k2] is [256-k1][8191-k2]), the
 //                four products, packed in pairs
 //   k_big_rows (inverse) and k_big_out: the same two passes backwards; only the rows
@@ -47,6 +48,17 @@ __device__ __forceinline__ float2 big_twiddle(unsigned m, const float2 *__restri
 {
     return cmul(tw[8u * (m >> 11)], fine[m & 2047u]);
 }
+
+// W_N^(k1 j) for the row elements j = t + 256 r a thread touches: W_N^(k1 t) once per thread
+// (two table loads), times W_N^(256 k1 r) = W_8192^(k1 r), a warp-uniform table entry
+struct RowTwiddle {
+    float2 base;
+    unsigned k1;
+    const float2 *tw;
+    __device__ __forceinline__ RowTwiddle(unsigned k1_, unsigned t, const float2 *__restrict__ tw_, const float2 *__restrict__ fine)
+        : base(big_twiddle(k1_ * t, tw_, fine)), k1(k1_), tw(tw_) {}
+    __device__ __forceinline__ float2 at(int r) const { return cmul(base, tw[(k1 * (unsigned)r) & (kN - 1)]); }
+};
 
 // 256-point transform of every column of the [256][32] strip in shared memory, in place:
 // on return row r = 16 p + q holds X[p + 16 q].  Two radix-16 stages, items (column, b) and
@@ -89,18 +101,28 @@ __global__ void __launch_bounds__(kColThreads) k_big_cols(const BigColJob *jobs,
     const int tid = threadIdx.x, c = tid & 31;
     const int n2 = blockIdx.x * kCols + c;
     // z[n] = x0[base + n] + i x1[base + n] for lo <= n < hi, else 0
-    for (int n1 = tid >> 5; n1 < kN1; n1 += 8) {
-        const i64 n = (i64)n1 * kN2 + n2;
-        float2 z = make_float2(0.f, 0.f);
-        if (n >= J.lo && n < J.hi) z = make_float2(J.x0[J.base + n], J.x1[J.base + n]);
-        sm[n1 * kCols + c] = z;
+    const float *__restrict__ x0 = J.x0 + J.base, *__restrict__ x1 = J.x1 + J.base;
+    const i64 lo = J.lo, hi = J.hi;
+#pragma unroll 1
+    for (int g = 0; g < 4; g++) {   // 8 rows per thread in flight
+        float2 z[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int n1 = (tid >> 5) + 8 * (8 * g + u);
+            const i64 n = (i64)n1 * kN2 + n2;
+            z[u] = (n >= lo && n < hi) ? make_float2(x0[n], x1[n]) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) sm[((tid >> 5) + 8 * (8 * g + u)) * kCols + c] = z[u];
     }
     __syncthreads();
     strip_fft256(sm, tid, tw);
-    for (int r = tid >> 5; r < kN1; r += 8) {
+    (void)fine;
+#pragma unroll 8
+    for (int i = 0; i < 32; i++) {
+        const int r = (tid >> 5) + 8 * i;
         const int k1 = (r >> 4) + 16 * (r & 15);
-        const float2 y = cmul(sm[r * kCols + c], big_twiddle((unsigned)n2 * (unsigned)k1, tw, fine));
-        J.out[(size_t)k1 * kN2 + n2] = y;
+        J.out[(size_t)k1 * kN2 + n2] = sm[r * kCols + c];
     }
 }
 
@@ -115,12 +137,17 @@ __global__ void __launch_bounds__(kT, 2) k_big_rows(const BigRowJob *jobs, const
     float2 *row = J.buf + (size_t)k1 * kN2;
     for (int idx = t; idx < kTab; idx += kT) tab[idx] = tw[(16 * (idx & 31) * (idx >> 5)) & (kN - 1)];
     const float2 w1a = tw[2 * t], w1b = tw[2 * t + 1];
+    const RowTwiddle W((unsigned)k1, (unsigned)t, tw, fine);
     {
         float2 v[32];
 #pragma unroll
-        for (int r = 0; r < 32; r++) {
-            const float2 x = row[t + 256 * r];
-            v[r] = J.inverse ? make_float2(x.x, -x.y) : x;   // IFFT(g) = conj(FFT(conj g))
+        for (int r = 0; r < 32; r++) v[r] = row[t + 256 * r];
+        if (J.inverse) {
+#pragma unroll
+            for (int r = 0; r < 32; r++) v[r].y = -v[r].y;   // IFFT(g) = conj(FFT(conj g))
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; r++) v[r] = cmul(v[r], W.at(r));   // the twiddle between the two passes
         }
         pass1_store(v, t, buf);
     }
@@ -139,13 +166,13 @@ __global__ void __launch_bounds__(kT, 2) k_big_rows(const BigRowJob *jobs, const
         spectrum_store(u0, u1, t, buf);
     }
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
     for (int r = 0; r < 32; r++) {
         const int j = t + 256 * r;
         float2 x = buf[j];
         if (J.inverse) {
-            // back through the twiddle of the forward column pass: conj(X) conj(W_N^(n2 k1))
-            const float2 w = big_twiddle((unsigned)j * (unsigned)k1, tw, fine);
+            // back through the twiddle between the passes: conj(X) conj(W_N^(n2 k1))
+            const float2 w = W.at(r);
             x = cmul(make_float2(x.x, -x.y), make_float2(w.x, -w.y));
         }
         row[j] = x;
@@ -184,9 +211,14 @@ __global__ void __launch_bounds__(kColThreads) k_big_out(const BigOutJob *jobs, 
     const BigOutJob &J = jobs[blockIdx.y];
     const int tid = threadIdx.x, c = tid & 31;
     const int n2 = blockIdx.x * kCols + c;
-    for (int k1 = tid >> 5; k1 < kN1; k1 += 8) {
-        const float2 g = J.G[(size_t)k1 * kN2 + n2];
-        sm[k1 * kCols + c] = make_float2(g.x, -g.y);
+    const float2 *__restrict__ G = J.G + n2;
+#pragma unroll 1
+    for (int g4 = 0; g4 < 4; g4++) {
+        float2 z[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) z[u] = G[(size_t)((tid >> 5) + 8 * (8 * g4 + u)) * kN2];
+#pragma unroll
+        for (int u = 0; u < 8; u++) sm[((tid >> 5) + 8 * (8 * g4 + u)) * kCols + c] = make_float2(z[u].x, -z[u].y);
     }
     __syncthreads();
     strip_fft256(sm, tid, tw);

@@ -190,7 +190,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_fft_finish(const FftJob *jobs, 
 __global__ void __launch_bounds__(256) k_select_candidates(const SelJob *jobs)
 {
     __shared__ float s_red[256];
-    __shared__ int s_cnt[256];
     __shared__ int s_base;
     const SelJob &J = jobs[blockIdx.x];
     const int tid = threadIdx.x;
@@ -216,34 +215,30 @@ __global__ void __launch_bounds__(256) k_select_candidates(const SelJob *jobs)
     m2 = s_red[0];
     __syncthreads();
     const float thr1 = m1 - J.tol, thr2 = m2 - J.tol;
+    // candidates are few: collect them with a shared-memory ticket, then order them by rank
+    // (ascending lag, as the reference scans).  More than 256 means overflow anyway.
+    __shared__ int s_list[256];
     if (tid == 0) s_base = 0;
     __syncthreads();
-    // ascending compaction, 256 lags at a time
-    for (int base = 0; base < n; base += 256) {
-        const int i = base + tid;
-        bool take = false;
-        if (i < n) {
-            const float a = fabsf(J.approx[i]);
-            take = a >= thr1 || (i < J.sanity && a >= thr2);
-            if (!take && J.neighbours) {
-                if (i > 0 && fabsf(J.approx[i - 1]) >= thr1) take = true;
-                if (i + 1 < n && fabsf(J.approx[i + 1]) >= thr1) take = true;
-            }
+    for (int i = tid; i < n; i += 256) {
+        const float a = fabsf(J.approx[i]);
+        bool take = a >= thr1 || (i < J.sanity && a >= thr2);
+        if (!take && J.neighbours) {
+            if (i > 0 && fabsf(J.approx[i - 1]) >= thr1) take = true;
+            if (i + 1 < n && fabsf(J.approx[i + 1]) >= thr1) take = true;
         }
-        s_cnt[tid] = take ? 1 : 0;
-        __syncthreads();
-        // inclusive scan (Hillis-Steele)
-        for (int o = 1; o < 256; o <<= 1) {
-            const int v = tid >= o ? s_cnt[tid - o] : 0;
-            __syncthreads();
-            s_cnt[tid] += v;
-            __syncthreads();
+        if (take) {
+            const int pos = atomicAdd(&s_base, 1);
+            if (pos < 256) s_list[pos] = i;
         }
-        const int pos = s_base + s_cnt[tid] - 1;
-        if (take && pos < J.max_cand) J.cand[pos] = i;
-        __syncthreads();
-        if (tid == 255) s_base += s_cnt[255];
-        __syncthreads();
+    }
+    __syncthreads();
+    const int found = s_base;
+    if (found <= 256 && tid < found) {
+        const int mine = s_list[tid];
+        int rank = 0;
+        for (int k = 0; k < found; k++) rank += s_list[k] < mine ? 1 : 0;
+        if (rank < J.max_cand) J.cand[rank] = mine;
     }
     if (tid == 0) {
         *J.n_cand = s_base;  // may exceed max_cand: the peak kernel raises the overflow flag
@@ -296,42 +291,61 @@ __device__ __forceinline__ void cand_sweep_ng(int ng, const float *s_t, const fl
 // 128-bit loads (two for the signal, picked apart by the compile-time shift A), 4 steps in
 // flight: 192 bytes of loads per thread instead of 48, which is what this latency-bound
 // sweep needs.  Returns the thread's partial sum over samples [0, 4 * (len / 4)).
-template <int A, bool F64>
-__device__ __forceinline__ double cand_sweep_vec(const float *__restrict__ tp, const float *__restrict__ sp, int len,
-                                                 float sc_t, float sc_s)
+template <int A, int NC, bool F64>
+__device__ __forceinline__ void cand_sweep_vec(const float *__restrict__ tp, const float *__restrict__ sp, int len,
+                                               float sc_t, float sc_s, double (&acc)[NC])
 {
+    constexpr int NV = (A + NC + 2) / 4 + 1;   // 128-bit signal loads that cover samples A .. A + NC + 2
     const float4 *__restrict__ tp4 = reinterpret_cast<const float4 *>(tp);
     const float4 *__restrict__ sp4 = reinterpret_cast<const float4 *>(sp - A);
     const int n4 = len >> 2;
-    double acc = 0.0;
-    auto mac = [&](const float4 &t, const float4 &lo, const float4 &hi) {
-        float sv[4];
-        if (A == 0) { sv[0] = lo.x; sv[1] = lo.y; sv[2] = lo.z; sv[3] = lo.w; }
-        else if (A == 1) { sv[0] = lo.y; sv[1] = lo.z; sv[2] = lo.w; sv[3] = hi.x; }
-        else if (A == 2) { sv[0] = lo.z; sv[1] = lo.w; sv[2] = hi.x; sv[3] = hi.y; }
-        else { sv[0] = lo.w; sv[1] = hi.x; sv[2] = hi.y; sv[3] = hi.z; }
-        const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = 0.0;
+    auto mac = [&](const float4 &t, const float4 (&s)[NV]) {
+        float w[4 * NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) { w[4 * v] = s[v].x; w[4 * v + 1] = s[v].y; w[4 * v + 2] = s[v].z; w[4 * v + 3] = s[v].w; }
+#pragma unroll
+        for (int i = 0; i < 4 * NV; i++) w[i] = __fmul_rn(w[i], sc_s);
+        const float tv[4] = {__fmul_rn(t.x, sc_t), __fmul_rn(t.y, sc_t), __fmul_rn(t.z, sc_t), __fmul_rn(t.w, sc_t)};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const float a = __fmul_rn(tv[k], sc_t), b = __fmul_rn(sv[k], sc_s);
-            if (F64) acc = __dadd_rn(acc, __dmul_rn((double)a, (double)b));
-            else acc = __dadd_rn(acc, (double)__fmul_rn(a, b));
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                if (F64) acc[c] = __dadd_rn(acc[c], __dmul_rn((double)tv[k], (double)w[A + k + c]));
+                else acc[c] = __dadd_rn(acc[c], (double)__fmul_rn(tv[k], w[A + k + c]));
+            }
         }
     };
+    constexpr int U = NC == 1 ? 4 : 2;   // steps in flight
     int j = threadIdx.x;
-    for (; j + 3 * kCandThreads < n4; j += 4 * kCandThreads) {
-        float4 t[4], lo[4], hi[4];
+    for (; j + (U - 1) * kCandThreads < n4; j += U * kCandThreads) {
+        float4 t[U], sv[U][NV];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < U; u++) {
             t[u] = tp4[j + u * kCandThreads];
-            lo[u] = sp4[j + u * kCandThreads];
-            hi[u] = A ? sp4[j + u * kCandThreads + 1] : lo[u];
+#pragma unroll
+            for (int v = 0; v < NV; v++) sv[u][v] = sp4[j + u * kCandThreads + v];
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) mac(t[u], lo[u], hi[u]);
+        for (int u = 0; u < U; u++) mac(t[u], sv[u]);
     }
-    for (; j < n4; j += kCandThreads) mac(tp4[j], sp4[j], A ? sp4[j + 1] : sp4[j]);
-    return acc;
+    for (; j < n4; j += kCandThreads) {
+        float4 sv[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) sv[v] = sp4[j + v];
+        mac(tp4[j], sv);
+    }
+}
+
+template <int NC, bool F64>
+__device__ __forceinline__ void cand_sweep_vec_a(int a, const float *__restrict__ tp, const float *__restrict__ sp, int len,
+                                                 float sc_t, float sc_s, double (&acc)[NC])
+{
+    if (a == 0) cand_sweep_vec<0, NC, F64>(tp, sp, len, sc_t, sc_s, acc);
+    else if (a == 1) cand_sweep_vec<1, NC, F64>(tp, sp, len, sc_t, sc_s, acc);
+    else if (a == 2) cand_sweep_vec<2, NC, F64>(tp, sp, len, sc_t, sc_s, acc);
+    else cand_sweep_vec<3, NC, F64>(tp, sp, len, sc_t, sc_s, acc);
 }
 
 // One CTA: block b of the template (B samples) of one pair, every candidate.
@@ -372,25 +386,31 @@ __global__ void __launch_bounds__(kCandThreads) k_corr_candidates(const PairJob 
 #pragma unroll
         for (int c = 0; c < kCandGroup; c++) acc[c] = 0.0;
         const i64 s_first = blk_start + J.lag0 + dmin;
-        if (ng == 1 && s_first >= 0 && s_first + blk_len + 4 <= J.sl && ((J.t_off + blk_start) & 3) == 0 &&
+        const bool run3 = ng == 3 && off[1] == 1 && off[2] == 2;   // a peak and its two neighbours (EXTENDED)
+        if ((ng == 1 || run3) && s_first >= 0 && s_first + blk_len + 12 <= J.sl && ((J.t_off + blk_start) & 3) == 0 &&
             (reinterpret_cast<uintptr_t>(J.t_re) & 15) == 0 && (reinterpret_cast<uintptr_t>(J.s_re) & 15) == 0) {
             const float *__restrict__ tp = J.t_re + J.t_off + blk_start;
             const float *__restrict__ sp = J.s_re + s_first;
             const int len = (int)blk_len;
             const int a = (int)(s_first & 3);
-            double v;
-            if (exact_f64) {
-                v = a == 0 ? cand_sweep_vec<0, true>(tp, sp, len, sc_t, sc_s) : a == 1 ? cand_sweep_vec<1, true>(tp, sp, len, sc_t, sc_s)
-                  : a == 2 ? cand_sweep_vec<2, true>(tp, sp, len, sc_t, sc_s) : cand_sweep_vec<3, true>(tp, sp, len, sc_t, sc_s);
+            if (run3) {
+                double v[3];
+                if (exact_f64) cand_sweep_vec_a<3, true>(a, tp, sp, len, sc_t, sc_s, v);
+                else cand_sweep_vec_a<3, false>(a, tp, sp, len, sc_t, sc_s, v);
+                acc[0] = v[0]; acc[1] = v[1]; acc[2] = v[2];
             } else {
-                v = a == 0 ? cand_sweep_vec<0, false>(tp, sp, len, sc_t, sc_s) : a == 1 ? cand_sweep_vec<1, false>(tp, sp, len, sc_t, sc_s)
-                  : a == 2 ? cand_sweep_vec<2, false>(tp, sp, len, sc_t, sc_s) : cand_sweep_vec<3, false>(tp, sp, len, sc_t, sc_s);
+                double v[1];
+                if (exact_f64) cand_sweep_vec_a<1, true>(a, tp, sp, len, sc_t, sc_s, v);
+                else cand_sweep_vec_a<1, false>(a, tp, sp, len, sc_t, sc_s, v);
+                acc[0] = v[0];
             }
             for (int i = (len & ~3) + tid; i < len; i += kCandThreads) {  // the block's last len % 4 samples
-                const float t = __fmul_rn(tp[i], sc_t), q = __fmul_rn(sp[i], sc_s);
-                v = exact_f64 ? __dadd_rn(v, __dmul_rn((double)t, (double)q)) : __dadd_rn(v, (double)__fmul_rn(t, q));
+                const float t = __fmul_rn(tp[i], sc_t);
+                for (int c = 0; c < ng; c++) {
+                    const float q = __fmul_rn(sp[i + c], sc_s);
+                    acc[c] = exact_f64 ? __dadd_rn(acc[c], __dmul_rn((double)t, (double)q)) : __dadd_rn(acc[c], (double)__fmul_rn(t, q));
+                }
             }
-            acc[0] = v;
         } else if (ng <= 2 && s_first >= 0 && s_first + blk_len + span <= J.sl) {
             // sharp peak (the common case): stream both signals straight from global
             // memory, 4 independent strides in flight per thread, no staging, no barriers

@@ -83,13 +83,7 @@ def timed(fn, reps=3):
     return (time.perf_counter() - t0) / reps, out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--quick", action="store_true")
-    args = ap.parse_args()
-    dev = torch.device("cuda", 0)
-    res = []
-
+def cfg1(args, dev, res):
     # ---- config 1: 3-station 10 s capture, the reference's own chunked run (binary + source arithmetic)
     block = 2_000_000 if args.quick else 20_000_000
     delays, _ = delays_for(bench.STATION_LLH)
@@ -105,7 +99,11 @@ def main():
         res.append({"config": f"1 ({name} arithmetic, chunk {chunk})", "ms": dt * 1e3,
                     "pair_msamples_per_s": 6 * chunk / dt / 1e6, "lags": [int(x) for x in t["lag"]], "ok": bool(ok)})
 
+
+def cfg3(args, dev, res):
     # ---- config 3: 100 s capture, sliding 1 s windows, +-50k lags, one fix per window
+    delays, _ = delays_for(bench.STATION_LLH)
+    want = [int(delays[j] - delays[i]) for i in range(3) for j in range(i + 1, 3)]
     block = 8_000_000 if args.quick else 66_666_666
     caps = synth(dev, 3, block, delays)
     W, L = 2_000_000, 50_000
@@ -120,13 +118,16 @@ def main():
             pos, status, _ = e.solve(bench.STATION_LLH, rd)
             return pk, pos
 
-        dt, (pk, pos) = timed(run3, reps=2)
+        dt, (pk, pos) = timed(run3, reps=args.reps)
     ok = all([int(x) for x in pk[w]["lag"]] == want for w in range(nw))
     res.append({"config": f"3 (EXTENDED, {nw} windows x 3 pairs, W=2e6, +-{L} lags)", "ms": dt * 1e3,
                 "pair_msamples_per_s": nw * 3 * W / dt / 1e6, "fixes_per_s": nw / dt, "ok": bool(ok),
                 "max_abs_frac": float(np.abs(pk["frac"]).max())})
 
+
+def cfg4(args, dev, res):
     # ---- config 4: 16 stations (120 pairs), windowed
+    W = 2_000_000
     st16 = ring_stations(16)
     d16, _ = delays_for(st16)
     block = 4_000_000 if args.quick else 66_666_666
@@ -136,12 +137,15 @@ def main():
     with T.Engine(T.MODE_EXTENDED, n_stations=16, max_lag=2000, fast_demod=1) as e:
         for k in range(16):
             e.load_u8_device(k, caps[k].data_ptr(), caps[k].numel(), keep=caps[k])
-        dt, pk = timed(lambda: e.xcorr(T.KIND_TGT, 0, W, nw, W), reps=2)
+        dt, pk = timed(lambda: e.xcorr(T.KIND_TGT, 0, W, nw, W), reps=args.reps)
     ok = all([int(x) for x in pk[w]["lag"]] == want16 for w in range(nw))
     res.append({"config": f"4 (EXTENDED, 16 stations, {nw} windows x 120 pairs, +-2000 lags)", "ms": dt * 1e3,
                 "pair_msamples_per_s": nw * 120 * W / dt / 1e6, "fixes_per_s": nw / dt, "ok": bool(ok)})
 
+
+def cfg5(args, dev, res):
     # ---- config 5: 1000 x 1000 grid, 16 stations, 64 windows
+    st16 = ring_stations(16)
     _, dist = delays_for(st16)
     rd = np.array([dist[j] - dist[i] for i in range(16) for j in range(i + 1, 16)])
     rng = np.random.default_rng(5)
@@ -149,11 +153,30 @@ def main():
     rds = rd[None, :] + rng.normal(0, 50e-9 * C, (sets, rd.size))
     desc = [41.26 - 0.25, -96.02 - 0.25, 0.0005, 0.0005, 1000, 1000, 400.0]
     with T.Engine(T.MODE_BINARY) as e:
-        dt, (out, cost, idx) = timed(lambda: e.grid(st16, desc, rds), reps=2)
+        dt, (out, cost, idx) = timed(lambda: e.grid(st16, desc, rds), reps=args.reps)
+        t0 = time.perf_counter()
+        fine, rms, status, iters = e.solve_ls(st16, rds, init_llh=out, dims=2)
+        dt_ls = time.perf_counter() - t0
     err_m = [float(np.linalg.norm(bench.llh_to_ecef(*o) - bench.llh_to_ecef(*bench.TX_LLH))) for o in out]
+    err_ls = [float(np.linalg.norm(bench.llh_to_ecef(o[0], o[1], bench.TX_LLH[2]) - bench.llh_to_ecef(*bench.TX_LLH)))
+              for o in fine]
     res.append({"config": f"5 (grid 1000x1000, 16 stations, {sets} sets)", "ms": dt * 1e3,
                 "cell_sets_per_s": 1e6 * sets / dt, "fixes_per_s": sets / dt, "median_err_m": float(np.median(err_m)),
-                "ok": bool(np.median(err_m) < 60.0)})
+                "ls_refine_ms": dt_ls * 1e3, "ls_median_err_m": float(np.median(err_ls)), "ls_median_rms_m": float(np.median(rms)),
+                "ok": bool(np.median(err_m) < 60.0 and int(status.max()) == 0)})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", type=int, default=0, help="run one config only (1, 3, 4 or 5)")
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    res = []
+    for n, fn in ((1, cfg1), (3, cfg3), (4, cfg4), (5, cfg5)):
+        if args.only in (0, n):
+            fn(args, dev, res)
     for r in res:
         print(json.dumps(r))
 
