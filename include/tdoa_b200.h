@@ -100,7 +100,11 @@ typedef struct {
     int32_t guard_samples; /* samples dropped at the start of blocks 2 and 3 (the retune
                               transient, collector.go:85 / rtl_sdr.c:117-135); 0 = the
                               reference's split (processor.go:208-267)                */
-    int32_t reserved[4];
+    int32_t decimate;      /* EXTENDED mode only: D > 1 appends a decimating box-car
+                              (mean of D consecutive samples, rtl_fm.c:302-322 style) to the
+                              preprocessing chain; correlation at fs / D over max_lag / D
+                              lags, records in samples of the capture (lag + frac)       */
+    int32_t reserved[3];
 } tdoa_config;
 
 /* Fill *cfg with the reference-matching defaults of `mode`. */
@@ -140,7 +144,8 @@ TDOA_API int tdoa_unpack(tdoa_engine *e, int32_t station, int64_t first, int64_t
 
 /* preprocessSignal probe (processor.go:469-499 / ELF 0x49cd40): preprocesses samples
  * [start, start+len) of `kind` of `station` in the engine's mode and returns the
- * normalised complex64 signal, its initial power and the branch taken. */
+ * normalised complex64 signal, its initial power and the branch taken.  With
+ * decimate = D only the first len / D entries of out_c64 are written. */
 TDOA_API int tdoa_preprocess(tdoa_engine *e, int32_t station, int32_t kind, int64_t start, int64_t len,
                              float *out_c64, double *power, int32_t *branch);
 

@@ -198,6 +198,17 @@ def preprocess_binary(s):
 
 
 # ----------------------------------------------------------- correlators
+def preprocess_binary_dec(s, D: int):
+    """Engine-defined: the binary's chain, decimating box-car (mean of D), normalise."""
+    s = _c64(s)
+    out = np.empty(max(s.size // max(D, 1), 1) if D > 1 else s.size, np.complex64)
+    L = lib()
+    L.orc_preprocess_binary_dec.argtypes = [_vp, _i64, C.c_int, _vp]
+    L.orc_preprocess_binary_dec.restype = C.c_int
+    br = L.orc_preprocess_binary_dec(_p(s), s.size, D, _p(out))
+    return out[:s.size // D] if D > 1 else out, br
+
+
 def tdcorr_source(s1, s2, max_lag=20000, block=1000, want_all=False):
     s1, s2 = _c64(s1), _c64(s2)
     d = np.zeros(1, np.int64)

@@ -317,6 +317,48 @@ ORC_API int orc_preprocess_binary(const c64 *in, int64_t n, c64 *out)
     return branch;
 }
 
+/* Engine-defined decimating box-car ("parity unpinned"; model: the integrate-and-dump low-pass
+ * of the vendored rtl_fm.c:302-322): y[m] = (x[mD] + ... + x[mD+D-1]) / D, m < n / D, sequential
+ * f32 sums in ascending order, one f32 divide per component.  Returns n / D. */
+ORC_API int64_t orc_decimate(const c64 *in, int64_t n, int D, c64 *out)
+{
+    int64_t m_out = D > 0 ? n / D : 0;
+    for (int64_t m = 0; m < m_out; m++) {
+        float ar = in[m * D].re, ai = in[m * D].im;
+        for (int k = 1; k < D; k++) { ar += in[m * D + k].re; ai += in[m * D + k].im; }
+        out[m].re = ar / (float)D;
+        out[m].im = ai / (float)D;
+    }
+    return m_out;
+}
+
+/* preprocessSignal (binary) with the decimator between the chain and normalizeSignal;
+ * out holds n / D samples.  D <= 1: orc_preprocess_binary. */
+ORC_API int orc_preprocess_binary_dec(const c64 *in, int64_t n, int D, c64 *out)
+{
+    if (D <= 1) return orc_preprocess_binary(in, n, out);
+    double p = orc_signal_power(in, n);
+    c64 *a = (c64 *)malloc((size_t)(n ? n : 1) * sizeof(c64));
+    c64 *b = (c64 *)malloc((size_t)(n ? n : 1) * sizeof(c64));
+    int branch;
+    const c64 *pre;
+    if (p > 0.01) {
+        orc_discriminator(in, n, a); orc_remove_dc(a, n, b, NULL); orc_lowpass(b, n, 10, a);
+        pre = a; branch = 0;
+    } else if (p > 0.001) {
+        orc_envelope(in, n, a); orc_remove_dc(a, n, b, NULL);
+        pre = b; branch = 1;
+    } else {
+        orc_remove_dc(in, n, a, NULL); orc_bandpass(a, n, 100.0, 200000.0, 2000000.0, b);
+        pre = b; branch = 2;
+    }
+    c64 *d = (c64 *)malloc((size_t)(n / D + 1) * sizeof(c64));
+    int64_t m = orc_decimate(pre, n, D, d);
+    orc_normalize(d, m, out);
+    free(a); free(b); free(d);
+    return branch;
+}
+
 /* ---------------------------------------------------------- correlators */
 
 /* processor.go:646-736  timeDomainCorrelation (SOURCE).  `all` (optional) gets

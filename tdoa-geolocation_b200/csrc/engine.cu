@@ -62,6 +62,7 @@ constexpr i64 kCopyChunkDefault = (i64)16 << 20;  // samples per copy chunk (32 
 struct Sig {
     SigSrc src{};
     i64 n = 0;
+    i64 n_out = -1;       // samples of the preprocessed signal (n / decimate); -1: n
     float *plane[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     float *out_re = nullptr, *out_im = nullptr;  // pre-normalise result (scale in stats)
     double *stats = nullptr;
@@ -398,7 +399,7 @@ int ensure_plane(tdoa_engine *e, Sig &s, int idx, bool cplx)
     return TDOA_OK;
 }
 
-enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_SEQSUM, K_BOXCAR, K_BOXCAR_SMALL, K_NOTCH };
+enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_SEQSUM, K_BOXCAR, K_BOXCAR_SMALL, K_NOTCH, K_DECIMATE };
 
 // queue of (stage, kernel) steps: step k of every signal that runs the same kernel at
 // that stage is batched into one launch; stages run in order
@@ -480,12 +481,15 @@ int run_pipeline(tdoa_engine *e, Pipeline &pl)
                     break;
                 }
                 case K_NOTCH: launch_notch_combine(d_jobs, nj, st.max_n, e->stream); break;
+                case K_DECIMATE: launch_decimate(d_jobs, nj, st.max_n, e->stream); break;
             }
             count_launch(e);
         }
     }
     return TDOA_OK;
 }
+
+inline int decimation(const tdoa_engine *e) { return e->cfg.mode == TDOA_MODE_EXTENDED && e->cfg.decimate > 1 ? e->cfg.decimate : 1; }
 
 // shipped binary (ELF 0x49cd40): > 0.01 strong, > 0.001 moderate, else weak
 inline int binary_branch(double power0) { return power0 > 0.01 ? 0 : (power0 > 0.001 ? 1 : 2); }
@@ -697,6 +701,25 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs, bool allow_defer = false)
                 pl.add(g++, K_BOXCAR, box_job(s, 1, 0, true, cutoff_window(200000.0), BOX_LP, false, true));
                 s.out_re = s.plane[0][0]; s.out_im = s.plane[0][1];
             }
+        }
+    }
+    // EXTENDED mode, decimate = D > 1: the mode's chain, then the decimating box-car; the
+    // correlators see n / D samples at fs / D
+    const int D = decimation(e);
+    if (D > 1) {
+        const size_t last = pl.stages.size();
+        for (auto &s : sigs) {
+            s.n_out = s.n / D;
+            if (s.n == 0) continue;
+            SigJob j = base_job(s);
+            j.q_re = s.out_re; j.q_im = s.out_im;
+            float *dre = nullptr, *dim = nullptr;
+            if ((rc = alloc_t(e, &dre, (size_t)std::max<i64>(s.n_out, 1)))) return rc;
+            if (s.out_im && (rc = alloc_t(e, &dim, (size_t)std::max<i64>(s.n_out, 1)))) return rc;
+            j.p_re = dre; j.p_im = dim;
+            j.window = D; j.want_power = 1;
+            pl.add(last, K_DECIMATE, j);
+            s.out_re = dre; s.out_im = dim;
         }
     }
     return run_pipeline(e, pl);
@@ -1059,7 +1082,8 @@ int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pa
         K.flags = ((uint32_t)s1.branch << 8) | ((uint32_t)s2.branch << 10);
         K.sanity = 0;
         K.lag_origin = 0;
-        if (s1.n == 0 || s2.n == 0) {  // processor.go:622-625
+        const i64 n1 = s1.n_out >= 0 ? s1.n_out : s1.n, n2 = s2.n_out >= 0 ? s2.n_out : s2.n;
+        if (n1 == 0 || n2 == 0) {  // processor.go:622-625
             K.flags |= TDOA_PEAK_EMPTY;
             K.nb = 0; K.n_lags = 0; K.n_lags2 = 0; K.corr = K.corr2 = nullptr;
             K.variant = CORR_BINARY;
@@ -1068,15 +1092,15 @@ int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pa
         }
         // processor.go:653-661: the shorter input is the template
         const Sig *tp = &s1, *sg = &s2;
-        if (s1.n > s2.n) { tp = &s2; sg = &s1; }
-        const i64 tl = tp->n, sl = sg->n;
+        if (n1 > n2) { tp = &s2; sg = &s1; }
+        const i64 tl = std::min(n1, n2), sl = std::max(n1, n2);
         J.t_re = tp->out_re; J.t_im = tp->out_im; J.t_stats = tp->stats;
         J.s_re = sg->out_re; J.s_im = sg->out_im; J.s_stats = sg->stats;
         J.sl = sl;
         J.lag0 = 0;
         J.t_off = 0;
         if (cfg.mode == TDOA_MODE_EXTENDED) {
-            const i64 W = std::min(tl, sl), L = cfg.max_lag;
+            const i64 W = std::min(tl, sl), L = cfg.max_lag / decimation(e);
             const i64 n = W - 2 * L;
             J.variant = CORR_EXTENDED;
             J.t_off = L;
@@ -1221,6 +1245,10 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
             d_first = nullptr;
             if (w0 == 0 && (rc = alloc_t(e, &d_first, pairs.size()))) return rc;
             if ((rc = correlate(e, sigs, pairs, d_out + (size_t)w0 * P, d_first))) return rc;
+            if (decimation(e) > 1) {
+                launch_lag_units(d_out + (size_t)w0 * P, (int)pairs.size(), decimation(e), e->stream);
+                count_launch(e);
+            }
             cudaEventRecord(e->ev[3], e->stream);
             bool any_deferred = false;
             for (auto &sg : sigs) any_deferred |= sg.deferred;
@@ -1354,6 +1382,8 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
         return fail(nullptr, TDOA_E_INVALID, "tdoa_create: bad mode %d", cfg->mode);
     if (cfg->n_stations < 2 || cfg->n_stations > 64)
         return fail(nullptr, TDOA_E_INVALID, "tdoa_create: n_stations must be 2..64, got %d", cfg->n_stations);
+    if (cfg->decimate < 0 || cfg->decimate > 4096 || (cfg->decimate > 1 && cfg->mode != TDOA_MODE_EXTENDED))
+        return fail(nullptr, TDOA_E_INVALID, "tdoa_create: decimate is an EXTENDED-mode option (1..4096), got %d", cfg->decimate);
     if (cfg->max_lag < 0 || cfg->block_size < 1 || cfg->chunk_samples < 0 || cfg->sanity_lag < 0 || cfg->guard_samples < 0 ||
         cfg->copy_chunk < 0)
         return fail(nullptr, TDOA_E_INVALID, "tdoa_create: negative size in config");
@@ -1703,6 +1733,7 @@ int tdoa_preprocess(tdoa_engine *e, int32_t station, int32_t kind, int64_t start
     if ((rc = preprocess(e, sigs))) return rc;
     if (power) *power = sigs[0].power0;
     if (branch) *branch = sigs[0].branch;
+    if (decimation(e) > 1) len = sigs[0].n_out;  // the first len / D entries of out_c64 are written
     if (len > 0) {
         Sig &sg = sigs[0];
         float *d_nre = nullptr, *d_nim = nullptr, *d_c64 = nullptr;
@@ -1710,6 +1741,7 @@ int tdoa_preprocess(tdoa_engine *e, int32_t station, int32_t kind, int64_t start
             (rc = alloc_t(e, &d_c64, (size_t)2 * len)))
             return rc;
         SigJob j = base_job(sg);
+        j.n = len;  // the preprocessed signal's length (n / D with the decimator)
         j.q_re = sg.out_re; j.q_im = sg.out_im; j.p_re = d_nre; j.p_im = d_nim;
         std::vector<SigJob> jobs(1, j);
         const SigJob *d_jobs = nullptr;

@@ -105,6 +105,7 @@ void launch_seqsum(const SigJob *d_jobs, int n_jobs, cudaStream_t st);
 void launch_boxcar(const SigJob *d_jobs, int n_jobs, i64 max_n, int max_window, cudaStream_t st);
 void launch_notch_combine(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
 void launch_normalize(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
+void launch_decimate(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);  // window = D, n = input samples
 void launch_interleave(const float *re, const float *im, i64 n, float *out_c64, cudaStream_t st);
 void launch_deinterleave(const float *c64, i64 n, float *re, float *im, cudaStream_t st);
 int boxcar_grid_x(i64 n);
@@ -128,6 +129,7 @@ int fast_grid_x(i64 n);
 void launch_corr_brute(const PairJob *d_jobs, int n_jobs, i64 max_nb, int max_lags, cudaStream_t st);
 void launch_corr_finalize(const PairJob *d_jobs, int n_jobs, int max_lags, cudaStream_t st);
 void launch_peak(const PeakJob *d_jobs, int n_jobs, cudaStream_t st);
+void launch_lag_units(PeakRec *d_recs, int n, int D, cudaStream_t st);
 
 // ---- analyze.cu (fast_analyzer.go / analyzer.go)
 struct QualJob {

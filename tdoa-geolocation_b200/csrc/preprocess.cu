@@ -274,6 +274,45 @@ __global__ void __launch_bounds__(kThreads) k_normalize(const SigJob *jobs)
     }
 }
 
+// ---------------------------------------------------------------- decimating box-car
+// Engine-defined (EXTENDED mode, cfg.decimate = D > 1; the reference's processor never
+// decimates -- the integrate-and-dump low-pass of the vendored rtl_fm.c:302-322 is the
+// model): y[m] = (x[mD] + ... + x[mD + D-1]) / D, m < n / D, sums sequential f32 in
+// ascending order, one f32 divide; plus the power of y for normalizeSignal.
+// One thread per output: a warp reads 32 D consecutive floats.
+__global__ void __launch_bounds__(kThreads) k_decimate(const SigJob *jobs)
+{
+    __shared__ double scratch[32];
+    const SigJob &J = jobs[blockIdx.y];
+    const int D = J.window;
+    const i64 m_out = J.n / D;
+    const float fd = (float)D;
+    double pacc = 0.0;
+    const i64 stride = (i64)gridDim.x * kThreads;
+    for (i64 m = (i64)blockIdx.x * kThreads + threadIdx.x; m < m_out; m += stride) {
+        const float *__restrict__ qr = J.q_re + m * D;
+        float ar = qr[0];
+        for (int k = 1; k < D; k++) ar = __fadd_rn(ar, qr[k]);
+        ar = __fdiv_rn(ar, fd);
+        float ai = 0.f;
+        if (J.q_im) {
+            const float *__restrict__ qi = J.q_im + m * D;
+            ai = qi[0];
+            for (int k = 1; k < D; k++) ai = __fadd_rn(ai, qi[k]);
+            ai = __fdiv_rn(ai, fd);
+        }
+        J.p_re[m] = ar;
+        if (J.p_im) J.p_im[m] = ai;
+        pacc += (double)mag2_f32(ar, ai);
+    }
+    double part[1] = {block_sum(pacc, scratch)}, total[1];
+    if (grid_sum_last<1>(part, J.partials, J.counter, gridDim.x, blockIdx.x, scratch, total)) {
+        const double pw = m_out > 0 ? total[0] / (double)m_out : 0.0;
+        J.stats[ST_POWER1] = pw;
+        J.stats[ST_SCALE] = pw > 0.0 ? (double)(float)(1.0 / sqrt(pw)) : 1.0;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k_interleave(const float *re, const float *im, i64 n, float2 *out)
 {
     const i64 stride = (i64)gridDim.x * kThreads;
@@ -344,6 +383,10 @@ void launch_boxcar(const SigJob *d_jobs, int n_jobs, i64 max_n, int max_window, 
 void launch_notch_combine(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)
 {
     k_notch_combine<<<dim3(stream_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
+}
+void launch_decimate(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)
+{
+    k_decimate<<<dim3(stream_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
 }
 void launch_normalize(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)
 {

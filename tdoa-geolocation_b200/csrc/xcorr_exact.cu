@@ -223,6 +223,25 @@ void launch_corr_finalize(const PairJob *d_jobs, int n_jobs, int max_lags, cudaS
     k_corr_finalize<<<grid, kCorrThreads, 0, st>>>(d_jobs);
 }
 
+// lags found on decimated signals, back in samples of the capture: lag + frac -> D (lag + frac)
+__global__ void k_lag_units(PeakRec *recs, int n, int D)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PeakRec r = recs[i];
+    const double total = (double)D * ((double)r.lag + (double)r.frac);
+    const double whole = rint(total);
+    r.lag = (int32_t)whole;
+    r.frac = (float)(total - whole);
+    r.first_lag *= D;
+    recs[i] = r;
+}
+
+void launch_lag_units(PeakRec *d_recs, int n, int D, cudaStream_t st)
+{
+    if (n > 0 && D > 1) k_lag_units<<<(n + 127) / 128, 128, 0, st>>>(d_recs, n, D);
+}
+
 void launch_peak(const PeakJob *d_jobs, int n_jobs, cudaStream_t st)
 {
     if (n_jobs <= 0) return;

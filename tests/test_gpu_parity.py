@@ -256,6 +256,39 @@ def test_extended_wide_lags_use_the_big_transform():
     assert [int(g["lag"]) for g in ref] == [-400, 1300, 1700]
 
 
+@pytest.mark.parametrize("D", [4, 8])
+def test_extended_decimating_boxcar(D):
+    """decimate = D (EXTENDED only, engine-defined): the binary's chain, then the mean of D
+    consecutive samples, then normalise; correlation at fs / D over max_lag / D lags; records in
+    samples of the capture.  Oracle: orc_preprocess_binary_dec + orc_xcorr_two_sided."""
+    L, W = 320, 48000
+    true_t = (25, 60, 0)
+    raws = fm_capture(60000, (40, 0, 17), true_t, seed=13, dev_tgt=20e3)
+    oracle.set_seq_dc_limit(0)
+    with T.Engine(T.MODE_EXTENDED, max_lag=L, decimate=D) as e:
+        load_all(e, raws)
+        for st in range(3):
+            got, p0, br = e.preprocess(st, T.KIND_TGT, 500, W)
+            want, wbr = oracle.preprocess_binary_dec(split(raws[st])[1][500:500 + W], D)
+            assert br == wbr == 0 and got.size == W // D
+            assert np.max(np.abs(got - want)) <= 4e-6
+        pk = e.xcorr(T.KIND_TGT, 500, W, 1, 0)[0]
+        for p, (i, j) in enumerate([(0, 1), (0, 2), (1, 2)]):
+            yi, _ = oracle.preprocess_binary_dec(split(raws[i])[1][500:500 + W], D)
+            yj, _ = oracle.preprocess_binary_dec(split(raws[j])[1][500:500 + W], D)
+            c = oracle.xcorr_two_sided(yi, yj, L // D)
+            idx, frac, val = oracle.peak_parabolic(c)
+            want_total = D * (idx - L // D + frac)
+            got_total = int(pk[p]["lag"]) + float(pk[p]["frac"])
+            assert abs(got_total - want_total) <= 1e-3 * D       # 1e-3 samples at the decimated rate
+            assert abs(float(pk[p]["corr"]) - val) <= CORR_TOL
+            assert abs(float(pk[p]["frac"])) <= 0.5 + 1e-6
+            assert abs(got_total - (true_t[j] - true_t[i])) <= 0.75   # the injected delay, to sub-sample accuracy
+    oracle.set_seq_dc_limit(-1)
+    with pytest.raises(T.TdoaError):
+        T.Engine(T.MODE_BINARY, decimate=4)
+
+
 # ------------------------------------------------------------------ geodesy + solvers
 def test_baselines_and_solver(eng_binary):
     base = eng_binary.baselines(STATION_LLH)
