@@ -312,6 +312,13 @@ def main_ours(args):
     clamp = [max(w, 0) for w in want]  # the reference searches non-negative lags only
     lags_ok = got_r == clamp and got_t == clamp
 
+    # the same peaks through the engine's least-squares fix (all three range differences,
+    # elevation held): the reference's own solver stops after ten half steps wherever it is
+    # (processor.go:932-1020), which for these delays is nowhere near the transmitter
+    ls_pos, ls_rms, ls_status, _ = eng.solve_ls(STATION_LLH, tgt["lag"].astype(np.float64) / FS * C_LIGHT,
+                                                init_llh=[float(STATION_LLH[:, 0].mean()), float(STATION_LLH[:, 1].mean()), TX_LLH[2]], dims=2)
+    ls_err = float(np.linalg.norm(llh_to_ecef(*ls_pos) - llh_to_ecef(*TX_LLH)))
+
     def timed(fn, steps, warmup, collect_stats=False):
         for _ in range(warmup):
             fn()
@@ -402,7 +409,11 @@ def main_ours(args):
             "roofline_kernels": kernels,
             "stage_ms_per_step": {k: stage[k] / args.steps for k in ("ms_preprocess", "ms_fft", "ms_exact")},
             "parity_check": {"lags_match_injected_delays": bool(lags_ok), "ref_lags": got_r, "tgt_lags": got_t,
-                             "injected": want, "n_candidates": [int(x) >> 16 & 255 for x in list(ref["flags"]) + list(tgt["flags"])], "fix_llh": [float(x) for x in pos], "fix_status": int(status)},
+                             "injected": want, "n_candidates": [int(x) >> 16 & 255 for x in list(ref["flags"]) + list(tgt["flags"])], "fix_llh": [float(x) for x in pos], "fix_status": int(status),
+                             "fix_note": "fix_llh is solveTDOA as the reference states it (its 10th half step, Z frozen); "
+                                         "ls_fix_llh is tdoa_solve_ls on the same lags",
+                             "ls_fix_llh": [float(x) for x in ls_pos], "ls_fix_error_m": ls_err, "ls_fix_rms_m": float(ls_rms),
+                             "ls_fix_status": int(ls_status)},
             "cpu_baseline": {k: v for k, v in cb.items() if k != "ok"} if cb else None,
         }
     if world > 1:
