@@ -220,7 +220,7 @@ def main_reference(args):
         "e2e": {"value": value, "unit": "pair-Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "fixes_per_s": 0.0, "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    OUT.emit(json.dumps(line))
     return 0
 
 
@@ -276,13 +276,12 @@ def main_ours(args):
                 stage[k] += st[k]
 
     def step_resident():
-        ref = eng.xcorr(T.KIND_REF)[0]
+        # tdoa_process = ProcessTDOA from the pair loops to the fix (processor.go:816-929): REF pair
+        # loop, TGT pair loop, time / range differences, solveTDOA, queued on the device without
+        # an intermediate host synchronisation; records and fix come back to the host
+        r = eng.process(STATION_LLH)
         collect()
-        tgt = eng.xcorr(T.KIND_TGT)[0]
-        collect()
-        # processor.go:899-903: range differences from the target time differences
-        rd = tgt["lag"].astype(np.float64) / FS * C_LIGHT
-        pos, status, _ = eng.solve(STATION_LLH, rd)
+        ref, tgt, pos, status = r["ref"], r["tgt"], r["position"], r["status"]
         if world > 1:
             # the path's single collective: every rank's peak records
             rec = torch.from_numpy(np.concatenate([ref, tgt]).view(np.uint8).copy()).to(device, non_blocking=True)
@@ -420,12 +419,38 @@ def main_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        OUT.emit(json.dumps(line))
     eng.close()
     return 0
 
 
+class OnlyJsonOnStdout:
+    """Everything the libraries print while the run is in progress (e.g. NCCL's version
+    banner) goes to stderr; stdout carries the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
+OUT = None
+
+
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -433,9 +458,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--block", type=int, default=66_666_666, help="samples per block (default: 100 s capture)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return main_reference(args)
-    return main_ours(args)
+    with OnlyJsonOnStdout() as OUT:
+        if args.impl == "reference":
+            return main_reference(args)
+        return main_ours(args)
 
 
 if __name__ == "__main__":

@@ -159,6 +159,17 @@ TDOA_API int tdoa_xcorr(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t
 TDOA_API int tdoa_xcorr_device(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
                                int32_t n_windows, int64_t hop, tdoa_peak *d_out);
 
+/* ProcessTDOA from the pair loops to the fix as ONE call (processor.go:816-929 on window 0
+ * with the config's chunk): the REF pair loop, the TGT pair loop, dt = delay / fs, the
+ * mode's time differences (SOURCE: target only, :853; binary modes: target - reference,
+ * pair by pair), range differences (:899-903) and solveTDOA -- all queued on the device
+ * without an intermediate host synchronisation.  ref_out / tgt_out [P]; time_diffs,
+ * range_diffs [P] (may be NULL); fix_llh[3]; *fix_status 0 or TDOA_E_SINGULAR.
+ * tdoa_xcorr_info() afterwards reports both kinds. */
+TDOA_API int tdoa_process(tdoa_engine *e, const double *stations_llh, tdoa_peak *ref_out, tdoa_peak *tgt_out,
+                          double *time_diffs, double *range_diffs, double *fix_llh, int32_t *fix_status,
+                          int32_t *fix_iters);
+
 /* crossCorrelate seam (processor.go:619-643): two host complex64 slices
  * (interleaved re,im), returns (delay, correlation).  Empty input -> (0, 0.0). */
 TDOA_API int tdoa_cross_correlate(tdoa_engine *e, const float *sig1_c64, int64_t n1,

@@ -23,7 +23,7 @@ ERRORS = {-1: "TDOA_E_INVALID", -2: "TDOA_E_NODEVICE", -3: "TDOA_E_CUDA", -4: "T
 # every symbol include/tdoa_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "tdoa_default_config", "tdoa_create", "tdoa_destroy", "tdoa_last_error", "tdoa_host_alloc", "tdoa_host_free",
-    "tdoa_load_u8", "tdoa_load_file", "tdoa_load_u8_pinned", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_xcorr_info", "tdoa_analyze",
+    "tdoa_load_u8", "tdoa_load_file", "tdoa_load_u8_pinned", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_process", "tdoa_xcorr_info", "tdoa_analyze",
     "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_solve_ls", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
     "tdoa_set_stream", "tdoa_synchronize", "tdoa_selftest",
 ]
@@ -138,6 +138,7 @@ def load_library():
     L.tdoa_preprocess.argtypes = [vp, i32, i32, i64, i64, vp, f64p, C.POINTER(i32)]
     L.tdoa_xcorr.argtypes = [vp, i32, i64, i64, i32, i64, vp]
     L.tdoa_xcorr_info.argtypes = [vp, i32, vp, vp]
+    L.tdoa_process.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.tdoa_analyze.argtypes = [vp, i32, i32, vp, vp]
     L.tdoa_xcorr_device.argtypes = [vp, i32, i64, i64, i32, i64, vp]
     L.tdoa_cross_correlate.argtypes = [vp, vp, i64, vp, i64, C.POINTER(PeakStruct)]
@@ -368,6 +369,21 @@ class Engine:
         if single:
             return out[0], int(status[0]), int(iters[0])
         return out, status, iters
+
+    def process(self, stations_llh) -> dict:
+        """ProcessTDOA from the pair loops to the fix in one call (processor.go:816-929), queued on the
+        device without intermediate host synchronisation."""
+        st = np.ascontiguousarray(stations_llh, dtype=np.float64).reshape(-1, 3)
+        if st.shape[0] != self.n_stations:
+            raise ValueError(f"stations_llh has {st.shape[0]} rows, the engine holds {self.n_stations} stations")
+        P = self.n_pairs
+        ref, tgt = np.zeros(P, PEAK_DTYPE), np.zeros(P, PEAK_DTYPE)
+        td, rd, fix = np.zeros(P, np.float64), np.zeros(P, np.float64), np.zeros(3, np.float64)
+        status, iters = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.tdoa_process(self._h, _ptr(st), _ptr(ref), _ptr(tgt), _ptr(td), _ptr(rd), _ptr(fix),
+                                           C.byref(status), C.byref(iters)))
+        return {"ref": ref, "tgt": tgt, "time_differences": td, "range_differences": rd, "position": fix,
+                "status": int(status.value), "iters": int(iters.value)}
 
     def solve_ls(self, stations_llh, range_diffs, init_llh=None, dims: int = 2):
         """Levenberg-Marquardt fix over all pair range differences (engine-defined).

@@ -122,6 +122,7 @@ struct tdoa_engine {
     struct Span { cudaEvent_t a = nullptr, b = nullptr; int tag = 0; };
     std::vector<Span> spans;
     size_t spans_used = 0;
+    float ms_corr = 0.f;   // correlation stage of the current call (ms_exact = ms_corr - ms_fft)
 };
 
 namespace {
@@ -218,7 +219,7 @@ int upload(tdoa_engine *e, const std::vector<T> &v, const T **d_out)
 inline void count_launch(tdoa_engine *e, int n = 1) { e->st.launches_total += n; }
 
 // ---- per-kernel device time: an event pair around a launch, read back at the call's sync
-enum { SPAN_DEMOD = 0, SPAN_BOXCAR = 1, SPAN_CAND = 2 };
+enum { SPAN_DEMOD = 0, SPAN_BOXCAR = 1, SPAN_CAND = 2, SPAN_STAGE_PRE = 3, SPAN_STAGE_CORR = 4, SPAN_FFT = 5, SPAN_FFT_SEG = 6 };
 
 int span_begin(tdoa_engine *e, int tag)
 {
@@ -248,6 +249,10 @@ void spans_collect(tdoa_engine *e)
             case SPAN_DEMOD: e->st.ms_demod += ms; e->st.demod_launches++; break;
             case SPAN_BOXCAR: e->st.ms_boxcar += ms; e->st.boxcar_launches++; break;
             case SPAN_CAND: e->st.ms_cand += ms; e->st.cand_launches++; break;
+            case SPAN_STAGE_PRE: e->st.ms_preprocess += ms; break;
+            case SPAN_STAGE_CORR: e->ms_corr += ms; break;
+            case SPAN_FFT: e->st.ms_fft += ms; break;
+            case SPAN_FFT_SEG: e->st.ms_fft_seg += ms; break;
         }
     }
     e->spans_used = 0;
@@ -960,10 +965,13 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
         return rc;
     const TileJob *d_t = nullptr;
     if (tiled && (rc = upload(e, tjobs, &d_t))) return rc;
-    cudaEventRecord(e->ev_fft[0], e->stream);
-    if (tiled) launch_fft_tiles(d_t, (int)tjobs.size(), max_cta, e->d_tw, e->stream);
-    else launch_fft_segments(d_f, (int)fjobs.size(), max_cta, e->d_tw, e->stream);
-    cudaEventRecord(e->ev_fft[1], e->stream);
+    const int sp_fft = span_begin(e, SPAN_FFT);
+    {
+        const int sp_seg = span_begin(e, SPAN_FFT_SEG);
+        if (tiled) launch_fft_tiles(d_t, (int)tjobs.size(), max_cta, e->d_tw, e->stream);
+        else launch_fft_segments(d_f, (int)fjobs.size(), max_cta, e->d_tw, e->stream);
+        span_end(e, sp_seg);
+    }
     launch_fft_reduce(d_f, (int)fjobs.size(), e->stream);
     launch_fft_finish(d_f, (int)fjobs.size(), e->d_tw, e->stream);
     // ---- big tiles, in batches that share four 16 MiB buffers per tile
@@ -1050,7 +1058,7 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
         }
     }
     launch_select_candidates(d_s, np, e->stream);
-    cudaEventRecord(e->ev[5], e->stream);
+    span_end(e, sp_fft);
     {
         const int sp = span_begin(e, SPAN_CAND);
         launch_corr_candidates(d_p, d_c, np, max_nb, e->stream);
@@ -1063,8 +1071,10 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     return TDOA_OK;
 }
 
+// optimistic = true: queue only -- the candidate-overflow check (and the lag-by-lag redo it may
+// ask for) is left to the caller, who looks at the records' flags after its own synchronisation
 int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pair> &pairs, PeakRec *d_out,
-              double *d_first = nullptr)
+              double *d_first = nullptr, bool optimistic = false)
 {
     if (pairs.empty()) return TDOA_OK;
     const tdoa_config &cfg = e->cfg;
@@ -1154,13 +1164,11 @@ int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pa
     if ((rc = run_brute(e, brute))) return rc;
     if (!viafft.empty()) {
         if ((rc = run_fft(e, viafft))) return rc;
+        if (optimistic) return TDOA_OK;
         // candidate overflow (a flat correlation surface): redo those pairs lag by lag
         std::vector<PeakRec> h(np);
         CU(cudaMemcpyAsync(h.data(), d_out, (size_t)np * sizeof(PeakRec), cudaMemcpyDeviceToHost, e->stream));
         CU(cudaStreamSynchronize(e->stream));
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, e->ev_fft[0], e->ev_fft[1]) == cudaSuccess) e->st.ms_fft_seg += ms;
-        if (cudaEventElapsedTime(&ms, e->ev_fft[0], e->ev[5]) == cudaSuccess) e->st.ms_fft += ms;
         std::vector<CorrPlan *> redo;
         for (CorrPlan *pl : viafft)
             if (h[pl->peak.out - d_out].flags & 0x10u) redo.push_back(pl);
@@ -1171,21 +1179,65 @@ int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pa
 
 // ---------------------------------------------------------------- xcorr over windows
 
-int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len, int32_t n_windows, int64_t hop,
-               tdoa_peak *out, bool out_is_device)
+// What an optimistic (host-sync-free) pass over one signal kind leaves to be checked once
+// the caller has synchronised: the statistics of its signals (branch guesses, the
+// reference's diagnostics) and the first-pass correlations.
+struct Pending {
+    int kind = 0;
+    std::vector<Sig> sigs;       // window 0 (the only window of an optimistic pass)
+    double *d_first = nullptr;
+    bool valid = false;
+};
+
+void stats_reset(tdoa_engine *e)
 {
-    if (!e) return TDOA_E_INVALID;
-    int rc = begin_call(e);
-    if (rc) return rc;
-    if (!out) return fail(e, TDOA_E_INVALID, "tdoa_xcorr: out is NULL");
+    e->st.ms_preprocess = e->st.ms_fft = e->st.ms_fft_seg = e->st.ms_exact = e->st.ms_total = 0.f;
+    e->st.fft_launches = 0; e->st.fft_pair_samples = 0;
+    e->st.ms_demod = e->st.ms_boxcar = e->st.ms_cand = 0.f;
+    e->st.demod_launches = e->st.demod_samples = e->st.boxcar_launches = e->st.boxcar_samples = 0;
+    e->st.cand_launches = e->st.cand_pair_samples = 0;
+    e->ms_corr = 0.f;
+    e->spans_used = 0;
+}
+
+// window 0 of the last pass over `kind`: what the reference prints (tdoa_xcorr_info)
+void fill_info(tdoa_engine *e, int kind, const std::vector<Sig> &sigs, const double *h_stats, int S)
+{
+    e->info_sig[kind].assign(S, tdoa_signal_info{});
+    for (int s = 0; s < S; s++) {
+        tdoa_signal_info &I = e->info_sig[kind][s];
+        const double *st = h_stats + (size_t)s * ST_COUNT;
+        I.power0 = st[ST_POWER0]; I.dc_re = st[ST_DC_RE]; I.dc_im = st[ST_DC_IM]; I.power1 = st[ST_POWER1];
+        I.branch = sigs[s].branch; I.n = sigs[s].n;
+    }
+}
+
+// true: every speculated signal really was on the "strong FM" branch (memo updated either way)
+bool verify_deferred(tdoa_engine *e, std::vector<Sig> &sigs, const double *h_stats)
+{
+    bool ok = true;
+    for (size_t i = 0; i < sigs.size(); i++) {
+        Sig &sg = sigs[i];
+        if (!sg.deferred) continue;
+        sg.power0 = h_stats[i * ST_COUNT + ST_POWER0];
+        const int actual = sg.n == 0 ? 0 : binary_branch(sg.power0);
+        if (sg.memo >= 0) e->branch_memo[sg.memo] = (int8_t)actual;
+        ok &= actual == 0;
+    }
+    return ok;
+}
+
+// Validates the window arguments and fills the per-station window length.
+int window_lengths(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len, int32_t n_windows, int64_t hop,
+                   std::vector<i64> &len)
+{
     if (kind != TDOA_KIND_REF && kind != TDOA_KIND_TGT) return fail(e, TDOA_E_INVALID, "tdoa_xcorr: bad kind %d", kind);
     if (n_windows < 1 || win_start < 0 || win_len < 0 || (n_windows > 1 && hop <= 0))
         return fail(e, TDOA_E_INVALID, "tdoa_xcorr: bad window arguments");
-    const int S = e->cfg.n_stations, P = S * (S - 1) / 2;
+    const int S = e->cfg.n_stations;
     for (int s = 0; s < S; s++)
         if (!e->stations[s].loaded) return fail(e, TDOA_E_STATE, "tdoa_xcorr: station %d has no capture loaded", s);
-    // window length per station
-    std::vector<i64> len(S);
+    len.assign(S, 0);
     for (int s = 0; s < S; s++) {
         const i64 n = signal_length(e->stations[s], kind, e->cfg.guard_samples);
         if (win_len == 0) {
@@ -1203,18 +1255,19 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
             len[s] = win_len;
         }
     }
-    if ((rc = queue_lazy_copies(e, kind))) return rc;
-    PeakRec *d_out = nullptr;
-    if (out_is_device) d_out = reinterpret_cast<PeakRec *>(out);
-    else if ((rc = alloc_t(e, &d_out, (size_t)n_windows * P))) return rc;
+    return TDOA_OK;
+}
 
-    e->st.ms_fft = 0.f; e->st.ms_fft_seg = 0.f; e->st.fft_launches = 0; e->st.fft_pair_samples = 0;
-    e->st.ms_demod = e->st.ms_boxcar = e->st.ms_cand = 0.f;
-    e->st.demod_launches = e->st.demod_samples = e->st.boxcar_launches = e->st.boxcar_samples = 0;
-    e->st.cand_launches = e->st.cand_pair_samples = 0;
-    e->spans_used = 0;
-    cudaEventRecord(e->ev[0], e->stream);
-    float ms_pre = 0.f, ms_corr = 0.f;
+// The pair loops of one signal kind over the windows, records to d_out (device).
+// pend == nullptr: every check is made here (the stream is synchronised as needed).
+// pend != nullptr: one window, everything only QUEUED -- branch guesses and candidate
+// overflow are the caller's to check after its synchronisation (tdoa_process).
+int xcorr_core(tdoa_engine *e, int32_t kind, int64_t win_start, const std::vector<i64> &len, int32_t n_windows,
+               int64_t hop, PeakRec *d_out, Pending *pend)
+{
+    int rc;
+    const int S = e->cfg.n_stations, P = S * (S - 1) / 2;
+    if ((rc = queue_lazy_copies(e, kind))) return rc;
     // windows are processed in groups that keep the working set bounded
     i64 per_window_bytes = 0;
     for (int s = 0; s < S; s++) per_window_bytes += len[s] * 4 * 4;
@@ -1238,18 +1291,31 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
         }
         double *d_first = nullptr;
         std::vector<double> h_stats;
+        // scratch of this group: everything allocated / staged from here on (what the caller
+        // allocated before -- record buffers, the other kind's planes -- is not ours to free)
+        const size_t alloc_mark = e->call_allocs.size(), frame_mark = e->frame_used;
+        auto drop_group_scratch = [&]() {
+            for (size_t k = alloc_mark; k < e->call_allocs.size(); k++) cudaFreeAsync(e->call_allocs[k], e->stream);
+            e->call_allocs.resize(alloc_mark);
+            e->frame_used = frame_mark;  // the stream is idle: descriptor staging can be reused
+        };
         for (int attempt = 0; attempt < 2; attempt++) {
-            cudaEventRecord(e->ev[1], e->stream);
+            const int sp_pre = span_begin(e, SPAN_STAGE_PRE);
             if ((rc = preprocess(e, sigs, attempt == 0))) return rc;
-            cudaEventRecord(e->ev[2], e->stream);
+            span_end(e, sp_pre);
+            const int sp_corr = span_begin(e, SPAN_STAGE_CORR);
             d_first = nullptr;
             if (w0 == 0 && (rc = alloc_t(e, &d_first, pairs.size()))) return rc;
-            if ((rc = correlate(e, sigs, pairs, d_out + (size_t)w0 * P, d_first))) return rc;
+            if ((rc = correlate(e, sigs, pairs, d_out + (size_t)w0 * P, d_first, pend != nullptr))) return rc;
             if (decimation(e) > 1) {
                 launch_lag_units(d_out + (size_t)w0 * P, (int)pairs.size(), decimation(e), e->stream);
                 count_launch(e);
             }
-            cudaEventRecord(e->ev[3], e->stream);
+            span_end(e, sp_corr);
+            if (pend) {
+                pend->kind = kind; pend->sigs = sigs; pend->d_first = d_first; pend->valid = true;
+                return TDOA_OK;
+            }
             bool any_deferred = false;
             for (auto &sg : sigs) any_deferred |= sg.deferred;
             if (!any_deferred && w0 != 0) break;
@@ -1259,24 +1325,11 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
             CU(cudaMemcpyAsync(h_stats.data(), sigs[0].stats, h_stats.size() * sizeof(double), cudaMemcpyDeviceToHost,
                                e->stream));
             CU(cudaStreamSynchronize(e->stream));
-            bool wrong = false;
-            for (size_t i = 0; i < sigs.size(); i++) {
-                Sig &sg = sigs[i];
-                if (!sg.deferred) continue;
-                sg.power0 = h_stats[i * ST_COUNT + ST_POWER0];
-                const int actual = sg.n == 0 ? 0 : binary_branch(sg.power0);
-                if (sg.memo >= 0) e->branch_memo[sg.memo] = (int8_t)actual;
-                wrong |= actual != 0;
-            }
-            if (!wrong) break;
+            if (verify_deferred(e, sigs, h_stats.data())) break;
             // a guess was wrong (the capture is not "strong FM"): drop the group's scratch and
             // redo it with the powers read first; the memo now keeps those signals off the fused path
             spans_collect(e);
-            for (void *p : e->call_allocs)
-                if (p != d_out) cudaFreeAsync(p, e->stream);
-            e->call_allocs.clear();
-            e->frame_used = 0;
-            if (!out_is_device) e->call_allocs.push_back(d_out);
+            drop_group_scratch();
             for (auto &sg : sigs) {
                 Sig fresh;
                 fresh.n = sg.n; fresh.src = sg.src; fresh.memo = sg.memo;
@@ -1289,29 +1342,34 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
             e->info_first[kind].assign(P, 0.0);
             CU(cudaMemcpyAsync(e->info_first[kind].data(), d_first, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
             CU(cudaStreamSynchronize(e->stream));
-            e->info_sig[kind].assign(S, tdoa_signal_info{});
-            for (int s = 0; s < S; s++) {
-                tdoa_signal_info &I = e->info_sig[kind][s];
-                const double *st = h_stats.data() + (size_t)s * ST_COUNT;
-                I.power0 = st[ST_POWER0]; I.dc_re = st[ST_DC_RE]; I.dc_im = st[ST_DC_IM]; I.power1 = st[ST_POWER1];
-                I.branch = sigs[s].branch; I.n = sigs[s].n;
-            }
+            fill_info(e, kind, sigs, h_stats.data(), S);
         }
         // free this group's planes before the next group allocates
         if (w0 + group < n_windows) {
             CU(cudaStreamSynchronize(e->stream));
-            float a = 0.f, b = 0.f;
-            cudaEventElapsedTime(&a, e->ev[1], e->ev[2]);
-            cudaEventElapsedTime(&b, e->ev[2], e->ev[3]);
-            ms_pre += a; ms_corr += b;
             spans_collect(e);
-            for (void *p : e->call_allocs)
-                if (p != d_out) cudaFreeAsync(p, e->stream);
-            e->call_allocs.clear();
-            e->frame_used = 0;  // the stream is idle: descriptor staging can be reused
-            if (!out_is_device) e->call_allocs.push_back(d_out);
+            drop_group_scratch();
         }
     }
+    return TDOA_OK;
+}
+
+int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len, int32_t n_windows, int64_t hop,
+               tdoa_peak *out, bool out_is_device)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (!out) return fail(e, TDOA_E_INVALID, "tdoa_xcorr: out is NULL");
+    std::vector<i64> len;
+    if ((rc = window_lengths(e, kind, win_start, win_len, n_windows, hop, len))) return rc;
+    const int S = e->cfg.n_stations, P = S * (S - 1) / 2;
+    PeakRec *d_out = nullptr;
+    if (out_is_device) d_out = reinterpret_cast<PeakRec *>(out);
+    else if ((rc = alloc_t(e, &d_out, (size_t)n_windows * P))) return rc;
+    stats_reset(e);
+    cudaEventRecord(e->ev[0], e->stream);
+    if ((rc = xcorr_core(e, kind, win_start, len, n_windows, hop, d_out, nullptr))) return rc;
     cudaEventRecord(e->ev[4], e->stream);
     if (!out_is_device)
         CU(cudaMemcpyAsync(out, d_out, (size_t)n_windows * P * sizeof(tdoa_peak), cudaMemcpyDeviceToHost, e->stream));
@@ -1319,13 +1377,10 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
     if (rc) return rc;
     e->st.launches_last = e->st.launches_total - e->launches_at_call;
     if (!out_is_device) {
-        float a = 0.f, b = 0.f, t = 0.f;
+        float t = 0.f;
         spans_collect(e);
-        cudaEventElapsedTime(&a, e->ev[1], e->ev[2]);
-        cudaEventElapsedTime(&b, e->ev[2], e->ev[3]);
         cudaEventElapsedTime(&t, e->ev[0], e->ev[4]);
-        e->st.ms_preprocess = ms_pre + a;
-        e->st.ms_exact = ms_corr + b - e->st.ms_fft;
+        e->st.ms_exact = e->ms_corr - e->st.ms_fft;
         e->st.ms_total = t;
     }
     return TDOA_OK;
@@ -1764,6 +1819,107 @@ int tdoa_xcorr_device(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t w
                       int64_t hop, tdoa_peak *d_out)
 {
     return xcorr_impl(e, kind, win_start, win_len, n_windows, hop, d_out, true);
+}
+
+int tdoa_process(tdoa_engine *e, const double *stations_llh, tdoa_peak *ref_out, tdoa_peak *tgt_out, double *time_diffs,
+                 double *range_diffs, double *fix_llh, int32_t *fix_status, int32_t *fix_iters)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (!stations_llh || !ref_out || !tgt_out || !fix_llh || !fix_status)
+        return fail(e, TDOA_E_INVALID, "tdoa_process: NULL argument");
+    const int S = e->cfg.n_stations, P = S * (S - 1) / 2;
+    if (S < 3) return fail(e, TDOA_E_INVALID, "need at least 3 collector stations, got %d", S);  // processor.go:740-742
+    std::vector<i64> len_ref, len_tgt;
+    if ((rc = window_lengths(e, TDOA_KIND_REF, 0, 0, 1, 0, len_ref)) || (rc = window_lengths(e, TDOA_KIND_TGT, 0, 0, 1, 0, len_tgt)))
+        return rc;
+    PeakRec *d_ref = nullptr, *d_tgt = nullptr;
+    double *d_td = nullptr, *d_rd = nullptr, *d_fix = nullptr;
+    int *d_status = nullptr, *d_iters = nullptr;
+    if ((rc = alloc_t(e, &d_ref, (size_t)P)) || (rc = alloc_t(e, &d_tgt, (size_t)P)) || (rc = alloc_t(e, &d_td, (size_t)P)) ||
+        (rc = alloc_t(e, &d_rd, (size_t)P)) || (rc = alloc_t(e, &d_fix, 3)) || (rc = alloc_t(e, &d_status, 1)) ||
+        (rc = alloc_t(e, &d_iters, 1)))
+        return rc;
+    // the station table rides with the descriptors (a kernel fetches it): a copy-engine
+    // transfer would wait behind the bulk copies of a lazily loaded capture
+    const double *d_llh = nullptr;
+    {
+        std::vector<double> llh(stations_llh, stations_llh + (size_t)3 * S);
+        if ((rc = upload(e, llh, &d_llh))) return rc;
+    }
+    stats_reset(e);
+    cudaEventRecord(e->ev[0], e->stream);
+    auto fix_chain = [&]() {
+        launch_range_diffs(d_ref, d_tgt, P, e->cfg.sample_rate, e->cfg.mode, d_td, d_rd, e->stream);
+        launch_solve(d_llh, d_rd, 1, P, d_fix, d_status, d_iters, e->stream);
+        count_launch(e, 2);
+    };
+    // optimistic pass: both pair loops and the fix are only queued; one synchronisation
+    Pending pend[2];
+    if ((rc = xcorr_core(e, TDOA_KIND_REF, 0, len_ref, 1, 0, d_ref, &pend[0])) ||
+        (rc = xcorr_core(e, TDOA_KIND_TGT, 0, len_tgt, 1, 0, d_tgt, &pend[1])))
+        return rc;
+    fix_chain();
+    cudaEventRecord(e->ev[4], e->stream);
+    std::vector<PeakRec> h_pk((size_t)2 * P);
+    std::vector<double> h_stats[2], h_first[2];
+    auto read_back = [&]() -> int {
+        CU(cudaMemcpyAsync(h_pk.data(), d_ref, (size_t)P * sizeof(PeakRec), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(h_pk.data() + P, d_tgt, (size_t)P * sizeof(PeakRec), cudaMemcpyDeviceToHost, e->stream));
+        if (time_diffs) CU(cudaMemcpyAsync(time_diffs, d_td, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (range_diffs) CU(cudaMemcpyAsync(range_diffs, d_rd, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(fix_llh, d_fix, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(fix_status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        if (fix_iters) CU(cudaMemcpyAsync(fix_iters, d_iters, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        return TDOA_OK;
+    };
+    if ((rc = read_back())) return rc;
+    bool ok = true;
+    for (int k = 0; k < 2; k++) {
+        if (!pend[k].valid) continue;   // the pass ran with its own checks (not speculated)
+        h_stats[k].resize(pend[k].sigs.size() * ST_COUNT);
+        h_first[k].assign(P, 0.0);
+        CU(cudaMemcpyAsync(h_stats[k].data(), pend[k].sigs[0].stats, h_stats[k].size() * sizeof(double), cudaMemcpyDeviceToHost,
+                           e->stream));
+        CU(cudaMemcpyAsync(h_first[k].data(), pend[k].d_first, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < 2; k++) {
+        if (!pend[k].valid) continue;
+        ok &= verify_deferred(e, pend[k].sigs, h_stats[k].data());
+        for (int p = 0; p < P; p++) ok &= (h_pk[(size_t)k * P + p].flags & 0x10u) == 0;   // candidate overflow
+    }
+    if (ok) {
+        for (int k = 0; k < 2; k++) {
+            if (!pend[k].valid) continue;
+            e->info_first[k] = h_first[k];
+            fill_info(e, k, pend[k].sigs, h_stats[k].data(), S);
+        }
+    } else {
+        // a branch guess was wrong or a pair overflowed its candidate list: run the pair
+        // loops again with every check made on the way (the memo keeps the guesses off)
+        spans_collect(e);
+        if ((rc = xcorr_core(e, TDOA_KIND_REF, 0, len_ref, 1, 0, d_ref, nullptr)) ||
+            (rc = xcorr_core(e, TDOA_KIND_TGT, 0, len_tgt, 1, 0, d_tgt, nullptr)))
+            return rc;
+        fix_chain();
+        cudaEventRecord(e->ev[4], e->stream);
+        if ((rc = read_back())) return rc;
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    std::memcpy(ref_out, h_pk.data(), (size_t)P * sizeof(tdoa_peak));
+    std::memcpy(tgt_out, h_pk.data() + P, (size_t)P * sizeof(tdoa_peak));
+    if (*fix_status != 0) *fix_status = TDOA_E_SINGULAR;
+    rc = end_call(e, true);
+    if (rc) return rc;
+    e->st.launches_last = e->st.launches_total - e->launches_at_call;
+    float t = 0.f;
+    spans_collect(e);
+    cudaEventElapsedTime(&t, e->ev[0], e->ev[4]);
+    e->st.ms_exact = e->ms_corr - e->st.ms_fft;
+    e->st.ms_total = t;
+    return TDOA_OK;
 }
 
 int tdoa_cross_correlate(tdoa_engine *e, const float *sig1_c64, int64_t n1, const float *sig2_c64, int64_t n2,

@@ -153,6 +153,8 @@ void launch_solve(const double *d_llh, const double *d_rd, int n_sets, int rd_st
 void launch_solve_ls(const double *d_llh, int n_st, const double *d_rd, int n_sets, int rd_stride, const double *d_init,
                      int dims, double *d_out_llh, double *d_rms, int *d_status, int *d_iters, cudaStream_t st);
 int solve_ls_max_stations();
+void launch_range_diffs(const PeakRec *d_ref, const PeakRec *d_tgt, int n_pairs, double fs, int mode, double *d_td,
+                        double *d_rd, cudaStream_t st);
 void launch_grid_cells(const double *d_llh, int n_st, const double *d_grid_desc, int nlat, int nlon,
                        const double *d_rd, int n_sets, int rd_stride, double *d_best_cost, i64 *d_best_idx,
                        double *d_out_llh, void *d_scratch, cudaStream_t st);

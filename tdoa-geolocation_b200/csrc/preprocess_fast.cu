@@ -260,10 +260,11 @@ __device__ __forceinline__ float lean_one(double pr, double pi, double cr, doubl
 
 __device__ __forceinline__ void lean_lookup(unsigned addr, double &v, float &sq)
 {
-    unsigned r0, r1, r2, r3;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-    v = hilo(r1, r0);
-    sq = __uint_as_float(r2);
+    // one 128-bit load as two f64 registers: the value lands in an aligned register pair
+    // (no moves), the f32 square is the low word of the second
+    double packed;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v), "=d"(packed) : "r"(addr));
+    sq = __int_as_float(__double2loint(packed));
 }
 
 // grid_sum_last with the "am I last" flag in caller-provided shared memory

@@ -390,6 +390,29 @@ void launch_solve(const double *d_llh, const double *d_rd, int n_sets, int rd_st
     k_solve<<<(n_sets + 63) / 64, 64, 0, st>>>(d_llh, d_rd, n_sets, rd_stride, d_out_llh, d_status, d_iters);
 }
 
+// ProcessTDOA between the pair loops and the solver (processor.go:821, :853, :899-903; shipped
+// binary: "REFERENCE SIGNAL SYNCHRONIZATION"): dt = delay / fs per pair; SOURCE keeps the
+// target differences, the binary's modes subtract the reference differences pair by pair;
+// range difference = dt * c.  EXTENDED adds the sub-sample offset to the delay.
+__global__ void k_range_diffs(const PeakRec *ref, const PeakRec *tgt, int n_pairs, double fs, int mode, double *td_out,
+                              double *rd_out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    double lt = (double)tgt[p].lag, lr = (double)ref[p].lag;
+    if (mode == TDOA_MODE_EXTENDED) { lt += (double)tgt[p].frac; lr += (double)ref[p].frac; }
+    const double tt = lt / fs, tr = lr / fs;
+    const double td = mode == TDOA_MODE_SOURCE ? tt : tt - tr;
+    td_out[p] = td;
+    rd_out[p] = td * 299792458.0;
+}
+
+void launch_range_diffs(const PeakRec *d_ref, const PeakRec *d_tgt, int n_pairs, double fs, int mode, double *d_td,
+                        double *d_rd, cudaStream_t st)
+{
+    if (n_pairs > 0) k_range_diffs<<<(n_pairs + 63) / 64, 64, 0, st>>>(d_ref, d_tgt, n_pairs, fs, mode, d_td, d_rd);
+}
+
 int solve_ls_max_stations() { return kLsMaxStations; }
 
 void launch_solve_ls(const double *d_llh, int n_st, const double *d_rd, int n_sets, int rd_stride, const double *d_init,

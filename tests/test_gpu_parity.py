@@ -515,3 +515,41 @@ def test_guard_samples_trim_the_retuned_blocks():
         for got, k in ((ref[p], 0), (tgt[p], 1)):
             d, c, _ = oracle.cross_correlate_binary(sigs[i][k], sigs[j][k])
             assert int(got["lag"]) == d and abs(float(got["corr"]) - c) <= CORR_TOL
+
+
+# ------------------------------------------------------------------ ProcessTDOA as one call
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_process_equals_the_separate_calls(case):
+    """tdoa_process queues both pair loops and the fix without synchronising in between and
+    checks its branch guesses afterwards; the weak / moderate captures take its fall-back.
+    Records, diagnostics, differences and fix must be those of tdoa_xcorr x 2 + tdoa_solve."""
+    raws, meta = load_golden(case)
+    for mode in (T.MODE_BINARY, T.MODE_SOURCE):
+        with T.Engine(mode) as a, T.Engine(mode) as b:
+            load_all(a, raws)
+            load_all(b, raws)
+            ref, tgt = a.xcorr(T.KIND_REF)[0], a.xcorr(T.KIND_TGT)[0]
+            info = [a.xcorr_info(k) for k in (T.KIND_REF, T.KIND_TGT)]
+            for rep in range(2):   # second call: the branch memo is warm
+                r = b.process(STATION_LLH)
+                for name in ("lag", "corr", "flags", "first_lag", "n_blocks"):
+                    assert np.array_equal(r["ref"][name], ref[name]), (name, rep)
+                    assert np.array_equal(r["tgt"][name], tgt[name]), (name, rep)
+                fs = a.cfg.sample_rate
+                tt, tr = tgt["lag"].astype(np.float64) / fs, ref["lag"].astype(np.float64) / fs
+                td = tt if mode == T.MODE_SOURCE else tt - tr       # processor.go:853 / the binary's correction
+                assert np.array_equal(r["time_differences"], td)
+                assert np.array_equal(r["range_differences"], td * 299792458.0)
+                pos, status, iters = a.solve(STATION_LLH, td * 299792458.0)
+                assert r["status"] == status and r["iters"] == iters   # (fm_delays: the reference's solver goes singular)
+                assert np.array_equal(r["position"], pos)
+                for k in (T.KIND_REF, T.KIND_TGT):
+                    got_sig, got_first = b.xcorr_info(k)
+                    assert got_sig == info[k][0] and np.array_equal(got_first, info[k][1])
+    if case == "fm_strong":
+        want_ref, want_tgt = oracle.process_capture_binary(raws)
+        with T.Engine(T.MODE_BINARY) as e:
+            load_all(e, raws)
+            r = e.process(STATION_LLH)
+        for got, want in zip(list(r["ref"]) + list(r["tgt"]), want_ref + want_tgt):
+            assert int(got["lag"]) == want[0] and abs(float(got["corr"]) - want[1]) <= CORR_TOL
