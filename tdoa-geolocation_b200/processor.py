@@ -206,6 +206,10 @@ class TDOAProcessor:
         for (i, j), d in zip(pairs, base):
             P("%s - %s: %.2f km" % (stations[i].name, stations[j].name, d / 1000))
         fs = eng.cfg.sample_rate
+        # the whole numeric path in one engine call (tdoa_process): both pair loops, the time and
+        # range differences and solveTDOA are queued on the GPU without a host round trip; what
+        # follows only prints what the reference prints, in its order
+        done = eng.process(llh)
         results = {}
         for kind, label in ((N.KIND_REF, "REF"), (N.KIND_TGT, "TGT")):
             if kind == N.KIND_REF:
@@ -216,7 +220,7 @@ class TDOAProcessor:
                 P("\n=== TARGET SIGNAL CORRELATION TEST ===")
                 if binary:
                     P("Testing strong %.1f MHz FM broadcast signal:" % (self.target_freq / 1e6))
-            peaks = eng.xcorr(kind)[0]
+            peaks = done["ref" if kind == N.KIND_REF else "tgt"]
             info, first = eng.xcorr_info(kind) if binary else (None, None)
             tds = []
             for p_idx, ((i, j), pk) in enumerate(zip(pairs, peaks)):
@@ -278,10 +282,12 @@ class TDOAProcessor:
                 P("Station geometry triangle area: %.1f m²" % area)
                 m = llh[:3].mean(axis=0)
                 P("Initial guess: %.6f°, %.6f°, %.1fm" % (m[0], m[1], m[2]))
-        try:
-            lat, lon, elev = self.solve_tdoa(stations, rds)
-        except RuntimeError as exc:
-            raise RuntimeError(f"TDOA solution failed: {exc}") from exc
+        # same arithmetic on the device: dt = delay / fs, (target - reference), * c
+        if self.mode in (N.MODE_SOURCE, N.MODE_BINARY):
+            assert np.array_equal(np.asarray(rds, np.float64), done["range_differences"])
+        if done["status"] != 0:
+            raise RuntimeError("TDOA solution failed: singular Jacobian matrix")  # processor.go:997-999, :920
+        lat, lon, elev = (float(x) for x in done["position"])
         P("\n*** CALCULATED TRANSMITTER LOCATION ***")
         P("Latitude:  %.6f°" % lat)
         P("Longitude: %.6f°" % lon)
