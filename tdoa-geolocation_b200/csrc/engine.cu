@@ -897,16 +897,34 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     int max_cta = 0;
     i64 max_nb = 0;
     std::vector<int> first_job(np, 0);  // index into fjobs of the plan's first lag chunk
+    // one arena for the per-pair scratch (16 stations x 33 windows = 3960 pairs: tens of
+    // thousands of separate stream-ordered allocations would cost more host time than the kernels)
+    auto up256 = [](size_t b) { return (b + 255) & ~size_t(255); };
+    size_t arena_bytes = 0;
+    for (int p = 0; p < np; p++) {
+        const PairJob &J = plans[p]->job;
+        arena_bytes += up256((size_t)J.n_lags * sizeof(float)) + up256(sizeof(float)) + up256(kMaxCand * sizeof(int)) +
+                       up256(sizeof(int)) + up256((size_t)kMaxCand * std::max<i64>(J.nb, 1) * sizeof(double));
+        if (!big_plan[p]) {
+            const int n_chunks = (J.n_lags + kLagW - 1) / kLagW;
+            const int n_seg = (int)((J.n_t + kSeg - 1) / kSeg);
+            const int n_cta = std::max(1, std::min(n_seg, cta_budget));
+            arena_bytes += (size_t)n_chunks * (up256(fft_partials_bytes(n_cta)) + up256((size_t)kFftBins * sizeof(float2)));
+        }
+    }
+    char *arena = nullptr;
+    if ((rc = alloc(e, reinterpret_cast<void **>(&arena), arena_bytes))) return rc;
+    size_t arena_off = 0;
+    auto take = [&](size_t bytes) { void *q = arena + arena_off; arena_off += up256(bytes); return q; };
     for (int p = 0; p < np; p++) {
         CorrPlan *pl = plans[p];
         PairJob &J = pl->job;
         PeakJob &K = pl->peak;
-        float *d_approx = nullptr, *d_amax = nullptr;
-        int *d_cand = nullptr, *d_ncand = nullptr;
-        if ((rc = alloc_t(e, &d_approx, (size_t)J.n_lags)) || (rc = alloc_t(e, &d_amax, 1)) ||
-            (rc = alloc_t(e, &d_cand, (size_t)kMaxCand)) || (rc = alloc_t(e, &d_ncand, 1)) ||
-            (rc = alloc_t(e, &J.blocksums, (size_t)kMaxCand * std::max<i64>(J.nb, 1))))
-            return rc;
+        float *d_approx = static_cast<float *>(take((size_t)J.n_lags * sizeof(float)));
+        float *d_amax = static_cast<float *>(take(sizeof(float)));
+        int *d_cand = static_cast<int *>(take(kMaxCand * sizeof(int)));
+        int *d_ncand = static_cast<int *>(take(sizeof(int)));
+        J.blocksums = static_cast<double *>(take((size_t)kMaxCand * std::max<i64>(J.nb, 1) * sizeof(double)));
         first_job[p] = (int)fjobs.size();
         for (int c0 = 0; c0 < J.n_lags && !big_plan[p]; c0 += kLagW) {
             FftJob F{};
@@ -916,9 +934,8 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
             F.n_lags = std::min(kLagW, J.n_lags - c0);
             F.n_seg = (int)((J.n_t + kSeg - 1) / kSeg);
             F.n_cta = std::max(1, std::min(F.n_seg, cta_budget));
-            if ((rc = alloc(e, reinterpret_cast<void **>(&F.partials), fft_partials_bytes(F.n_cta))) ||
-                (rc = alloc_t(e, &F.spectrum, (size_t)kFftBins)))
-                return rc;
+            F.partials = static_cast<float2 *>(take(fft_partials_bytes(F.n_cta)));
+            F.spectrum = static_cast<float2 *>(take((size_t)kFftBins * sizeof(float2)));
             F.approx = d_approx + c0;
             max_cta = std::max(max_cta, F.n_cta);
             fjobs.push_back(F);
