@@ -30,6 +30,7 @@ UNITS = [
     ("xcorr_fft.cu", []),
     ("xcorr_tile.cu", []),
     ("xcorr_big.cu", []),
+    ("xcorr_spec.cu", []),
     ("engine.cu", []),
 ]
 

@@ -818,6 +818,9 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     // are taken two at a time, and a tile carries the (<= 4) pairs that exist among them.
     struct Tile { int plan[4]; const float *t[2]; const float *s[2]; };
     std::vector<Tile> tiles;
+    struct SpecGroup { std::vector<int> plans; std::vector<const float *> rows, cols; };
+    std::vector<SpecGroup> spec_groups;
+    std::vector<char> spec_plan(np, 0);
     const bool tiled = e->cfg.use_fft != 2;
     {
         std::vector<char> done(np, 0);
@@ -841,6 +844,20 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
             std::vector<const float *> rows;
             for (int p : grp)
                 if (std::find(rows.begin(), rows.end(), plans[p]->job.t_re) == rows.end()) rows.push_back(plans[p]->job.t_re);
+            // many pairs on few stations: transform each station once and form the pairs from
+            // the parked spectra (xcorr_spec.cu) instead of 2 x 2 tiles
+            if ((int)grp.size() >= kSpecMinPairs && K0.n_lags < kBigMinLags && e->cfg.use_fft != 4) {
+                std::vector<const float *> cols;
+                for (int p : grp)
+                    if (std::find(cols.begin(), cols.end(), plans[p]->job.s_re) == cols.end()) cols.push_back(plans[p]->job.s_re);
+                if ((rows.size() + 1) / 2 + (cols.size() + 1) / 2 <= (size_t)kSpecMaxPacked) {
+                    SpecGroup G;
+                    G.plans = grp; G.rows = rows; G.cols = cols;
+                    spec_groups.push_back(G);
+                    for (int p : grp) spec_plan[p] = 1;
+                    continue;
+                }
+            }
             for (size_t r = 0; r < rows.size(); r += 2) {
                 const float *tr[2] = {rows[r], r + 1 < rows.size() ? rows[r + 1] : rows[r]};
                 std::vector<const float *> cols;
@@ -883,7 +900,7 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     // lag chunks
     int n_fft_jobs = 0, n_tile_jobs = 0;
     for (int p = 0; p < np; p++)
-        if (!big_plan[p]) n_fft_jobs += (plans[p]->job.n_lags + kLagW - 1) / kLagW;
+        if (!big_plan[p] && !spec_plan[p]) n_fft_jobs += (plans[p]->job.n_lags + kLagW - 1) / kLagW;
     for (size_t ti = 0; ti < tiles.size(); ti++) {
         if (big_tile[ti]) continue;
         const Tile &T = tiles[ti];
@@ -905,7 +922,9 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
         const PairJob &J = plans[p]->job;
         arena_bytes += up256((size_t)J.n_lags * sizeof(float)) + up256(sizeof(float)) + up256(kMaxCand * sizeof(int)) +
                        up256(sizeof(int)) + up256((size_t)kMaxCand * std::max<i64>(J.nb, 1) * sizeof(double));
-        if (!big_plan[p]) {
+        if (spec_plan[p]) {
+            arena_bytes += (size_t)((J.n_lags + 2047) / 2048) * up256((size_t)kFftBins * sizeof(float2));
+        } else if (!big_plan[p]) {
             const int n_chunks = (J.n_lags + kLagW - 1) / kLagW;
             const int n_seg = (int)((J.n_t + kSeg - 1) / kSeg);
             const int n_cta = std::max(1, std::min(n_seg, cta_budget));
@@ -926,7 +945,7 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
         int *d_ncand = static_cast<int *>(take(sizeof(int)));
         J.blocksums = static_cast<double *>(take((size_t)kMaxCand * std::max<i64>(J.nb, 1) * sizeof(double)));
         first_job[p] = (int)fjobs.size();
-        for (int c0 = 0; c0 < J.n_lags && !big_plan[p]; c0 += kLagW) {
+        for (int c0 = 0; c0 < J.n_lags && !big_plan[p] && !spec_plan[p]; c0 += kLagW) {
             FftJob F{};
             F.t = J.t_re; F.s = J.s_re; F.t_stats = J.t_stats; F.s_stats = J.s_stats;
             F.t_off = J.t_off; F.n_t = J.n_t; F.sl = J.sl;
@@ -991,6 +1010,103 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
     }
     launch_fft_reduce(d_f, (int)fjobs.size(), e->stream);
     launch_fft_finish(d_f, (int)fjobs.size(), e->d_tw, e->stream);
+    // ---- station-spectra groups: units of (group, lag chunk), in batches that share one
+    // spectra buffer; the pair spectra go straight to the finish kernel
+    if (!spec_groups.empty()) {
+        struct Unit { int grp; int c0, lw, seg, n_seg; size_t spec_elems; };
+        std::vector<Unit> units;
+        std::vector<FftJob> sf;                       // finish jobs of the spec plans, unit by unit
+        std::vector<std::vector<int>> unit_fjob;      // per unit: index into sf of each plan of the group
+        for (size_t gi = 0; gi < spec_groups.size(); gi++) {
+            const SpecGroup &G = spec_groups[gi];
+            const PairJob &K = plans[G.plans[0]]->job;
+            const int lw = K.n_lags <= 2048 ? 2048 : 4096;   // lags per chunk; segment = 8192 - lw samples
+            const int n_pk = (int)((G.rows.size() + 1) / 2 + (G.cols.size() + 1) / 2);
+            for (int c0 = 0; c0 < K.n_lags; c0 += lw) {
+                Unit U;
+                U.grp = (int)gi; U.c0 = c0; U.lw = std::min(lw, K.n_lags - c0); U.seg = kFftN - lw;
+                U.n_seg = (int)std::max<i64>(1, (K.n_t + U.seg - 1) / U.seg);
+                U.spec_elems = (size_t)U.n_seg * n_pk * kFftN;
+                std::vector<int> idx;
+                for (int p : G.plans) {
+                    const PairJob &J = plans[p]->job;
+                    FftJob F{};
+                    F.t = J.t_re; F.s = J.s_re; F.t_stats = J.t_stats; F.s_stats = J.s_stats;
+                    F.t_off = J.t_off; F.n_t = J.n_t; F.sl = J.sl; F.s_off = (i64)J.lag0 + c0;
+                    F.n_lags = U.lw; F.n_seg = U.n_seg; F.n_cta = 0; F.partials = nullptr;
+                    F.spectrum = static_cast<float2 *>(take((size_t)kFftBins * sizeof(float2)));
+                    F.approx = const_cast<float *>(sjobs[p].approx) + c0;
+                    idx.push_back((int)sf.size());
+                    sf.push_back(F);
+                }
+                unit_fjob.push_back(idx);
+                units.push_back(U);
+            }
+        }
+        size_t max_unit = 0;
+        for (const Unit &U : units) max_unit = std::max(max_unit, U.spec_elems);
+        const size_t budget_elems = std::max<size_t>(max_unit, ((size_t)4 << 30) / sizeof(float2));
+        float2 *spec_buf = nullptr;
+        {
+            size_t total = 0;
+            for (const Unit &U : units) total += U.spec_elems;
+            if ((rc = alloc_t(e, &spec_buf, std::min(total, budget_elems)))) return rc;
+        }
+        for (size_t u0 = 0; u0 < units.size();) {
+            std::vector<SpecFftJob> fj;
+            std::vector<SpecAccJob> aj;
+            size_t used = 0;
+            int max_seg = 0;
+            size_t u1 = u0;
+            while (u1 < units.size() && (u1 == u0 || used + units[u1].spec_elems <= budget_elems)) {
+                const Unit &U = units[u1];
+                const SpecGroup &G = spec_groups[U.grp];
+                const PairJob &K = plans[G.plans[0]]->job;
+                const int n_pk_t = (int)((G.rows.size() + 1) / 2), n_pk_s = (int)((G.cols.size() + 1) / 2);
+                const int n_pk = n_pk_t + n_pk_s;
+                float2 *spec = spec_buf + used;
+                for (int m = 0; m < n_pk; m++) {
+                    SpecFftJob F{};
+                    const bool tpl = m < n_pk_t;
+                    const std::vector<const float *> &src = tpl ? G.rows : G.cols;
+                    const size_t a = (size_t)2 * (tpl ? m : m - n_pk_t);
+                    F.x0 = src[a]; F.x1 = a + 1 < src.size() ? src[a + 1] : src[a];
+                    F.stride = U.seg; F.n_seg = U.n_seg;
+                    if (tpl) { F.base = K.t_off; F.lo = K.t_off; F.hi = K.t_off + K.n_t; F.seg_len = U.seg; }
+                    else { F.base = (i64)K.lag0 + U.c0; F.lo = 0; F.hi = K.sl; F.seg_len = kFftN; }
+                    F.out = spec + (size_t)m * kFftN; F.out_seg_stride = (i64)n_pk * kFftN;
+                    fj.push_back(F);
+                }
+                // pairs of the group, <= kSpecMaxPairs per accumulation job
+                for (size_t q0 = 0; q0 < G.plans.size(); q0 += kSpecMaxPairs) {
+                    SpecAccJob A{};
+                    A.spec = spec; A.n_pk_t = n_pk_t; A.n_pk_s = n_pk_s; A.n_seg = U.n_seg;
+                    A.n_pairs = (int)std::min<size_t>(kSpecMaxPairs, G.plans.size() - q0);
+                    for (int q = 0; q < A.n_pairs; q++) {
+                        const PairJob &J = plans[G.plans[q0 + q]]->job;
+                        A.pair_t[q] = (unsigned char)(std::find(G.rows.begin(), G.rows.end(), J.t_re) - G.rows.begin());
+                        A.pair_s[q] = (unsigned char)(std::find(G.cols.begin(), G.cols.end(), J.s_re) - G.cols.begin());
+                        A.spectrum[q] = sf[unit_fjob[u1][q0 + q]].spectrum;
+                    }
+                    aj.push_back(A);
+                }
+                used += U.spec_elems;
+                max_seg = std::max(max_seg, U.n_seg);
+                u1++;
+            }
+            const SpecFftJob *d_fj = nullptr;
+            const SpecAccJob *d_aj = nullptr;
+            if ((rc = upload(e, fj, &d_fj)) || (rc = upload(e, aj, &d_aj))) return rc;
+            launch_spec_fft(d_fj, (int)fj.size(), max_seg, e->d_tw, e->stream);
+            launch_spec_acc(d_aj, (int)aj.size(), e->stream);
+            count_launch(e, 2);
+            u0 = u1;
+        }
+        const FftJob *d_sf = nullptr;
+        if ((rc = upload(e, sf, &d_sf))) return rc;
+        launch_fft_finish(d_sf, (int)sf.size(), e->d_tw, e->stream);
+        count_launch(e);
+    }
     // ---- big tiles, in batches that share four 16 MiB buffers per tile
     {
         std::vector<int> bt;
@@ -1508,6 +1624,7 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
     if (err == cudaSuccess && demod_setup(e->stream) != 0) err = cudaErrorUnknown;
     if (err == cudaSuccess && fft_tile_setup() != 0) err = cudaErrorUnknown;
     if (err == cudaSuccess && big_setup(e->stream, &e->d_tw_fine) != 0) err = cudaErrorUnknown;
+    if (err == cudaSuccess && spec_setup() != 0) err = cudaErrorUnknown;
     if (err == cudaSuccess && quality_setup() != 0) err = cudaErrorUnknown;
     if (err != cudaSuccess) {
         g_create_error = std::string("tdoa_create: ") + cudaGetErrorString(err);

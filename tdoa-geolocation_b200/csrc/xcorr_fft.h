@@ -89,6 +89,34 @@ void launch_big_rows(const BigRowJob *d_jobs, int n_jobs, const float2 *d_tw, co
 void launch_big_cross(const BigCrossJob *d_jobs, int n_jobs, cudaStream_t st);
 void launch_big_out(const BigOutJob *d_jobs, int n_jobs, const float2 *d_tw, cudaStream_t st);
 
+// ---- many stations per window: each station-segment transformed once, pairs formed from the
+// parked spectra (xcorr_spec.cu)
+constexpr int kSpecMaxPacked = 16;   // packed transforms (two stations each) per job: templates + signals
+constexpr int kSpecMaxPairs = 128;   // pairs accumulated by one job
+constexpr int kSpecBins = 64;        // frequency bins per accumulation CTA
+constexpr int kSpecMinPairs = 10;    // smaller groups stay with the 2 x 2 tiles
+
+struct SpecFftJob {     // one packed transform, all its segments
+    const float *x0, *x1;   // planes: z = x0 + i x1
+    i64 base;               // plane index of sample 0 of segment 0
+    i64 stride;             // samples between segment starts
+    i64 lo, hi;             // plane indices outside [lo, hi) read as zero
+    int seg_len;            // samples of a segment that carry data (the rest of the 8192 is zero)
+    int n_seg;
+    float2 *out;            // spectrum of segment g at out + g * out_seg_stride
+    i64 out_seg_stride;     // floats2 between segments (n_packed * 8192)
+};
+struct SpecAccJob {
+    const float2 *spec;     // [n_seg][n_pk_t + n_pk_s][8192]
+    int n_pk_t, n_pk_s, n_seg, n_pairs;
+    unsigned char pair_t[kSpecMaxPairs];   // template slot (0 .. 2 n_pk_t - 1) of each pair
+    unsigned char pair_s[kSpecMaxPairs];   // signal slot   (0 .. 2 n_pk_s - 1)
+    float2 *spectrum[kSpecMaxPairs];       // [4097] summed cross-spectrum conj(T) S of each pair
+};
+int spec_setup();
+void launch_spec_fft(const SpecFftJob *d_jobs, int n_jobs, int max_seg, const float2 *d_tw, cudaStream_t st);
+void launch_spec_acc(const SpecAccJob *d_jobs, int n_jobs, cudaStream_t st);
+
 int fft_setup(cudaStream_t st, float2 **d_tw);
 size_t fft_partials_bytes(int n_cta);
 void launch_fft_segments(const FftJob *d_jobs, int n_jobs, int max_cta, const float2 *d_tw, cudaStream_t st);

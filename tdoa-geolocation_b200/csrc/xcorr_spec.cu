@@ -1,0 +1,156 @@
+// xcorr_spec.cu -- many stations per window (BASELINE config 4: 16 stations, 120 pairs):
+// every station-segment is transformed ONCE, the pairs are formed from the parked spectra.
+//
+// The 2 x 2 station tiles of xcorr_tile.cu transform a station again in every tile it
+// appears in: 16 stations need 36 tiles = 72 transforms per segment where 16 suffice
+// (15 template roles + 15 signal roles, two real signals per complex transform).  Here:
+//   k_spec_fft : one CTA = one 8192-point transform (fft_tile_core.cuh) of a pair of
+//                planes -- template segments zero padded after `seg` samples, signal
+//                segments 8192 samples long -- written as a spectrum to global memory
+//                ([segment][packed transform][8192]; parked in L2 / HBM)
+//   k_spec_acc : one CTA = 64 frequency bins of one (window, lag chunk) for ALL its pairs:
+//                per segment it unpacks T_i[k], S_j[k] of every station from Z[k], Z[N-k]
+//                into shared memory and adds conj(T_i) S_j into per-thread registers
+//                (<= 32 pairs per thread); after the last segment the pair spectra go
+//                straight to k_fft_finish (xcorr_fft.cu), no partials, no reduce.
+// Because the segment length is a parameter here, a search of 2049..4096 lags runs as ONE
+// chunk of 4096-sample segments instead of two chunks of 6144-sample segments.
+#include "fft_tile_core.cuh"
+#include "kernels.h"
+#include "xcorr_fft.h"
+
+namespace tdoa {
+
+using namespace fft2;
+
+namespace {
+
+constexpr int kRowSmem = (kBuf + kTab) * (int)sizeof(float2);
+constexpr int kAccBins = kSpecBins;            // 64 bins per CTA
+constexpr int kAccThreads = 256;
+constexpr int kAccGroups = kAccThreads / kAccBins;   // 4 pair groups
+constexpr int kAccPer = kSpecMaxPairs / kAccGroups;  // 32 accumulators per thread
+
+// ---------------------------------------------------------------- transforms
+__global__ void __launch_bounds__(kT, 2) k_spec_fft(const SpecFftJob *jobs, const float2 *__restrict__ tw)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const SpecFftJob &J = jobs[blockIdx.y];
+    const int seg = blockIdx.x;
+    if (seg >= J.n_seg) return;
+    const int t = threadIdx.x;
+    float2 *buf = sm, *tab = sm + kBuf;
+    for (int idx = t; idx < kTab; idx += kT) tab[idx] = tw[(16 * (idx & 31) * (idx >> 5)) & (kN - 1)];
+    const float2 w1a = tw[2 * t], w1b = tw[2 * t + 1];
+    {
+        // z[m] = x0[i] + i x1[i], i = base + seg * stride + m, for m < seg_len and lo <= i < hi
+        const i64 first = J.base + (i64)seg * J.stride;
+        const float *__restrict__ x0 = J.x0, *__restrict__ x1 = J.x1;
+        float2 v[32];
+        if (first >= J.lo && first + J.seg_len <= J.hi && (J.seg_len & 255) == 0) {
+            const int rows = J.seg_len >> 8;
+#pragma unroll
+            for (int r = 0; r < 32; r++) v[r] = r < rows ? make_float2(x0[first + t + 256 * r], x1[first + t + 256 * r]) : make_float2(0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const int m = t + 256 * r;
+                const i64 i = first + m;
+                v[r] = (m < J.seg_len && i >= J.lo && i < J.hi) ? make_float2(x0[i], x1[i]) : make_float2(0.f, 0.f);
+            }
+        }
+        pass1_store(v, t, buf);
+    }
+    __syncthreads();
+    {
+        float2 u0[16], u1[16];
+        pass_load(buf, t, u0, u1);
+        __syncthreads();
+        pass2_twiddle(u0, u1, t, tab);
+        pass2_store(u0, u1, t, buf);
+        __syncthreads();
+        pass_load(buf, t, u0, u1);
+        __syncthreads();
+        pass3_compute(u0, w1a);
+        pass3_compute(u1, w1b);
+        // X[2t + 512 r], X[2t + 1 + 512 r]: straight to global memory, 16 bytes per thread and row
+        float4 *out = reinterpret_cast<float4 *>(J.out + (size_t)seg * J.out_seg_stride) + t;
+#pragma unroll
+        for (int r = 0; r < 16; r++) out[256 * r] = make_float4(u0[r].x, u0[r].y, u1[r].x, u1[r].y);
+    }
+}
+
+// ---------------------------------------------------------------- pair accumulation
+__global__ void __launch_bounds__(kAccThreads) k_spec_acc(const SpecAccJob *jobs)
+{
+    __shared__ float2 s_st[2 * kSpecMaxPacked][kAccBins];   // unpacked station spectra of the CTA's bins
+    const SpecAccJob &J = jobs[blockIdx.y];
+    const int k0 = blockIdx.x * kAccBins;
+    const int nb = min(kAccBins, kN / 2 + 1 - k0);
+    if (nb <= 0) return;
+    const int tid = threadIdx.x, b = tid & (kAccBins - 1), g = tid >> 6;
+    const int n_pk = J.n_pk_t + J.n_pk_s;
+    const int per = (J.n_pairs + kAccGroups - 1) / kAccGroups;   // pairs per thread group, <= kAccPer
+    float2 acc[kAccPer];
+#pragma unroll
+    for (int q = 0; q < kAccPer; q++) acc[q] = make_float2(0.f, 0.f);
+    for (int seg = 0; seg < J.n_seg; seg++) {
+        const float2 *__restrict__ sp = J.spec + (size_t)seg * n_pk * kN;
+        __syncthreads();
+        for (int item = tid; item < n_pk * kAccBins; item += kAccThreads) {
+            const int m = item >> 6, bb = item & (kAccBins - 1);
+            if (bb < nb) {
+                const int k = k0 + bb;
+                const float2 a = sp[(size_t)m * kN + k], c = sp[(size_t)m * kN + ((kN - k) & (kN - 1))];
+                // Z = FFT(x0 + i x1): X0[k] = (Z[k] + conj Z[N-k]) / 2, X1[k] = (Z[k] - conj Z[N-k]) / (2i)
+                s_st[2 * m][bb] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+                s_st[2 * m + 1][bb] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
+            }
+        }
+        __syncthreads();
+        if (b < nb) {
+            int last_i = -1;
+            float2 ti = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < kAccPer; q++) {
+                const int p = g * per + q;
+                if (q < per && p < J.n_pairs) {
+                    const int i = J.pair_t[p], j = J.pair_s[p];
+                    if (i != last_i) { ti = s_st[i][b]; last_i = i; }
+                    const float2 sj = s_st[2 * J.n_pk_t + j][b];
+                    // conj(T) S
+                    acc[q].x = fmaf(ti.x, sj.x, fmaf(ti.y, sj.y, acc[q].x));
+                    acc[q].y = fmaf(ti.x, sj.y, fmaf(-ti.y, sj.x, acc[q].y));
+                }
+            }
+        }
+    }
+    if (b < nb) {
+#pragma unroll
+        for (int q = 0; q < kAccPer; q++) {
+            const int p = g * per + q;
+            if (q < per && p < J.n_pairs) J.spectrum[p][k0 + b] = acc[q];
+        }
+    }
+}
+
+}  // namespace
+
+int spec_setup()
+{
+    return cudaFuncSetAttribute(k_spec_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem) == cudaSuccess ? 0 : -1;
+}
+
+void launch_spec_fft(const SpecFftJob *d_jobs, int n_jobs, int max_seg, const float2 *d_tw, cudaStream_t st)
+{
+    if (n_jobs <= 0 || max_seg <= 0) return;
+    k_spec_fft<<<dim3(max_seg, n_jobs), kT, kRowSmem, st>>>(d_jobs, d_tw);
+}
+
+void launch_spec_acc(const SpecAccJob *d_jobs, int n_jobs, cudaStream_t st)
+{
+    if (n_jobs <= 0) return;
+    k_spec_acc<<<dim3((kN / 2 + 1 + kAccBins - 1) / kAccBins, n_jobs), kAccThreads, 0, st>>>(d_jobs);
+}
+
+}  // namespace tdoa

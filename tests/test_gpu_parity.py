@@ -289,6 +289,36 @@ def test_extended_decimating_boxcar(D):
         T.Engine(T.MODE_BINARY, decimate=4)
 
 
+@pytest.mark.parametrize("L", [300, 1500, 3000])
+def test_many_stations_spectra_path(L):
+    """>= 10 pairs of one window: every station-segment is transformed once and the pairs are
+    formed from the parked spectra (xcorr_spec.cu); 2049..4096 lags run as one chunk of
+    4096-sample segments.  Same records as the 2 x 2 tile path (use_fft=4) and as the oracle."""
+    W = 40000 + 2 * L
+    d = (0, 35, 11, 140, 77, 260)
+    raws = fm_capture(W + 3000, d, d, seed=31)
+    oracle.set_seq_dc_limit(0)
+    with T.Engine(T.MODE_EXTENDED, n_stations=6, max_lag=L) as e, \
+            T.Engine(T.MODE_EXTENDED, n_stations=6, max_lag=L, use_fft=4) as e4:
+        load_all(e, raws)
+        load_all(e4, raws)
+        got = e.xcorr(T.KIND_TGT, 700, W, 2, 1500)
+        old = e4.xcorr(T.KIND_TGT, 700, W, 2, 1500)
+        for name in ("lag", "corr", "frac", "flags"):
+            assert np.array_equal(got[name], old[name]), name
+        pairs = [(i, j) for i in range(6) for j in range(i + 1, 6)]
+        assert [int(x) for x in got[0]["lag"]] == [d[j] - d[i] if abs(d[j] - d[i]) <= L else int(x)
+                                                   for (i, j), x in zip(pairs, got[0]["lag"])]
+        for p in (0, 7, 14):
+            i, j = pairs[p]
+            yi, _ = oracle.preprocess_binary(split(raws[i])[1][700:700 + W])
+            yj, _ = oracle.preprocess_binary(split(raws[j])[1][700:700 + W])
+            idx, frac, val = oracle.peak_parabolic(oracle.xcorr_two_sided(yi, yj, L))
+            assert int(got[0][p]["lag"]) == idx - L
+            assert abs(float(got[0][p]["frac"]) - frac) <= 1e-3 and abs(float(got[0][p]["corr"]) - val) <= CORR_TOL
+    oracle.set_seq_dc_limit(-1)
+
+
 # ------------------------------------------------------------------ geodesy + solvers
 def test_baselines_and_solver(eng_binary):
     base = eng_binary.baselines(STATION_LLH)
