@@ -1045,7 +1045,7 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
         }
         size_t max_unit = 0;
         for (const Unit &U : units) max_unit = std::max(max_unit, U.spec_elems);
-        const size_t budget_elems = std::max<size_t>(max_unit, ((size_t)4 << 30) / sizeof(float2));
+        const size_t budget_elems = std::max<size_t>(max_unit, ((size_t)18 << 30) / sizeof(float2));  // 18 GiB of parked spectra per batch
         float2 *spec_buf = nullptr;
         {
             size_t total = 0;

@@ -11,7 +11,7 @@
 //   k_spec_acc : one CTA = 64 frequency bins of one (window, lag chunk) for ALL its pairs:
 //                per segment it unpacks T_i[k], S_j[k] of every station from Z[k], Z[N-k]
 //                into shared memory and adds conj(T_i) S_j into per-thread registers
-//                (<= 32 pairs per thread); after the last segment the pair spectra go
+//                (<= 16 pairs per thread); after the last segment the pair spectra go
 //                straight to k_fft_finish (xcorr_fft.cu), no partials, no reduce.
 // Because the segment length is a parameter here, a search of 2049..4096 lags runs as ONE
 // chunk of 4096-sample segments instead of two chunks of 6144-sample segments.
@@ -27,9 +27,9 @@ namespace {
 
 constexpr int kRowSmem = (kBuf + kTab) * (int)sizeof(float2);
 constexpr int kAccBins = kSpecBins;            // 64 bins per CTA
-constexpr int kAccThreads = 256;
-constexpr int kAccGroups = kAccThreads / kAccBins;   // 4 pair groups
-constexpr int kAccPer = kSpecMaxPairs / kAccGroups;  // 32 accumulators per thread
+constexpr int kAccThreads = 512;
+constexpr int kAccGroups = kAccThreads / kAccBins;   // 8 pair groups
+constexpr int kAccPer = kSpecMaxPairs / kAccGroups;  // 16 accumulators per thread
 
 // ---------------------------------------------------------------- transforms
 __global__ void __launch_bounds__(kT, 2) k_spec_fft(const SpecFftJob *jobs, const float2 *__restrict__ tw)
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kT, 2) k_spec_fft(const SpecFftJob *jobs, cons
 }
 
 // ---------------------------------------------------------------- pair accumulation
-__global__ void __launch_bounds__(kAccThreads) k_spec_acc(const SpecAccJob *jobs)
+__global__ void __launch_bounds__(kAccThreads, 2) k_spec_acc(const SpecAccJob *jobs)
 {
     __shared__ float2 s_st[2 * kSpecMaxPacked][kAccBins];   // unpacked station spectra of the CTA's bins
     const SpecAccJob &J = jobs[blockIdx.y];
@@ -91,22 +91,44 @@ __global__ void __launch_bounds__(kAccThreads) k_spec_acc(const SpecAccJob *jobs
     const int tid = threadIdx.x, b = tid & (kAccBins - 1), g = tid >> 6;
     const int n_pk = J.n_pk_t + J.n_pk_s;
     const int per = (J.n_pairs + kAccGroups - 1) / kAccGroups;   // pairs per thread group, <= kAccPer
+    __shared__ unsigned char s_pt[kSpecMaxPairs], s_ps[kSpecMaxPairs];
+    if (tid < kSpecMaxPairs) { s_pt[tid] = J.pair_t[tid]; s_ps[tid] = J.pair_s[tid]; }
+    const int n_pairs = J.n_pairs, sig0 = 2 * J.n_pk_t, n_seg = J.n_seg;
     float2 acc[kAccPer];
 #pragma unroll
     for (int q = 0; q < kAccPer; q++) acc[q] = make_float2(0.f, 0.f);
-    for (int seg = 0; seg < J.n_seg; seg++) {
+    // software pipeline: the next segment's spectrum values (2 (Z[k], Z[N-k]) pairs per thread)
+    // travel in registers while this segment's pairs are accumulated
+    constexpr int kItems = kSpecMaxPacked * kAccBins / kAccThreads;   // 2
+    float2 ra[kItems], rc[kItems];
+    auto fetch = [&](int seg) {
         const float2 *__restrict__ sp = J.spec + (size_t)seg * n_pk * kN;
-        __syncthreads();
-        for (int item = tid; item < n_pk * kAccBins; item += kAccThreads) {
+#pragma unroll
+        for (int u = 0; u < kItems; u++) {
+            const int item = tid + u * kAccThreads;
             const int m = item >> 6, bb = item & (kAccBins - 1);
-            if (bb < nb) {
+            if (m < n_pk && bb < nb) {
                 const int k = k0 + bb;
-                const float2 a = sp[(size_t)m * kN + k], c = sp[(size_t)m * kN + ((kN - k) & (kN - 1))];
+                ra[u] = sp[(size_t)m * kN + k];
+                rc[u] = sp[(size_t)m * kN + ((kN - k) & (kN - 1))];
+            }
+        }
+    };
+    fetch(0);
+    for (int seg = 0; seg < n_seg; seg++) {
+        __syncthreads();   // the previous segment's station spectra have been consumed
+#pragma unroll
+        for (int u = 0; u < kItems; u++) {
+            const int item = tid + u * kAccThreads;
+            const int m = item >> 6, bb = item & (kAccBins - 1);
+            if (m < n_pk && bb < nb) {
+                const float2 a = ra[u], c = rc[u];
                 // Z = FFT(x0 + i x1): X0[k] = (Z[k] + conj Z[N-k]) / 2, X1[k] = (Z[k] - conj Z[N-k]) / (2i)
                 s_st[2 * m][bb] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
                 s_st[2 * m + 1][bb] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
             }
         }
+        if (seg + 1 < n_seg) fetch(seg + 1);
         __syncthreads();
         if (b < nb) {
             int last_i = -1;
@@ -114,10 +136,10 @@ __global__ void __launch_bounds__(kAccThreads) k_spec_acc(const SpecAccJob *jobs
 #pragma unroll
             for (int q = 0; q < kAccPer; q++) {
                 const int p = g * per + q;
-                if (q < per && p < J.n_pairs) {
-                    const int i = J.pair_t[p], j = J.pair_s[p];
+                if (q < per && p < n_pairs) {
+                    const int i = s_pt[p], j = s_ps[p];
                     if (i != last_i) { ti = s_st[i][b]; last_i = i; }
-                    const float2 sj = s_st[2 * J.n_pk_t + j][b];
+                    const float2 sj = s_st[sig0 + j][b];
                     // conj(T) S
                     acc[q].x = fmaf(ti.x, sj.x, fmaf(ti.y, sj.y, acc[q].x));
                     acc[q].y = fmaf(ti.x, sj.y, fmaf(-ti.y, sj.x, acc[q].y));
@@ -129,7 +151,7 @@ __global__ void __launch_bounds__(kAccThreads) k_spec_acc(const SpecAccJob *jobs
 #pragma unroll
         for (int q = 0; q < kAccPer; q++) {
             const int p = g * per + q;
-            if (q < per && p < J.n_pairs) J.spectrum[p][k0 + b] = acc[q];
+            if (q < per && p < n_pairs) J.spectrum[p][k0 + b] = acc[q];
         }
     }
 }
