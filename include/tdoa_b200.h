@@ -86,8 +86,12 @@ typedef struct {
     int32_t sanity_lag;    /* 120 (binary re-search window); 0 disables              */
     int32_t fast_demod;    /* 0: f64 products + f64 atan2 as the reference;
                               1: f32 discriminator (<= 2 ulp), EXTENDED only default */
-    int32_t use_fft;       /* 1: FFT candidate search + exact re-evaluation;
-                              0: evaluate every lag in the time domain               */
+    int32_t use_fft;       /* 1: FFT candidate search + exact re-evaluation (2 x 2 station
+                              tiles; station spectra parked once per segment for >= 10
+                              pairs per window; a 2^21-point transform for >= 8192 lags);
+                              0: evaluate every lag in the time domain;
+                              test switches: 2 one transform per pair, 3 no 2^21-point
+                              transform, 4 no parked spectra                         */
     int32_t device;        /* CUDA device ordinal                                    */
     int32_t seq_dc_limit;  /* removeDCBias (processor.go:299-319): signals of up to this many
                               samples get the reference's sequential f32 accumulator,

@@ -485,6 +485,13 @@ def test_pinned_lazy_load_equals_synchronous_load(copy_chunk):
                     assert np.array_equal(got[kind]["lag"], want[kind]["lag"])
                     assert np.allclose(got[kind]["corr"], want[kind]["corr"], rtol=0, atol=1e-12)
                     assert np.array_equal(got[kind]["n_blocks"], want[kind]["n_blocks"])
+            # the one-call path on a capture that is still arriving (what bench.py's e2e leg does)
+            for k, b in enumerate(bufs):
+                e.load_u8_pinned(k, b)
+            r = e.process(STATION_LLH)
+            for kind, key in ((T.KIND_REF, "ref"), (T.KIND_TGT, "tgt")):
+                assert np.array_equal(r[key]["lag"], want[kind]["lag"])
+                assert np.allclose(r[key]["corr"], want[kind]["corr"], rtol=0, atol=1e-12)
             # other readers of the capture wait for the copies too
             for k, b in enumerate(bufs):
                 e.load_u8_pinned(k, b)

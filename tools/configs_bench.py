@@ -100,6 +100,23 @@ def cfg1(args, dev, res):
                     "pair_msamples_per_s": 6 * chunk / dt / 1e6, "lags": [int(x) for x in t["lag"]], "ok": bool(ok)})
 
 
+def cfg2x(args, dev, res):
+    # ---- config 2, extended variant: full-length target signals, +-50k lags, one fix
+    delays, _ = delays_for(bench.STATION_LLH)
+    want = [int(delays[j] - delays[i]) for i in range(3) for j in range(i + 1, 3)]
+    block = 8_000_000 if args.quick else 66_666_666
+    caps = synth(dev, 3, block, delays)
+    L = 50_000
+    with T.Engine(T.MODE_EXTENDED, max_lag=L, chunk_samples=0) as e:
+        for k in range(3):
+            e.load_u8_device(k, caps[k].data_ptr(), caps[k].numel(), keep=caps[k])
+        dt, r = timed(lambda: e.process(bench.STATION_LLH), reps=args.reps)
+    ok = [int(x) for x in r["tgt"]["lag"]] == want and [int(x) for x in r["ref"]["lag"]] == want
+    res.append({"config": f"2x (EXTENDED, full length {2 * block}/{block} samples, +-{L} lags, f64 discriminator, 3 REF + 3 TGT pairs + fix)",
+                "ms": dt * 1e3, "pair_msamples_per_s": 9 * block / dt / 1e6, "ok": bool(ok),
+                "max_abs_frac": float(max(np.abs(r["tgt"]["frac"]).max(), np.abs(r["ref"]["frac"]).max()))})
+
+
 def cfg3(args, dev, res):
     # ---- config 3: 100 s capture, sliding 1 s windows, +-50k lags, one fix per window
     delays, _ = delays_for(bench.STATION_LLH)
@@ -169,12 +186,12 @@ def cfg5(args, dev, res):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", type=int, default=0, help="run one config only (1, 3, 4 or 5)")
+    ap.add_argument("--only", type=int, default=0, help="run one config only (1, 2, 3, 4 or 5)")
     ap.add_argument("--reps", type=int, default=2)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     res = []
-    for n, fn in ((1, cfg1), (3, cfg3), (4, cfg4), (5, cfg5)):
+    for n, fn in ((1, cfg1), (2, cfg2x), (3, cfg3), (4, cfg4), (5, cfg5)):
         if args.only in (0, n):
             fn(args, dev, res)
     for r in res:
