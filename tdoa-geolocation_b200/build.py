@@ -77,7 +77,26 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         if res.returncode:
             sys.stderr.write(res.stderr)
             raise RuntimeError("link failed")
+    build_host(force)
     return OUT
+
+
+HOST_SRC = HERE / "host" / "processor_b200.cpp"
+HOST_OUT = HERE / "processor_b200"
+
+
+def build_host(force: bool = False) -> Path:
+    """The reference's `processor` command over the C ABI (host/processor_b200.cpp): plain g++,
+    links libtdoa_b200.so, finds it next to itself at run time."""
+    if force or _stale(HOST_OUT, [HOST_SRC, OUT, *INCLUDE.glob("*.h")]):
+        cxx = shutil.which("g++") or "g++"
+        cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-I", str(INCLUDE), str(HOST_SRC), "-o", str(HOST_OUT),
+               "-L", str(HERE), "-ltdoa_b200", "-Wl,-rpath,$ORIGIN"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode:
+            sys.stderr.write(res.stderr)
+            raise RuntimeError("g++ failed on processor_b200.cpp")
+    return HOST_OUT
 
 
 if __name__ == "__main__":

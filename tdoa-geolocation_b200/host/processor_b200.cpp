@@ -1,0 +1,357 @@
+// processor_b200 -- the reference's `processor` command on the B200 engine.
+//
+//   processor_b200 [--source] <reference_freq_hz> <target_freq_hz> <stations.csv> <collector1.dat> ...
+//
+// Host-side mirror of processor.go in the reference's own shape (Go is not installed in this
+// image, the reference is compiled code, so the mirror is C++): a TDOAProcessor with the
+// reference's methods -- loadStations (:52), getStationFromFilename (:110), loadIQData
+// (:166), ProcessTDOA (:739), solveTDOA (:932) -- same argument meaning, same error texts,
+// same stdout, line for line (the default follows the shipped binary's revision, --source
+// follows processor.go as committed).  Every numeric step is a call into the C ABI of
+// libtdoa_b200.so (include/tdoa_b200.h); there is no arithmetic on samples here and no CPU
+// fallback: without a B200 tdoa_create fails and so does this program.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "tdoa_b200.h"
+
+namespace {
+
+constexpr double kSpeedOfLight = 299792458.0;  // processor.go:899
+
+std::string fmt(const char *f, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof(buf), f, ap);
+    va_end(ap);
+    return buf;
+}
+
+struct Station {  // processor.go:15-20
+    std::string name;
+    double latitude = 0, longitude = 0, elevation = 0;
+};
+
+class TDOAProcessor {  // processor.go:29-33
+public:
+    TDOAProcessor(double refFreq, double targetFreq, const std::string &csv, int mode)
+        : referenceFreq(refFreq), targetFreq(targetFreq), mode(mode)
+    {
+        loadStations(csv);
+    }
+    ~TDOAProcessor() { if (engine) tdoa_destroy(engine); }
+
+    // processor.go:52-107
+    void loadStations(const std::string &csv)
+    {
+        std::ifstream f(csv);
+        if (!f) throw std::runtime_error("failed to load stations: failed to open CSV file: " + csv);
+        std::string line;
+        int lineNo = 0;
+        bool haveRef = false;
+        const std::string refName = fmt("%.0f", referenceFreq);  // :96
+        while (std::getline(f, line)) {
+            lineNo++;
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (lineNo == 1 || line.empty()) continue;  // header skipped (:66)
+            std::vector<std::string> rec;
+            std::stringstream ss(line);
+            std::string cell;
+            while (std::getline(ss, cell, ',')) rec.push_back(cell);
+            if (rec.size() != 4) throw std::runtime_error(fmt("failed to load stations: invalid CSV format at line %d", lineNo));
+            Station st;
+            st.name = rec[0];
+            try {
+                st.latitude = std::stod(rec[1]); st.longitude = std::stod(rec[2]); st.elevation = std::stod(rec[3]);
+            } catch (const std::exception &) {
+                throw std::runtime_error(fmt("failed to load stations: invalid number at line %d", lineNo));
+            }
+            stations[st.name] = st;
+            if (st.name == refName) { refStation = st; haveRef = true; }
+        }
+        if (!haveRef)
+            throw std::runtime_error(fmt("failed to load stations: reference frequency %.0f not found in stations", referenceFreq));
+        printf("Loaded %zu stations including reference %.0f MHz\n", stations.size(), referenceFreq / 1e6);
+    }
+
+    // processor.go:110-122.  The reference ranges over a Go map (random order); nested names
+    // are resolved here by preferring the longest name.
+    Station getStationFromFilename(const std::string &filename) const
+    {
+        const size_t slash = filename.find_last_of('/');
+        const std::string base = slash == std::string::npos ? filename : filename.substr(slash + 1);
+        std::vector<std::string> names;
+        for (const auto &kv : stations) names.push_back(kv.first);
+        std::sort(names.begin(), names.end(), [](const std::string &a, const std::string &b) {
+            return a.size() != b.size() ? a.size() > b.size() : a < b;
+        });
+        for (const auto &n : names)
+            if (base.find(n) != std::string::npos) return stations.at(n);
+        throw std::runtime_error("could not identify station from filename: " + filename);
+    }
+
+    // processor.go:166-205: the bytes go to the GPU (tdoa_load_file); the complex64 samples stay there
+    long long loadIQData(int slot, const std::string &filename)
+    {
+        printf("Loading I/Q data from: %s\n", filename.c_str());
+        int64_t n = 0;
+        if (tdoa_load_file(engine, slot, filename.c_str(), &n) != TDOA_OK) throw std::runtime_error(tdoa_last_error(engine));
+        std::ifstream f(filename, std::ios::binary | std::ios::ate);
+        printf("File size: %lld bytes, samples: %lld\n", (long long)f.tellg(), (long long)n);
+        printf("Successfully loaded %lld complex samples\n", (long long)n);
+        return n;
+    }
+
+    // processor.go:739-929; by default every stdout line of the shipped binary
+    void ProcessTDOA(const std::vector<std::string> &datFiles)
+    {
+        if (datFiles.size() < 3)
+            throw std::runtime_error(fmt("need at least 3 collector stations, got %zu", datFiles.size()));  // :740-742
+        const bool binary = mode == TDOA_MODE_BINARY;
+        printf("Processing TDOA for target frequency %.3f MHz\n", targetFreq / 1e6);
+        printf("Reference: %s at %.6f°, %.6f°, %.1fm\n", refStation.name.c_str(), refStation.latitude, refStation.longitude,
+               refStation.elevation);
+        const int S = (int)datFiles.size(), P = S * (S - 1) / 2;
+        tdoa_config cfg;
+        tdoa_default_config(mode, &cfg);
+        cfg.n_stations = S;
+        if (tdoa_create(&engine, &cfg) != TDOA_OK) throw std::runtime_error(tdoa_last_error(nullptr));
+        std::vector<Station> st;
+        for (int slot = 0; slot < S; slot++) {
+            Station s;
+            try { s = getStationFromFilename(datFiles[slot]); }
+            catch (const std::exception &e) { throw std::runtime_error("failed to identify station for " + datFiles[slot] + ": " + e.what()); }
+            long long n = 0;
+            try { n = loadIQData(slot, datFiles[slot]); }
+            catch (const std::exception &e) { throw std::runtime_error("failed to load data from " + datFiles[slot] + ": " + e.what()); }
+            if (binary) {
+                const long long b = n / 3;  // processor.go:211-236, :244-265
+                printf("Extracting reference signal from dual-frequency data\n");
+                printf("Total samples: %lld, block size: %lld\n", n, b);
+                printf("Extracted %lld reference samples from blocks 1 and 3\n", 2 * b);
+                printf("Extracting target signal from dual-frequency data\n");
+                printf("Total samples: %lld, block size: %lld\n", n, b);
+                printf("Extracted %lld target samples from block 2\n", b);
+                printf("Coherent integration time: 500 ms (expecting ~10.0 dB processing gain)\n");
+            }
+            st.push_back(s);
+            printf("Loaded collector: %s at %.6f°, %.6f°, %.1fm\n", s.name.c_str(), s.latitude, s.longitude, s.elevation);
+        }
+        std::vector<double> llh;
+        for (const auto &s : st) { llh.push_back(s.latitude); llh.push_back(s.longitude); llh.push_back(s.elevation); }
+        printf("\nBaseline distances (3D):\n");
+        std::vector<double> base(P);
+        check(tdoa_baselines(engine, llh.data(), S, base.data()));
+        std::vector<std::pair<int, int>> pairs;
+        for (int i = 0; i < S; i++)
+            for (int j = i + 1; j < S; j++) pairs.push_back({i, j});
+        for (int p = 0; p < P; p++)
+            printf("%s - %s: %.2f km\n", st[pairs[p].first].name.c_str(), st[pairs[p].second].name.c_str(), base[p] / 1000);
+        const double fs = cfg.sample_rate;
+        // the whole numeric path in one engine call: both pair loops, time and range differences, solveTDOA
+        std::vector<tdoa_peak> peaks[2] = {std::vector<tdoa_peak>(P), std::vector<tdoa_peak>(P)};
+        std::vector<double> dev_td(P), dev_rd(P);
+        double fix[3] = {0, 0, 0};
+        int32_t fixStatus = 0, fixIters = 0;
+        check(tdoa_process(engine, llh.data(), peaks[0].data(), peaks[1].data(), dev_td.data(), dev_rd.data(), fix, &fixStatus,
+                           &fixIters));
+        std::vector<double> tds[2];
+        for (int kind = 0; kind < 2; kind++) {
+            const char *label = kind == TDOA_KIND_REF ? "REF" : "TGT";
+            if (kind == TDOA_KIND_REF) {
+                printf("\n=== REFERENCE SIGNAL CORRELATION TEST ===\n");
+                if (binary) printf("Testing weak %.1f MHz NOAA weather signal:\n", referenceFreq / 1e6);
+            } else {
+                printf("\n=== TARGET SIGNAL CORRELATION TEST ===\n");
+                if (binary) printf("Testing strong %.1f MHz FM broadcast signal:\n", targetFreq / 1e6);
+            }
+            std::vector<tdoa_signal_info> info(S);
+            std::vector<double> first(P);
+            if (binary) check(tdoa_xcorr_info(engine, kind, info.data(), first.data()));
+            for (int p = 0; p < P; p++) {
+                const tdoa_peak &pk = peaks[kind][p];
+                const double td = (double)pk.lag / fs;  // processor.go:821
+                tds[kind].push_back(td);
+                if (binary) printPairBinary(info[pairs[p].first], info[pairs[p].second], pk, first[p], fs, cfg);
+                printf("%s %s - %s: delay=%d samples (%.3f μs), correlation=%.6f\n", label, st[pairs[p].first].name.c_str(),
+                       st[pairs[p].second].name.c_str(), pk.lag, td * 1e6, pk.corr);
+            }
+        }
+        std::vector<double> td(P);
+        if (!binary) {
+            td = tds[1];  // processor.go:853: target differences only
+        } else {
+            printf("\n=== REFERENCE SIGNAL SYNCHRONIZATION ===\n");
+            printf("Using reference signal to synchronize collector timing...\n");
+            for (int k = 0; k < P; k++) printf("Reference timing offset %d: %.3f μs\n", k, tds[0][k] * 1e6);
+            printf("\n=== APPLYING TIMING CORRECTIONS TO TARGET SIGNAL ===\n");
+            for (int k = 0; k < P; k++) {
+                td[k] = tds[1][k] - tds[0][k];
+                printf("Target delay %d: %.3f μs (raw) - %.3f μs (ref offset) = %.3f μs (corrected)\n", k, tds[1][k] * 1e6,
+                       tds[0][k] * 1e6, td[k] * 1e6);
+            }
+            printf("\n=== CORRELATION COMPARISON ===\n");
+            printf("Reference signal (%.1f MHz): Used for timing synchronization\n", referenceFreq / 1e6);
+            printf("Target signal (%.1f MHz): Corrected with reference timing offsets\n", targetFreq / 1e6);
+            printf("Using corrected target signal for TDOA calculation\n");
+        }
+        std::vector<double> rd(P);
+        for (int k = 0; k < P; k++) rd[k] = td[k] * kSpeedOfLight;  // :899-903
+        if (binary) {
+            printf("\nTDOA triangulation:\n");
+            printf("Corrected time differences: %s\n", join(td, 1e6, "%.3f μs").c_str());
+            printf("Corrected distance differences: %s\n", join(rd, 1.0, "%.1f m").c_str());
+            printf("\nDiagnostic test with example delays:\n");  // processor.go:885-889
+            printf("Simulating 10 μs, 5 μs, -3 μs delays...\n");
+            const double us[3] = {10.0, 5.0, -3.0};
+            for (int k = 0; k < 3; k++) printf("Test delay %d: %.1f μs → %.1f m\n", k + 1, us[k], us[k] * 1e-6 * kSpeedOfLight);
+        }
+        printf("\n=== TDOA GEOLOCATION ===\n");
+        printf("Time differences (μs): ");
+        for (double t : td) printf("%.3f ", t * 1e6);
+        printf("\nRange differences (m): ");
+        for (double r : rd) printf("%.1f ", r);
+        printf("\n");
+        if (binary) {
+            // shipped binary: measurements beyond 1.2 x 17 km are dropped before its solver (which
+            // then aborts on every input, SURVEY.md finding 4; the fix printed below is processor.go's
+            // solveTDOA on the unfiltered differences)
+            printf("Validating range differences against baseline distances...\n");
+            const double limit = 20400.0;
+            int valid = 0;
+            for (int k = 0; k < P; k++) {
+                if (std::fabs(rd[k]) <= limit) {
+                    printf("VALID: Range difference %d: %.1fm (within ±%.1fm limit)\n", k, rd[k], limit);
+                    valid++;
+                } else {
+                    printf("FILTERING OUT: Range difference %d: %.1fm exceeds expected maximum %.1fm\n", k, rd[k], limit);
+                    printf("This measurement is unreliable and will be excluded\n");
+                }
+            }
+            if (valid == P) {
+                printf("Using %d of %d range difference measurements\n", valid, P);
+                double e[3][3];
+                for (int k = 0; k < 3; k++) ecef(st[k], e[k]);
+                const double area = 0.5 * std::fabs((e[1][0] - e[0][0]) * (e[2][1] - e[0][1]) - (e[2][0] - e[0][0]) * (e[1][1] - e[0][1]));
+                printf("Station geometry triangle area: %.1f m²\n", area);
+                printf("Initial guess: %.6f°, %.6f°, %.1fm\n", (st[0].latitude + st[1].latitude + st[2].latitude) / 3,
+                       (st[0].longitude + st[1].longitude + st[2].longitude) / 3, (st[0].elevation + st[1].elevation + st[2].elevation) / 3);
+            }
+        }
+        fflush(stdout);
+        // the device did the same arithmetic (delay / fs, target - reference, * c) before its solveTDOA
+        for (int k = 0; k < P; k++)
+            if (rd[k] != dev_rd[k]) throw std::runtime_error(fmt("range difference %d: host %.17g, device %.17g", k, rd[k], dev_rd[k]));
+        if (fixStatus != 0) throw std::runtime_error("TDOA solution failed: singular Jacobian matrix");  // :997-999, :920
+        printf("\n*** CALCULATED TRANSMITTER LOCATION ***\n");
+        printf("Latitude:  %.6f°\n", fix[0]);
+        printf("Longitude: %.6f°\n", fix[1]);
+        printf("Elevation: %.1f m\n", fix[2]);
+    }
+
+private:
+    void check(int rc) const
+    {
+        if (rc != TDOA_OK) throw std::runtime_error(tdoa_last_error(engine));
+    }
+
+    static std::string join(const std::vector<double> &v, double scale, const char *f)
+    {
+        std::string s;
+        for (size_t k = 0; k < v.size(); k++) s += (k ? ", " : "") + fmt(f, v[k] * scale);
+        return s;
+    }
+
+    // processor.go:125-148 latLonToECEF (WGS-84): host copy for the printed triangle area only
+    static void ecef(const Station &s, double *out)
+    {
+        const double a = 6378137.0, f = 1.0 / 298.257223563, e2 = 2 * f - f * f;
+        const double la = s.latitude * M_PI / 180.0, lo = s.longitude * M_PI / 180.0;
+        const double n = a / std::sqrt(1 - e2 * std::sin(la) * std::sin(la));
+        out[0] = (n + s.elevation) * std::cos(la) * std::cos(lo);
+        out[1] = (n + s.elevation) * std::cos(la) * std::sin(lo);
+        out[2] = (n * (1 - e2) + s.elevation) * std::sin(la);
+    }
+
+    // stdout of the shipped binary while it works on one pair (ELF 0x49cd40, 0x49d6a0)
+    void printPairBinary(const tdoa_signal_info &s1, const tdoa_signal_info &s2, const tdoa_peak &pk, double firstCorr, double fs,
+                         const tdoa_config &cfg) const
+    {
+        static const char *branchText[3] = {"Strong FM signal - using instantaneous frequency correlation approach",
+                                            "Moderate signal - envelope correlation approach",
+                                            "Weak signal - standard processing with timing preservation"};
+        printf("=== Cross-Correlation Analysis ===\n");
+        printf("\n--- Signal Preprocessing ---\n");
+        const tdoa_signal_info *sg[2] = {&s1, &s2};
+        for (int k = 0; k < 2; k++) {
+            printf("Preprocessing Signal %d signal (%lld samples)\n", k + 1, (long long)sg[k]->n);
+            printf("Initial signal power: %.9f\n", sg[k]->power0);
+            printf("%s\n", branchText[sg[k]->branch]);
+            printf("Removed DC bias: %.6f + %.6fi\n", sg[k]->dc_re, sg[k]->dc_im);
+            if (sg[k]->branch == 2) printf("Bandpass filter: %.1f - %.1f Hz (at %.0f Hz sample rate)\n", 100.0, 200000.0, 2000000.0);
+            printf("Normalized signal power: %.6f → %.6f\n", sg[k]->power1, sg[k]->power1 > 0 ? 1.0 : 0.0);
+        }
+        printf("\n--- Time Domain Correlation ---\n");
+        printf("Performing time domain correlation\n");
+        const long long tl = std::min(s1.n, s2.n), sl = std::max(s1.n, s2.n);
+        printf("Template: %lld samples, Signal: %lld samples\n", tl, sl);
+        if (tl == sl) printf("Reduced template to %lld samples to allow %d sample delay search\n", tl - cfg.max_lag, cfg.max_lag);
+        printf("Using coherent integration with %d-sample blocks\n", cfg.block_size);
+        const long long nLags = tl == sl ? cfg.max_lag : std::max<long long>(1, std::min<long long>(cfg.max_lag, sl - tl));
+        printf("Time domain progress: 0/%lld (coherent blocks: %d)\n", nLags, pk.n_blocks);
+        printf("Time domain correlation: %.6f at delay %d samples\n", firstCorr, pk.first_lag);
+        if (cfg.sanity_lag > 0 && pk.first_lag > cfg.sanity_lag) {
+            printf("WARNING: Delay %d samples (%.1f μs) exceeds reasonable range for baseline distances\n", pk.first_lag,
+                   pk.first_lag / fs * 1e6);
+            printf("Maximum expected delay: 56.7 μs for 17 km baseline\n");
+            printf("This suggests correlation algorithm found wrong peak\n");
+            if (pk.flags & TDOA_PEAK_RESEARCHED)
+                printf("Found better peak within reasonable range: delay=%d samples (%.1f μs), correlation=%.6f\n", pk.lag,
+                       pk.lag / fs * 1e6, pk.corr);
+        }
+        printf("\n--- Result: Time Domain with Preprocessing ---\n");
+        printf("Correlation: %.6f at delay %d samples\n", pk.corr, pk.lag);
+    }
+
+    double referenceFreq, targetFreq;
+    int mode;
+    std::map<std::string, Station> stations;
+    Station refStation;
+    tdoa_engine *engine = nullptr;
+};
+
+}  // namespace
+
+// processor.go:1047-1076
+int main(int argc, char **argv)
+{
+    int mode = TDOA_MODE_BINARY;
+    std::vector<std::string> args(argv + 1, argv + argc);
+    if (!args.empty() && args[0] == "--source") { mode = TDOA_MODE_SOURCE; args.erase(args.begin()); }
+    if (args.size() < 6) {
+        printf("Usage: processor <reference_freq_hz> <target_freq_hz> <stations.csv> <collector1.dat> <collector2.dat> "
+               "<collector3.dat> [...]\n");
+        return 1;
+    }
+    try {
+        const double refFreq = std::stod(args[0]), tgtFreq = std::stod(args[1]);
+        TDOAProcessor p(refFreq, tgtFreq, args[2], mode);
+        p.ProcessTDOA(std::vector<std::string>(args.begin() + 3, args.end()));
+    } catch (const std::exception &e) {
+        fflush(stdout);
+        fprintf(stderr, "TDOA processing failed: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -413,6 +413,32 @@ def test_processor_stdout_is_the_shipped_binarys(tmp_path, case):
         assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
 
 
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_cpp_host_mirror_stdout_is_the_shipped_binarys(tmp_path, case):
+    """processor_b200 (host/processor_b200.cpp: the reference's command over the C ABI) prints, line
+    for line, what the reference's shipped `processor` printed for the same captures."""
+    import subprocess
+    raws, meta = load_golden(case)
+    files = []
+    for name, raw in zip(["kx0u", "n3pay", "kf0mtl"], raws):
+        f = tmp_path / f"sim-{name}-1.dat"
+        raw.tofile(f)
+        files.append(str(f))
+    exe = GOLDEN.parent.parent / "tdoa-geolocation_b200" / "processor_b200"
+    r = subprocess.run([str(exe), "162400000", "92300000", str(GOLDEN / "stations.csv"), *files], capture_output=True, text=True)
+    assert r.returncode in (0, 1), r.stderr          # 1: singular fix, an error in the source solver too
+    if r.returncode == 1:
+        assert "singular Jacobian matrix" in r.stderr
+    else:
+        assert "*** CALCULATED TRANSMITTER LOCATION ***" in r.stdout
+    skip = "Loading I/Q data from:"
+    ours = [l for l in r.stdout.splitlines() if not l.startswith(skip)]
+    gold = [l for l in (GOLDEN / f"{case}.stdout.txt").read_text().splitlines() if not l.startswith(skip)]
+    assert len(ours) >= len(gold)
+    for k, (a, b) in enumerate(zip(ours, gold)):
+        assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
+
+
 # ------------------------------------------------------------------ discriminator bit parity
 def test_discriminator_bits_match_oracle(eng_binary):
     """Strong-FM branch, sample by sample: the custom f64 arctangent rounds to the same

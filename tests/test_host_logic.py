@@ -57,3 +57,37 @@ def test_cli_usage():
     from importlib import import_module
     proc = import_module("tdoa-geolocation_b200.processor")
     assert proc.main(["1", "2", "x.csv"]) == 1
+
+
+# ------------------------------------------------------------------ the C++ host mirror (processor_b200)
+def _host_binary():
+    from pathlib import Path
+    return Path(__file__).resolve().parent.parent / "tdoa-geolocation_b200" / "processor_b200"
+
+
+def test_processor_b200_usage_and_station_table():
+    """processor.go:1048-1051 usage line and exit status; loadStations (:52-107) runs on the host."""
+    import subprocess
+    exe = _host_binary()
+    assert exe.exists(), "run python tdoa-geolocation_b200/build.py"
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("Usage: processor <reference_freq_hz> <target_freq_hz> <stations.csv>")
+    golden = str(_host_binary().parent.parent / "tests" / "golden" / "stations.csv")
+    r = subprocess.run([str(exe), "1", "92300000", golden, "a.dat", "b.dat", "c.dat"], capture_output=True, text=True)
+    assert r.returncode == 1 and "reference frequency 1 not found in stations" in r.stderr
+    r = subprocess.run([str(exe), "162400000", "92300000", golden, "a.dat", "b.dat"], capture_output=True, text=True)
+    assert r.returncode == 1   # fewer than three collectors: the usage line (processor.go:1048)
+
+
+def test_processor_b200_has_no_cpu_path():
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("checks the no-GPU refusal")
+    golden = str(_host_binary().parent.parent / "tests" / "golden" / "stations.csv")
+    r = subprocess.run([str(_host_binary()), "162400000", "92300000", golden, "a.dat", "b.dat", "c.dat"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "Loaded 5 stations including reference 162 MHz" in r.stdout
+    assert "TDOA processing failed" in r.stderr and "no CPU path" in r.stderr
