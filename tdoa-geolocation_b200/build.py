@@ -81,21 +81,23 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     return OUT
 
 
-HOST_SRC = HERE / "host" / "processor_b200.cpp"
+HOST_PROGRAMS = ["processor_b200", "fast_analyzer_b200"]
 HOST_OUT = HERE / "processor_b200"
 
 
 def build_host(force: bool = False) -> Path:
-    """The reference's `processor` command over the C ABI (host/processor_b200.cpp): plain g++,
-    links libtdoa_b200.so, finds it next to itself at run time."""
-    if force or _stale(HOST_OUT, [HOST_SRC, OUT, *INCLUDE.glob("*.h")]):
-        cxx = shutil.which("g++") or "g++"
-        cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-I", str(INCLUDE), str(HOST_SRC), "-o", str(HOST_OUT),
-               "-L", str(HERE), "-ltdoa_b200", "-Wl,-rpath,$ORIGIN"]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode:
-            sys.stderr.write(res.stderr)
-            raise RuntimeError("g++ failed on processor_b200.cpp")
+    """The reference's commands over the C ABI (host/*.cpp: processor, fast_analyzer): plain g++,
+    linked against libtdoa_b200.so, which they find next to themselves at run time."""
+    for name in HOST_PROGRAMS:
+        src, out = HERE / "host" / f"{name}.cpp", HERE / name
+        if force or _stale(out, [src, OUT, *INCLUDE.glob("*.h")]):
+            cxx = shutil.which("g++") or "g++"
+            cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-I", str(INCLUDE), str(src), "-o", str(out),
+                   "-L", str(HERE), "-ltdoa_b200", "-Wl,-rpath,$ORIGIN"]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode:
+                sys.stderr.write(res.stderr)
+                raise RuntimeError(f"g++ failed on {name}.cpp")
     return HOST_OUT
 
 

@@ -89,3 +89,27 @@ def test_fast_analyzer_cli_lines(eng, tmp_path):
     np.zeros(4, np.uint8).tofile(tiny)
     buf = io.StringIO()
     assert T.analyzer.fast_main([str(tiny)], out=buf) == 1 and "file too small" in buf.getvalue()
+
+
+def test_cpp_fast_analyzer_command(tmp_path):
+    """fast_analyzer_b200 (host/fast_analyzer_b200.cpp): the two CSV lines gain_calibrator.go:266-297
+    parses, equal to the restatement's; the reference's error line and exit status for a tiny file."""
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "tdoa-geolocation_b200" / "fast_analyzer_b200"
+    for name in ("tone", "clipped"):
+        raw = captures()[name]
+        f = tmp_path / f"kx0u-{name}.dat"
+        raw.tofile(f)
+        r = subprocess.run([str(exe), str(f)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        want = oracle.analyze_capture(raw, fast=True)
+        for line, label, w in zip(r.stdout.splitlines(), ("REF", "TGT"), want):
+            assert line == "%s,%.1f,%.1f,%s,%s" % (label, w["snr_db"], w["power_db"], str(bool(w["has_clipping"])).lower(),
+                                                   str(bool(w["has_overload"])).lower())
+    tiny = tmp_path / "tiny.dat"
+    np.zeros(4, np.uint8).tofile(tiny)
+    r = subprocess.run([str(exe), str(tiny)], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("Error: ") and "file too small" in r.stdout
+    r = subprocess.run([str(exe), str(tmp_path / "absent.dat")], capture_output=True, text=True)
+    assert r.returncode == 1 and "failed to open file" in r.stdout
