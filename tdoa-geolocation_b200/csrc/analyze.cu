@@ -151,7 +151,6 @@ __global__ void __launch_bounds__(1024) k_quality_spectrum(const QualJob *jobs, 
 {
     extern __shared__ double s_sorted[];   // next power of two >= M doubles
     __shared__ double s_red[32];
-    __shared__ double s_dc[2];
     const QualJob &J = jobs[blockIdx.x];
     const int tid = threadIdx.x;
     const i64 n = J.n;

@@ -116,7 +116,6 @@ struct tdoa_engine {
     std::vector<int8_t> branch_memo;  // last preprocess branch per (station, kind); -1 unknown
     std::vector<tdoa_signal_info> info_sig[2];  // window 0 of the last xcorr per kind
     std::vector<double> info_first[2];
-    cudaEvent_t ev_fft[2] = {nullptr, nullptr};
     int sm_count = 148;
     // per-kernel timing spans of the current call (events are created once and reused)
     struct Span { cudaEvent_t a = nullptr, b = nullptr; int tag = 0; };
@@ -1618,7 +1617,6 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
         tdoa_destroy(e);
         return err == cudaErrorMemoryAllocation ? TDOA_E_NOMEM : TDOA_E_CUDA;
     }
-    for (int i = 0; i < 2 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev_fft[i]);
     e->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if (err == cudaSuccess && fft_setup(e->stream, &e->d_tw) != 0) err = cudaErrorUnknown;
     if (err == cudaSuccess && demod_setup(e->stream) != 0) err = cudaErrorUnknown;
@@ -1663,8 +1661,6 @@ void tdoa_destroy(tdoa_engine *e)
     if (e->d_frame) cudaFree(e->d_frame);
     if (e->d_tw) cudaFree(e->d_tw);
     if (e->d_tw_fine) cudaFree(e->d_tw_fine);
-    for (auto &ev : e->ev_fft)
-        if (ev) cudaEventDestroy(ev);
     for (auto &sp : e->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     if (e->frame_done) cudaEventDestroy(e->frame_done);
     for (auto &ev : e->ev)
