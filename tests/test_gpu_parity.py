@@ -616,3 +616,29 @@ def test_process_equals_the_separate_calls(case):
             r = e.process(STATION_LLH)
         for got, want in zip(list(r["ref"]) + list(r["tgt"]), want_ref + want_tgt):
             assert int(got["lag"]) == want[0] and abs(float(got["corr"]) - want[1]) <= CORR_TOL
+
+
+# ------------------------------------------------------------------ every search path against the every-lag path
+@pytest.mark.parametrize("S,L,W,hop,nw", [
+    (5, 700, 30000, 9000, 2),      # 10 pairs: parked spectra, 2048-lag chunks, odd station count (a transform with one plane)
+    (17, 1100, 26000, 0, 1),       # 136 pairs: two accumulation jobs share one set of spectra; 4096-lag chunk
+    (3, 4500, 50000, 20000, 2),    # 9001 lags: the 2^21-point transform
+    (4, 2500, 40000, 0, 1),        # 6 pairs, 5001 lags: 2 x 2 tiles, three 2048-lag chunks
+])
+def test_search_paths_agree_with_every_lag_evaluation(S, L, W, hop, nw):
+    """Whatever ranks the lags (tiles, parked spectra, the big transform), the record must be the one the
+    exhaustive time-domain evaluation of every lag (use_fft=0, the reference's order) produces."""
+    rng = np.random.default_rng(S * 1000 + L)
+    d = tuple(int(x) for x in rng.integers(0, min(L, 400), S))
+    raws = fm_capture(W + hop * (nw - 1) + 2000, d, d, seed=S)
+    with T.Engine(T.MODE_EXTENDED, n_stations=S, max_lag=L) as e, T.Engine(T.MODE_EXTENDED, n_stations=S, max_lag=L, use_fft=0) as b:
+        load_all(e, raws)
+        load_all(b, raws)
+        got = e.xcorr(T.KIND_TGT, 300, W, nw, hop)
+        want = b.xcorr(T.KIND_TGT, 300, W, nw, hop)
+    assert np.array_equal(got["lag"], want["lag"])
+    assert np.allclose(got["corr"], want["corr"], rtol=0, atol=1e-12)
+    assert np.allclose(got["frac"], want["frac"], rtol=0, atol=1e-6)
+    pairs = [(i, j) for i in range(S) for j in range(i + 1, S)]
+    for w in range(nw):
+        assert [int(x) for x in got[w]["lag"]] == [d[j] - d[i] for i, j in pairs]
