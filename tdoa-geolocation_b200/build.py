@@ -57,6 +57,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h")) + [Path(__file__)]
     objs = []
+    todo = []
     for src, extra in UNITS:
         s = CSRC / src
         if not s.exists():
@@ -64,9 +65,20 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         o = OBJ / (s.stem + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc(), *ARCH, *COMMON, *extra, "-c", str(s), "-o", str(o)]
-            res = subprocess.run(cmd, capture_output=True, text=True)
-            (OBJ / (s.stem + ".ptxas.log")).write_text(res.stderr)
+            todo.append((src, s, o, extra))
+
+    def compile_unit(item):
+        src, s, o, extra = item
+        cmd = [nvcc(), *ARCH, *COMMON, *extra, "-c", str(s), "-o", str(o)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        (OBJ / (s.stem + ".ptxas.log")).write_text(res.stderr)
+        return src, res
+
+    if todo:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as pool:
+            results = list(pool.map(compile_unit, todo))   # translation units are independent
+        for src, res in results:
             if verbose or res.returncode:
                 sys.stderr.write(res.stderr)
             if res.returncode:
