@@ -91,7 +91,8 @@ typedef struct {
                               pairs per window; a 2^21-point transform for >= 8192 lags);
                               0: evaluate every lag in the time domain;
                               test switches: 2 one transform per pair, 3 no 2^21-point
-                              transform, 4 no parked spectra                         */
+                              transform, 4 no parked spectra, 5 plain one-add-at-a-
+                              time walk for the sequential DC sum                    */
     int32_t device;        /* CUDA device ordinal                                    */
     int32_t seq_dc_limit;  /* removeDCBias (processor.go:299-319): signals of up to this many
                               samples get the reference's sequential f32 accumulator,

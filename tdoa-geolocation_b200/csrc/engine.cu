@@ -475,7 +475,31 @@ int run_pipeline(tdoa_engine *e, Pipeline &pl)
                 case K_UNPACK: launch_unpack(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
                 case K_DEMOD: launch_demod(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
                 case K_ENVELOPE: launch_envelope(d_jobs, nj, st.max_n, stream_grid_x(st.max_n), e->stream); break;
-                case K_SEQSUM: launch_seqsum(d_jobs, nj, e->stream); break;
+                case K_SEQSUM:
+                    if (st.max_n < 32768 || e->cfg.use_fft == 5) {   // short chains (5: test switch): the plain walk
+                        launch_seqsum(d_jobs, nj, e->stream);
+                    } else {
+                        // chunk-parallel evaluation of the same chain (seqsum.cu), one job per component
+                        std::vector<SeqJob> sq;
+                        for (const SigJob &j : st.jobs) {
+                            const float *planes[2] = {j.q_re, j.q_im};
+                            for (int c = 0; c < 2; c++) {
+                                SeqJob q{};
+                                q.x = planes[c]; q.n = j.n; q.out = j.stats + (c == 0 ? ST_DC_RE : ST_DC_IM);
+                                if (q.x) {
+                                    void *scratch = nullptr;
+                                    if ((rc = alloc(e, &scratch, seqsum_scratch_bytes(j.n)))) return rc;
+                                    seqsum_carve(q, scratch);
+                                }
+                                sq.push_back(q);
+                            }
+                        }
+                        const SeqJob *d_sq = nullptr;
+                        if ((rc = upload(e, sq, &d_sq))) return rc;
+                        launch_seqsum_chunked(d_sq, (int)sq.size(), st.max_n, e->stream);
+                        count_launch(e, 3);
+                    }
+                    break;
                 case K_BOXCAR: launch_boxcar(d_jobs, nj, st.max_n, 0, e->stream); break;
                 case K_BOXCAR_SMALL: {
                     const int sp = span_begin(e, SPAN_BOXCAR);

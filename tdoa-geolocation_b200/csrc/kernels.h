@@ -102,6 +102,18 @@ void launch_unpack(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cuda
 void launch_demod(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cudaStream_t st);
 void launch_envelope(const SigJob *d_jobs, int n_jobs, i64 max_n, int grid_x, cudaStream_t st);
 void launch_seqsum(const SigJob *d_jobs, int n_jobs, cudaStream_t st);
+// ---- seqsum.cu: the same sequential f32 chain, chunk-parallel and still bit for bit
+struct SeqJob {
+    const float *x;    // one component plane (nullptr: identically zero, *out = 0)
+    i64 n;
+    double *out;       // ST_DC_RE or ST_DC_IM slot: f32(sum / n) widened (processor.go:309)
+    i64 n_chunks;      // filled by seqsum_carve
+    double *csum, *pre;
+    void *infos;
+};
+size_t seqsum_scratch_bytes(i64 n);
+void seqsum_carve(SeqJob &J, void *scratch);
+void launch_seqsum_chunked(const SeqJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
 void launch_boxcar(const SigJob *d_jobs, int n_jobs, i64 max_n, int max_window, cudaStream_t st);
 void launch_notch_combine(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
 void launch_normalize(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);

@@ -642,3 +642,30 @@ def test_search_paths_agree_with_every_lag_evaluation(S, L, W, hop, nw):
     pairs = [(i, j) for i in range(S) for j in range(i + 1, S)]
     for w in range(nw):
         assert [int(x) for x in got[w]["lag"]] == [d[j] - d[i] for i, j in pairs]
+
+
+# ------------------------------------------------------------------ the sequential DC chain, chunk-parallel
+@pytest.mark.parametrize("case", ["fm_strong", "moderate", "weak_noise", "big_fm", "big_weak"])
+def test_chunked_sequential_dc_is_the_plain_walk(case):
+    """removeDCBias's sequential f32 accumulator (processor.go:304-309): the chunk-parallel
+    evaluation (seqsum.cu) must give the bits of the plain one-add-at-a-time walk (use_fft=5
+    keeps the old kernel) -- DC of every signal, hence every record."""
+    if case == "big_fm":
+        raws = fm_capture(700_000, (0, 9, 31), (0, 9, 31), seed=5)                      # 1.4 M / 0.7 M samples per signal
+    elif case == "big_weak":
+        rng = np.random.default_rng(9)
+        raws = [rng.integers(118, 138, 2 * 3 * 500_000, dtype=np.uint8) for _ in range(3)]   # weak branch: complex, zero-mean
+    else:
+        raws, _ = load_golden(case)
+    for mode in (T.MODE_BINARY, T.MODE_SOURCE):
+        # (SOURCE arithmetic never uses the FFT search, so the switch only selects the DC kernel there)
+        with T.Engine(mode, chunk_samples=0) as a, T.Engine(mode, chunk_samples=0, use_fft=5) as b:
+            load_all(a, raws)
+            load_all(b, raws)
+            for kind in (T.KIND_REF, T.KIND_TGT):
+                ga, gb = a.xcorr(kind)[0], b.xcorr(kind)[0]
+                ia, ib = a.xcorr_info(kind)[0], b.xcorr_info(kind)[0]
+                for sa, sb in zip(ia, ib):
+                    assert sa["dc_re"] == sb["dc_re"] and sa["dc_im"] == sb["dc_im"], (case, mode, kind)
+                    assert sa["power1"] == sb["power1"]
+                assert np.array_equal(ga["lag"], gb["lag"]) and np.array_equal(ga["corr"], gb["corr"])
