@@ -421,7 +421,10 @@ def main_ours(args):
                                        "one all_gather of 192-byte peak records per step" if world > 1 else "1 GPU"),
             "fixes_per_s": world / t_step,
             "e2e": {"value": e2e_value, "unit": "pair-Msamples/s", "h2d_bytes_per_step": 3 * nbytes,
-                    "d2h_bytes_per_step": 2 * 3 * 32 + 3 * 8 + 4 + 4, "ms_per_step": t_e2e * 1e3,
+                    # tdoa_process reads back: REF + TGT records, time and range differences, the fix
+                    # (llh, status, iterations), the per-signal statistics and first-pass correlations
+                    "d2h_bytes_per_step": 2 * 3 * 32 + 2 * 3 * 8 + 3 * 8 + 4 + 4 + 2 * 3 * 8 * 8 + 2 * 3 * 8,
+                    "ms_per_step": t_e2e * 1e3,
                     "fixes_per_s": world / t_e2e},
             "gpu_launches": launches,
             "host_affinity": numa,
