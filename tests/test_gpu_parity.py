@@ -147,6 +147,24 @@ def test_ragged_station_lengths(eng_binary):
         assert int(pk["lag"]) == orc[0] and abs(float(pk["corr"]) - orc[1]) <= CORR_TOL
 
 
+def test_process_on_ragged_and_tiny_captures(eng_binary):
+    """The one-call path on inputs the reference's loops treat specially: stations of different
+    lengths (the shorter input is the template, processor.go:653-661), captures shorter than one
+    block (no whole block -> (0, 0.0)), a 2-sample capture (N / 3 == 0: the data is returned
+    unchanged, :211-214)."""
+    raws = fm_capture(30000, (0, 4, 9), (0, 12, 30), seed=3)
+    raws[1] = raws[1][: 2 * 3 * 27000]
+    for variant in (raws, [r[: 2 * 3 * 2000] for r in raws], [raws[0], raws[1], raws[2][:4]]):
+        load_all(eng_binary, variant)
+        ref, tgt = eng_binary.xcorr(T.KIND_REF)[0], eng_binary.xcorr(T.KIND_TGT)[0]
+        r = eng_binary.process(STATION_LLH)
+        for name in ("lag", "corr", "flags", "n_blocks"):
+            assert np.array_equal(r["ref"][name], ref[name]) and np.array_equal(r["tgt"][name], tgt[name]), name
+        want_ref, want_tgt = oracle.process_capture_binary(variant)
+        for pk, orc in zip(list(r["ref"]) + list(r["tgt"]), want_ref + want_tgt):
+            assert int(pk["lag"]) == orc[0] and abs(float(pk["corr"]) - orc[1]) <= CORR_TOL
+
+
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_fft_path_equals_every_lag_path(case):
     """use_fft=1 (candidate search + exact re-evaluation) must pick the same peak as the
