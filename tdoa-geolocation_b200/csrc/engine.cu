@@ -1271,7 +1271,7 @@ int correlate(tdoa_engine *e, const std::vector<Sig> &sigs, const std::vector<Pa
             J.variant = CORR_EXTENDED;
             J.t_off = L;
             J.n_t = n > 0 ? n : 0;
-            J.block = 8192;
+            J.block = 65536;   // partial-sum chunk of the exact evaluation (engine-defined mode: any grouping)
             J.nb = n > 0 ? (n + J.block - 1) / J.block : 0;
             J.n_lags = (int)(2 * L + 1);
             K.lag_origin = (int)-L;
