@@ -475,8 +475,10 @@ __global__ void __launch_bounds__(kCandThreads) k_corr_candidates(const PairJob 
         // block reduction, fixed order
 #pragma unroll
         for (int c = 0; c < kCandGroup; c++) {
-            const double w = warp_sum(acc[c]);
-            if (lane == 0) s_red[c][wid] = w;
+            if (c < ng) {   // ng is uniform: a sharp peak reduces one value, not eight
+                const double w = warp_sum(acc[c]);
+                if (lane == 0) s_red[c][wid] = w;
+            }
         }
         __syncthreads();
         if (tid < ng) {
