@@ -642,6 +642,7 @@ def test_process_equals_the_separate_calls(case):
     (17, 1100, 26000, 0, 1),       # 136 pairs: two accumulation jobs share one set of spectra; 4096-lag chunk
     (3, 4500, 50000, 20000, 2),    # 9001 lags: the 2^21-point transform
     (4, 2500, 40000, 0, 1),        # 6 pairs, 5001 lags: 2 x 2 tiles, three 2048-lag chunks
+    (20, 300, 12000, 0, 1),        # 190 pairs on 20 stations: more packed transforms than one spectra job holds -> tiles
 ])
 def test_search_paths_agree_with_every_lag_evaluation(S, L, W, hop, nw):
     """Whatever ranks the lags (tiles, parked spectra, the big transform), the record must be the one the
