@@ -2018,14 +2018,36 @@ int tdoa_process(tdoa_engine *e, const double *stations_llh, tdoa_peak *ref_out,
     cudaEventRecord(e->ev[4], e->stream);
     std::vector<PeakRec> h_pk((size_t)2 * P);
     std::vector<double> h_stats[2], h_first[2];
+    // Everything comes back through the top of the pinned frame (the descriptors grow from its
+    // bottom): a device->host copy into pageable memory blocks the caller once per copy, into
+    // pinned memory it is just queued -- ten small copies, one synchronisation.
+    struct Back { void *dst; const void *pinned; size_t bytes; };
+    std::vector<Back> backs;
+    size_t back_top = kFrameBytes;
+    auto fetch = [&](void *dst, const void *d_src, size_t bytes) -> int {
+        const size_t need = (bytes + 63) & ~size_t(63);
+        if (back_top < need || back_top - need < e->frame_used + 4096) {   // no room: the plain (blocking) copy
+            CU(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, e->stream));
+            return TDOA_OK;
+        }
+        back_top -= need;
+        CU(cudaMemcpyAsync(e->h_frame + back_top, d_src, bytes, cudaMemcpyDeviceToHost, e->stream));
+        backs.push_back(Back{dst, e->h_frame + back_top, bytes});
+        return TDOA_OK;
+    };
+    auto deliver = [&]() {
+        for (const Back &b : backs) std::memcpy(b.dst, b.pinned, b.bytes);
+        backs.clear();
+        back_top = kFrameBytes;
+    };
     auto read_back = [&]() -> int {
-        CU(cudaMemcpyAsync(h_pk.data(), d_ref, (size_t)P * sizeof(PeakRec), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaMemcpyAsync(h_pk.data() + P, d_tgt, (size_t)P * sizeof(PeakRec), cudaMemcpyDeviceToHost, e->stream));
-        if (time_diffs) CU(cudaMemcpyAsync(time_diffs, d_td, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        if (range_diffs) CU(cudaMemcpyAsync(range_diffs, d_rd, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaMemcpyAsync(fix_llh, d_fix, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaMemcpyAsync(fix_status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-        if (fix_iters) CU(cudaMemcpyAsync(fix_iters, d_iters, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        int r;
+        if ((r = fetch(h_pk.data(), d_ref, (size_t)P * sizeof(PeakRec))) || (r = fetch(h_pk.data() + P, d_tgt, (size_t)P * sizeof(PeakRec))))
+            return r;
+        if (time_diffs && (r = fetch(time_diffs, d_td, (size_t)P * sizeof(double)))) return r;
+        if (range_diffs && (r = fetch(range_diffs, d_rd, (size_t)P * sizeof(double)))) return r;
+        if ((r = fetch(fix_llh, d_fix, 3 * sizeof(double))) || (r = fetch(fix_status, d_status, sizeof(int32_t)))) return r;
+        if (fix_iters && (r = fetch(fix_iters, d_iters, sizeof(int32_t)))) return r;
         return TDOA_OK;
     };
     if ((rc = read_back())) return rc;
@@ -2034,11 +2056,12 @@ int tdoa_process(tdoa_engine *e, const double *stations_llh, tdoa_peak *ref_out,
         if (!pend[k].valid) continue;   // the pass ran with its own checks (not speculated)
         h_stats[k].resize(pend[k].sigs.size() * ST_COUNT);
         h_first[k].assign(P, 0.0);
-        CU(cudaMemcpyAsync(h_stats[k].data(), pend[k].sigs[0].stats, h_stats[k].size() * sizeof(double), cudaMemcpyDeviceToHost,
-                           e->stream));
-        CU(cudaMemcpyAsync(h_first[k].data(), pend[k].d_first, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if ((rc = fetch(h_stats[k].data(), pend[k].sigs[0].stats, h_stats[k].size() * sizeof(double))) ||
+            (rc = fetch(h_first[k].data(), pend[k].d_first, (size_t)P * sizeof(double))))
+            return rc;
     }
     CU(cudaStreamSynchronize(e->stream));
+    deliver();
     for (int k = 0; k < 2; k++) {
         if (!pend[k].valid) continue;
         ok &= verify_deferred(e, pend[k].sigs, h_stats[k].data());
@@ -2061,6 +2084,7 @@ int tdoa_process(tdoa_engine *e, const double *stations_llh, tdoa_peak *ref_out,
         cudaEventRecord(e->ev[4], e->stream);
         if ((rc = read_back())) return rc;
         CU(cudaStreamSynchronize(e->stream));
+        deliver();
     }
     std::memcpy(ref_out, h_pk.data(), (size_t)P * sizeof(tdoa_peak));
     std::memcpy(tgt_out, h_pk.data() + P, (size_t)P * sizeof(tdoa_peak));
