@@ -109,7 +109,11 @@ typedef struct {
                               (mean of D consecutive samples, rtl_fm.c:302-322 style) to the
                               preprocessing chain; correlation at fs / D over max_lag / D
                               lags, records in samples of the capture (lag + frac)       */
-    int32_t reserved[3];
+    int32_t serial_kinds;  /* tdoa_process: 0 = the TGT pair loop is queued on a second stream beside
+                              the REF pair loop (their kernels share the SMs); 1 = one stream, one
+                              kernel at a time (what the per-kernel timings of tdoa_get_stats
+                              need to mean anything)                                        */
+    int32_t reserved[2];
 } tdoa_config;
 
 /* Fill *cfg with the reference-matching defaults of `mode`. */

@@ -40,7 +40,7 @@ class Config(C.Structure):
         ("sample_rate", C.c_double), ("mode", C.c_int32), ("n_stations", C.c_int32),
         ("chunk_samples", C.c_int32), ("max_lag", C.c_int32), ("block_size", C.c_int32),
         ("sanity_lag", C.c_int32), ("fast_demod", C.c_int32), ("use_fft", C.c_int32),
-        ("device", C.c_int32), ("seq_dc_limit", C.c_int32), ("copy_chunk", C.c_int32), ("guard_samples", C.c_int32), ("decimate", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("device", C.c_int32), ("seq_dc_limit", C.c_int32), ("copy_chunk", C.c_int32), ("guard_samples", C.c_int32), ("decimate", C.c_int32), ("serial_kinds", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 

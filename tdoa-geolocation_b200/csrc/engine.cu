@@ -93,6 +93,8 @@ struct tdoa_engine {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;   // host -> device copies of lazily loaded captures
+    cudaStream_t side_stream = nullptr;   // tdoa_process: the TGT pair loop runs beside the REF pair loop
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void *h_stage[2] = {nullptr, nullptr};        // tdoa_load_file: pinned staging, double buffered
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_reload = nullptr;
@@ -1620,6 +1622,9 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
     if (err == cudaSuccess) { e->own_stream = true; err = cudaMallocHost(&e->h_frame, kFrameBytes); }
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_reload, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
     if (err == cudaSuccess) {
         void *dp = nullptr;
         err = cudaHostGetDevicePointer(&dp, e->h_frame, 0);
@@ -1676,6 +1681,9 @@ void tdoa_destroy(tdoa_engine *e)
         for (cudaEvent_t ev : s.event_pool) cudaEventDestroy(ev);
     }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->side_stream) { cudaStreamSynchronize(e->side_stream); cudaStreamDestroy(e->side_stream); }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     for (int k = 0; k < 2; k++) {
         if (e->h_stage[k]) cudaFreeHost(e->h_stage[k]);
         if (e->ev_stage[k]) cudaEventDestroy(e->ev_stage[k]);
@@ -2010,10 +2018,20 @@ int tdoa_process(tdoa_engine *e, const double *stations_llh, tdoa_peak *ref_out,
         count_launch(e, 2);
     };
     // optimistic pass: both pair loops and the fix are only queued; one synchronisation
+    // The two pair loops do not depend on each other: the TGT loop is queued on a second stream,
+    // so its compute-bound discriminator shares the SMs with the REF loop's memory-bound kernels
+    // (and vice versa) instead of every kernel waiting for the previous one's tail.
     Pending pend[2];
-    if ((rc = xcorr_core(e, TDOA_KIND_REF, 0, len_ref, 1, 0, d_ref, &pend[0])) ||
-        (rc = xcorr_core(e, TDOA_KIND_TGT, 0, len_tgt, 1, 0, d_tgt, &pend[1])))
-        return rc;
+    cudaStream_t main_stream = e->stream;
+    CU(cudaEventRecord(e->ev_fork, main_stream));
+    CU(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+    if ((rc = xcorr_core(e, TDOA_KIND_REF, 0, len_ref, 1, 0, d_ref, &pend[0]))) return rc;
+    if (!e->cfg.serial_kinds) e->stream = e->side_stream;
+    rc = xcorr_core(e, TDOA_KIND_TGT, 0, len_tgt, 1, 0, d_tgt, &pend[1]);
+    e->stream = main_stream;
+    CU(cudaEventRecord(e->ev_join, e->side_stream));
+    CU(cudaStreamWaitEvent(main_stream, e->ev_join, 0));
+    if (rc) { cudaStreamSynchronize(e->side_stream); return rc; }
     fix_chain();
     cudaEventRecord(e->ev[4], e->stream);
     std::vector<PeakRec> h_pk((size_t)2 * P);
