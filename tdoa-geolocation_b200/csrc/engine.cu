@@ -1416,6 +1416,16 @@ int window_lengths(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_
     return TDOA_OK;
 }
 
+// windows per group: the planes of a group stay under 24 GiB
+int window_group(const tdoa_engine *e, const std::vector<i64> &len, int n_windows)
+{
+    i64 per_window_bytes = 0;
+    for (int s = 0; s < e->cfg.n_stations; s++) per_window_bytes += len[s] * 4 * 4;
+    const i64 budget = (i64)24 << 30;
+    const int group = (int)std::max<i64>(1, std::min<i64>(n_windows, budget / std::max<i64>(per_window_bytes, 1)));
+    return std::min(group, 64);
+}
+
 // The pair loops of one signal kind over the windows, records to d_out (device).
 // pend == nullptr: every check is made here (the stream is synchronised as needed).
 // pend != nullptr: one window, everything only QUEUED -- branch guesses and candidate
@@ -1427,11 +1437,7 @@ int xcorr_core(tdoa_engine *e, int32_t kind, int64_t win_start, const std::vecto
     const int S = e->cfg.n_stations, P = S * (S - 1) / 2;
     if ((rc = queue_lazy_copies(e, kind))) return rc;
     // windows are processed in groups that keep the working set bounded
-    i64 per_window_bytes = 0;
-    for (int s = 0; s < S; s++) per_window_bytes += len[s] * 4 * 4;
-    const i64 budget = (i64)24 << 30;
-    int group = (int)std::max<i64>(1, std::min<i64>(n_windows, budget / std::max<i64>(per_window_bytes, 1)));
-    group = std::min(group, 64);
+    const int group = window_group(e, len, n_windows);
     for (int w0 = 0; w0 < n_windows; w0 += group) {
         const int gw = std::min(group, n_windows - w0);
         std::vector<Sig> sigs((size_t)gw * S);
@@ -1527,10 +1533,55 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
     else if ((rc = alloc_t(e, &d_out, (size_t)n_windows * P))) return rc;
     stats_reset(e);
     cudaEventRecord(e->ev[0], e->stream);
-    if ((rc = xcorr_core(e, kind, win_start, len, n_windows, hop, d_out, nullptr))) return rc;
-    cudaEventRecord(e->ev[4], e->stream);
-    if (!out_is_device)
-        CU(cudaMemcpyAsync(out, d_out, (size_t)n_windows * P * sizeof(tdoa_peak), cudaMemcpyDeviceToHost, e->stream));
+    // Two halves of the windows side by side on two streams (as tdoa_process does with the two
+    // signal kinds): one half's compute-bound kernels share the SMs with the other half's
+    // memory-bound ones.  Both halves are only queued; branch guesses and candidate overflow are
+    // checked after the one synchronisation, and any failure falls back to the checked pass.
+    const int nA = (n_windows + 1) / 2, nB = n_windows - nA;
+    bool done = false;
+    if (!e->cfg.serial_kinds && !out_is_device && nB >= 1 && window_group(e, len, nA) >= nA) {
+        Pending pend[2];
+        cudaStream_t main_stream = e->stream;
+        CU(cudaEventRecord(e->ev_fork, main_stream));
+        CU(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+        if ((rc = xcorr_core(e, kind, win_start, len, nA, hop, d_out, &pend[0]))) return rc;
+        e->stream = e->side_stream;
+        rc = xcorr_core(e, kind, win_start + (i64)nA * hop, len, nB, hop, d_out + (size_t)nA * P, &pend[1]);
+        e->stream = main_stream;
+        CU(cudaEventRecord(e->ev_join, e->side_stream));
+        CU(cudaStreamWaitEvent(main_stream, e->ev_join, 0));
+        if (rc) { cudaStreamSynchronize(e->side_stream); return rc; }
+        cudaEventRecord(e->ev[4], e->stream);
+        std::vector<PeakRec> h_pk((size_t)n_windows * P);
+        std::vector<double> h_stats[2], h_first(P, 0.0);
+        CU(cudaMemcpyAsync(h_pk.data(), d_out, h_pk.size() * sizeof(PeakRec), cudaMemcpyDeviceToHost, e->stream));
+        for (int k = 0; k < 2; k++) {
+            if (!pend[k].valid) continue;
+            h_stats[k].resize(pend[k].sigs.size() * ST_COUNT);
+            CU(cudaMemcpyAsync(h_stats[k].data(), pend[k].sigs[0].stats, h_stats[k].size() * sizeof(double), cudaMemcpyDeviceToHost,
+                               e->stream));
+        }
+        if (pend[0].valid)
+            CU(cudaMemcpyAsync(h_first.data(), pend[0].d_first, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        bool ok = pend[0].valid && pend[1].valid;
+        for (int k = 0; k < 2 && ok; k++) ok &= verify_deferred(e, pend[k].sigs, h_stats[k].data());
+        for (size_t i = 0; i < h_pk.size() && ok; i++) ok &= (h_pk[i].flags & 0x10u) == 0;   // candidate overflow
+        if (ok) {
+            e->info_first[kind] = h_first;
+            fill_info(e, kind, pend[0].sigs, h_stats[0].data(), S);
+            std::memcpy(out, h_pk.data(), h_pk.size() * sizeof(PeakRec));
+            done = true;
+        } else {
+            spans_collect(e);
+        }
+    }
+    if (!done) {
+        if ((rc = xcorr_core(e, kind, win_start, len, n_windows, hop, d_out, nullptr))) return rc;
+        cudaEventRecord(e->ev[4], e->stream);
+        if (!out_is_device)
+            CU(cudaMemcpyAsync(out, d_out, (size_t)n_windows * P * sizeof(tdoa_peak), cudaMemcpyDeviceToHost, e->stream));
+    }
     rc = end_call(e, !out_is_device);
     if (rc) return rc;
     e->st.launches_last = e->st.launches_total - e->launches_at_call;
