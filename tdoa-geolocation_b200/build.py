@@ -94,7 +94,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     return OUT
 
 
-HOST_PROGRAMS = ["processor_b200", "fast_analyzer_b200"]
+HOST_PROGRAMS = ["processor_b200", "fast_analyzer_b200", "analyzer_b200"]
 HOST_OUT = HERE / "processor_b200"
 
 

@@ -113,3 +113,21 @@ def test_cpp_fast_analyzer_command(tmp_path):
     assert r.returncode == 1 and r.stdout.startswith("Error: ") and "file too small" in r.stdout
     r = subprocess.run([str(exe), str(tmp_path / "absent.dat")], capture_output=True, text=True)
     assert r.returncode == 1 and "failed to open file" in r.stdout
+
+
+def test_cpp_analyzer_command_prints_what_the_mirror_prints(tmp_path):
+    """analyzer_b200 (host/analyzer_b200.cpp, analyzer.go's report over the C ABI) against the Python
+    mirror of the same report on the same file: byte for byte."""
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "tdoa-geolocation_b200" / "analyzer_b200"
+    for name in ("fm", "clipped", "dead", "quiet", "noisy"):
+        f = tmp_path / f"kx0u-{name}.dat"
+        captures()[name].tofile(f)
+        r = subprocess.run([str(exe), str(f), "5"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        buf = io.StringIO()
+        assert T.analyzer.main([str(f), "5"], out=buf) == 0
+        assert r.stdout == buf.getvalue(), name
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("Usage: analyzer <data_file.dat>")
