@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) k_seq_analyse(const SeqJob *jobs)
     reinterpret_cast<ChunkRule *>(J.infos)[item] = chunk_rule(chunk_analyse(J.x + c * kChunk, count, guess_binade(J.pre[c], k)));
 }
 
-// one warp per chain; lane 0 carries the sum, all lanes stage the next batch with cp.async
+// one warp per chain: all lanes stage the next batch with cp.async and take part in the scan of the hops
 __global__ void __launch_bounds__(32) k_seq_apply(const SeqJob *jobs)
 {
     __shared__ __align__(16) unsigned char s_info[2][kInfoBytes];
@@ -111,18 +111,42 @@ __global__ void __launch_bounds__(32) k_seq_apply(const SeqJob *jobs)
         stage(b + 1, buf ^ 1);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
+        {
+            // Every lane carries the same sum (the whole walk is warp-uniform).  The hops of the
+            // batch's remaining chunks, for the binade and sign the sum has now, are combined by an
+            // inclusive scan; a ballot finds how far the sum can be taken in one step, the chunk
+            // after that (the sum leaves its binade there, or no guess was made for it) is added
+            // sample by sample, and the rest of the batch is scanned again from the new sum.
             const i64 c0 = b * kBatch;
             const int chunks = (int)min((i64)kBatch, nc - c0);
             const ChunkRule *ci = reinterpret_cast<const ChunkRule *>(s_info[buf]);
-            for (int c = 0; c < chunks; c++) {
-                int done;
-                s = rule_apply(s, ci + c * kGuesses, &done);
-                if (done) continue;
-                // no rule applies (the sum is leaving its binade, or is too small for the integer
-                // picture): this chunk is added sample by sample -- loads first, then the chain
-                const int count = (int)min((i64)kChunk, n - (c0 + c) * kChunk);
-                const float4 *xv = reinterpret_cast<const float4 *>(s_x[buf] + c * kChunk);
+            int pos = 0;
+            while (pos < chunks) {
+                int es;
+                bool neg;
+                const int m = mantissa_signed(s, &es, &neg);
+                Hop f = lane < pos ? hop_identity() : (lane < chunks ? hop_from_rules(ci + lane * kGuesses, es, neg) : hop_empty());
+#pragma unroll
+                for (int off = 1; off < kBatch; off <<= 1) {
+                    Hop p;
+                    p.d[0] = __shfl_up_sync(0xffffffffu, f.d[0], off); p.d[1] = __shfl_up_sync(0xffffffffu, f.d[1], off);
+                    p.lo[0] = __shfl_up_sync(0xffffffffu, f.lo[0], off); p.lo[1] = __shfl_up_sync(0xffffffffu, f.lo[1], off);
+                    p.hi[0] = __shfl_up_sync(0xffffffffu, f.hi[0], off); p.hi[1] = __shfl_up_sync(0xffffffffu, f.hi[1], off);
+                    if (lane >= off) f = hop_compose(p, f);
+                }
+                const unsigned ok = __ballot_sync(0xffffffffu, lane < pos || hop_admits(f, m));
+                const int upto = min(chunks, __ffs(~ok) - 1);   // lanes >= chunks are empty, so ~ok is never 0
+                const int d = __shfl_sync(0xffffffffu, (m & 1) ? f.d[1] : f.d[0], max(upto - 1, 0));
+                if (upto > pos) {
+                    int mo = m + d;
+                    if (mo < 0) mo = -mo;
+                    s = __uint_as_float((__float_as_uint(s) & 0xff800000u) | ((unsigned)mo & 0x7fffffu));
+                    pos = upto;
+                }
+                if (pos >= chunks) break;
+                // chunk pos, sample by sample -- loads first, then the chain
+                const int count = (int)min((i64)kChunk, n - (c0 + pos) * kChunk);
+                const float4 *xv = reinterpret_cast<const float4 *>(s_x[buf] + pos * kChunk);
                 if (count == kChunk) {
 #pragma unroll 1
                     for (int q = 0; q < kChunk / 64; q++) {   // 64 samples at a time: 16 loads in flight, then their chain
@@ -135,8 +159,9 @@ __global__ void __launch_bounds__(32) k_seq_apply(const SeqJob *jobs)
                         }
                     }
                 } else {
-                    for (int i = 0; i < count; i++) s = __fadd_rn(s, s_x[buf][c * kChunk + i]);
+                    for (int i = 0; i < count; i++) s = __fadd_rn(s, s_x[buf][pos * kChunk + i]);
                 }
+                pos++;
             }
         }
         __syncwarp();   // the buffer is free for the batch after next

@@ -166,6 +166,87 @@ TDOA_SQ float rule_apply(float s, const ChunkRule *rules, int *done)
     return s;
 }
 
+// ---- runs of chunks.  With the binade and the sign of the sum fixed, a chunk rule is a partial
+// map on the signed mantissa:  m -> m + d[m & 1]  for  lo[m & 1] <= m <= hi[m & 1]  (a "hop").
+// Hops are closed under composition -- the domain of "A then B" is the interval of A's domain
+// whose image lies in B's, per start parity -- and composition is associative, so the hops of a
+// batch of chunks can be combined by a parallel prefix scan: hop k of the scan takes the sum
+// across chunks 0..k at once, and its domain says exactly whether every one of those chunks
+// keeps the sum inside the binade.  The walk then costs one scan per run of good chunks instead
+// of one dependent step per chunk.
+struct Hop {
+    int d[2], lo[2], hi[2];
+};
+constexpr int kHopFar = 1 << 30;   // identity's bounds: |lo|, |hi|, |d| of any non-empty hop stay below 2^29
+
+TDOA_SQ Hop hop_identity()
+{
+    Hop h;
+    h.d[0] = h.d[1] = 0; h.lo[0] = h.lo[1] = -kHopFar; h.hi[0] = h.hi[1] = kHopFar;
+    return h;
+}
+TDOA_SQ Hop hop_empty()
+{
+    Hop h;
+    h.d[0] = h.d[1] = 0; h.lo[0] = h.lo[1] = 1; h.hi[0] = h.hi[1] = 0;
+    return h;
+}
+// the hop of a chunk for a sum in binade es with the given sign (empty if no guess was made for it)
+TDOA_SQ Hop hop_from_rules(const ChunkRule *rules, int es, bool neg)
+{
+    Hop h = hop_empty();
+#pragma unroll
+    for (int k = 0; k < kGuesses; k++) {
+        const ChunkRule &r = rules[k];
+        if (r.e != es || r.e <= -1000) continue;
+        h.d[0] = r.d[0]; h.d[1] = r.d[1];
+        h.lo[0] = h.lo[1] = neg ? r.neg_lo : r.pos_lo;
+        h.hi[0] = h.hi[1] = neg ? r.neg_hi : r.pos_hi;
+        break;
+    }
+    return h;
+}
+// a first, then b
+TDOA_SQ Hop hop_compose(const Hop &a, const Hop &b)
+{
+    Hop c;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const bool odd = ((h + a.d[h]) & 1) != 0;   // parity after a (two's complement: also right for negative d and m)
+        const int bd = odd ? b.d[1] : b.d[0], blo = odd ? b.lo[1] : b.lo[0], bhi = odd ? b.hi[1] : b.hi[0];   // selects, not indexing: registers
+        const int d = a.d[h] + bd;
+        int lo = blo - a.d[h], hi = bhi - a.d[h];
+        if (a.lo[h] > lo) lo = a.lo[h];
+        if (a.hi[h] < hi) hi = a.hi[h];
+        const bool empty = lo > hi || a.lo[h] > a.hi[h] || blo > bhi;
+        c.d[h] = empty ? 0 : d;
+        c.lo[h] = empty ? 1 : lo;
+        c.hi[h] = empty ? 0 : hi;
+    }
+    return c;
+}
+// signed mantissa and binade of a normal f32 (es = -127 for zero / denormal: no hop is made for that)
+TDOA_SQ int mantissa_signed(float s, int *es, bool *neg)
+{
+    const uint32_t b = f2u(s);
+    *es = (int)((b >> 23) & 0xffu) - 127;
+    *neg = (b >> 31) != 0;
+    const int m = (int)((b & 0x7fffffu) | 0x800000u);
+    return *neg ? -m : m;
+}
+TDOA_SQ bool hop_admits(const Hop &h, int m)
+{
+    const bool odd = (m & 1) != 0;
+    return m >= (odd ? h.lo[1] : h.lo[0]) && m <= (odd ? h.hi[1] : h.hi[0]);
+}
+// the sum after a hop that admits m: same sign, same binade
+TDOA_SQ float hop_apply(const Hop &h, float s, int m)
+{
+    int mo = m + ((m & 1) ? h.d[1] : h.d[0]);
+    if (mo < 0) mo = -mo;
+    return u2f((f2u(s) & 0xff800000u) | ((uint32_t)mo & 0x7fffffu));
+}
+
 // s after the chunk, exactly: through the summary whose guess provably applies, else sample by sample
 TDOA_SQ float chunk_apply(float s, const ChunkInfo *guesses, const float *x, int count, int *fast)
 {

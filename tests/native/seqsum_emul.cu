@@ -12,10 +12,53 @@
 
 using namespace tdoa::seqsum;
 
+static long g_scans = 0, g_chunks = 0;
+
 static float plain(const std::vector<float> &x)
 {
     float s = 0.f;
     for (float v : x) { volatile float t = s + v; s = t; }
+    return s;
+}
+
+// the device walk of k_seq_apply (seqsum.cu), lane by lane: batches of 16 chunks, an inclusive
+// Hillis-Steele scan of the hops for the sum's binade and sign, the first chunk that is not
+// admitted added sample by sample, the rest of the batch scanned again
+static float walk_scan(const std::vector<ChunkRule> &rules, const std::vector<float> &x, long *scans)
+{
+    const int kBatch = 16, kLanes = 32;
+    const int n = (int)x.size(), nc = (n + kChunk - 1) / kChunk;
+    float s = 0.f;
+    for (int c0 = 0; c0 < nc; c0 += kBatch) {
+        const int chunks = std::min(kBatch, nc - c0);
+        int pos = 0;
+        while (pos < chunks) {
+            int es;
+            bool neg;
+            const int m = mantissa_signed(s, &es, &neg);
+            Hop f[kLanes];
+            for (int lane = 0; lane < kLanes; lane++)
+                f[lane] = lane < pos ? hop_identity()
+                                     : (lane < chunks ? hop_from_rules(&rules[(size_t)(c0 + lane) * kGuesses], es, neg) : hop_empty());
+            for (int off = 1; off < kBatch; off <<= 1) {
+                Hop g[kLanes];
+                for (int lane = 0; lane < kLanes; lane++) g[lane] = lane >= off ? hop_compose(f[lane - off], f[lane]) : f[lane];
+                for (int lane = 0; lane < kLanes; lane++) f[lane] = g[lane];
+            }
+            (*scans)++;
+            int upto = pos;
+            while (upto < kLanes && (upto < pos || hop_admits(f[upto], m))) upto++;
+            upto = std::min(upto, chunks);
+            if (upto > pos) {
+                s = hop_apply(f[upto - 1], s, m);
+                pos = upto;
+            }
+            if (pos >= chunks) break;
+            const int count = std::min(kChunk, n - (c0 + pos) * kChunk);
+            for (int i = 0; i < count; i++) { volatile float t = s + x[(size_t)(c0 + pos) * kChunk + i]; s = t; }
+            pos++;
+        }
+    }
     return s;
 }
 
@@ -51,6 +94,10 @@ static float chunked(const std::vector<float> &x, double *fast_fraction)
             for (int i = 0; i < count; i++) { volatile float t = s2 + x[(size_t)c * kChunk + i]; s2 = t; }
     }
     if (f2u(s) != f2u(s2)) return std::nanf("");   // the two forms of the walk must agree
+    long scans = 0;
+    const float s3 = walk_scan(rules, x, &scans);
+    if (f2u(s) != f2u(s3)) return std::nanf("");   // and so must the scanned walk the device runs
+    g_scans += scans; g_chunks += nc;
     *fast_fraction = nc ? (double)fast / nc : 1.0;
     return s;
 }
@@ -105,6 +152,7 @@ int main()
         for (auto &v : x) v = (float)(0.4 + 0.2 * nrm(g));
         run(x, false);
     }
+    printf("scans %ld chunks %ld\n", g_scans, g_chunks);
     printf("mismatch %ld fast_fraction %.4f cases %d\n", mism, min_fast_typical, cases);
     return mism ? 1 : 0;
 }
