@@ -14,7 +14,7 @@ using namespace seqsum;
 
 namespace {
 
-constexpr int kBatch = 16;                                   // chunks staged per step of the walk
+constexpr int kBatch = 16;                                   // chunks staged per step of the walk (lanes 0..15 of the scan)
 constexpr int kInfoBytes = kBatch * kGuesses * (int)sizeof(ChunkRule);   // 1536
 constexpr int kSampBytes = kBatch * kChunk * (int)sizeof(float);         // 16384
 
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) k_seq_chunksum(const SeqJob *jobs)
     if (!J.x || c >= J.n_chunks) return;
     const float *__restrict__ x = J.x + c * kChunk;
     const int count = (int)min((i64)kChunk, J.n - c * kChunk);
-    double s = 0.0;   // exact: 256 f32 values fit a f64 sum without rounding for any realistic range
+    double s = 0.0;   // exact: a chunk of f32 values fits a f64 sum without rounding for any realistic range
     for (int i = 0; i < count; i++) s += (double)x[i];
     J.csum[c] = s;
 }
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(32) k_seq_apply(const SeqJob *jobs)
                     if (lane >= off) f = hop_compose(p, f);
                 }
                 const unsigned ok = __ballot_sync(0xffffffffu, lane < pos || hop_admits(f, m));
-                const int upto = min(chunks, __ffs(~ok) - 1);   // lanes >= chunks are empty, so ~ok is never 0
+                const int upto = ok == 0xffffffffu ? chunks : min(chunks, __ffs(~ok) - 1);
                 const int d = __shfl_sync(0xffffffffu, (m & 1) ? f.d[1] : f.d[0], max(upto - 1, 0));
                 if (upto > pos) {
                     int mo = m + d;
