@@ -143,6 +143,11 @@ public:
                 printf("Extracting target signal from dual-frequency data\n");
                 printf("Total samples: %lld, block size: %lld\n", n, b);
                 printf("Extracted %lld target samples from block 2\n", b);
+                // processor.go:772-780 with the shipped binary's chunk: the engine's BINARY mode
+                // cuts both signals the same way (chunk_samples = 1 000 000)
+                const long long chunk = 1000000;
+                if (2 * b > chunk) printf("Using test chunk: %lld samples (%.1f ms)\n", chunk, (double)chunk / 2e6 * 1000);
+                if (b > chunk) printf("Using target test chunk: %lld samples (%.1f ms)\n", chunk, (double)chunk / 2e6 * 1000);
                 printf("Coherent integration time: 500 ms (expecting ~10.0 dB processing gain)\n");
             }
             st.push_back(s);

@@ -196,6 +196,11 @@ class TDOAProcessor:
                 P("Extracting target signal from dual-frequency data")
                 P("Total samples: %d, block size: %d" % (n, b))
                 P("Extracted %d target samples from block 2" % b)
+                chunk = 1_000_000  # processor.go:772-780 with the shipped binary's chunk (the engine's chunk_samples)
+                if 2 * b > chunk:
+                    P("Using test chunk: %d samples (%.1f ms)" % (chunk, chunk / 2e6 * 1000))
+                if b > chunk:
+                    P("Using target test chunk: %d samples (%.1f ms)" % (chunk, chunk / 2e6 * 1000))
                 P("Coherent integration time: 500 ms (expecting ~10.0 dB processing gain)")
             stations.append(st)
             P("Loaded collector: %s at %.6f°, %.6f°, %.1fm" % (st.name, st.latitude, st.longitude, st.elevation))

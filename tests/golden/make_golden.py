@@ -132,12 +132,47 @@ def case_weak_noise(B=40000):
     return out
 
 
+def case_fm_ragged(B=30001):
+    """Strong FM in a capture whose length is not a multiple of three (N = 3 B + 2): the block
+    is N / 3 in integer division and the two trailing samples belong to no block
+    (processor.go:211-214, :244-246)."""
+    ref, tgt = fm(B + 600, 22, 75e3), fm(B + 600, 23, 60e3)
+    out = {}
+    for k, (name, dr, dt) in enumerate(zip(STATIONS, (0, 4, 9), (0, 17, 2))):
+        def blk(sig, d, seed, n=B):
+            g = np.random.default_rng(seed)
+            return sig[400 - d:400 - d + n] + 0.02 * (g.standard_normal(n) + 1j * g.standard_normal(n))
+        tail = 0.3 * np.exp(1j * np.arange(2))   # two samples past the third block
+        out[name] = quantise(np.concatenate([blk(ref, dr, 130 + k), blk(tgt, dt, 140 + k), blk(ref, dr, 150 + k), tail]))
+    return out
+
+
+def case_fm_truncated(B=1_050_000):
+    """Blocks longer than the binary's 1 000 000-sample test chunk: REF (2 B samples) and TGT
+    (B samples) are both cut to their first 1 000 000 samples before the pair loops
+    (processor.go:772-780 with the shipped binary's chunk).  18 MB of captures: not stored --
+    the tests regenerate them from the seeds and check the SHA-256 kept in the .json."""
+    ref, tgt = fm(B + 600, 24, 75e3), fm(B + 600, 25, 60e3)
+    out = {}
+    for k, (name, dr, dt) in enumerate(zip(STATIONS, (0, 6, 13), (0, 41, 8))):
+        def blk(sig, d, seed):
+            g = np.random.default_rng(seed)
+            return sig[400 - d:400 - d + B] + 0.02 * (g.standard_normal(B) + 1j * g.standard_normal(B))
+        out[name] = quantise(np.concatenate([blk(ref, dr, 230 + k), blk(tgt, dt, 240 + k), blk(ref, dr, 250 + k)]))
+    return out
+
+
+# cases whose captures are regenerated from their seeds instead of being stored
+REGENERATED = {"fm_truncated"}
+
 CASES = {
     "fm_strong": case_fm_strong,
     "fm_delays": case_fm_delays,
     "moderate": case_moderate,
     "weak_tones": case_weak_tones,
     "weak_noise": case_weak_noise,
+    "fm_ragged": case_fm_ragged,
+    "fm_truncated": case_fm_truncated,
 }
 
 PAIR_RE = re.compile(r"^(REF|TGT) (\S+) - (\S+): delay=(-?\d+) samples \((-?[\d.]+) μs\), correlation=(-?[\d.]+)")
@@ -169,12 +204,15 @@ def parse_stdout(text: str):
             "branch": branches, "reasonable_lines": reasonable}
 
 
-def main():
+def main(only=None):
+    import hashlib
     from oracle import oracle
     oracle.build()
     (HERE / "stations.csv").write_text(STATION_CSV)
     summary = {}
     for name, fn in CASES.items():
+        if only and name not in only:
+            continue
         caps = fn()
         with tempfile.TemporaryDirectory() as td:
             paths = []
@@ -187,7 +225,10 @@ def main():
         parsed["returncode"] = rc
         parsed["stderr_tail"] = err.strip().splitlines()[-1:] if err.strip() else []
         assert len(parsed["pairs"]) == 6, (name, out[-2000:])
-        np.savez_compressed(HERE / f"{name}.npz", **caps)
+        if name in REGENERATED:
+            parsed["sha256"] = {st: hashlib.sha256(caps[st].tobytes()).hexdigest() for st in STATIONS}
+        else:
+            np.savez_compressed(HERE / f"{name}.npz", **caps)
         (HERE / f"{name}.json").write_text(json.dumps(parsed, indent=1, ensure_ascii=False) + "\n")
         (HERE / f"{name}.stdout.txt").write_text(out)
         summary[name] = [(p["kind"], p["delay"], p["corr"]) for p in parsed["pairs"]]
@@ -196,4 +237,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(only=set(sys.argv[1:]) or None)   # no arguments: every case

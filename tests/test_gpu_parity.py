@@ -12,7 +12,7 @@ import pytest
 
 import tdoa_b200 as T
 from oracle import oracle
-from helpers import GOLDEN, GOLDEN_CASES, STATION_LLH, fm_capture, load_golden, quantise
+from helpers import GOLDEN, GOLDEN_CASES, GOLDEN_LONG_CASES, STATION_LLH, fm_capture, load_golden, quantise
 
 pytestmark = pytest.mark.gpu
 
@@ -455,6 +455,47 @@ def test_cpp_host_mirror_stdout_is_the_shipped_binarys(tmp_path, case):
     assert len(ours) >= len(gold)
     for k, (a, b) in enumerate(zip(ours, gold)):
         assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
+
+
+@pytest.mark.parametrize("case", GOLDEN_LONG_CASES)
+def test_blocks_longer_than_the_test_chunk(tmp_path, case):
+    """Blocks of 1 050 000 samples: the shipped binary cuts REF and TGT to their first 1 000 000
+    samples before the pair loops (processor.go:772-780).  Records against what the binary
+    printed (bit-exact lags, correlation to the printed 6 decimals), and the C++ command's
+    stdout against the binary's, line for line."""
+    import subprocess
+    raws, meta = load_golden(case)
+    with T.Engine(T.MODE_BINARY) as e:
+        load_all(e, raws)
+        r = e.process(STATION_LLH)
+    for pk, gold in zip(list(r["ref"]) + list(r["tgt"]), meta["pairs"]):
+        assert int(pk["lag"]) == gold["delay"], gold
+        assert abs(float(pk["corr"]) - gold["corr"]) <= 0.5e-6 + CORR_TOL
+    files = []
+    for name, raw in zip(["kx0u", "n3pay", "kf0mtl"], raws):
+        f = tmp_path / f"sim-{name}-1.dat"
+        raw.tofile(f)
+        files.append(str(f))
+    exe = GOLDEN.parent.parent / "tdoa-geolocation_b200" / "processor_b200"
+    out = subprocess.run([str(exe), "162400000", "92300000", str(GOLDEN / "stations.csv"), *files], capture_output=True, text=True)
+    assert out.returncode in (0, 1), out.stderr
+    skip = "Loading I/Q data from:"
+    ours = [l for l in out.stdout.splitlines() if not l.startswith(skip)]
+    gold = [l for l in (GOLDEN / f"{case}.stdout.txt").read_text().splitlines() if not l.startswith(skip)]
+    assert len(ours) >= len(gold), out.stdout[-2000:]
+    for k, (a, b) in enumerate(zip(ours, gold)):
+        assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
+    buf = io.StringIO()
+    p = T.TDOAProcessor(162400000.0, 92300000.0, str(GOLDEN / "stations.csv"), out=buf)
+    try:
+        p.process_tdoa(files)
+    except RuntimeError:
+        pass
+    p.close()
+    ours = [l for l in buf.getvalue().splitlines() if not l.startswith(skip)]
+    assert len(ours) >= len(gold)
+    for k, (a, b) in enumerate(zip(ours, gold)):
+        assert _same_line(a, b), f"python mirror, line {k}: ours {a!r} != reference {b!r}"
 
 
 # ------------------------------------------------------------------ discriminator bit parity
