@@ -1,6 +1,6 @@
 // processor_b200 -- the reference's `processor` command on the B200 engine.
 //
-//   processor_b200 [--source] <reference_freq_hz> <target_freq_hz> <stations.csv> <collector1.dat> ...
+//   processor_b200 [--source] <ref_freq_hz> <target_freq_hz> <csv_file> <dat_file1> [dat_file2] [dat_file3] ...
 //
 // Host-side mirror of processor.go in the reference's own shape (Go is not installed in this
 // image, the reference is compiled code, so the mirror is C++): a TDOAProcessor with the
@@ -11,12 +11,17 @@
 // libtdoa_b200.so (include/tdoa_b200.h); there is no arithmetic on samples here and no CPU
 // fallback: without a B200 tdoa_create fails and so does this program.
 #include <algorithm>
+#include <cctype>
+#include <cerrno>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <ctime>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -38,6 +43,75 @@ std::string fmt(const char *f, ...)
     return buf;
 }
 
+// Go's text for an errno ("no such file or directory"): the C library's, first letter lower case
+std::string goStrerror(int e)
+{
+    std::string m = strerror(e);
+    if (!m.empty()) m[0] = (char)tolower((unsigned char)m[0]);
+    return m;
+}
+
+// strconv.ParseFloat(s, 64) as far as the command line needs it: the whole string must be a number
+bool parseFloat(const std::string &s, double *out, std::string *err)
+{
+    errno = 0;
+    char *end = nullptr;
+    const double v = strtod(s.c_str(), &end);
+    const bool all = !s.empty() && end == s.c_str() + s.size() && !isspace((unsigned char)s[0]);
+    if (!all) { *err = "strconv.ParseFloat: parsing \"" + s + "\": invalid syntax"; return false; }
+    if (errno == ERANGE && std::isinf(v)) { *err = "strconv.ParseFloat: parsing \"" + s + "\": value out of range"; return false; }
+    *out = v;
+    return true;
+}
+
+// encoding/csv's ReadAll as far as a station table needs it: records of comma-separated fields,
+// "quoted" fields with "" for a quote, blank lines skipped, every record as long as the first
+// (FieldsPerRecord = 0) -- with the package's error text otherwise
+std::vector<std::vector<std::string>> readCsvAll(std::istream &f)
+{
+    std::vector<std::vector<std::string>> records;
+    std::string line;
+    int lineNo = 0;
+    while (std::getline(f, line)) {
+        lineNo++;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) continue;
+        std::vector<std::string> rec;
+        std::string cell;
+        size_t i = 0;
+        while (true) {
+            cell.clear();
+            if (i < line.size() && line[i] == '"') {
+                i++;
+                while (true) {
+                    if (i >= line.size()) throw std::runtime_error(fmt("failed to read CSV: record on line %d; parse error on line %d, column %zu: extraneous or missing \" in quoted-field", lineNo, lineNo, i + 1));
+                    if (line[i] == '"') {
+                        if (i + 1 < line.size() && line[i + 1] == '"') { cell += '"'; i += 2; continue; }
+                        i++;
+                        break;
+                    }
+                    cell += line[i++];
+                }
+                if (i < line.size() && line[i] != ',')
+                    throw std::runtime_error(fmt("failed to read CSV: parse error on line %d, column %zu: extraneous or missing \" in quoted-field", lineNo, i + 1));
+            } else {
+                while (i < line.size() && line[i] != ',') {
+                    if (line[i] == '"') throw std::runtime_error(fmt("failed to read CSV: parse error on line %d, column %zu: bare \" in non-quoted-field", lineNo, i + 1));
+                    cell += line[i++];
+                }
+            }
+            rec.push_back(cell);
+            if (i >= line.size()) break;
+            i++;   // the comma
+            if (i == line.size()) { rec.push_back(""); break; }
+        }
+        if (!records.empty() && rec.size() != records[0].size())
+            throw std::runtime_error(fmt("failed to read CSV: record on line %d: wrong number of fields", lineNo));
+        records.push_back(rec);
+    }
+    return records;
+}
+
 struct Station {  // processor.go:15-20
     std::string name;
     double latitude = 0, longitude = 0, elevation = 0;
@@ -56,27 +130,22 @@ public:
     void loadStations(const std::string &csv)
     {
         std::ifstream f(csv);
-        if (!f) throw std::runtime_error("failed to load stations: failed to open CSV file: " + csv);
-        std::string line;
-        int lineNo = 0;
+        if (!f) throw std::runtime_error("failed to load stations: failed to open CSV file: open " + csv + ": " + goStrerror(errno));
+        std::vector<std::vector<std::string>> records;
+        try { records = readCsvAll(f); }
+        catch (const std::exception &e) { throw std::runtime_error(std::string("failed to load stations: ") + e.what()); }
         bool haveRef = false;
         const std::string refName = fmt("%.0f", referenceFreq);  // :96
-        while (std::getline(f, line)) {
-            lineNo++;
-            if (!line.empty() && line.back() == '\r') line.pop_back();
-            if (lineNo == 1 || line.empty()) continue;  // header skipped (:66)
-            std::vector<std::string> rec;
-            std::stringstream ss(line);
-            std::string cell;
-            while (std::getline(ss, cell, ',')) rec.push_back(cell);
+        for (size_t i = 1; i < records.size(); i++) {            // header skipped (:66); message lines are i + 2 of records[1:]
+            const std::vector<std::string> &rec = records[i];
+            const int lineNo = (int)i + 1;
             if (rec.size() != 4) throw std::runtime_error(fmt("failed to load stations: invalid CSV format at line %d", lineNo));
             Station st;
             st.name = rec[0];
-            try {
-                st.latitude = std::stod(rec[1]); st.longitude = std::stod(rec[2]); st.elevation = std::stod(rec[3]);
-            } catch (const std::exception &) {
-                throw std::runtime_error(fmt("failed to load stations: invalid number at line %d", lineNo));
-            }
+            std::string err;
+            if (!parseFloat(rec[1], &st.latitude, &err)) throw std::runtime_error(fmt("failed to load stations: invalid latitude at line %d: %s", lineNo, err.c_str()));
+            if (!parseFloat(rec[2], &st.longitude, &err)) throw std::runtime_error(fmt("failed to load stations: invalid longitude at line %d: %s", lineNo, err.c_str()));
+            if (!parseFloat(rec[3], &st.elevation, &err)) throw std::runtime_error(fmt("failed to load stations: invalid elevation at line %d: %s", lineNo, err.c_str()));
             stations[st.name] = st;
             if (st.name == refName) { refStation = st; haveRef = true; }
         }
@@ -338,25 +407,44 @@ private:
 
 }  // namespace
 
+// log.Fatalf: "2006/01/02 15:04:05 " + message on stderr, exit status 1
+static int fatalf(const std::string &msg)
+{
+    fflush(stdout);
+    char stamp[32];
+    const time_t now = time(nullptr);
+    struct tm tmv;
+    localtime_r(&now, &tmv);
+    strftime(stamp, sizeof(stamp), "%Y/%m/%d %H:%M:%S", &tmv);
+    fprintf(stderr, "%s %s\n", stamp, msg.c_str());
+    return 1;
+}
+
 // processor.go:1047-1076
 int main(int argc, char **argv)
 {
     int mode = TDOA_MODE_BINARY;
     std::vector<std::string> args(argv + 1, argv + argc);
     if (!args.empty() && args[0] == "--source") { mode = TDOA_MODE_SOURCE; args.erase(args.begin()); }
-    if (args.size() < 6) {
-        printf("Usage: processor <reference_freq_hz> <target_freq_hz> <stations.csv> <collector1.dat> <collector2.dat> "
-               "<collector3.dat> [...]\n");
+    if (args.size() < 4) {   // :1048-1052
+        printf("Usage: %s <ref_freq_hz> <target_freq_hz> <csv_file> <dat_file1> [dat_file2] [dat_file3] ...\n", argv[0]);
+        printf("Example: ./processor 162400000 101700000 lat-lon-table.csv kx0u-data.dat n3pay-data.dat kf0mtl-data.dat\n");
         return 1;
     }
+    double refFreq = 0, tgtFreq = 0;
+    std::string err;
+    if (!parseFloat(args[0], &refFreq, &err)) return fatalf("Invalid reference frequency: " + err);   // :1054-1057
+    if (!parseFloat(args[1], &tgtFreq, &err)) return fatalf("Invalid target frequency: " + err);      // :1059-1062
+    std::unique_ptr<TDOAProcessor> p;
     try {
-        const double refFreq = std::stod(args[0]), tgtFreq = std::stod(args[1]);
-        TDOAProcessor p(refFreq, tgtFreq, args[2], mode);
-        p.ProcessTDOA(std::vector<std::string>(args.begin() + 3, args.end()));
+        p.reset(new TDOAProcessor(refFreq, tgtFreq, args[2], mode));
     } catch (const std::exception &e) {
-        fflush(stdout);
-        fprintf(stderr, "TDOA processing failed: %s\n", e.what());
-        return 1;
+        return fatalf(std::string("Failed to create processor: ") + e.what());   // :1067-1070
+    }
+    try {
+        p->ProcessTDOA(std::vector<std::string>(args.begin() + 3, args.end()));
+    } catch (const std::exception &e) {
+        return fatalf(std::string("TDOA processing failed: ") + e.what());       // :1072-1075
     }
     return 0;
 }

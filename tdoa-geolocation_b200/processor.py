@@ -11,7 +11,6 @@ ProcessTDOA :739, solveTDOA :932.
 """
 from __future__ import annotations
 
-import csv
 import os
 import sys
 from dataclasses import dataclass
@@ -59,17 +58,23 @@ class TDOAProcessor:
         try:
             f = open(csv_path, newline="")
         except OSError as exc:
-            raise RuntimeError(f"failed to load stations: failed to open CSV file: {exc}") from exc
+            raise RuntimeError("failed to load stations: failed to open CSV file: open %s: %s"
+                               % (csv_path, _go_strerror(exc))) from exc
         with f:
-            records = list(csv.reader(f))
+            try:
+                records = _read_csv_all(f.read())
+            except ValueError as exc:
+                raise RuntimeError(f"failed to load stations: failed to read CSV: {exc}") from exc
         for i, rec in enumerate(records[1:]):  # header skipped (:66)
             if len(rec) != 4:
                 raise RuntimeError(f"failed to load stations: invalid CSV format at line {i + 2}")
-            try:
-                lat, lon, elev = float(rec[1]), float(rec[2]), float(rec[3])
-            except ValueError as exc:
-                raise RuntimeError(f"failed to load stations: invalid number at line {i + 2}: {exc}") from exc
-            st = Station(rec[0], lat, lon, elev)
+            vals = []
+            for what, cell in zip(("latitude", "longitude", "elevation"), rec[1:]):
+                try:
+                    vals.append(_parse_float(cell))
+                except ValueError as exc:
+                    raise RuntimeError(f"failed to load stations: invalid {what} at line {i + 2}: {exc}") from exc
+            st = Station(rec[0], *vals)
             self.stations[rec[0]] = st
             if rec[0] == "%.0f" % self.reference_freq:  # :96
                 self.ref_station = st
@@ -312,19 +317,112 @@ def ecef(lat, lon, h):
             (n * (1 - e2) + h) * math.sin(la))
 
 
-def main(argv=None) -> int:
-    """processor <ref_freq_hz> <target_freq_hz> <stations.csv> <dat...>  (processor.go:1047-1076)"""
+def _go_strerror(exc: OSError) -> str:
+    """Go's text for an errno: the C library's with a lower-case first letter."""
+    msg = os.strerror(exc.errno) if exc.errno else str(exc)
+    return msg[:1].lower() + msg[1:]
+
+
+def _parse_float(text: str) -> float:
+    """strconv.ParseFloat(s, 64) as far as the station table and the command line need it."""
+    bad = ValueError('strconv.ParseFloat: parsing "%s": invalid syntax' % text)
+    if not text or text != text.strip() or "_" in text:
+        raise bad
+    try:
+        v = float(text)
+    except ValueError:
+        try:
+            v = float.fromhex(text) if text.lower().lstrip("+-").startswith("0x") else None
+        except ValueError:
+            v = None
+        if v is None:
+            raise bad from None
+    if v in (float("inf"), float("-inf")) and "inf" not in text.lower():
+        raise ValueError('strconv.ParseFloat: parsing "%s": value out of range' % text)
+    return v
+
+
+def _read_csv_all(text: str):
+    """encoding/csv ReadAll as far as a station table needs it (the C++ mirror's readCsvAll):
+    quoted fields with "" for a quote, blank lines skipped, every record as long as the first."""
+    records = []
+    for line_no, line in enumerate(text.split("\n"), 1):
+        if line.endswith("\r"):
+            line = line[:-1]
+        if not line:
+            continue
+        rec, i = [], 0
+        while True:
+            cell = ""
+            if i < len(line) and line[i] == '"':
+                i += 1
+                while True:
+                    if i >= len(line):
+                        raise ValueError('record on line %d; parse error on line %d, column %d: extraneous or missing " in quoted-field'
+                                         % (line_no, line_no, i + 1))
+                    if line[i] == '"':
+                        if i + 1 < len(line) and line[i + 1] == '"':
+                            cell += '"'
+                            i += 2
+                            continue
+                        i += 1
+                        break
+                    cell += line[i]
+                    i += 1
+                if i < len(line) and line[i] != ",":
+                    raise ValueError('parse error on line %d, column %d: extraneous or missing " in quoted-field' % (line_no, i + 1))
+            else:
+                while i < len(line) and line[i] != ",":
+                    if line[i] == '"':
+                        raise ValueError('parse error on line %d, column %d: bare " in non-quoted-field' % (line_no, i + 1))
+                    cell += line[i]
+                    i += 1
+            rec.append(cell)
+            if i >= len(line):
+                break
+            i += 1
+            if i == len(line):
+                rec.append("")
+                break
+        if records and len(rec) != len(records[0]):
+            raise ValueError("record on line %d: wrong number of fields" % line_no)
+        records.append(rec)
+    return records
+
+
+def _fatalf(msg: str) -> int:
+    """log.Fatalf: '2006/01/02 15:04:05 ' + message on stderr, exit status 1."""
+    import time
+    sys.stdout.flush()
+    print(time.strftime("%Y/%m/%d %H:%M:%S"), msg, file=sys.stderr)
+    return 1
+
+
+def main(argv=None, prog: str = "processor") -> int:
+    """processor <ref_freq_hz> <target_freq_hz> <csv_file> <dat_file1> ...  (processor.go:1047-1076)"""
     argv = list(sys.argv[1:] if argv is None else argv)
-    if len(argv) < 6:
-        print("Usage: processor <reference_freq_hz> <target_freq_hz> <stations.csv> <collector1.dat> "
-              "<collector2.dat> <collector3.dat> [...]")
+    if len(argv) < 4:   # :1048-1052
+        print(f"Usage: {prog} <ref_freq_hz> <target_freq_hz> <csv_file> <dat_file1> [dat_file2] [dat_file3] ...")
+        print("Example: ./processor 162400000 101700000 lat-lon-table.csv kx0u-data.dat n3pay-data.dat kf0mtl-data.dat")
         return 1
     try:
-        p = TDOAProcessor(float(argv[0]), float(argv[1]), argv[2])
+        ref_freq = _parse_float(argv[0])
+    except ValueError as exc:
+        return _fatalf(f"Invalid reference frequency: {exc}")
+    try:
+        tgt_freq = _parse_float(argv[1])
+    except ValueError as exc:
+        return _fatalf(f"Invalid target frequency: {exc}")
+    try:
+        p = TDOAProcessor(ref_freq, tgt_freq, argv[2])
+    except RuntimeError as exc:
+        return _fatalf(f"Failed to create processor: {exc}")
+    try:
         p.process_tdoa(argv[3:])
     except RuntimeError as exc:
-        print(f"TDOA processing failed: {exc}", file=sys.stderr)
-        return 1
+        return _fatalf(f"TDOA processing failed: {exc}")
+    finally:
+        p.close()
     return 0
 
 

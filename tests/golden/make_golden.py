@@ -162,6 +162,25 @@ def case_fm_truncated(B=1_050_000):
     return out
 
 
+def case_fm_uneven():
+    """Captures of different lengths (blocks of 36000 / 41000 / 38500 samples, the second file one
+    byte longer than a whole sample): the shorter signal of a pair is the template
+    (processor.go:652-662), the lag range follows the length difference, and the odd trailing
+    byte is dropped by the integer division in loadIQData (:188)."""
+    Bs = (36000, 41000, 38500)
+    ref, tgt = fm(max(Bs) + 600, 26, 75e3), fm(max(Bs) + 600, 27, 60e3)
+    out = {}
+    for k, (name, B, dr, dt) in enumerate(zip(STATIONS, Bs, (0, 8, 3), (0, 21, 5))):
+        def blk(sig, d, seed):
+            g = np.random.default_rng(seed)
+            return sig[400 - d:400 - d + B] + 0.02 * (g.standard_normal(B) + 1j * g.standard_normal(B))
+        raw = quantise(np.concatenate([blk(ref, dr, 330 + k), blk(tgt, dt, 340 + k), blk(ref, dr, 350 + k)]))
+        if k == 1:
+            raw = np.concatenate([raw, np.array([200], np.uint8)])
+        out[name] = raw
+    return out
+
+
 # cases whose captures are regenerated from their seeds instead of being stored
 REGENERATED = {"fm_truncated"}
 
@@ -173,6 +192,7 @@ CASES = {
     "weak_noise": case_weak_noise,
     "fm_ragged": case_fm_ragged,
     "fm_truncated": case_fm_truncated,
+    "fm_uneven": case_fm_uneven,
 }
 
 PAIR_RE = re.compile(r"^(REF|TGT) (\S+) - (\S+): delay=(-?\d+) samples \((-?[\d.]+) μs\), correlation=(-?[\d.]+)")
@@ -236,5 +256,64 @@ def main(only=None):
     return summary
 
 
+# ---- the command line: what the reference binary prints and returns before it touches a sample
+CLI_FILES = {
+    "bad_fields.csv": "Name,Latitude,Longitude,Elevation\n162400000,41.2,-95.9,349\nkx0u,41.1,-95.9\n",
+    "bad_lat.csv": "Name,Latitude,Longitude,Elevation\n162400000,41.2,-95.9,349\nkx0u,abc,-95.9,300\n",
+    "bad_lon.csv": "Name,Latitude,Longitude,Elevation\n162400000,41.2,-95.9,349\nkx0u,41.1,xyz,300\n",
+    "bad_elev.csv": "Name,Latitude,Longitude,Elevation\n162400000,41.2,-95.9,349\nkx0u,41.1,-95.2,3o0\n",
+    "header_only.csv": "Name,Latitude,Longitude,Elevation\n",
+    "three_columns.csv": "Name,Latitude,Longitude\n162400000,41.2,-95.9\n",
+    "bare_quote.csv": 'Name,Latitude,Longitude,Elevation\n\n162400000,41.2,-95.9,349\n"kx,0u",41.1,-95.9,3\nab"c,1,2,3\n',
+    "quoted_ok.csv": 'Name,Latitude,Longitude,Elevation\r\n\r\n"162400000",41.2,-95.9,349\r\n"kx""0u",41.1,-95.9,3\r\n',
+}
+CLI_CASES = {   # {csv} = tests/golden/stations.csv, {dir} = a directory holding CLI_FILES
+    "no_arguments": [],
+    "three_arguments": ["162400000", "92300000", "{csv}"],
+    "two_collectors": ["162400000", "92300000", "{csv}", "a-kx0u.dat", "b-n3pay.dat"],
+    "one_collector": ["162400000", "92300000", "{csv}", "a-kx0u.dat"],
+    "missing_csv": ["162400000", "92300000", "{dir}/nonexistent.csv", "a", "b", "c"],
+    "reference_not_in_table": ["999", "92300000", "{csv}", "a", "b", "c"],
+    "bad_reference_frequency": ["abc", "92300000", "{csv}", "a", "b", "c"],
+    "bad_target_frequency": ["162400000", " 5", "{csv}", "a", "b", "c"],
+    "frequency_out_of_range": ["1e400", "92300000", "{csv}", "a", "b", "c"],
+    "csv_wrong_field_count": ["162400000", "92300000", "{dir}/bad_fields.csv", "a", "b", "c"],
+    "csv_bad_latitude": ["162400000", "92300000", "{dir}/bad_lat.csv", "a", "b", "c"],
+    "csv_bad_longitude": ["162400000", "92300000", "{dir}/bad_lon.csv", "a", "b", "c"],
+    "csv_bad_elevation": ["162400000", "92300000", "{dir}/bad_elev.csv", "a", "b", "c"],
+    "csv_header_only": ["162400000", "92300000", "{dir}/header_only.csv", "a", "b", "c"],
+    "csv_three_columns": ["162400000", "92300000", "{dir}/three_columns.csv", "a", "b", "c"],
+    "csv_bare_quote": ["162400000", "92300000", "{dir}/bare_quote.csv", "a", "b", "c"],
+    "csv_quoted_fields_two_collectors": ["162400000", "92300000", "{dir}/quoted_ok.csv", "a", "b"],
+}
+
+
+def cli_golden():
+    """tests/golden/cli_errors.json: stdout, stderr (time stamp removed) and exit status of the
+    reference binary for CLI_CASES; paths are kept as the {csv} / {dir} / {prog} place-holders."""
+    from oracle import oracle
+    oracle.build()
+    exe = str(ROOT / "oracle" / "_ref" / "processor")
+    out = {"files": CLI_FILES, "cases": {}}
+    with tempfile.TemporaryDirectory() as td:
+        for name, text in CLI_FILES.items():
+            (Path(td) / name).write_bytes(text.encode())
+        csv = str(HERE / "stations.csv")
+        for case, args in CLI_CASES.items():
+            argv = [a.replace("{csv}", csv).replace("{dir}", td) for a in args]
+            r = subprocess.run([exe, *argv], capture_output=True, text=True, cwd=td)
+            def back(t):
+                return t.replace(csv, "{csv}").replace(td, "{dir}").replace(exe, "{prog}")
+            err = [back(l[20:]) for l in r.stderr.splitlines()]   # "2006/01/02 15:04:05 "
+            assert all(re.match(r"\d{4}/\d\d/\d\d \d\d:\d\d:\d\d ", l) for l in r.stderr.splitlines()), r.stderr
+            out["cases"][case] = {"args": args, "returncode": r.returncode, "stdout": [back(l) for l in r.stdout.splitlines()],
+                                  "stderr": err}
+            print(case, r.returncode, err[-1:] or out["cases"][case]["stdout"][-1:])
+    (HERE / "cli_errors.json").write_text(json.dumps(out, indent=1, ensure_ascii=False) + "\n")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["cli"]:
+        cli_golden()
+        sys.exit(0)
     main(only=set(sys.argv[1:]) or None)   # no arguments: every case

@@ -8,7 +8,7 @@ import numpy as np
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 STATIONS = ["kx0u", "n3pay", "kf0mtl"]
-GOLDEN_CASES = ["fm_strong", "fm_delays", "moderate", "weak_tones", "weak_noise", "fm_ragged"]
+GOLDEN_CASES = ["fm_strong", "fm_delays", "moderate", "weak_tones", "weak_noise", "fm_ragged", "fm_uneven"]
 # golden records whose captures are regenerated from their seeds (18 MB: not stored); 1 M-sample chunk
 GOLDEN_LONG_CASES = ["fm_truncated"]
 FS = 2e6
