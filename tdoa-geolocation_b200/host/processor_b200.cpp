@@ -206,17 +206,24 @@ public:
             catch (const std::exception &e) { throw std::runtime_error("failed to load data from " + datFiles[slot] + ": " + e.what()); }
             if (binary) {
                 const long long b = n / 3;  // processor.go:211-236, :244-265
+                const long long nRef = n < 3 ? n : 2 * b, nTgt = n < 3 ? n : b;   // fewer than 3 samples: returned unchanged
                 printf("Extracting reference signal from dual-frequency data\n");
-                printf("Total samples: %lld, block size: %lld\n", n, b);
-                printf("Extracted %lld reference samples from blocks 1 and 3\n", 2 * b);
+                if (n < 3) printf("Warning: Data too small for dual-frequency extraction\n");
+                else {
+                    printf("Total samples: %lld, block size: %lld\n", n, b);
+                    printf("Extracted %lld reference samples from blocks 1 and 3\n", 2 * b);
+                }
                 printf("Extracting target signal from dual-frequency data\n");
-                printf("Total samples: %lld, block size: %lld\n", n, b);
-                printf("Extracted %lld target samples from block 2\n", b);
+                if (n < 3) printf("Warning: Data too small for dual-frequency extraction\n");
+                else {
+                    printf("Total samples: %lld, block size: %lld\n", n, b);
+                    printf("Extracted %lld target samples from block 2\n", b);
+                }
                 // processor.go:772-780 with the shipped binary's chunk: the engine's BINARY mode
                 // cuts both signals the same way (chunk_samples = 1 000 000)
                 const long long chunk = 1000000;
-                if (2 * b > chunk) printf("Using test chunk: %lld samples (%.1f ms)\n", chunk, (double)chunk / 2e6 * 1000);
-                if (b > chunk) printf("Using target test chunk: %lld samples (%.1f ms)\n", chunk, (double)chunk / 2e6 * 1000);
+                if (nRef > chunk) printf("Using test chunk: %lld samples (%.1f ms)\n", chunk, (double)chunk / 2e6 * 1000);
+                if (nTgt > chunk) printf("Using target test chunk: %lld samples (%.1f ms)\n", chunk, (double)chunk / 2e6 * 1000);
                 printf("Coherent integration time: 500 ms (expecting ~10.0 dB processing gain)\n");
             }
             st.push_back(s);
@@ -366,6 +373,10 @@ private:
                                             "Moderate signal - envelope correlation approach",
                                             "Weak signal - standard processing with timing preservation"};
         printf("=== Cross-Correlation Analysis ===\n");
+        if (s1.n == 0 || s2.n == 0) {   // processor.go:622-625
+            printf("Warning: Empty signals for correlation\n");
+            return;
+        }
         printf("\n--- Signal Preprocessing ---\n");
         const tdoa_signal_info *sg[2] = {&s1, &s2};
         for (int k = 0; k < 2; k++) {
@@ -374,7 +385,7 @@ private:
             printf("%s\n", branchText[sg[k]->branch]);
             printf("Removed DC bias: %.6f + %.6fi\n", sg[k]->dc_re, sg[k]->dc_im);
             if (sg[k]->branch == 2) printf("Bandpass filter: %.1f - %.1f Hz (at %.0f Hz sample rate)\n", 100.0, 200000.0, 2000000.0);
-            printf("Normalized signal power: %.6f → %.6f\n", sg[k]->power1, sg[k]->power1 > 0 ? 1.0 : 0.0);
+            if (sg[k]->power1 > 0) printf("Normalized signal power: %.6f → 1.000000\n", sg[k]->power1);   // processor.go:338-340, :349
         }
         printf("\n--- Time Domain Correlation ---\n");
         printf("Performing time domain correlation\n");

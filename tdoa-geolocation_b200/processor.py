@@ -141,6 +141,9 @@ class TDOAProcessor:
     def _print_pair_binary(self, sig1, sig2, pk, first_corr, fs, max_lag, block, sanity):
         P = self._print
         P("=== Cross-Correlation Analysis ===")
+        if sig1["n"] == 0 or sig2["n"] == 0:   # processor.go:622-625
+            P("Warning: Empty signals for correlation")
+            return
         P("\n--- Signal Preprocessing ---")
         for k, sg in ((1, sig1), (2, sig2)):
             P("Preprocessing Signal %d signal (%d samples)" % (k, sg["n"]))
@@ -149,7 +152,8 @@ class TDOAProcessor:
             P("Removed DC bias: %.6f + %.6fi" % (sg["dc_re"], sg["dc_im"]))
             if sg["branch"] == 2:
                 P("Bandpass filter: %.1f - %.1f Hz (at %.0f Hz sample rate)" % (100.0, 200000.0, 2000000.0))
-            P("Normalized signal power: %.6f → %.6f" % (sg["power1"], 1.0 if sg["power1"] > 0 else 0.0))
+            if sg["power1"] > 0:   # processor.go:338-340, :349
+                P("Normalized signal power: %.6f → 1.000000" % sg["power1"])
         P("\n--- Time Domain Correlation ---")
         P("Performing time domain correlation")
         tl, sl = min(sig1["n"], sig2["n"]), max(sig1["n"], sig2["n"])
@@ -195,16 +199,23 @@ class TDOAProcessor:
                 raise RuntimeError(f"failed to load data from {fn}: {exc}") from exc
             if binary:
                 b = n // 3  # processor.go:211-236, :244-265
+                n_ref, n_tgt = (n, n) if n < 3 else (2 * b, b)   # fewer than 3 samples: returned unchanged
                 P("Extracting reference signal from dual-frequency data")
-                P("Total samples: %d, block size: %d" % (n, b))
-                P("Extracted %d reference samples from blocks 1 and 3" % (2 * b))
+                if n < 3:
+                    P("Warning: Data too small for dual-frequency extraction")
+                else:
+                    P("Total samples: %d, block size: %d" % (n, b))
+                    P("Extracted %d reference samples from blocks 1 and 3" % (2 * b))
                 P("Extracting target signal from dual-frequency data")
-                P("Total samples: %d, block size: %d" % (n, b))
-                P("Extracted %d target samples from block 2" % b)
+                if n < 3:
+                    P("Warning: Data too small for dual-frequency extraction")
+                else:
+                    P("Total samples: %d, block size: %d" % (n, b))
+                    P("Extracted %d target samples from block 2" % b)
                 chunk = 1_000_000  # processor.go:772-780 with the shipped binary's chunk (the engine's chunk_samples)
-                if 2 * b > chunk:
+                if n_ref > chunk:
                     P("Using test chunk: %d samples (%.1f ms)" % (chunk, chunk / 2e6 * 1000))
-                if b > chunk:
+                if n_tgt > chunk:
                     P("Using target test chunk: %d samples (%.1f ms)" % (chunk, chunk / 2e6 * 1000))
                 P("Coherent integration time: 500 ms (expecting ~10.0 dB processing gain)")
             stations.append(st)

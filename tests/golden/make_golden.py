@@ -162,20 +162,52 @@ def case_fm_truncated(B=1_050_000):
     return out
 
 
+def _degenerate_third(third: np.ndarray):
+    caps = case_fm_strong(B=20000)
+    caps[STATIONS[2]] = third
+    return caps
+
+
+def case_tiny_third():
+    """Third capture of two samples: fewer than three samples are "too small for dual-frequency
+    extraction" and returned unchanged as REF and as TGT (processor.go:211-214, :244-246)."""
+    return _degenerate_third(np.array([200, 90, 30, 160], np.uint8))
+
+
+def case_three_sample_third():
+    """Third capture of exactly three samples: one-sample blocks (REF two samples, TGT one)."""
+    return _degenerate_third(np.array([200, 90, 30, 160, 140, 100], np.uint8))
+
+
+def case_empty_third():
+    """Third capture empty: crossCorrelate warns and returns (0, 0.0) (processor.go:622-625)."""
+    return _degenerate_third(np.zeros(0, np.uint8))
+
+
+def case_fm_close_lengths():
+    """Lengths that differ by less than the 2000-lag search (blocks of 40000 / 40300 / 39800): the
+    lag range shrinks to the length difference (processor.go:664-672) and true delays beyond it
+    are out of reach."""
+    return _uneven((40000, 40300, 39800), 28, (0, 8, 3), (0, 21, 5), 430)
+
+
 def case_fm_uneven():
     """Captures of different lengths (blocks of 36000 / 41000 / 38500 samples, the second file one
     byte longer than a whole sample): the shorter signal of a pair is the template
     (processor.go:652-662), the lag range follows the length difference, and the odd trailing
     byte is dropped by the integer division in loadIQData (:188)."""
-    Bs = (36000, 41000, 38500)
-    ref, tgt = fm(max(Bs) + 600, 26, 75e3), fm(max(Bs) + 600, 27, 60e3)
+    return _uneven((36000, 41000, 38500), 26, (0, 8, 3), (0, 21, 5), 330, odd_byte=True)
+
+
+def _uneven(Bs, seed, d_ref, d_tgt, noise_seed, odd_byte=False):
+    ref, tgt = fm(max(Bs) + 600, seed, 75e3), fm(max(Bs) + 600, seed + 1, 60e3)
     out = {}
-    for k, (name, B, dr, dt) in enumerate(zip(STATIONS, Bs, (0, 8, 3), (0, 21, 5))):
-        def blk(sig, d, seed):
-            g = np.random.default_rng(seed)
+    for k, (name, B, dr, dt) in enumerate(zip(STATIONS, Bs, d_ref, d_tgt)):
+        def blk(sig, d, s):
+            g = np.random.default_rng(s)
             return sig[400 - d:400 - d + B] + 0.02 * (g.standard_normal(B) + 1j * g.standard_normal(B))
-        raw = quantise(np.concatenate([blk(ref, dr, 330 + k), blk(tgt, dt, 340 + k), blk(ref, dr, 350 + k)]))
-        if k == 1:
+        raw = quantise(np.concatenate([blk(ref, dr, noise_seed + k), blk(tgt, dt, noise_seed + 10 + k), blk(ref, dr, noise_seed + 20 + k)]))
+        if odd_byte and k == 1:
             raw = np.concatenate([raw, np.array([200], np.uint8)])
         out[name] = raw
     return out
@@ -193,6 +225,10 @@ CASES = {
     "fm_ragged": case_fm_ragged,
     "fm_truncated": case_fm_truncated,
     "fm_uneven": case_fm_uneven,
+    "fm_close_lengths": case_fm_close_lengths,
+    "tiny_third": case_tiny_third,
+    "three_sample_third": case_three_sample_third,
+    "empty_third": case_empty_third,
 }
 
 PAIR_RE = re.compile(r"^(REF|TGT) (\S+) - (\S+): delay=(-?\d+) samples \((-?[\d.]+) μs\), correlation=(-?[\d.]+)")

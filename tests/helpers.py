@@ -8,7 +8,9 @@ import numpy as np
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 STATIONS = ["kx0u", "n3pay", "kf0mtl"]
-GOLDEN_CASES = ["fm_strong", "fm_delays", "moderate", "weak_tones", "weak_noise", "fm_ragged", "fm_uneven"]
+GOLDEN_CASES = ["fm_strong", "fm_delays", "moderate", "weak_tones", "weak_noise", "fm_ragged", "fm_uneven", "fm_close_lengths"]
+# degenerate third capture (2 samples / 3 samples / empty): records and stdout only
+GOLDEN_DEGENERATE_CASES = ["tiny_third", "three_sample_third", "empty_third"]
 # golden records whose captures are regenerated from their seeds (18 MB: not stored); 1 M-sample chunk
 GOLDEN_LONG_CASES = ["fm_truncated"]
 FS = 2e6

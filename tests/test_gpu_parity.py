@@ -12,7 +12,7 @@ import pytest
 
 import tdoa_b200 as T
 from oracle import oracle
-from helpers import GOLDEN, GOLDEN_CASES, GOLDEN_LONG_CASES, STATION_LLH, fm_capture, load_golden, quantise
+from helpers import GOLDEN, GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, STATION_LLH, fm_capture, load_golden, quantise
 
 pytestmark = pytest.mark.gpu
 
@@ -457,10 +457,12 @@ def test_cpp_host_mirror_stdout_is_the_shipped_binarys(tmp_path, case):
         assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
 
 
-@pytest.mark.parametrize("case", GOLDEN_LONG_CASES)
+@pytest.mark.parametrize("case", GOLDEN_LONG_CASES + GOLDEN_DEGENERATE_CASES)
 def test_blocks_longer_than_the_test_chunk(tmp_path, case):
     """Blocks of 1 050 000 samples: the shipped binary cuts REF and TGT to their first 1 000 000
-    samples before the pair loops (processor.go:772-780).  Records against what the binary
+    samples before the pair loops (processor.go:772-780).  Degenerate cases: a third capture of 2
+    samples (returned unchanged as REF and TGT), of 3 samples (one-sample blocks), empty
+    (crossCorrelate warns and returns (0, 0.0)).  Records against what the binary
     printed (bit-exact lags, correlation to the printed 6 decimals), and the C++ command's
     stdout against the binary's, line for line."""
     import subprocess

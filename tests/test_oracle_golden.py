@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from helpers import GOLDEN_CASES, GOLDEN_LONG_CASES, STATION_LLH, load_golden
+from helpers import GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, STATION_LLH, load_golden
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -18,6 +18,18 @@ def test_binary_pairs_match_reference_stdout(case):
         assert kind == want["kind"]
         assert delay == want["delay"], (case, want)
         # the reference prints %.6f
+        assert abs(corr - want["corr"]) <= 0.51e-6, (case, corr, want)
+
+
+@pytest.mark.parametrize("case", GOLDEN_DEGENERATE_CASES)
+def test_binary_degenerate_captures(case):
+    """A capture of 2 samples (returned unchanged as REF and TGT), of 3 samples (one-sample
+    blocks) and an empty one: the records the binary printed."""
+    raws, meta = load_golden(case)
+    ref, tgt = oracle.process_capture_binary(raws)
+    got = [("REF",) + r for r in ref] + [("TGT",) + r for r in tgt]
+    for (kind, delay, corr, _), want in zip(got, meta["pairs"]):
+        assert (kind, delay) == (want["kind"], want["delay"]), (case, want)
         assert abs(corr - want["corr"]) <= 0.51e-6, (case, corr, want)
 
 
