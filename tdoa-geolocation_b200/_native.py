@@ -33,6 +33,7 @@ class TdoaError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"{ERRORS.get(code, code)}: {message}")
         self.code = code
+        self.message = message   # tdoa_last_error's text alone (the host mirror prints it as the reference would)
 
 
 class Config(C.Structure):

@@ -1832,6 +1832,15 @@ int tdoa_load_u8_pinned(tdoa_engine *e, int32_t station, const uint8_t *pinned_i
 // loadIQData for a file (processor.go:166-191): the capture is read in 32 MB pieces into two
 // pinned staging buffers and copied to the device from there, the read of one piece
 // overlapping the PCIe copy of the previous one; nothing of the file stays in host memory.
+// Go's text for an errno (os.PathError: "open <path>: no such file or directory"): the C
+// library's message with a lower-case first letter
+static std::string go_errno(int err)
+{
+    std::string m = strerror(err);
+    if (!m.empty() && m[0] >= 'A' && m[0] <= 'Z') m[0] = (char)(m[0] - 'A' + 'a');
+    return m;
+}
+
 int tdoa_load_file(tdoa_engine *e, int32_t station, const char *path, int64_t *n_samples)
 {
     if (!e) return TDOA_E_INVALID;
@@ -1840,12 +1849,12 @@ int tdoa_load_file(tdoa_engine *e, int32_t station, const char *path, int64_t *n
     if (station < 0 || station >= e->cfg.n_stations) return fail(e, TDOA_E_INVALID, "tdoa_load_file: bad station %d", station);
     if (!path) return fail(e, TDOA_E_INVALID, "tdoa_load_file: NULL path");
     const int fd = open(path, O_RDONLY);
-    if (fd < 0) return fail(e, TDOA_E_IO, "failed to open file: %s: %s", path, strerror(errno));  // processor.go:170-172
+    if (fd < 0) return fail(e, TDOA_E_IO, "failed to open file: open %s: %s", path, go_errno(errno).c_str());  // processor.go:170-172
     struct stat sb;
     if (fstat(fd, &sb) != 0) {
         const int err = errno;
         close(fd);
-        return fail(e, TDOA_E_IO, "failed to get file size: %s", strerror(err));  // processor.go:177-179
+        return fail(e, TDOA_E_IO, "failed to get file size: stat %s: %s", path, go_errno(err).c_str());  // processor.go:177-179
     }
     const size_t nbytes = (size_t)sb.st_size;
     Station &s = e->stations[station];
@@ -1878,7 +1887,8 @@ int tdoa_load_file(tdoa_engine *e, int32_t station, const char *path, int64_t *n
                 const int err = errno;
                 close(fd);
                 cudaStreamSynchronize(e->copy_stream);
-                return fail(e, TDOA_E_IO, "failed to read data: %s", r == 0 ? "unexpected end of file" : strerror(err));  // :189-191
+                if (r == 0) return fail(e, TDOA_E_IO, "failed to read data: unexpected end of file");
+                return fail(e, TDOA_E_IO, "failed to read data: read %s: %s", path, go_errno(err).c_str());  // :189-191
             }
             got += (size_t)r;
         }

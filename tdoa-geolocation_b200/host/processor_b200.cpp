@@ -27,6 +27,9 @@
 #include <string>
 #include <vector>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "tdoa_b200.h"
 
 namespace {
@@ -174,10 +177,14 @@ public:
     long long loadIQData(int slot, const std::string &filename)
     {
         printf("Loading I/Q data from: %s\n", filename.c_str());
+        // the reference prints the size between opening and reading (:176-183); a file that cannot
+        // be opened is reported by tdoa_load_file with the reference's text
+        struct stat sb;
+        const bool have = stat(filename.c_str(), &sb) == 0 && access(filename.c_str(), R_OK) == 0;
+        if (have) printf("File size: %lld bytes, samples: %lld\n", (long long)sb.st_size, (long long)sb.st_size / 2);
         int64_t n = 0;
         if (tdoa_load_file(engine, slot, filename.c_str(), &n) != TDOA_OK) throw std::runtime_error(tdoa_last_error(engine));
-        std::ifstream f(filename, std::ios::binary | std::ios::ate);
-        printf("File size: %lld bytes, samples: %lld\n", (long long)f.tellg(), (long long)n);
+        if (!have) printf("File size: %lld bytes, samples: %lld\n", (long long)n * 2, (long long)n);
         printf("Successfully loaded %lld complex samples\n", (long long)n);
         return n;
     }

@@ -109,12 +109,19 @@ class TDOAProcessor:
     # -- processor.go:166-205 (bytes go to the GPU; the complex64 samples stay there)
     def load_iq_data(self, slot: int, filename: str, n_stations: int) -> int:
         self._print(f"Loading I/Q data from: {filename}")
+        # the reference prints the size between opening and reading (:176-183); a file that cannot
+        # be opened is reported by tdoa_load_file with the reference's text
+        have = os.path.exists(filename) and os.access(filename, os.R_OK)
+        if have:
+            size = os.stat(filename).st_size
+            self._print(f"File size: {size} bytes, samples: {size // 2}")
         try:
             # tdoa_load_file: streamed to the device through pinned staging, never held on the host
             n = self.engine(n_stations).load_file(slot, filename)
         except N.TdoaError as exc:
-            raise RuntimeError(str(exc)) from exc   # "failed to open file: ..." as processor.go:170-172
-        self._print(f"File size: {os.path.getsize(filename)} bytes, samples: {n}")
+            raise RuntimeError(exc.message) from exc   # "failed to open file: ..." as processor.go:170-172
+        if not have:
+            self._print(f"File size: {2 * n} bytes, samples: {n}")
         self._print(f"Successfully loaded {n} complex samples")
         return n
 

@@ -324,6 +324,25 @@ CLI_CASES = {   # {csv} = tests/golden/stations.csv, {dir} = a directory holding
 }
 
 
+# command lines that get as far as the captures (the mirrors need the engine for these: GPU tests).
+# {dir} holds sim-kx0u-1.dat and sim-n3pay-1.dat (the fm_strong golden captures) and the directory
+# sim-kf0mtl-dir.dat
+CLI_ENGINE_CASES = {
+    "unknown_station": ["162400000", "92300000", "{csv}", "{dir}/sim-kx0u-1.dat", "{dir}/sim-n3pay-1.dat", "{dir}/sim-nobody-1.dat"],
+    "missing_third_file": ["162400000", "92300000", "{csv}", "{dir}/sim-kx0u-1.dat", "{dir}/sim-n3pay-1.dat", "{dir}/sim-kf0mtl-missing.dat"],
+    "missing_first_file": ["162400000", "92300000", "{csv}", "{dir}/sim-kx0u-missing.dat", "{dir}/sim-n3pay-1.dat", "{dir}/sim-kf0mtl-1.dat"],
+    "directory_as_capture": ["162400000", "92300000", "{csv}", "{dir}/sim-kx0u-1.dat", "{dir}/sim-n3pay-1.dat", "{dir}/sim-kf0mtl-dir.dat"],
+}
+
+
+def cli_engine_setup(td):
+    """Files the CLI_ENGINE_CASES refer to (also called by the GPU test)."""
+    caps = np.load(HERE / "fm_strong.npz")
+    for st in STATIONS[:2]:
+        caps[st].tofile(Path(td) / f"sim-{st}-1.dat")
+    (Path(td) / "sim-kf0mtl-dir.dat").mkdir(exist_ok=True)
+
+
 def cli_golden():
     """tests/golden/cli_errors.json: stdout, stderr (time stamp removed) and exit status of the
     reference binary for CLI_CASES; paths are kept as the {csv} / {dir} / {prog} place-holders."""
@@ -335,7 +354,9 @@ def cli_golden():
         for name, text in CLI_FILES.items():
             (Path(td) / name).write_bytes(text.encode())
         csv = str(HERE / "stations.csv")
-        for case, args in CLI_CASES.items():
+        cli_engine_setup(td)
+        out["engine_cases"] = sorted(CLI_ENGINE_CASES)
+        for case, args in {**CLI_CASES, **CLI_ENGINE_CASES}.items():
             argv = [a.replace("{csv}", csv).replace("{dir}", td) for a in args]
             r = subprocess.run([exe, *argv], capture_output=True, text=True, cwd=td)
             def back(t):

@@ -6,6 +6,7 @@ rounded sum instead of the reference's sequential f32 accumulator, so preprocess
 samples may differ in the last bits (<= 2e-6 abs on unit-power signals) and printed
 correlations by <= 1e-6."""
 import io
+import re
 
 import numpy as np
 import pytest
@@ -498,6 +499,50 @@ def test_blocks_longer_than_the_test_chunk(tmp_path, case):
     assert len(ours) >= len(gold)
     for k, (a, b) in enumerate(zip(ours, gold)):
         assert _same_line(a, b), f"python mirror, line {k}: ours {a!r} != reference {b!r}"
+
+
+def _cli_engine_cases():
+    import json
+    return json.loads((GOLDEN / "cli_errors.json").read_text())
+
+
+@pytest.mark.parametrize("case", _cli_engine_cases()["engine_cases"])
+def test_capture_file_errors_are_the_reference_binarys(tmp_path, capsys, case):
+    """A capture whose name matches no station, a missing capture, a directory in place of one:
+    stdout, stderr (after the log time stamp) and exit status of both host mirrors against the
+    reference binary's (tests/golden/cli_errors.json; processor.go:110-122, :166-191, :757-765)."""
+    import importlib.util
+    import subprocess
+    spec = importlib.util.spec_from_file_location("make_golden", GOLDEN / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    mg.cli_engine_setup(tmp_path)
+    want = _cli_engine_cases()["cases"][case]
+    csv_path = str(GOLDEN / "stations.csv")
+    argv = [a.replace("{csv}", csv_path).replace("{dir}", str(tmp_path)) for a in want["args"]]
+    size_line = re.compile(r"^File size: \d+ bytes, samples: \d+$")   # a directory's size is the file system's business
+
+    def same(got_lines, want_lines):
+        assert len(got_lines) == len(want_lines), (got_lines[-3:], want_lines[-3:])
+        for a, b in zip(got_lines, want_lines):
+            if "sim-kf0mtl-dir.dat" in " ".join(want["args"]) and size_line.match(a) and size_line.match(b):
+                continue
+            assert a == b
+
+    exe = str(GOLDEN.parent.parent / "tdoa-geolocation_b200" / "processor_b200")
+    r = subprocess.run([exe, *argv], capture_output=True, text=True, cwd=tmp_path)
+    back = lambda t: t.replace(csv_path, "{csv}").replace(str(tmp_path), "{dir}").replace(exe, "{prog}")
+    assert r.returncode == want["returncode"]
+    same([back(l) for l in r.stdout.splitlines()], want["stdout"])
+    same([back(l[20:]) for l in r.stderr.splitlines()], want["stderr"])
+    from importlib import import_module
+    proc = import_module("tdoa-geolocation_b200.processor")
+    capsys.readouterr()
+    rc = proc.main(argv, prog="{prog}")
+    got = capsys.readouterr()
+    assert rc == want["returncode"]
+    same([back(l) for l in got.out.splitlines()], want["stdout"])
+    same([back(l[20:]) for l in got.err.splitlines()], want["stderr"])
 
 
 # ------------------------------------------------------------------ discriminator bit parity
