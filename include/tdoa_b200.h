@@ -195,6 +195,22 @@ TDOA_API int tdoa_solve(tdoa_engine *e, const double *stations_llh, int32_t n_st
                         const double *range_diffs, int32_t n_sets, int32_t rd_stride,
                         double *out_llh, int32_t *status, int32_t *iters);
 
+/* solveTDOA of the SHIPPED BINARY (ELF 0x4a0360; a later revision than processor.go:932-1020,
+ * restated from its disassembly and pinned by the iteration traces it prints): the range
+ * differences with |rd| <= 20400 m are kept in order; the binary solves only when exactly
+ * two remain (res1 = (r2 - r1) - valid[0], res2 = (r3 - r1) - valid[1]; Newton step times 0.7,
+ * steps over 1000 m scaled to 1000 m first; single-equation fall-back when |det| < 1e-12;
+ * converged when both residuals < 1 m; at most 10 iterations; Z frozen).
+ * *status: 0 a fix in out_llh[3]; 1 fewer than two valid ("insufficient valid measurements: only
+ * %d of %d range differences are reliable"); 2 more than two valid ("no valid range difference
+ * measurements remain"); 3 "singular Jacobian matrix at iteration %d (det=%.2e)".
+ * n_valid, n_iter (iterations whose trace line the binary prints), converged, and
+ * trace[10][5] = {det, res1, res2, step length, code: 0 plain step, 1 step limited, 2 / 3
+ * single equation 1 / 2} may each be NULL. */
+TDOA_API int tdoa_solve_binary(tdoa_engine *e, const double *stations_llh, int32_t n_stations,
+                               const double *range_diffs, int32_t n_rd, double *out_llh, int32_t *status,
+                               int32_t *n_valid, int32_t *n_iter, int32_t *converged, double *trace);
+
 /* Dense lat-lon grid multilateration (no reference equivalent): for each set the
  * cell minimising sum_{i<j} ((r_j - r_i) - rd_ij)^2.
  * grid_desc = {lat0, lon0, dlat, dlon, nlat, nlon, elev}. */

@@ -79,6 +79,8 @@ def lib():
         L.orc_baseline.restype = _f64
         L.orc_solve_tdoa.argtypes = [_vp, _vp, _vp, _vp]
         L.orc_solve_tdoa.restype = C.c_int
+        L.orc_solve_binary.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
+        L.orc_solve_binary.restype = C.c_int
         L.orc_grid_solve.argtypes = [_vp, C.c_int, _vp, _f64, _f64, _f64, _f64, C.c_int, C.c_int,
                                      _f64, _vp, _vp, _vp]
         L.orc_solve_ls.argtypes = [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]
@@ -301,6 +303,17 @@ def solve_tdoa(stations_llh, range_diffs):
     it = np.zeros(1, np.int32)
     status = lib().orc_solve_tdoa(_p(st), _p(rd), _p(out), _p(it))
     return out, status, int(it[0])
+
+
+def solve_binary(stations_llh, range_diffs):
+    """solveTDOA of the shipped binary (orc_solve_binary): (llh, status, n_valid, n_iter, converged, trace)."""
+    st = np.ascontiguousarray(stations_llh, np.float64)
+    rd = np.ascontiguousarray(range_diffs, np.float64)
+    out = np.zeros(3, np.float64)
+    nv, ni, cv = (np.zeros(1, np.int32) for _ in range(3))
+    trace = np.zeros((10, 5), np.float64)
+    status = lib().orc_solve_binary(_p(st), len(st), _p(rd), len(rd), _p(out), _p(nv), _p(ni), _p(cv), _p(trace))
+    return out, status, int(nv[0]), int(ni[0]), bool(cv[0]), trace[:int(ni[0])]
 
 
 def solve_ls(stations_llh, range_diffs, init_llh=None, dims=2):

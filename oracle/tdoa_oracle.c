@@ -629,6 +629,77 @@ ORC_API int orc_solve_tdoa(const double *st_llh, const double *rd, double *out_l
     return 0;
 }
 
+/* ELF 0x4a0360  solveTDOA of the SHIPPED BINARY (a later revision than processor.go:932-1020;
+ * restated from its disassembly and pinned by the iteration trace it prints):
+ *   - measurements with |rd| > 20400 m (1.2 x 17 km) are dropped, the others compacted in
+ *     order into `valid`; fewer than two -> status 1 ("insufficient valid measurements");
+ *   - start at the ECEF of the mean lat/lon/elevation of stations 0..2; Z is never updated;
+ *   - every iteration first checks len(valid) == 2 -- any other count -> status 2 ("no valid
+ *     range difference measurements remain"), so the binary only ever solves with exactly two;
+ *   - res1 = (r2 - r1) - valid[0], res2 = (r3 - r1) - valid[1]; both < 1 m -> converged;
+ *   - |det| < 1e-12: single-equation fall-back (0.1 of -res1/J11 when |J11| > |J21| and
+ *     |J12| > 1e-10, else 0.1 of -res2/J21 when |J21| > 1e-10, else status 3), X only;
+ *   - otherwise the Newton step times 0.7, a step longer than 1000 m first scaled to 1000 m;
+ *   - at most 10 iterations.
+ * trace (10 x 5 doubles, may be NULL): per iteration det, res1, res2, step length (0 on the
+ * singular branch), code (0 plain step, 1 limited step, 2 / 3 single equation 1 / 2).
+ * n_iter = iterations whose line was printed; converged = 1 when the loop ended by the 1 m test. */
+ORC_API int orc_solve_binary(const double *st_llh, int n_st, const double *rd, int n_rd, double *out_llh,
+                             int *n_valid, int *n_iter, int *converged, double *trace)
+{
+    (void)n_st;
+    double valid[2] = {0.0, 0.0};
+    int nv = 0;
+    for (int k = 0; k < n_rd; k++)
+        if (fabs(rd[k]) <= 20400.0) { if (nv < 2) valid[nv] = rd[k]; nv++; }
+    if (n_valid) *n_valid = nv;
+    if (n_iter) *n_iter = 0;
+    if (converged) *converged = 0;
+    out_llh[0] = out_llh[1] = out_llh[2] = 0.0;
+    if (nv < 2) return 1;
+    double s[3][3];
+    for (int k = 0; k < 3; k++) orc_llh_to_ecef(st_llh[3 * k], st_llh[3 * k + 1], st_llh[3 * k + 2], s[k]);
+    double x[3];
+    orc_llh_to_ecef((st_llh[0] + st_llh[3] + st_llh[6]) / 3.0, (st_llh[1] + st_llh[4] + st_llh[7]) / 3.0,
+                    (st_llh[2] + st_llh[5] + st_llh[8]) / 3.0, x);
+    for (int it = 0; it < 10; it++) {
+        double r[3];
+        for (int k = 0; k < 3; k++)
+            r[k] = sqrt((x[0] - s[k][0]) * (x[0] - s[k][0]) + (x[1] - s[k][1]) * (x[1] - s[k][1]) +
+                        (x[2] - s[k][2]) * (x[2] - s[k][2]));
+        const double dx1 = (x[0] - s[0][0]) / r[0], dy1 = (x[1] - s[0][1]) / r[0];
+        const double dx2 = (x[0] - s[1][0]) / r[1], dy2 = (x[1] - s[1][1]) / r[1];
+        const double dx3 = (x[0] - s[2][0]) / r[2], dy3 = (x[1] - s[2][1]) / r[2];
+        if (nv != 2) return 2;
+        const double res1 = (r[1] - r[0]) - valid[0];
+        const double res2 = (r[2] - r[0]) - valid[1];
+        const double J11 = dx2 - dx1, J12 = dy2 - dy1, J21 = dx3 - dx1, J22 = dy3 - dy1;
+        if (fabs(res1) < 1.0 && fabs(res2) < 1.0) { if (converged) *converged = 1; break; }
+        const double det = J22 * J11 - J21 * J12;
+        if (n_iter) *n_iter = it + 1;
+        double *tr = trace ? trace + 5 * it : NULL;
+        if (tr) { tr[0] = det; tr[1] = res1; tr[2] = res2; tr[3] = 0.0; tr[4] = 0.0; }
+        if (fabs(det) < 1e-12) {
+            double d;
+            if (fabs(J11) > fabs(J21) && fabs(J12) > 1e-10) { d = -res1 / J11; if (tr) tr[4] = 2.0; }
+            else if (fabs(J21) > 1e-10) { d = -res2 / J21; if (tr) tr[4] = 3.0; }
+            else return 3;
+            x[0] += d * 0.1;
+        } else {
+            const double dx = (-res1 * J22 + J12 * res2) / det;
+            const double dy = (res1 * J21 - J11 * res2) / det;
+            const double step = sqrt(dx * dx + dy * dy);
+            double scale = 0.7;
+            if (step > 1000.0) { scale = 1000.0 / step * 0.7; if (tr) tr[4] = 1.0; }
+            if (tr) tr[3] = step;
+            x[0] += dx * scale;
+            x[1] += dy * scale;
+        }
+    }
+    orc_ecef_to_llh(x[0], x[1], x[2], out_llh);
+    return 0;
+}
+
 /* ------------------------------------------------- grid multilateration
  * No reference equivalent ("parity unpinned").  Cost of a cell =
  *   sum over pairs i<j (lexicographic) of ((r_j - r_i) - rd_ij)^2, f64,

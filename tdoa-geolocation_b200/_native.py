@@ -24,7 +24,7 @@ ERRORS = {-1: "TDOA_E_INVALID", -2: "TDOA_E_NODEVICE", -3: "TDOA_E_CUDA", -4: "T
 ABI_SYMBOLS = [
     "tdoa_default_config", "tdoa_create", "tdoa_destroy", "tdoa_last_error", "tdoa_host_alloc", "tdoa_host_free",
     "tdoa_load_u8", "tdoa_load_file", "tdoa_load_u8_pinned", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_process", "tdoa_xcorr_info", "tdoa_analyze",
-    "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_solve_ls", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
+    "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_solve_binary", "tdoa_solve_ls", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
     "tdoa_set_stream", "tdoa_synchronize", "tdoa_selftest",
 ]
 
@@ -145,6 +145,7 @@ def load_library():
     L.tdoa_cross_correlate.argtypes = [vp, vp, i64, vp, i64, C.POINTER(PeakStruct)]
     L.tdoa_baselines.argtypes = [vp, vp, i32, vp]
     L.tdoa_solve.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
+    L.tdoa_solve_binary.argtypes = [vp, vp, i32, vp, i32, vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp]
     L.tdoa_solve_ls.argtypes = [vp, vp, i32, vp, i32, i32, vp, i32, vp, vp, vp, vp]
     L.tdoa_grid.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp]
     L.tdoa_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -370,6 +371,18 @@ class Engine:
         if single:
             return out[0], int(status[0]), int(iters[0])
         return out, status, iters
+
+    def solve_binary(self, stations_llh, range_diffs):
+        """solveTDOA of the shipped binary (tdoa_solve_binary): (llh, status, n_valid, n_iter, converged,
+        trace[n_iter][5] = det, res1, res2, step, code)."""
+        st = np.ascontiguousarray(stations_llh, dtype=np.float64).reshape(-1, 3)
+        rd = np.ascontiguousarray(range_diffs, dtype=np.float64).reshape(-1)
+        out = np.zeros(3, np.float64)
+        status, nv, ni, cv = (C.c_int32(0) for _ in range(4))
+        trace = np.zeros((10, 5), np.float64)
+        self._check(self._lib.tdoa_solve_binary(self._h, _ptr(st), st.shape[0], _ptr(rd), rd.size, _ptr(out),
+                                                C.byref(status), C.byref(nv), C.byref(ni), C.byref(cv), _ptr(trace)))
+        return out, status.value, nv.value, ni.value, bool(cv.value), trace[:ni.value]
 
     def process(self, stations_llh) -> dict:
         """ProcessTDOA from the pair loops to the fix in one call (processor.go:816-929), queued on the

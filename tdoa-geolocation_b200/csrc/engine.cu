@@ -2264,6 +2264,39 @@ int tdoa_solve(tdoa_engine *e, const double *stations_llh, int32_t n_stations, c
     return TDOA_OK;
 }
 
+int tdoa_solve_binary(tdoa_engine *e, const double *stations_llh, int32_t n_stations, const double *range_diffs, int32_t n_rd,
+                      double *out_llh, int32_t *status, int32_t *n_valid, int32_t *n_iter, int32_t *converged, double *trace)
+{
+    if (!e) return TDOA_E_INVALID;
+    int rc = begin_call(e);
+    if (rc) return rc;
+    if (!stations_llh || !range_diffs || !out_llh || !status || n_stations < 3 || n_rd < 0)
+        return fail(e, TDOA_E_INVALID, "tdoa_solve_binary: bad arguments (need >= 3 stations)");
+    double *d_llh = nullptr, *d_rd = nullptr, *d_out = nullptr, *d_trace = nullptr;
+    int *d_info = nullptr;
+    if ((rc = alloc_t(e, &d_llh, (size_t)3 * n_stations)) || (rc = alloc_t(e, &d_rd, (size_t)std::max(n_rd, 1))) ||
+        (rc = alloc_t(e, &d_out, 3)) || (rc = alloc_t(e, &d_trace, 50)) || (rc = alloc_t(e, &d_info, 4)))
+        return rc;
+    CU(cudaMemcpyAsync(d_llh, stations_llh, (size_t)3 * n_stations * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (n_rd > 0) CU(cudaMemcpyAsync(d_rd, range_diffs, (size_t)n_rd * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemsetAsync(d_trace, 0, 50 * sizeof(double), e->stream));
+    launch_solve_binary(d_llh, d_rd, n_rd, d_out, d_info, d_trace, e->stream);
+    count_launch(e);
+    int h_info[4] = {0, 0, 0, 0};
+    double h_trace[50];
+    CU(cudaMemcpyAsync(out_llh, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(h_info, d_info, sizeof(h_info), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(h_trace, d_trace, sizeof(h_trace), cudaMemcpyDeviceToHost, e->stream));
+    rc = end_call(e, true);
+    if (rc) return rc;
+    *status = h_info[0];
+    if (n_valid) *n_valid = h_info[1];
+    if (n_iter) *n_iter = h_info[2];
+    if (converged) *converged = h_info[3];
+    if (trace) std::memcpy(trace, h_trace, sizeof(h_trace));
+    return TDOA_OK;
+}
+
 int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_stations, const double *grid_desc,
               const double *range_diffs, int32_t n_sets, int32_t rd_stride, double *out_llh, double *out_cost,
               int64_t *out_index)

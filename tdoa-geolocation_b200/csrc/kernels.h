@@ -162,6 +162,8 @@ void launch_quality(const QualJob *d_jobs, int n_jobs, int n_stat_cta, int max_m
 void launch_baselines(const double *d_llh, int n_st, double *d_out, cudaStream_t st);
 void launch_solve(const double *d_llh, const double *d_rd, int n_sets, int rd_stride, double *d_out_llh,
                   int *d_status, int *d_iters, cudaStream_t st);
+void launch_solve_binary(const double *d_llh, const double *d_rd, int n_rd, double *d_out_llh, int *d_info, double *d_trace,
+                         cudaStream_t st);
 void launch_solve_ls(const double *d_llh, int n_st, const double *d_rd, int n_sets, int rd_stride, const double *d_init,
                      int dims, double *d_out_llh, double *d_rms, int *d_status, int *d_iters, cudaStream_t st);
 int solve_ls_max_stations();

@@ -105,6 +105,74 @@ __global__ void k_solve(const double *llh, const double *rd_all, int n_sets, int
     out_llh[3 * set + 2] = o[2];
 }
 
+// solveTDOA of the SHIPPED BINARY (ELF 0x4a0360; oracle: orc_solve_binary, same statement, pinned
+// by the iteration traces the binary prints): measurements with |rd| > 20400 m are dropped and
+// the rest compacted; fewer than two -> status 1; any count but two -> status 2 (the binary solves
+// with exactly two); res1 = (r2 - r1) - valid[0], res2 = (r3 - r1) - valid[1]; both < 1 m ->
+// converged; |det| < 1e-12 -> 0.1 of a single-equation step in X (status 3 if neither equation
+// can be used); else the Newton step times 0.7, a step longer than 1000 m first scaled to 1000 m;
+// at most 10 iterations; Z is never updated.
+// info[4] = {status, n_valid, n_iter, converged}; trace[10][5] = {det, res1, res2, step, code}
+// (code 0 plain step, 1 limited step, 2 / 3 single equation 1 / 2).
+__global__ void k_solve_binary(const double *llh, const double *rd, int n_rd, double *out_llh, int *info, double *trace)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double valid[2] = {0.0, 0.0};
+    int nv = 0;
+    for (int k = 0; k < n_rd; k++)
+        if (fabs(rd[k]) <= 20400.0) {
+            if (nv < 2) valid[nv] = rd[k];
+            nv++;
+        }
+    int status = 0, n_iter = 0, converged = 0;
+    double o[3] = {0.0, 0.0, 0.0};
+    if (nv < 2) {
+        status = 1;
+    } else {
+        double s[3][3];
+        for (int k = 0; k < 3; k++) llh_to_ecef(llh[3 * k], llh[3 * k + 1], llh[3 * k + 2], s[k]);
+        double x[3];
+        llh_to_ecef((llh[0] + llh[3] + llh[6]) / 3.0, (llh[1] + llh[4] + llh[7]) / 3.0, (llh[2] + llh[5] + llh[8]) / 3.0, x);
+        for (int it = 0; it < 10 && status == 0; it++) {
+            double r[3];
+            for (int k = 0; k < 3; k++)
+                r[k] = sqrt((x[0] - s[k][0]) * (x[0] - s[k][0]) + (x[1] - s[k][1]) * (x[1] - s[k][1]) +
+                            (x[2] - s[k][2]) * (x[2] - s[k][2]));
+            const double dx1 = (x[0] - s[0][0]) / r[0], dy1 = (x[1] - s[0][1]) / r[0];
+            const double dx2 = (x[0] - s[1][0]) / r[1], dy2 = (x[1] - s[1][1]) / r[1];
+            const double dx3 = (x[0] - s[2][0]) / r[2], dy3 = (x[1] - s[2][1]) / r[2];
+            if (nv != 2) { status = 2; break; }
+            const double res1 = (r[1] - r[0]) - valid[0];
+            const double res2 = (r[2] - r[0]) - valid[1];
+            const double J11 = dx2 - dx1, J12 = dy2 - dy1, J21 = dx3 - dx1, J22 = dy3 - dy1;
+            if (fabs(res1) < 1.0 && fabs(res2) < 1.0) { converged = 1; break; }
+            const double det = J22 * J11 - J21 * J12;
+            n_iter = it + 1;
+            double *tr = trace + 5 * it;
+            tr[0] = det; tr[1] = res1; tr[2] = res2; tr[3] = 0.0; tr[4] = 0.0;
+            if (fabs(det) < 1e-12) {
+                double d = 0.0;
+                if (fabs(J11) > fabs(J21) && fabs(J12) > 1e-10) { d = -res1 / J11; tr[4] = 2.0; }
+                else if (fabs(J21) > 1e-10) { d = -res2 / J21; tr[4] = 3.0; }
+                else { status = 3; break; }
+                x[0] += d * 0.1;
+            } else {
+                const double dx = (-res1 * J22 + J12 * res2) / det;
+                const double dy = (res1 * J21 - J11 * res2) / det;
+                const double step = sqrt(dx * dx + dy * dy);
+                double scale = 0.7;
+                if (step > 1000.0) { scale = 1000.0 / step * 0.7; tr[4] = 1.0; }
+                tr[3] = step;
+                x[0] += dx * scale;
+                x[1] += dy * scale;
+            }
+        }
+        if (status == 0) ecef_to_llh(x[0], x[1], x[2], o);
+    }
+    out_llh[0] = o[0]; out_llh[1] = o[1]; out_llh[2] = o[2];
+    info[0] = status; info[1] = nv; info[2] = n_iter; info[3] = converged;
+}
+
 // ---------------------------------------------------------------- least-squares fix
 // SURVEY.md 8f rank 4 (no reference equivalent; oracle: orc_solve_ls, same statement):
 // all P = S(S-1)/2 range differences, Levenberg-Marquardt in the local east/north/up
@@ -388,6 +456,12 @@ void launch_solve(const double *d_llh, const double *d_rd, int n_sets, int rd_st
 {
     if (n_sets <= 0) return;
     k_solve<<<(n_sets + 63) / 64, 64, 0, st>>>(d_llh, d_rd, n_sets, rd_stride, d_out_llh, d_status, d_iters);
+}
+
+void launch_solve_binary(const double *d_llh, const double *d_rd, int n_rd, double *d_out_llh, int *d_info, double *d_trace,
+                         cudaStream_t st)
+{
+    k_solve_binary<<<1, 32, 0, st>>>(d_llh, d_rd, n_rd, d_out_llh, d_info, d_trace);
 }
 
 // ProcessTDOA between the pair loops and the solver (processor.go:821, :853, :899-903; shipped

@@ -298,8 +298,10 @@ public:
         for (int k = 0; k < P; k++) rd[k] = td[k] * kSpeedOfLight;  // :899-903
         if (binary) {
             printf("\nTDOA triangulation:\n");
-            printf("Corrected time differences: %s\n", join(td, 1e6, "%.3f μs").c_str());
-            printf("Corrected distance differences: %s\n", join(rd, 1.0, "%.1f m").c_str());
+            // the binary prints the first three here, whatever the number of pairs
+            const std::vector<double> td3(td.begin(), td.begin() + 3), rd3(rd.begin(), rd.begin() + 3);
+            printf("Corrected time differences: %s\n", join(td3, 1e6, "%.3f μs").c_str());
+            printf("Corrected distance differences: %s\n", join(rd3, 1.0, "%.1f m").c_str());
             printf("\nDiagnostic test with example delays:\n");  // processor.go:885-889
             printf("Simulating 10 μs, 5 μs, -3 μs delays...\n");
             const double us[3] = {10.0, 5.0, -3.0};
@@ -312,9 +314,8 @@ public:
         for (double r : rd) printf("%.1f ", r);
         printf("\n");
         if (binary) {
-            // shipped binary: measurements beyond 1.2 x 17 km are dropped before its solver (which
-            // then aborts on every input, SURVEY.md finding 4; the fix printed below is processor.go's
-            // solveTDOA on the unfiltered differences)
+            // shipped binary: measurements beyond 1.2 x 17 km are dropped before its solver, which
+            // then works only with exactly two left (ELF 0x4a0360)
             printf("Validating range differences against baseline distances...\n");
             const double limit = 20400.0;
             int valid = 0;
@@ -327,21 +328,46 @@ public:
                     printf("This measurement is unreliable and will be excluded\n");
                 }
             }
-            if (valid == P) {
-                printf("Using %d of %d range difference measurements\n", valid, P);
-                double e[3][3];
-                for (int k = 0; k < 3; k++) ecef(st[k], e[k]);
-                const double area = 0.5 * std::fabs((e[1][0] - e[0][0]) * (e[2][1] - e[0][1]) - (e[2][0] - e[0][0]) * (e[1][1] - e[0][1]));
-                printf("Station geometry triangle area: %.1f m²\n", area);
-                printf("Initial guess: %.6f°, %.6f°, %.1fm\n", (st[0].latitude + st[1].latitude + st[2].latitude) / 3,
-                       (st[0].longitude + st[1].longitude + st[2].longitude) / 3, (st[0].elevation + st[1].elevation + st[2].elevation) / 3);
+            // the binary's own solveTDOA (ELF 0x4a0360) from here on: tdoa_solve_binary
+            if (valid < 2)
+                throw std::runtime_error(fmt("TDOA solution failed: insufficient valid measurements: only %d of %d range differences are reliable", valid, P));
+            printf("Using %d of %d range difference measurements\n", valid, P);
+            double e[3][3];
+            for (int k = 0; k < 3; k++) ecef(st[k], e[k]);
+            const double area = 0.5 * std::fabs((e[1][0] - e[0][0]) * (e[2][1] - e[0][1]) - (e[2][0] - e[0][0]) * (e[1][1] - e[0][1]));
+            printf("Station geometry triangle area: %.1f m²\n", area);
+            if (area < 1e7) {
+                printf("WARNING: Poor station geometry (small triangle area)\n");
+                printf("This may cause TDOA solution instability\n");
             }
+            printf("Initial guess: %.6f°, %.6f°, %.1fm\n", (st[0].latitude + st[1].latitude + st[2].latitude) / 3,
+                   (st[0].longitude + st[1].longitude + st[2].longitude) / 3, (st[0].elevation + st[1].elevation + st[2].elevation) / 3);
         }
         fflush(stdout);
         // the device did the same arithmetic (delay / fs, target - reference, * c) before its solveTDOA
         for (int k = 0; k < P; k++)
             if (rd[k] != dev_rd[k]) throw std::runtime_error(fmt("range difference %d: host %.17g, device %.17g", k, rd[k], dev_rd[k]));
-        if (fixStatus != 0) throw std::runtime_error("TDOA solution failed: singular Jacobian matrix");  // :997-999, :920
+        if (binary) {
+            int32_t bStatus = 0, nValid = 0, nIter = 0, conv = 0;
+            double trace[10][5];
+            check(tdoa_solve_binary(engine, llh.data(), S, rd.data(), P, fix, &bStatus, &nValid, &nIter, &conv, &trace[0][0]));
+            if (bStatus == 2) throw std::runtime_error("TDOA solution failed: no valid range difference measurements remain");
+            for (int k = 0; k < nIter; k++) {
+                const double *t = trace[k];
+                printf("Iteration %d: det=%.2e, residuals=[%.1f, %.1f]\n", k, t[0], t[1], t[2]);
+                const int code = (int)t[4];
+                if (code == 1) printf("Large step detected (%.1fm) - limiting to %.1fm\n", t[3], 1000.0 * (1000.0 / t[3] * 0.7));
+                if (code >= 2 || (bStatus == 3 && k == nIter - 1))
+                    printf("Singular matrix detected (det=%.2e) - trying alternative approach\n", t[0]);
+                if (code >= 2) printf("Using single equation approach (equation %d)\n", code - 1);
+                if (bStatus == 3 && k == nIter - 1)
+                    throw std::runtime_error(fmt("TDOA solution failed: singular Jacobian matrix at iteration %d (det=%.2e)", k, t[0]));
+                if (k == 9) printf("Maximum iterations reached\n");
+            }
+            if (conv) printf("Converged after %d iterations\n", nIter);
+        } else if (fixStatus != 0) {
+            throw std::runtime_error("TDOA solution failed: singular Jacobian matrix");  // :997-999, :920
+        }
         printf("\n*** CALCULATED TRANSMITTER LOCATION ***\n");
         printf("Latitude:  %.6f°\n", fix[0]);
         printf("Longitude: %.6f°\n", fix[1]);

@@ -281,8 +281,9 @@ class TDOAProcessor:
         rds = [td * SPEED_OF_LIGHT for td in tds]  # :899-903
         if binary:
             P("\nTDOA triangulation:")
-            P("Corrected time differences: " + ", ".join("%.3f μs" % (td * 1e6) for td in tds))
-            P("Corrected distance differences: " + ", ".join("%.1f m" % rd for rd in rds))
+            # the binary prints the first three here, whatever the number of pairs
+            P("Corrected time differences: " + ", ".join("%.3f μs" % (td * 1e6) for td in tds[:3]))
+            P("Corrected distance differences: " + ", ".join("%.1f m" % rd for rd in rds[:3]))
             P("\nDiagnostic test with example delays:")  # processor.go:885-889
             P("Simulating 10 μs, 5 μs, -3 μs delays...")
             for k, us in enumerate((10.0, 5.0, -3.0)):
@@ -303,16 +304,42 @@ class TDOAProcessor:
                 else:
                     P("FILTERING OUT: Range difference %d: %.1fm exceeds expected maximum %.1fm" % (k, rd, limit))
                     P("This measurement is unreliable and will be excluded")
-            if valid == len(rds):
-                P("Using %d of %d range difference measurements" % (valid, len(rds)))
-                e0, e1, e2 = (ecef(*s.llh) for s in stations[:3])
-                area = 0.5 * abs((e1[0] - e0[0]) * (e2[1] - e0[1]) - (e2[0] - e0[0]) * (e1[1] - e0[1]))
-                P("Station geometry triangle area: %.1f m²" % area)
-                m = llh[:3].mean(axis=0)
-                P("Initial guess: %.6f°, %.6f°, %.1fm" % (m[0], m[1], m[2]))
+            # the binary's own solveTDOA (ELF 0x4a0360) from here on: tdoa_solve_binary
+            if valid < 2:
+                raise RuntimeError("TDOA solution failed: insufficient valid measurements: only %d of %d range differences are reliable"
+                                   % (valid, len(rds)))
+            P("Using %d of %d range difference measurements" % (valid, len(rds)))
+            e0, e1, e2 = (ecef(*s.llh) for s in stations[:3])
+            area = 0.5 * abs((e1[0] - e0[0]) * (e2[1] - e0[1]) - (e2[0] - e0[0]) * (e1[1] - e0[1]))
+            P("Station geometry triangle area: %.1f m²" % area)
+            if area < 1e7:
+                P("WARNING: Poor station geometry (small triangle area)")
+                P("This may cause TDOA solution instability")
+            m = llh[:3].mean(axis=0)
+            P("Initial guess: %.6f°, %.6f°, %.1fm" % (m[0], m[1], m[2]))
         # same arithmetic on the device: dt = delay / fs, (target - reference), * c
         if self.mode in (N.MODE_SOURCE, N.MODE_BINARY):
             assert np.array_equal(np.asarray(rds, np.float64), done["range_differences"])
+        if binary:
+            pos, b_status, _, n_iter, conv, trace = eng.solve_binary(llh, np.asarray(rds, np.float64))
+            if b_status == 2:
+                raise RuntimeError("TDOA solution failed: no valid range difference measurements remain")
+            for k, t in enumerate(trace):
+                P("Iteration %d: det=%.2e, residuals=[%.1f, %.1f]" % (k, t[0], t[1], t[2]))
+                code, last = int(t[4]), b_status == 3 and k == n_iter - 1
+                if code == 1:
+                    P("Large step detected (%.1fm) - limiting to %.1fm" % (t[3], 1000.0 * (1000.0 / t[3] * 0.7)))
+                if code >= 2 or last:
+                    P("Singular matrix detected (det=%.2e) - trying alternative approach" % t[0])
+                if code >= 2:
+                    P("Using single equation approach (equation %d)" % (code - 1))
+                if last:
+                    raise RuntimeError("TDOA solution failed: singular Jacobian matrix at iteration %d (det=%.2e)" % (k, t[0]))
+                if k == 9:
+                    P("Maximum iterations reached")
+            if conv:
+                P("Converged after %d iterations" % n_iter)
+            done = dict(done, position=pos, status=0)
         if done["status"] != 0:
             raise RuntimeError("TDOA solution failed: singular Jacobian matrix")  # processor.go:997-999, :920
         lat, lon, elev = (float(x) for x in done["position"])

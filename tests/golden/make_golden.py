@@ -184,6 +184,42 @@ def case_empty_third():
     return _degenerate_third(np.zeros(0, np.uint8))
 
 
+def case_fm_reordered():
+    """The fm_delays captures given to the command in another order (n3pay, kf0mtl, kx0u): pairs
+    follow the order of the arguments, not of the station table (processor.go:816-817)."""
+    caps = case_fm_delays()
+    return {k: caps[k] for k in ("n3pay", "kf0mtl", "kx0u")}
+
+
+def case_fm_two_valid(B=30000):
+    """Exactly two valid range differences, close to the geometry of the start point: the one
+    input class on which the shipped binary's solver (ELF 0x4a0360) runs to convergence
+    (0.7-damped Newton steps, "Converged after 4 iterations") and prints a location.  Delays
+    REF (0, 930, 6) / TGT (0, 900, 0): the third pair's true delay is negative on both signals,
+    its peak is a spurious one far outside the 20.4 km limit."""
+    ref, tgt = fm(B + 2900, 60, 75e3), fm(B + 2900, 61, 60e3)
+    out = {}
+    for k, (name, dr, dt) in enumerate(zip(STATIONS, (0, 930, 6), (0, 900, 0))):
+        def blk(sig, d, seed):
+            g = np.random.default_rng(seed)
+            return sig[2600 - d:2600 - d + B] + 0.02 * (g.standard_normal(B) + 1j * g.standard_normal(B))
+        out[name] = quantise(np.concatenate([blk(ref, dr, 700 + k), blk(tgt, dt, 710 + k), blk(ref, dr, 720 + k)]))
+    return out
+
+
+def case_four_stations(B=30000):
+    """Four collectors (the table's KEVO as the fourth): six pairs per signal in i < j order; the
+    binary's validation and solver stages see six range differences."""
+    ref, tgt = fm(B + 600, 32, 75e3), fm(B + 600, 33, 60e3)
+    out = {}
+    for k, (name, dr, dt) in enumerate(zip(STATIONS + ["KEVO"], (0, 5, 11, 2), (0, 33, 14, 25))):
+        def blk(sig, d, seed):
+            g = np.random.default_rng(seed)
+            return sig[400 - d:400 - d + B] + 0.02 * (g.standard_normal(B) + 1j * g.standard_normal(B))
+        out[name] = quantise(np.concatenate([blk(ref, dr, 530 + k), blk(tgt, dt, 540 + k), blk(ref, dr, 550 + k)]))
+    return out
+
+
 def case_fm_close_lengths():
     """Lengths that differ by less than the 2000-lag search (blocks of 40000 / 40300 / 39800): the
     lag range shrinks to the length difference (processor.go:664-672) and true delays beyond it
@@ -226,6 +262,9 @@ CASES = {
     "fm_truncated": case_fm_truncated,
     "fm_uneven": case_fm_uneven,
     "fm_close_lengths": case_fm_close_lengths,
+    "fm_reordered": case_fm_reordered,
+    "four_stations": case_four_stations,
+    "fm_two_valid": case_fm_two_valid,
     "tiny_third": case_tiny_third,
     "three_sample_third": case_three_sample_third,
     "empty_third": case_empty_third,
@@ -272,7 +311,7 @@ def main(only=None):
         caps = fn()
         with tempfile.TemporaryDirectory() as td:
             paths = []
-            for st in STATIONS:
+            for st in caps:   # the order of the dictionary is the order of the arguments
                 p = Path(td) / f"sim-{st}-1.dat"
                 caps[st].tofile(p)
                 paths.append(p)
@@ -280,9 +319,11 @@ def main(only=None):
         parsed = parse_stdout(out)
         parsed["returncode"] = rc
         parsed["stderr_tail"] = err.strip().splitlines()[-1:] if err.strip() else []
-        assert len(parsed["pairs"]) == 6, (name, out[-2000:])
+        parsed["order"] = list(caps)
+        n_st = len(caps)
+        assert len(parsed["pairs"]) == n_st * (n_st - 1), (name, out[-2000:])
         if name in REGENERATED:
-            parsed["sha256"] = {st: hashlib.sha256(caps[st].tobytes()).hexdigest() for st in STATIONS}
+            parsed["sha256"] = {st: hashlib.sha256(caps[st].tobytes()).hexdigest() for st in caps}
         else:
             np.savez_compressed(HERE / f"{name}.npz", **caps)
         (HERE / f"{name}.json").write_text(json.dumps(parsed, indent=1, ensure_ascii=False) + "\n")

@@ -9,6 +9,8 @@ import numpy as np
 GOLDEN = Path(__file__).resolve().parent / "golden"
 STATIONS = ["kx0u", "n3pay", "kf0mtl"]
 GOLDEN_CASES = ["fm_strong", "fm_delays", "moderate", "weak_tones", "weak_noise", "fm_ragged", "fm_uneven", "fm_close_lengths"]
+# another argument order; four collectors (meta["order"] = the station of every capture): records and stdout
+GOLDEN_ORDER_CASES = ["fm_reordered", "four_stations", "fm_two_valid"]   # fm_reordered / fm_two_valid: the binary's solver gives a fix
 # degenerate third capture (2 samples / 3 samples / empty): records and stdout only
 GOLDEN_DEGENERATE_CASES = ["tiny_third", "three_sample_third", "empty_third"]
 # golden records whose captures are regenerated from their seeds (18 MB: not stored); 1 M-sample chunk
@@ -37,10 +39,10 @@ def load_golden(name: str):
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         caps = mod.CASES[name]()
-        for s in STATIONS:
+        for s in meta.get("order", STATIONS):
             if hashlib.sha256(caps[s].tobytes()).hexdigest() != meta["sha256"][s]:
                 pytest.skip(f"{name}: this numpy regenerates a different capture than the one the reference was run on")
-    raws = [np.ascontiguousarray(caps[s]) for s in STATIONS]
+    raws = [np.ascontiguousarray(caps[s]) for s in meta.get("order", STATIONS)]   # the order of the command's arguments
     return raws, meta
 
 

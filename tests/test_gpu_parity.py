@@ -13,7 +13,7 @@ import pytest
 
 import tdoa_b200 as T
 from oracle import oracle
-from helpers import GOLDEN, GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, STATION_LLH, fm_capture, load_golden, quantise
+from helpers import GOLDEN, GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, GOLDEN_ORDER_CASES, STATION_LLH, fm_capture, load_golden, quantise
 
 pytestmark = pytest.mark.gpu
 
@@ -406,6 +406,16 @@ def _same_line(a: str, b: str, tol: float = 1.5e-6) -> bool:
     return all(abs(float(x) - float(y)) <= tol * max(1.0, abs(float(y))) for x, y in zip(num.findall(a), num.findall(b)))
 
 
+def _same_outcome(failure, meta):
+    """The binary's own solver (ELF 0x4a0360) gives a fix only with exactly two valid range
+    differences; otherwise the command ends with its error text and status 1."""
+    want = [l[20:] for l in meta["stderr_tail"]]   # after the log time stamp
+    if meta["returncode"] == 0:
+        assert failure is None
+    else:
+        assert failure is not None and want == ["TDOA processing failed: " + failure]
+
+
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_processor_stdout_is_the_shipped_binarys(tmp_path, case):
     """the host mirror prints, line for line, what the reference's
@@ -419,15 +429,17 @@ def test_processor_stdout_is_the_shipped_binarys(tmp_path, case):
         files.append(str(f))
     buf = io.StringIO()
     p = T.TDOAProcessor(162400000.0, 92300000.0, str(GOLDEN / "stations.csv"), out=buf)
+    failure = None
     try:
         p.process_tdoa(files)
-    except RuntimeError:
-        pass  # a singular fix is an error in the source solver too; the stdout before it still counts
+    except RuntimeError as exc:
+        failure = str(exc)
     p.close()
+    _same_outcome(failure, meta)
     skip = "Loading I/Q data from:"
     ours = [l for l in buf.getvalue().splitlines() if not l.startswith(skip)]
     gold = [l for l in (GOLDEN / f"{case}.stdout.txt").read_text().splitlines() if not l.startswith(skip)]
-    assert len(ours) >= len(gold)
+    assert len(ours) == len(gold)
     for k, (a, b) in enumerate(zip(ours, gold)):
         assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
 
@@ -445,60 +457,105 @@ def test_cpp_host_mirror_stdout_is_the_shipped_binarys(tmp_path, case):
         files.append(str(f))
     exe = GOLDEN.parent.parent / "tdoa-geolocation_b200" / "processor_b200"
     r = subprocess.run([str(exe), "162400000", "92300000", str(GOLDEN / "stations.csv"), *files], capture_output=True, text=True)
-    assert r.returncode in (0, 1), r.stderr          # 1: singular fix, an error in the source solver too
-    if r.returncode == 1:
-        assert "singular Jacobian matrix" in r.stderr
-    else:
-        assert "*** CALCULATED TRANSMITTER LOCATION ***" in r.stdout
+    assert r.returncode == meta["returncode"], r.stderr
+    assert [l[20:] for l in r.stderr.splitlines()] == [l[20:] for l in meta["stderr_tail"]]
     skip = "Loading I/Q data from:"
     ours = [l for l in r.stdout.splitlines() if not l.startswith(skip)]
     gold = [l for l in (GOLDEN / f"{case}.stdout.txt").read_text().splitlines() if not l.startswith(skip)]
-    assert len(ours) >= len(gold)
+    assert len(ours) == len(gold)
     for k, (a, b) in enumerate(zip(ours, gold)):
         assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
 
 
-@pytest.mark.parametrize("case", GOLDEN_LONG_CASES + GOLDEN_DEGENERATE_CASES)
+@pytest.mark.parametrize("case", GOLDEN_LONG_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_ORDER_CASES)
 def test_blocks_longer_than_the_test_chunk(tmp_path, case):
     """Blocks of 1 050 000 samples: the shipped binary cuts REF and TGT to their first 1 000 000
     samples before the pair loops (processor.go:772-780).  Degenerate cases: a third capture of 2
     samples (returned unchanged as REF and TGT), of 3 samples (one-sample blocks), empty
-    (crossCorrelate warns and returns (0, 0.0)).  Records against what the binary
+    (crossCorrelate warns and returns (0, 0.0)).  Captures given in another order, and four
+    collectors: pairs i < j in the order of the arguments.  Records against what the binary
     printed (bit-exact lags, correlation to the printed 6 decimals), and the C++ command's
     stdout against the binary's, line for line."""
     import subprocess
     raws, meta = load_golden(case)
-    with T.Engine(T.MODE_BINARY) as e:
+    names = meta.get("order", ["kx0u", "n3pay", "kf0mtl"])
+    table = {row.split(",")[0]: [float(v) for v in row.split(",")[1:]]
+             for row in (GOLDEN / "stations.csv").read_text().splitlines()[1:]}
+    llh = np.array([table[n] for n in names])
+    with T.Engine(T.MODE_BINARY, n_stations=len(raws)) as e:
         load_all(e, raws)
-        r = e.process(STATION_LLH)
+        r = e.process(llh)
+    assert len(r["ref"]) + len(r["tgt"]) == len(meta["pairs"])
     for pk, gold in zip(list(r["ref"]) + list(r["tgt"]), meta["pairs"]):
         assert int(pk["lag"]) == gold["delay"], gold
         assert abs(float(pk["corr"]) - gold["corr"]) <= 0.5e-6 + CORR_TOL
     files = []
-    for name, raw in zip(["kx0u", "n3pay", "kf0mtl"], raws):
+    for name, raw in zip(names, raws):
         f = tmp_path / f"sim-{name}-1.dat"
         raw.tofile(f)
         files.append(str(f))
     exe = GOLDEN.parent.parent / "tdoa-geolocation_b200" / "processor_b200"
     out = subprocess.run([str(exe), "162400000", "92300000", str(GOLDEN / "stations.csv"), *files], capture_output=True, text=True)
-    assert out.returncode in (0, 1), out.stderr
+    assert out.returncode == meta["returncode"], out.stderr
+    assert [l[20:] for l in out.stderr.splitlines()] == [l[20:] for l in meta["stderr_tail"]]
     skip = "Loading I/Q data from:"
     ours = [l for l in out.stdout.splitlines() if not l.startswith(skip)]
     gold = [l for l in (GOLDEN / f"{case}.stdout.txt").read_text().splitlines() if not l.startswith(skip)]
-    assert len(ours) >= len(gold), out.stdout[-2000:]
+    assert len(ours) == len(gold), out.stdout[-2000:]
     for k, (a, b) in enumerate(zip(ours, gold)):
         assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
     buf = io.StringIO()
     p = T.TDOAProcessor(162400000.0, 92300000.0, str(GOLDEN / "stations.csv"), out=buf)
+    failure = None
     try:
         p.process_tdoa(files)
-    except RuntimeError:
-        pass
+    except RuntimeError as exc:
+        failure = str(exc)
     p.close()
+    _same_outcome(failure, meta)
     ours = [l for l in buf.getvalue().splitlines() if not l.startswith(skip)]
-    assert len(ours) >= len(gold)
+    assert len(ours) == len(gold)
     for k, (a, b) in enumerate(zip(ours, gold)):
         assert _same_line(a, b), f"python mirror, line {k}: ours {a!r} != reference {b!r}"
+
+
+def _check_binary_solver(eng, llh, rd):
+    got = eng.solve_binary(llh, rd)
+    want = oracle.solve_binary(llh, rd)
+    assert got[1:5] == want[1:5], (rd, got[1:5], want[1:5])           # status, n_valid, n_iter, converged
+    assert got[5].shape == want[5].shape
+    if len(want[5]):
+        assert np.array_equal(got[5][:, 4], want[5][:, 4])             # which branch every iteration took
+        assert np.allclose(got[5][:, :4], want[5][:, :4], rtol=1e-9, atol=1e-9)
+    assert np.allclose(got[0][:2], want[0][:2], rtol=0, atol=1e-10) and abs(got[0][2] - want[0][2]) <= 1e-5
+    return want
+
+
+def test_binary_solver_equals_oracle(eng_binary):
+    """tdoa_solve_binary (solveTDOA of the shipped binary, ELF 0x4a0360) against orc_solve_binary --
+    itself pinned by the binary's printed traces (tests/test_oracle_golden.py) -- over all its
+    branches: fewer / more than two valid measurements, limited and damped steps, convergence,
+    ten iterations and both single-equation fall-backs."""
+    rng = np.random.default_rng(12)
+    seen = set()
+    for _ in range(60):
+        rd = rng.uniform(-30000.0, 30000.0, 3)
+        if rng.random() < 0.5:
+            rd[rng.integers(3)] = 25000.0 + rng.uniform(0, 1e4)        # one filtered: the solver runs
+        if rng.random() < 0.3:
+            rd[:2] = np.array([-4450.9, -952.5]) + rng.normal(0, 200.0, 2)   # near the start point: converges
+            rd[2] = 4e4
+        w = _check_binary_solver(eng_binary, STATION_LLH, rd)
+        seen.add((w[1], w[4], bool(len(w[5]) and (w[5][:, 4] == 1).any()), w[3] == 10))
+    assert {s[0] for s in seen} == {0, 1, 2} and any(s[1] for s in seen) and any(s[2] for s in seen) and any(s[3] for s in seen)
+    back = np.array([STATION_LLH[0], STATION_LLH[1], STATION_LLH[0]])
+    w = _check_binary_solver(eng_binary, back, [100.0, 300.0, 5e4])                        # det = 0: equation 1 alone
+    assert w[1] == 0 and (w[5][:, 4] == 2).all()
+    twin = np.array([STATION_LLH[0], STATION_LLH[1], STATION_LLH[1]])
+    w = _check_binary_solver(eng_binary, twin, [100.0, 300.0, 5e4])                        # det = 0: equation 2 alone
+    assert w[1] == 0 and (w[5][:, 4] == 3).all()
+    four = np.vstack([STATION_LLH, [[41.30888549464701, -96.02619229605524, 356.0]]])
+    assert _check_binary_solver(eng_binary, four, [100.0, 5e4, 5e4, 5e4, -200.0, 5e4])[2] == 2   # six measurements, two valid
 
 
 def _cli_engine_cases():

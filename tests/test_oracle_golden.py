@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from helpers import GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, STATION_LLH, load_golden
+from helpers import GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, GOLDEN_ORDER_CASES, STATION_LLH, load_golden
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -21,13 +21,15 @@ def test_binary_pairs_match_reference_stdout(case):
         assert abs(corr - want["corr"]) <= 0.51e-6, (case, corr, want)
 
 
-@pytest.mark.parametrize("case", GOLDEN_DEGENERATE_CASES)
+@pytest.mark.parametrize("case", GOLDEN_DEGENERATE_CASES + GOLDEN_ORDER_CASES)
 def test_binary_degenerate_captures(case):
     """A capture of 2 samples (returned unchanged as REF and TGT), of 3 samples (one-sample
-    blocks) and an empty one: the records the binary printed."""
+    blocks) and an empty one; captures given in another order; four collectors (pairs i < j in
+    the order of the arguments, processor.go:816-817): the records the binary printed."""
     raws, meta = load_golden(case)
     ref, tgt = oracle.process_capture_binary(raws)
     got = [("REF",) + r for r in ref] + [("TGT",) + r for r in tgt]
+    assert len(got) == len(meta["pairs"]) == len(raws) * (len(raws) - 1)
     for (kind, delay, corr, _), want in zip(got, meta["pairs"]):
         assert (kind, delay) == (want["kind"], want["delay"]), (case, want)
         assert abs(corr - want["corr"]) <= 0.51e-6, (case, corr, want)
@@ -66,6 +68,60 @@ def test_binary_preprocess_diagnostics(case):
         assert abs(p - p_want) <= 0.51e-9 * max(1.0, abs(p_want) / 1e-9 * 1e-9) + 1e-9
         _, br = oracle.preprocess_binary(s)
         assert br == br_want
+
+
+def _golden_solver_inputs(case):
+    import json
+    from helpers import GOLDEN, STATIONS
+    meta = json.loads((GOLDEN / f"{case}.json").read_text())
+    names = meta.get("order", STATIONS)
+    table = {row.split(",")[0]: [float(v) for v in row.split(",")[1:]]
+             for row in (GOLDEN / "stations.csv").read_text().splitlines()[1:]}
+    llh = np.array([table[n] for n in names])
+    P = len(names) * (len(names) - 1) // 2
+    ref = [q["delay"] for q in meta["pairs"][:P]]
+    tgt = [q["delay"] for q in meta["pairs"][P:]]
+    rd = [(t / 2e6 - r / 2e6) * 299792458.0 for t, r in zip(tgt, ref)]   # the binary's correction, then * c
+    return meta, llh, rd, (GOLDEN / f"{case}.stdout.txt").read_text()
+
+
+ALL_GOLDEN = GOLDEN_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_LONG_CASES + GOLDEN_ORDER_CASES
+
+
+@pytest.mark.parametrize("case", ALL_GOLDEN)
+def test_binary_solver_outcome_and_trace(case):
+    """solveTDOA of the shipped binary (ELF 0x4a0360, orc_solve_binary) against what the binary
+    printed for every golden capture: which of its three outcomes (fewer than two valid range
+    differences / more than two / a fix), every "Iteration k: det=..., residuals=[...]" line, every
+    "Large step detected" line, the convergence line and the location to the printed digits."""
+    import re
+    meta, llh, rd, text = _golden_solver_inputs(case)
+    out, status, n_valid, n_iter, conv, trace = oracle.solve_binary(llh, rd)
+    err = meta["stderr_tail"][0][20:] if meta["stderr_tail"] else ""
+    assert n_valid == sum(1 for l in text.splitlines() if l.startswith("VALID: Range difference"))
+    if status == 1:
+        assert err == ("TDOA processing failed: TDOA solution failed: insufficient valid measurements: only %d of %d "
+                       "range differences are reliable" % (n_valid, len(rd)))
+        return
+    if status == 2:
+        assert err == "TDOA processing failed: TDOA solution failed: no valid range difference measurements remain"
+        assert "Iteration 0" not in text
+        return
+    assert status == 0 and meta["returncode"] == 0
+    lines = ["Iteration %d: det=%.2e, residuals=[%.1f, %.1f]" % (k, t[0], t[1], t[2]) for k, t in enumerate(trace)]
+    assert lines == [l for l in text.splitlines() if l.startswith("Iteration ")]
+    big = ["Large step detected (%.1fm) - limiting to %.1fm" % (t[3], 1000.0 * (1000.0 / t[3] * 0.7)) for t in trace if t[4] == 1]
+    assert big == [l for l in text.splitlines() if l.startswith("Large step detected")]
+    assert ("Converged after %d iterations" % n_iter in text) == conv
+    assert ("Maximum iterations reached" in text) == (n_iter == 10)
+    lat, lon, elev = (float(re.search(p, text).group(1)) for p in
+                      (r"Latitude:\s+(-?[\d.]+)°", r"Longitude:\s+(-?[\d.]+)°", r"Elevation:\s+(-?[\d.]+) m"))
+    assert "%.6f" % out[0] == "%.6f" % lat and "%.6f" % out[1] == "%.6f" % lon and "%.1f" % out[2] == "%.1f" % elev
+
+
+def test_binary_solver_gives_a_fix_on_two_goldens():
+    fixes = [c for c in ALL_GOLDEN if _golden_solver_inputs(c)[0]["returncode"] == 0]
+    assert sorted(fixes) == ["fm_reordered", "fm_two_valid"]   # ten limited steps / four damped steps to convergence
 
 
 def test_baselines_known_answers():
