@@ -379,16 +379,24 @@ def test_processor_mirror_stdout(tmp_path):
         f = tmp_path / f"sim-{name}-1.dat"
         raw.tofile(f)
         files.append(str(f))
+    # the binary's revision: its own solver refuses three valid measurements (ELF 0x4a0360)
     buf = io.StringIO()
     p = T.TDOAProcessor(162400000.0, 92300000.0, str(GOLDEN / "stations.csv"), out=buf)
-    res = p.process_tdoa(files)
+    with pytest.raises(RuntimeError, match="TDOA solution failed: no valid range difference measurements remain"):
+        p.process_tdoa(files)
     p.close()
     text = buf.getvalue()
     gold = (GOLDEN / "fm_strong.stdout.txt").read_text()
     for line in gold.splitlines():
         if line.startswith(("REF ", "TGT ")) or line.endswith(" km"):
             assert line in text, line
-    assert "*** CALCULATED TRANSMITTER LOCATION ***" in text
+    assert "*** CALCULATED TRANSMITTER LOCATION ***" not in text
+    # processor.go as committed: solveTDOA on the target differences (processor.go:853, :932-1020)
+    buf = io.StringIO()
+    p = T.TDOAProcessor(162400000.0, 92300000.0, str(GOLDEN / "stations.csv"), mode=T.MODE_SOURCE, out=buf)
+    res = p.process_tdoa(files)
+    p.close()
+    assert "*** CALCULATED TRANSMITTER LOCATION ***" in buf.getvalue()
     rd = np.array(res["range_differences"])
     want, status, _ = oracle.solve_tdoa(STATION_LLH, rd)
     assert status == 0 and np.allclose(res["position"], want, atol=1e-9)
