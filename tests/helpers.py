@@ -11,6 +11,9 @@ STATIONS = ["kx0u", "n3pay", "kf0mtl"]
 GOLDEN_CASES = ["fm_strong", "fm_delays", "moderate", "weak_tones", "weak_noise", "fm_ragged", "fm_uneven", "fm_close_lengths"]
 # another argument order; four collectors (meta["order"] = the station of every capture): records and stdout
 GOLDEN_ORDER_CASES = ["fm_reordered", "four_stations", "fm_two_valid"]   # fm_reordered / fm_two_valid: the binary's solver gives a fix
+# fm_two_valid's captures with other station tables (meta["csv"]): the solver's single-equation fall-back
+# (coincident stations, det = 0) and the poor-geometry warning
+GOLDEN_TABLE_CASES = ["twin_stations", "back_stations", "close_stations"]
 # degenerate third capture (2 samples / 3 samples / empty): records and stdout only
 GOLDEN_DEGENERATE_CASES = ["tiny_third", "three_sample_third", "empty_third"]
 # golden records whose captures are regenerated from their seeds (18 MB: not stored); 1 M-sample chunk
@@ -27,8 +30,9 @@ STATION_LLH = np.array([
 
 def load_golden(name: str):
     meta = json.loads((GOLDEN / f"{name}.json").read_text())
-    if (GOLDEN / f"{name}.npz").exists():
-        caps = np.load(GOLDEN / f"{name}.npz")
+    stored = meta.get("captures", name)   # some cases share another case's captures
+    if (GOLDEN / f"{stored}.npz").exists():
+        caps = np.load(GOLDEN / f"{stored}.npz")
     else:
         # regenerated from the seeds in tests/golden/make_golden.py; the .json keeps the SHA-256 of
         # what the reference binary was run on (a different numpy stream would be a different capture)

@@ -13,7 +13,7 @@ import pytest
 
 import tdoa_b200 as T
 from oracle import oracle
-from helpers import GOLDEN, GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, GOLDEN_ORDER_CASES, STATION_LLH, fm_capture, load_golden, quantise
+from helpers import GOLDEN, GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, GOLDEN_ORDER_CASES, GOLDEN_TABLE_CASES, STATION_LLH, fm_capture, load_golden, quantise
 
 pytestmark = pytest.mark.gpu
 
@@ -475,20 +475,22 @@ def test_cpp_host_mirror_stdout_is_the_shipped_binarys(tmp_path, case):
         assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
 
 
-@pytest.mark.parametrize("case", GOLDEN_LONG_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_ORDER_CASES)
+@pytest.mark.parametrize("case", GOLDEN_LONG_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_ORDER_CASES + GOLDEN_TABLE_CASES)
 def test_blocks_longer_than_the_test_chunk(tmp_path, case):
     """Blocks of 1 050 000 samples: the shipped binary cuts REF and TGT to their first 1 000 000
     samples before the pair loops (processor.go:772-780).  Degenerate cases: a third capture of 2
     samples (returned unchanged as REF and TGT), of 3 samples (one-sample blocks), empty
     (crossCorrelate warns and returns (0, 0.0)).  Captures given in another order, and four
-    collectors: pairs i < j in the order of the arguments.  Records against what the binary
+    collectors: pairs i < j in the order of the arguments.  Station tables with coincident or
+    close stations: the solver's single-equation fall-back and poor-geometry warning.  Records against what the binary
     printed (bit-exact lags, correlation to the printed 6 decimals), and the C++ command's
     stdout against the binary's, line for line."""
     import subprocess
     raws, meta = load_golden(case)
     names = meta.get("order", ["kx0u", "n3pay", "kf0mtl"])
+    csv_file = str(GOLDEN / meta.get("csv", "stations.csv"))
     table = {row.split(",")[0]: [float(v) for v in row.split(",")[1:]]
-             for row in (GOLDEN / "stations.csv").read_text().splitlines()[1:]}
+             for row in open(csv_file).read().splitlines()[1:]}
     llh = np.array([table[n] for n in names])
     with T.Engine(T.MODE_BINARY, n_stations=len(raws)) as e:
         load_all(e, raws)
@@ -503,7 +505,7 @@ def test_blocks_longer_than_the_test_chunk(tmp_path, case):
         raw.tofile(f)
         files.append(str(f))
     exe = GOLDEN.parent.parent / "tdoa-geolocation_b200" / "processor_b200"
-    out = subprocess.run([str(exe), "162400000", "92300000", str(GOLDEN / "stations.csv"), *files], capture_output=True, text=True)
+    out = subprocess.run([str(exe), "162400000", "92300000", csv_file, *files], capture_output=True, text=True)
     assert out.returncode == meta["returncode"], out.stderr
     assert [l[20:] for l in out.stderr.splitlines()] == [l[20:] for l in meta["stderr_tail"]]
     skip = "Loading I/Q data from:"
@@ -513,7 +515,7 @@ def test_blocks_longer_than_the_test_chunk(tmp_path, case):
     for k, (a, b) in enumerate(zip(ours, gold)):
         assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
     buf = io.StringIO()
-    p = T.TDOAProcessor(162400000.0, 92300000.0, str(GOLDEN / "stations.csv"), out=buf)
+    p = T.TDOAProcessor(162400000.0, 92300000.0, csv_file, out=buf)
     failure = None
     try:
         p.process_tdoa(files)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from helpers import GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, GOLDEN_ORDER_CASES, STATION_LLH, load_golden
+from helpers import GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, GOLDEN_ORDER_CASES, GOLDEN_TABLE_CASES, STATION_LLH, load_golden
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -76,7 +76,7 @@ def _golden_solver_inputs(case):
     meta = json.loads((GOLDEN / f"{case}.json").read_text())
     names = meta.get("order", STATIONS)
     table = {row.split(",")[0]: [float(v) for v in row.split(",")[1:]]
-             for row in (GOLDEN / "stations.csv").read_text().splitlines()[1:]}
+             for row in (GOLDEN / meta.get("csv", "stations.csv")).read_text().splitlines()[1:]}
     llh = np.array([table[n] for n in names])
     P = len(names) * (len(names) - 1) // 2
     ref = [q["delay"] for q in meta["pairs"][:P]]
@@ -85,7 +85,7 @@ def _golden_solver_inputs(case):
     return meta, llh, rd, (GOLDEN / f"{case}.stdout.txt").read_text()
 
 
-ALL_GOLDEN = GOLDEN_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_LONG_CASES + GOLDEN_ORDER_CASES
+ALL_GOLDEN = GOLDEN_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_LONG_CASES + GOLDEN_ORDER_CASES + GOLDEN_TABLE_CASES
 
 
 @pytest.mark.parametrize("case", ALL_GOLDEN)
@@ -112,6 +112,10 @@ def test_binary_solver_outcome_and_trace(case):
     assert lines == [l for l in text.splitlines() if l.startswith("Iteration ")]
     big = ["Large step detected (%.1fm) - limiting to %.1fm" % (t[3], 1000.0 * (1000.0 / t[3] * 0.7)) for t in trace if t[4] == 1]
     assert big == [l for l in text.splitlines() if l.startswith("Large step detected")]
+    single = ["Using single equation approach (equation %d)" % (t[4] - 1) for t in trace if t[4] >= 2]
+    assert single == [l for l in text.splitlines() if l.startswith("Using single equation approach")]
+    singular = ["Singular matrix detected (det=%.2e) - trying alternative approach" % t[0] for t in trace if t[4] >= 2]
+    assert singular == [l for l in text.splitlines() if l.startswith("Singular matrix detected")]
     assert ("Converged after %d iterations" % n_iter in text) == conv
     assert ("Maximum iterations reached" in text) == (n_iter == 10)
     lat, lon, elev = (float(re.search(p, text).group(1)) for p in
@@ -119,9 +123,10 @@ def test_binary_solver_outcome_and_trace(case):
     assert "%.6f" % out[0] == "%.6f" % lat and "%.6f" % out[1] == "%.6f" % lon and "%.1f" % out[2] == "%.1f" % elev
 
 
-def test_binary_solver_gives_a_fix_on_two_goldens():
+def test_binary_solver_gives_a_fix_on_five_goldens():
     fixes = [c for c in ALL_GOLDEN if _golden_solver_inputs(c)[0]["returncode"] == 0]
-    assert sorted(fixes) == ["fm_reordered", "fm_two_valid"]   # ten limited steps / four damped steps to convergence
+    # ten limited steps / four damped steps to convergence / single equation 1 and 2 / poor geometry
+    assert sorted(fixes) == ["back_stations", "close_stations", "fm_reordered", "fm_two_valid", "twin_stations"]
 
 
 def test_baselines_known_answers():
