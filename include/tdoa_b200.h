@@ -174,7 +174,9 @@ TDOA_API int tdoa_xcorr_device(tdoa_engine *e, int32_t kind, int64_t win_start, 
  * pair by pair), range differences (:899-903) and solveTDOA -- all queued on the device
  * without an intermediate host synchronisation.  ref_out / tgt_out [P]; time_diffs,
  * range_diffs [P] (may be NULL); fix_llh[3]; *fix_status 0 or TDOA_E_SINGULAR.
- * tdoa_xcorr_info() afterwards reports both kinds. */
+ * The fix is processor.go's solveTDOA (:932-1020) on rd[0], rd[1] in every mode; the shipped
+ * binary's own revision of the solver (filter, exactly-two rule) is tdoa_solve_binary on the
+ * range_diffs returned here.  tdoa_xcorr_info() afterwards reports both kinds. */
 TDOA_API int tdoa_process(tdoa_engine *e, const double *stations_llh, tdoa_peak *ref_out, tdoa_peak *tgt_out,
                           double *time_diffs, double *range_diffs, double *fix_llh, int32_t *fix_status,
                           int32_t *fix_iters);
