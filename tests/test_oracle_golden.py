@@ -88,26 +88,21 @@ def _golden_solver_inputs(case):
 ALL_GOLDEN = GOLDEN_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_LONG_CASES + GOLDEN_ORDER_CASES + GOLDEN_TABLE_CASES
 
 
-@pytest.mark.parametrize("case", ALL_GOLDEN)
-def test_binary_solver_outcome_and_trace(case):
-    """solveTDOA of the shipped binary (ELF 0x4a0360, orc_solve_binary) against what the binary
-    printed for every golden capture: which of its three outcomes (fewer than two valid range
-    differences / more than two / a fix), every "Iteration k: det=..., residuals=[...]" line, every
-    "Large step detected" line, the convergence line and the location to the printed digits."""
+def check_binary_solver_against_stdout(llh, rd, text, returncode, err):
+    """orc_solve_binary against what the binary printed (text) and how it ended (returncode, err =
+    its stderr line after the time stamp): outcome, iteration trace, every branch line, location."""
     import re
-    meta, llh, rd, text = _golden_solver_inputs(case)
     out, status, n_valid, n_iter, conv, trace = oracle.solve_binary(llh, rd)
-    err = meta["stderr_tail"][0][20:] if meta["stderr_tail"] else ""
     assert n_valid == sum(1 for l in text.splitlines() if l.startswith("VALID: Range difference"))
     if status == 1:
         assert err == ("TDOA processing failed: TDOA solution failed: insufficient valid measurements: only %d of %d "
                        "range differences are reliable" % (n_valid, len(rd)))
-        return
+        return status
     if status == 2:
         assert err == "TDOA processing failed: TDOA solution failed: no valid range difference measurements remain"
         assert "Iteration 0" not in text
-        return
-    assert status == 0 and meta["returncode"] == 0
+        return status
+    assert status == 0 and returncode == 0
     lines = ["Iteration %d: det=%.2e, residuals=[%.1f, %.1f]" % (k, t[0], t[1], t[2]) for k, t in enumerate(trace)]
     assert lines == [l for l in text.splitlines() if l.startswith("Iteration ")]
     big = ["Large step detected (%.1fm) - limiting to %.1fm" % (t[3], 1000.0 * (1000.0 / t[3] * 0.7)) for t in trace if t[4] == 1]
@@ -121,6 +116,19 @@ def test_binary_solver_outcome_and_trace(case):
     lat, lon, elev = (float(re.search(p, text).group(1)) for p in
                       (r"Latitude:\s+(-?[\d.]+)°", r"Longitude:\s+(-?[\d.]+)°", r"Elevation:\s+(-?[\d.]+) m"))
     assert "%.6f" % out[0] == "%.6f" % lat and "%.6f" % out[1] == "%.6f" % lon and "%.1f" % out[2] == "%.1f" % elev
+    return status
+
+
+@pytest.mark.parametrize("case", ALL_GOLDEN)
+def test_binary_solver_outcome_and_trace(case):
+    """solveTDOA of the shipped binary (ELF 0x4a0360, orc_solve_binary) against what the binary
+    printed for every golden capture: which of its three outcomes (fewer than two valid range
+    differences / more than two / a fix), every "Iteration k: det=..., residuals=[...]" line, every
+    "Large step detected" / single-equation line, the convergence line and the location to the
+    printed digits."""
+    meta, llh, rd, text = _golden_solver_inputs(case)
+    err = meta["stderr_tail"][0][20:] if meta["stderr_tail"] else ""
+    check_binary_solver_against_stdout(llh, rd, text, meta["returncode"], err)
 
 
 def test_binary_solver_gives_a_fix_on_five_goldens():
