@@ -144,7 +144,10 @@ TDOA_API int tdoa_load_file(tdoa_engine *e, int32_t station, const char *path, i
  * transfer.  The buffer must stay unchanged until tdoa_synchronize() returns or both
  * kinds have been correlated.  Captures under 384 KiB are copied synchronously. */
 TDOA_API int tdoa_load_u8_pinned(tdoa_engine *e, int32_t station, const uint8_t *pinned_iq, size_t nbytes);
-/* Same, capture already resident in device memory; not copied, caller keeps it alive. */
+/* Same, capture already resident in device memory; not copied, caller keeps it alive.
+ * d_iq must be 16-byte aligned (cudaMalloc memory is; an offset into a buffer may not be):
+ * the unpack / discriminator kernels fetch the capture in 16-byte words.  A misaligned
+ * pointer is rejected with TDOA_E_INVALID. */
 TDOA_API int tdoa_load_u8_device(tdoa_engine *e, int32_t station, const uint8_t *d_iq, size_t nbytes);
 
 /* loadIQData parity probe (processor.go:193-201): complex64 samples

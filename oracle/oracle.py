@@ -51,6 +51,7 @@ def lib():
         L.orc_remove_dc.argtypes = [_vp, _i64, _vp, _vp]
         L.orc_set_seq_dc_limit.argtypes = [_i64]
         L.orc_lowpass.argtypes = [_vp, _i64, C.c_int, _vp]
+        L.orc_set_wide_boxcar_f64.argtypes = [C.c_int]
         L.orc_cutoff_window.argtypes = [_f64, _f64]
         L.orc_cutoff_window.restype = C.c_int
         L.orc_bandpass.argtypes = [_vp, _i64, _f64, _f64, _f64, _vp]
@@ -137,6 +138,12 @@ def set_seq_dc_limit(n: int) -> None:
     """Signals longer than n samples get an exactly rounded DC sum (engine-defined
     extension, see tdoa_oracle.c); n < 0 restores the reference's arithmetic."""
     lib().orc_set_seq_dc_limit(int(n))
+
+
+def set_wide_boxcar_f64(min_window: int) -> None:
+    """EXTENDED mode's arithmetic (engine-defined): box-cars of >= min_window taps accumulate in
+    f64 and round once; 0 restores the reference's f32 tap walk."""
+    lib().orc_set_wide_boxcar_f64(int(min_window))
 
 
 def lowpass(s, window: int):
@@ -379,6 +386,144 @@ def process_capture_source(raws, chunk=2_000_000):
         for j in range(i + 1, n):
             out_tgt.append(cross_correlate_source(tgts[i], tgts[j]))
     return out_ref, out_tgt
+
+
+def source_stdout(dat_files, names, station_rows, raws, ref_station_row, target_freq, n_table_rows, chunk=2_000_000):
+    """What processor.go AS COMMITTED prints for a run (ProcessTDOA :739-929 and everything it
+    calls), restated print statement by print statement with the numbers of this oracle.  The
+    source cannot be run here (no Go toolchain): "parity unpinned" -- but every line it shares with
+    the shipped binary (most of them) has the format the binary's golden stdout pins.
+    dat_files: the command's file arguments; names / station_rows: station name and (lat, lon, elev)
+    of each, in argument order; returns (text, error message or None)."""
+    o = []
+    P = o.append
+    P("Loaded %d stations including reference %.0f MHz" % (n_table_rows, float(ref_station_row[0]) / 1e6))   # :105
+    P("Processing TDOA for target frequency %.3f MHz" % (target_freq / 1e6))                                # :744
+    P("Reference: %s at %.6f°, %.6f°, %.1fm" % tuple(ref_station_row))                                      # :745
+    refs, tgts = [], []
+    for f, name, row, raw in zip(dat_files, names, station_rows, raws):
+        n = raw.size // 2
+        P("Loading I/Q data from: %s" % f)                                   # :167
+        P("File size: %d bytes, samples: %d" % (raw.size, n))                # :184
+        P("Successfully loaded %d complex samples" % n)                      # :203
+        data = unpack_u8(raw)
+        b = n // 3
+        for what, kind in (("reference", "reference samples from blocks 1 and 3"), ("target", "target samples from block 2")):
+            P("Extracting %s signal from dual-frequency data" % what)       # :209, :242
+            if n < 3:
+                P("Warning: Data too small for dual-frequency extraction")  # :217, :251
+            else:
+                P("Total samples: %d, block size: %d" % (n, b))             # :221, :255
+                P("Extracted %d %s" % (2 * b if what == "reference" else b, kind))   # :236, :265
+        r, t = extract_reference(data), extract_target(data)
+        if r.size > chunk:
+            r = r[:chunk]
+            P("Using test chunk: %d samples (%.1f ms)" % (chunk, chunk / 2e6 * 1000))          # :775
+        if t.size > chunk:
+            t = t[:chunk]
+            P("Using target test chunk: %d samples (%.1f ms)" % (chunk, chunk / 2e6 * 1000))   # :779
+        P("Coherent integration time: %.0f ms (expecting ~%.1f dB processing gain)"
+          % (chunk / 2e6 * 1000, 10 * np.log10(chunk / 100000)))                              # :782
+        refs.append(r)
+        tgts.append(t)
+        P("Loaded collector: %s at %.6f°, %.6f°, %.1fm" % (name, row[0], row[1], row[2]))      # :797
+    S = len(raws)
+    pairs = [(i, j) for i in range(S) for j in range(i + 1, S)]
+    P("\nBaseline distances (3D):")                                          # :802
+    for i, j in pairs:
+        P("%s - %s: %.2f km" % (names[i], names[j], baseline(station_rows[i], station_rows[j]) / 1000))   # :806
+
+    bp = "Bandpass filter: %.1f - %.1f Hz (at %.0f Hz sample rate)"          # :359
+
+    def preprocess(sig, label):                                              # :469-499
+        P("Preprocessing %s signal (%d samples)" % (label, sig.size))
+        p0 = signal_power(sig)
+        P("Initial signal power: %.9f" % p0)
+        fs = 2000000.0
+        if p0 < 0.001:
+            P("Detected very weak signal - applying aggressive filtering")
+            P("Enhancing weak signal: %s" % label)                          # :438
+            x, dc = remove_dc(sig)
+            P("Removed DC bias: %.6f + %.6fi" % (dc.real, dc.imag))         # :317
+            for f0, bw in ((60, 5), (120, 5), (1000000, 50000)):            # :446-448
+                P(bp % (max(f0 - bw / 2, 0), min(f0 + bw / 2, fs / 2), fs))
+                x = notch(x, f0, bw, fs)
+            P(bp % (100.0, 40000.0, fs))
+            x = bandpass(x, 100.0, 40000.0, fs)
+            x = lowpass(x, 50)
+        else:
+            P("Standard signal processing")
+            x, dc = remove_dc(sig)
+            P("Removed DC bias: %.6f + %.6fi" % (dc.real, dc.imag))
+            P(bp % (500.0, 50000.0, fs))
+            x = bandpass(x, 500.0, 50000.0, fs)
+            x = lowpass(x, 100)
+        y, p1 = normalize(x)
+        if p1 > 0:                                                           # :338-340
+            P("Normalized signal power: %.6f → 1.000000" % p1)
+        return y
+
+    def cross(s1, s2):                                                       # :619-643
+        P("=== Cross-Correlation Analysis ===")
+        if s1.size == 0 or s2.size == 0:
+            P("Warning: Empty signals for correlation")
+            return 0, 0.0
+        P("\n--- Signal Preprocessing ---")
+        y1, y2 = preprocess(s1, "Signal 1"), preprocess(s2, "Signal 2")
+        P("\n--- Time Domain Correlation ---")
+        P("Performing time domain correlation")                             # :647
+        tl, sl = min(y1.size, y2.size), max(y1.size, y2.size)
+        P("Template: %d samples, Signal: %d samples" % (tl, sl))            # :660
+        ml = max(1, min(20000, sl - tl))                                     # :668-675
+        P("Using coherent integration with %d-sample blocks" % 1000)        # :684
+        nb = 0 if tl <= 1000 else (tl - 1000 + 999) // 1000                  # blocks of `for bs = 0; bs < tl - 1000; bs += 1000`
+        prog = "".join("Time domain progress: %d/%d (coherent blocks: %d)\r" % (d, ml, nb) for d in range(0, ml, 2000))   # :729-731
+        d, c = tdcorr_source(y1, y2)
+        P(prog + "\nTime domain correlation: %.6f at delay %d samples" % (c, d))   # :734
+        P("\n--- Result: Time Domain with Preprocessing ---")               # :639
+        P("Correlation: %.6f at delay %d samples" % (c, d))                 # :640
+        return d, c
+
+    tds = {}
+    for label, sigs, head, sub in (("REF", refs, "REFERENCE", "Testing weak 162.4 MHz NOAA weather signal:"),
+                                   ("TGT", tgts, "TARGET", "Testing strong 92.3 MHz FM broadcast signal:")):
+        P("\n=== %s SIGNAL CORRELATION TEST ===" % head)                     # :812, :832
+        P(sub)                                                               # :813, :833
+        tds[label] = []
+        for i, j in pairs:
+            d, c = cross(sigs[i], sigs[j])
+            td = float(d) / 2e6                                              # :821
+            tds[label].append(td)
+            P("%s %s - %s: delay=%d samples (%.3f μs), correlation=%.6f" % (label, names[i], names[j], d, td * 1e6, c))
+    td = tds["TGT"]                                                          # :853
+    P("\n=== CORRELATION COMPARISON ===")
+    P("Reference signal (162.4 MHz): Generally weaker correlation")
+    P("Target signal (92.3 MHz): Should show stronger correlation")
+    P("Using target signal for TDOA calculation")
+    P("\nTDOA triangulation:")
+    P("Time differences: %.3f μs, %.3f μs, %.3f μs" % (td[0] * 1e6, td[1] * 1e6, td[2] * 1e6))   # :869
+    c0 = 299792458.0
+    P("Distance differences: %.1f m, %.1f m, %.1f m" % (td[0] * c0, td[1] * c0, td[2] * c0))     # :878
+    P("\nDiagnostic test with example delays:")
+    P("Simulating 10 μs, 5 μs, -3 μs delays...")
+    for k, dl in enumerate((10e-6, 5e-6, -3e-6)):
+        P("Test delay %d: %.1f μs → %.1f m" % (k + 1, dl * 1e6, dl * c0))   # :888
+    P("\n=== TDOA GEOLOCATION ===")
+    rd = [t * c0 for t in td]
+    P("Time differences (μs): " + "".join("%.3f " % (t * 1e6) for t in td))
+    P("Range differences (m): " + "".join("%.1f " % r for r in rd))
+    m = np.asarray(station_rows[:3], np.float64)
+    P("Initial guess: %.6f°, %.6f°, %.1fm" % ((m[0, 0] + m[1, 0] + m[2, 0]) / 3.0, (m[0, 1] + m[1, 1] + m[2, 1]) / 3.0,
+                                            (m[0, 2] + m[1, 2] + m[2, 2]) / 3.0))     # :957
+    pos, status, iters = solve_tdoa(np.asarray(station_rows, np.float64), rd)
+    if status != 0:
+        return "\n".join(o) + "\n", "TDOA processing failed: TDOA solution failed: singular Jacobian matrix at iteration %d" % iters
+    P("Converged after %d iterations" % iters if iters < 10 else "Maximum iterations reached")   # :971, :1013
+    P("\n*** CALCULATED TRANSMITTER LOCATION ***")
+    P("Latitude:  %.6f°" % pos[0])
+    P("Longitude: %.6f°" % pos[1])
+    P("Elevation: %.1f m" % pos[2])
+    return "\n".join(o) + "\n", None
 
 
 def run_reference_binary(dat_paths, csv_path, ref_hz="162400000", tgt_hz="92300000", timeout=600):

@@ -121,12 +121,31 @@ ORC_API void orc_remove_dc(const c64 *in, int64_t n, c64 *out, c64 *dc_out)
     if (dc_out) *dc_out = dc;
 }
 
+/* Engine-defined arithmetic of EXTENDED mode ("parity unpinned"; the reference has no such mode):
+ * box-cars of at least this many taps accumulate their window in f64 and round once, at the
+ * divide, instead of walking the taps with an f32 accumulator.  0 (default) = never: the
+ * reference's arithmetic, which is what the golden vectors pin. */
+static int g_wide_min = 0;
+ORC_API void orc_set_wide_boxcar_f64(int min_window) { g_wide_min = min_window; }
+
 /* processor.go:270-296  applyLowPassFilter: centred box-car, edge-normalised,
  * taps summed in ascending j starting from a zero accumulator. */
 ORC_API void orc_lowpass(const c64 *in, int64_t n, int window, c64 *out)
 {
     if (window <= 1) { if (out != in) memcpy(out, in, (size_t)n * sizeof(c64)); return; }
     int64_t h = window / 2;
+    if (g_wide_min > 0 && window >= g_wide_min) {
+        for (int64_t i = 0; i < n; i++) {
+            double sr = 0.0, si = 0.0;
+            int64_t lo = i - h, hi = i + h;
+            if (lo < 0) lo = 0;
+            if (hi > n - 1) hi = n - 1;
+            for (int64_t j = lo; j <= hi; j++) { sr += in[j].re; si += in[j].im; }
+            out[i].re = (float)(sr / (double)(hi - lo + 1));
+            out[i].im = (float)(si / (double)(hi - lo + 1));
+        }
+        return;
+    }
     for (int64_t i = 0; i < n; i++) {
         float sr = 0.f, si = 0.f;
         int64_t lo = i - h, hi = i + h, cnt = 0;

@@ -365,6 +365,23 @@ int wait_kind(tdoa_engine *e, Station &s, int kind)
     return TDOA_OK;
 }
 
+// Once every queued copy has landed the chunk lists have served their purpose: later calls on the
+// same capture then take the batched path (one fused launch per kind) instead of one launch and
+// one event wait per chunk.  Called after a call's final synchronisation.
+void retire_lazy(tdoa_engine *e)
+{
+    bool any = false;
+    for (auto &s : e->stations) any |= s.lazy_queued;
+    if (!any) return;
+    if (cudaStreamQuery(e->copy_stream) != cudaSuccess) { cudaGetLastError(); return; }
+    for (auto &s : e->stations) {
+        if (!s.lazy_queued) continue;
+        s.h_lazy = nullptr; s.lazy_queued = false;
+        s.chunks[0].clear(); s.chunks[1].clear();
+        s.events_used = 0;
+    }
+}
+
 // for entry points that read a capture outside the chunk-following discriminator
 int capture_ready(tdoa_engine *e, Station &s)
 {
@@ -405,7 +422,7 @@ int ensure_plane(tdoa_engine *e, Sig &s, int idx, bool cplx)
     return TDOA_OK;
 }
 
-enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_SEQSUM, K_BOXCAR, K_BOXCAR_SMALL, K_NOTCH, K_DECIMATE };
+enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_SEQSUM, K_BOXCAR, K_BOXCAR_SMALL, K_BOXCAR_SLIDE, K_NOTCH, K_DECIMATE };
 
 // queue of (stage, kernel) steps: step k of every signal that runs the same kernel at
 // that stage is batched into one launch; stages run in order
@@ -510,6 +527,7 @@ int run_pipeline(tdoa_engine *e, Pipeline &pl)
                     for (const SigJob &j : st.jobs) e->st.boxcar_samples += j.n;
                     break;
                 }
+                case K_BOXCAR_SLIDE: launch_boxcar_slide(d_jobs, nj, st.max_n, e->stream); break;
                 case K_NOTCH: launch_notch_combine(d_jobs, nj, st.max_n, e->stream); break;
                 case K_DECIMATE: launch_decimate(d_jobs, nj, st.max_n, e->stream); break;
             }
@@ -726,8 +744,11 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs, bool allow_defer = false)
                 pl.add(g++, K_UNPACK, u);
                 if (wants_seq_dc(e, s.n)) pl.add(g, K_SEQSUM, seqsum_job(s, 0, true));
                 g++;
-                // removeDC -> bandpass(100 Hz, 200 kHz) -> normalise
-                pl.add(g++, K_BOXCAR, box_job(s, 0, 1, true, cutoff_window(100.0), BOX_HP, true, false));
+                // removeDC -> bandpass(100 Hz, 200 kHz) -> normalise.  The 1001-tap high-pass: tap by tap
+                // in the reference's f32 order where its digits are at stake (BINARY); EXTENDED, whose
+                // arithmetic is the engine's own, takes the window sums from an f64 prefix sum
+                pl.add(g++, mode == TDOA_MODE_EXTENDED ? K_BOXCAR_SLIDE : K_BOXCAR,
+                       box_job(s, 0, 1, true, cutoff_window(100.0), BOX_HP, true, false));
                 pl.add(g++, K_BOXCAR, box_job(s, 1, 0, true, cutoff_window(200000.0), BOX_LP, false, true));
                 s.out_re = s.plane[0][0]; s.out_im = s.plane[0][1];
             }
@@ -1587,6 +1608,7 @@ int xcorr_impl(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
     e->st.launches_last = e->st.launches_total - e->launches_at_call;
     if (!out_is_device) {
         float t = 0.f;
+        retire_lazy(e);
         spans_collect(e);
         cudaEventElapsedTime(&t, e->ev[0], e->ev[4]);
         e->st.ms_exact = e->ms_corr - e->st.ms_fft;
@@ -2172,6 +2194,7 @@ int tdoa_process(tdoa_engine *e, const double *stations_llh, tdoa_peak *ref_out,
     if (rc) return rc;
     e->st.launches_last = e->st.launches_total - e->launches_at_call;
     float t = 0.f;
+    retire_lazy(e);
     spans_collect(e);
     cudaEventElapsedTime(&t, e->ev[0], e->ev[4]);
     e->st.ms_exact = e->ms_corr - e->st.ms_fft;
@@ -2308,8 +2331,11 @@ int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_stations, co
     if (!stations_llh || !grid_desc || !range_diffs || !out_llh || n_stations < 2 || n_stations > 16 || n_sets < 0 ||
         rd_stride < P)
         return fail(e, TDOA_E_INVALID, "tdoa_grid: bad arguments (2..16 stations, rd_stride >= pairs)");
+    if (!(grid_desc[4] >= 1.0 && grid_desc[5] >= 1.0)) return fail(e, TDOA_E_INVALID, "tdoa_grid: empty grid");
+    // one CTA per 128 cells, gridDim.x is an int: reject what would wrap
+    if (grid_desc[4] > 2147483647.0 || grid_desc[5] > 2147483647.0 || grid_desc[4] * grid_desc[5] / 128.0 > 2147483647.0)
+        return fail(e, TDOA_E_INVALID, "tdoa_grid: grid of %.0f x %.0f cells is too large", grid_desc[4], grid_desc[5]);
     const int nlat = (int)grid_desc[4], nlon = (int)grid_desc[5];
-    if (nlat < 1 || nlon < 1) return fail(e, TDOA_E_INVALID, "tdoa_grid: empty grid");
     if (n_sets == 0) return end_call(e, true);
     double *d_llh = nullptr, *d_desc = nullptr, *d_rd = nullptr, *d_cost = nullptr, *d_out = nullptr;
     i64 *d_idx = nullptr;
@@ -2469,6 +2495,7 @@ int tdoa_synchronize(tdoa_engine *e)
     if (rc) return rc;
     CU(cudaStreamSynchronize(e->copy_stream));
     CU(cudaStreamSynchronize(e->stream));
+    retire_lazy(e);
     return TDOA_OK;
 }
 

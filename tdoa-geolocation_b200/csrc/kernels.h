@@ -115,6 +115,7 @@ size_t seqsum_scratch_bytes(i64 n);
 void seqsum_carve(SeqJob &J, void *scratch);
 void launch_seqsum_chunked(const SeqJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
 void launch_boxcar(const SigJob *d_jobs, int n_jobs, i64 max_n, int max_window, cudaStream_t st);
+void launch_boxcar_slide(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);   // EXTENDED: f64 prefix sums
 void launch_notch_combine(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
 void launch_normalize(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);
 void launch_decimate(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);  // window = D, n = input samples

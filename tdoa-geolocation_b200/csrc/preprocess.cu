@@ -248,6 +248,82 @@ __global__ void __launch_bounds__(kThreads) k_boxcar(const SigJob *jobs)
     }
 }
 
+// ---------------------------------------------------------------- wide box-car, O(1) per sample
+// EXTENDED mode only (engine-defined arithmetic; oracle: orc_lowpass_wide).  The reference's
+// box-car (processor.go:270-296) spends one f32 addition per tap and output -- 1001 per sample in
+// the weak branch's 100 Hz high-pass -- and only that brute-force walk reproduces its f32 rounding
+// chain bit for bit, so SOURCE and BINARY keep it (k_boxcar).  Here the window sum is the
+// difference of two entries of an f64 prefix sum over the staged tile: the same taps, the same edge
+// normalisation (divisor = taps in range), one rounding to f32 at the divide.  It differs from the
+// reference's chain by that chain's own f32 rounding (~1e-6 relative), which the mode does not promise.
+__global__ void __launch_bounds__(kThreads) k_boxcar_slide(const SigJob *jobs)
+{
+    constexpr int kLen = kBoxTile + 2 * kBoxHalfMax;
+    constexpr int kPer = (kLen + kThreads - 1) / kThreads;   // 12 consecutive entries per thread
+    __shared__ float s_x[kLen];
+    __shared__ double s_p[kLen];      // inclusive prefix sums of s_x
+    __shared__ double s_w[kThreads / 32];
+    __shared__ double scratch[32];
+    const SigJob &J = jobs[blockIdx.y];
+    const i64 n = J.n;
+    const int h = J.window <= 1 ? 0 : J.window / 2;
+    const i64 i0 = (i64)blockIdx.x * kBoxTile;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double pacc = 0.0;
+    if (i0 < n) {   // uniform per CTA
+        const i64 lo = max((i64)0, i0 - h);
+        const i64 hi = min(n, i0 + kBoxTile + h);  // exclusive
+        const int len = (int)(hi - lo);
+        const i64 iend = min(n, i0 + kBoxTile);
+        for (int comp = 0; comp < 2; comp++) {
+            const float *__restrict__ q = comp == 0 ? J.q_re : J.q_im;
+            float *__restrict__ p = comp == 0 ? J.p_re : J.p_im;
+            if (!q) break;
+            const float dc = J.sub_dc ? (float)J.stats[comp == 0 ? ST_DC_RE : ST_DC_IM] : 0.f;
+            __syncthreads();
+            for (int j = tid; j < len; j += kThreads) s_x[j] = J.sub_dc ? __fsub_rn(q[lo + j], dc) : q[lo + j];
+            __syncthreads();
+            // block-wide inclusive scan: a thread's 12 entries, then warps, then the warp totals
+            const int j0 = tid * kPer;
+            double loc[kPer], run = 0.0;
+#pragma unroll
+            for (int k = 0; k < kPer; k++) { run += j0 + k < len ? (double)s_x[j0 + k] : 0.0; loc[k] = run; }
+            double inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (lane == 31) s_w[wid] = inc;
+            __syncthreads();
+            double base = inc - run;                       // exclusive within the warp
+            for (int w = 0; w < wid; w++) base += s_w[w];  // fixed order
+#pragma unroll
+            for (int k = 0; k < kPer; k++) if (j0 + k < len) s_p[j0 + k] = base + loc[k];
+            __syncthreads();
+            for (i64 i = i0 + tid; i < iend; i += kThreads) {
+                float out = s_x[i - lo];
+                if (h > 0) {
+                    const i64 a = max((i64)0, i - h), b = min(n - 1, i + h);
+                    const int ja = (int)(a - lo), jb = (int)(b - lo);
+                    const double sum = s_p[jb] - (ja > 0 ? s_p[ja - 1] : 0.0);
+                    const float lp = (float)(sum / (double)(int)(b - a + 1));
+                    out = J.mode == BOX_HP ? __fsub_rn(out, lp) : lp;
+                }
+                p[i] = out;
+                pacc += (double)__fmul_rn(out, out);
+            }
+        }
+    }
+    if (J.want_power) {
+        // f32 re^2 + im^2 per sample in the reference (processor.go:328); here the two squares are
+        // added in f64 (the mode's own arithmetic, as above)
+        double part[1] = {block_sum(pacc, scratch)}, total[1];
+        if (grid_sum_last<1>(part, J.partials, J.counter, gridDim.x, blockIdx.x, scratch, total)) {
+            const double pw = n > 0 ? total[0] / (double)n : 0.0;
+            J.stats[ST_POWER1] = pw;
+            J.stats[ST_SCALE] = pw > 0.0 ? (double)(float)(1.0 / sqrt(pw)) : 1.0;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- notch combine
 // processor.go:428-431  out = s - 0.8 * band  (complex64 constant: one f32 rounding)
 __global__ void __launch_bounds__(kThreads) k_notch_combine(const SigJob *jobs)
@@ -379,6 +455,10 @@ void launch_boxcar(const SigJob *d_jobs, int n_jobs, i64 max_n, int max_window, 
 {
     (void)max_window;
     k_boxcar<<<dim3(boxcar_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
+}
+void launch_boxcar_slide(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)
+{
+    k_boxcar_slide<<<dim3(boxcar_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
 }
 void launch_notch_combine(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)
 {

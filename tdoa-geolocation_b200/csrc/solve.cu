@@ -148,7 +148,8 @@ __global__ void k_solve_binary(const double *llh, const double *rd, int n_rd, do
             if (fabs(res1) < 1.0 && fabs(res2) < 1.0) { converged = 1; break; }
             const double det = J22 * J11 - J21 * J12;
             n_iter = it + 1;
-            double *tr = trace + 5 * it;
+            double tr_local[5];
+            double *tr = trace ? trace + 5 * it : tr_local;   // trace may be NULL (tdoa_b200.h)
             tr[0] = det; tr[1] = res1; tr[2] = res2; tr[3] = 0.0; tr[4] = 0.0;
             if (fabs(det) < 1e-12) {
                 double d = 0.0;

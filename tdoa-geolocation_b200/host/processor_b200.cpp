@@ -211,7 +211,7 @@ public:
             long long n = 0;
             try { n = loadIQData(slot, datFiles[slot]); }
             catch (const std::exception &e) { throw std::runtime_error("failed to load data from " + datFiles[slot] + ": " + e.what()); }
-            if (binary) {
+            {
                 const long long b = n / 3;  // processor.go:211-236, :244-265
                 const long long nRef = n < 3 ? n : 2 * b, nTgt = n < 3 ? n : b;   // fewer than 3 samples: returned unchanged
                 printf("Extracting reference signal from dual-frequency data\n");
@@ -226,12 +226,13 @@ public:
                     printf("Total samples: %lld, block size: %lld\n", n, b);
                     printf("Extracted %lld target samples from block 2\n", b);
                 }
-                // processor.go:772-780 with the shipped binary's chunk: the engine's BINARY mode
-                // cuts both signals the same way (chunk_samples = 1 000 000)
-                const long long chunk = 1000000;
+                // processor.go:772-783 (testChunkSize 2 000 000; the shipped binary: 1 000 000): the
+                // engine cuts both signals the same way (chunk_samples of the mode)
+                const long long chunk = cfg.chunk_samples;
                 if (nRef > chunk) printf("Using test chunk: %lld samples (%.1f ms)\n", chunk, (double)chunk / 2e6 * 1000);
                 if (nTgt > chunk) printf("Using target test chunk: %lld samples (%.1f ms)\n", chunk, (double)chunk / 2e6 * 1000);
-                printf("Coherent integration time: 500 ms (expecting ~10.0 dB processing gain)\n");
+                printf("Coherent integration time: %.0f ms (expecting ~%.1f dB processing gain)\n", (double)chunk / 2e6 * 1000,
+                       10 * std::log10((double)chunk / 100000));
             }
             st.push_back(s);
             printf("Loaded collector: %s at %.6f°, %.6f°, %.1fm\n", s.name.c_str(), s.latitude, s.longitude, s.elevation);
@@ -259,19 +260,23 @@ public:
             const char *label = kind == TDOA_KIND_REF ? "REF" : "TGT";
             if (kind == TDOA_KIND_REF) {
                 printf("\n=== REFERENCE SIGNAL CORRELATION TEST ===\n");
+                // processor.go:813 prints the frequency as a literal; the shipped binary formats it
                 if (binary) printf("Testing weak %.1f MHz NOAA weather signal:\n", referenceFreq / 1e6);
+                else printf("Testing weak 162.4 MHz NOAA weather signal:\n");
             } else {
                 printf("\n=== TARGET SIGNAL CORRELATION TEST ===\n");
                 if (binary) printf("Testing strong %.1f MHz FM broadcast signal:\n", targetFreq / 1e6);
+                else printf("Testing strong 92.3 MHz FM broadcast signal:\n");   // processor.go:833
             }
             std::vector<tdoa_signal_info> info(S);
             std::vector<double> first(P);
-            if (binary) check(tdoa_xcorr_info(engine, kind, info.data(), first.data()));
+            check(tdoa_xcorr_info(engine, kind, info.data(), first.data()));
             for (int p = 0; p < P; p++) {
                 const tdoa_peak &pk = peaks[kind][p];
                 const double td = (double)pk.lag / fs;  // processor.go:821
                 tds[kind].push_back(td);
                 if (binary) printPairBinary(info[pairs[p].first], info[pairs[p].second], pk, first[p], fs, cfg);
+                else printPairSource(info[pairs[p].first], info[pairs[p].second], pk, cfg);
                 printf("%s %s - %s: delay=%d samples (%.3f μs), correlation=%.6f\n", label, st[pairs[p].first].name.c_str(),
                        st[pairs[p].second].name.c_str(), pk.lag, td * 1e6, pk.corr);
             }
@@ -279,6 +284,10 @@ public:
         std::vector<double> td(P);
         if (!binary) {
             td = tds[1];  // processor.go:853: target differences only
+            printf("\n=== CORRELATION COMPARISON ===\n");   // :855-858
+            printf("Reference signal (162.4 MHz): Generally weaker correlation\n");
+            printf("Target signal (92.3 MHz): Should show stronger correlation\n");
+            printf("Using target signal for TDOA calculation\n");
         } else {
             printf("\n=== REFERENCE SIGNAL SYNCHRONIZATION ===\n");
             printf("Using reference signal to synchronize collector timing...\n");
@@ -296,13 +305,13 @@ public:
         }
         std::vector<double> rd(P);
         for (int k = 0; k < P; k++) rd[k] = td[k] * kSpeedOfLight;  // :899-903
-        if (binary) {
+        {
             printf("\nTDOA triangulation:\n");
-            // the binary prints the first three here, whatever the number of pairs
+            // both revisions print the first three here, whatever the number of pairs (:869-879)
             const std::vector<double> td3(td.begin(), td.begin() + 3), rd3(rd.begin(), rd.begin() + 3);
-            printf("Corrected time differences: %s\n", join(td3, 1e6, "%.3f μs").c_str());
-            printf("Corrected distance differences: %s\n", join(rd3, 1.0, "%.1f m").c_str());
-            printf("\nDiagnostic test with example delays:\n");  // processor.go:885-889
+            printf("%s: %s\n", binary ? "Corrected time differences" : "Time differences", join(td3, 1e6, "%.3f μs").c_str());
+            printf("%s: %s\n", binary ? "Corrected distance differences" : "Distance differences", join(rd3, 1.0, "%.1f m").c_str());
+            printf("\nDiagnostic test with example delays:\n");  // processor.go:882-889
             printf("Simulating 10 μs, 5 μs, -3 μs delays...\n");
             const double us[3] = {10.0, 5.0, -3.0};
             for (int k = 0; k < 3; k++) printf("Test delay %d: %.1f μs → %.1f m\n", k + 1, us[k], us[k] * 1e-6 * kSpeedOfLight);
@@ -365,8 +374,15 @@ public:
                 if (k == 9) printf("Maximum iterations reached\n");
             }
             if (conv) printf("Converged after %d iterations\n", nIter);
-        } else if (fixStatus != 0) {
-            throw std::runtime_error("TDOA solution failed: singular Jacobian matrix");  // :997-999, :920
+        } else {
+            // processor.go:957, :971, :998, :1013 (solveTDOA ran inside tdoa_process; fixIters = the
+            // iteration it stopped at: converged, singular, or 10 = all ten steps taken)
+            printf("Initial guess: %.6f°, %.6f°, %.1fm\n", (st[0].latitude + st[1].latitude + st[2].latitude) / 3.0,
+                   (st[0].longitude + st[1].longitude + st[2].longitude) / 3.0, (st[0].elevation + st[1].elevation + st[2].elevation) / 3.0);
+            if (fixStatus != 0)
+                throw std::runtime_error(fmt("TDOA solution failed: singular Jacobian matrix at iteration %d", fixIters));  // :997-999, :920
+            if (fixIters < 10) printf("Converged after %d iterations\n", fixIters);
+            else printf("Maximum iterations reached\n");
         }
         printf("\n*** CALCULATED TRANSMITTER LOCATION ***\n");
         printf("Latitude:  %.6f°\n", fix[0]);
@@ -438,6 +454,50 @@ private:
                 printf("Found better peak within reasonable range: delay=%d samples (%.1f μs), correlation=%.6f\n", pk.lag,
                        pk.lag / fs * 1e6, pk.corr);
         }
+        printf("\n--- Result: Time Domain with Preprocessing ---\n");
+        printf("Correlation: %.6f at delay %d samples\n", pk.corr, pk.lag);
+    }
+
+    // stdout of processor.go while it works on one pair (crossCorrelate :619-643, preprocessSignal
+    // :469-499, enhanceWeakSignal :437-466, timeDomainCorrelation :646-736)
+    void printPairSource(const tdoa_signal_info &s1, const tdoa_signal_info &s2, const tdoa_peak &pk, const tdoa_config &cfg) const
+    {
+        printf("=== Cross-Correlation Analysis ===\n");
+        if (s1.n == 0 || s2.n == 0) {   // :622-625
+            printf("Warning: Empty signals for correlation\n");
+            return;
+        }
+        printf("\n--- Signal Preprocessing ---\n");
+        const tdoa_signal_info *sg[2] = {&s1, &s2};
+        for (int k = 0; k < 2; k++) {
+            printf("Preprocessing Signal %d signal (%lld samples)\n", k + 1, (long long)sg[k]->n);
+            printf("Initial signal power: %.9f\n", sg[k]->power0);
+            const char *bp = "Bandpass filter: %.1f - %.1f Hz (at %.0f Hz sample rate)\n";
+            if (sg[k]->branch == 2) {   // power < 0.001 (:476)
+                printf("Detected very weak signal - applying aggressive filtering\n");
+                printf("Enhancing weak signal: Signal %d\n", k + 1);
+                printf("Removed DC bias: %.6f + %.6fi\n", sg[k]->dc_re, sg[k]->dc_im);
+                printf(bp, 57.5, 62.5, 2000000.0);          // notch 60 / 5 (:446)
+                printf(bp, 117.5, 122.5, 2000000.0);        // notch 120 / 5 (:447)
+                printf(bp, 975000.0, 1000000.0, 2000000.0); // notch 1 MHz / 50 kHz, upper edge clamped to fs / 2 (:448, :420-422)
+                printf(bp, 100.0, 40000.0, 2000000.0);      // :457
+            } else {
+                printf("Standard signal processing\n");
+                printf("Removed DC bias: %.6f + %.6fi\n", sg[k]->dc_re, sg[k]->dc_im);
+                printf(bp, 500.0, 50000.0, 2000000.0);      // :489
+            }
+            if (sg[k]->power1 > 0) printf("Normalized signal power: %.6f → 1.000000\n", sg[k]->power1);   // :338-340, :349
+        }
+        printf("\n--- Time Domain Correlation ---\n");
+        printf("Performing time domain correlation\n");
+        const long long tl = std::min(s1.n, s2.n), sl = std::max(s1.n, s2.n);
+        printf("Template: %lld samples, Signal: %lld samples\n", tl, sl);
+        long long maxLag = std::min<long long>(cfg.max_lag, sl - tl);   // :668-675
+        if (maxLag < 1) maxLag = 1;
+        printf("Using coherent integration with %d-sample blocks\n", cfg.block_size);
+        // :729-731: every 2000th delay, carriage return instead of a new line
+        for (long long d = 0; d < maxLag; d += 2000) printf("Time domain progress: %lld/%lld (coherent blocks: %d)\r", d, maxLag, pk.n_blocks);
+        printf("\nTime domain correlation: %.6f at delay %d samples\n", pk.corr, pk.lag);
         printf("\n--- Result: Time Domain with Preprocessing ---\n");
         printf("Correlation: %.6f at delay %d samples\n", pk.corr, pk.lag);
     }

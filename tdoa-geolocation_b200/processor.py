@@ -11,6 +11,7 @@ ProcessTDOA :739, solveTDOA :932.
 """
 from __future__ import annotations
 
+import math
 import os
 import sys
 from dataclasses import dataclass
@@ -183,6 +184,44 @@ class TDOAProcessor:
         P("\n--- Result: Time Domain with Preprocessing ---")
         P("Correlation: %.6f at delay %d samples" % (pk["corr"], pk["lag"]))
 
+    def _print_pair_source(self, sig1, sig2, pk, max_lag, block):
+        """stdout of processor.go while it works on one pair (crossCorrelate :619-643, preprocessSignal
+        :469-499, enhanceWeakSignal :437-466, timeDomainCorrelation :646-736)."""
+        P = self._print
+        P("=== Cross-Correlation Analysis ===")
+        if sig1["n"] == 0 or sig2["n"] == 0:   # :622-625
+            P("Warning: Empty signals for correlation")
+            return
+        P("\n--- Signal Preprocessing ---")
+        bp = "Bandpass filter: %.1f - %.1f Hz (at %.0f Hz sample rate)"
+        for k, sg in ((1, sig1), (2, sig2)):
+            P("Preprocessing Signal %d signal (%d samples)" % (k, sg["n"]))
+            P("Initial signal power: %.9f" % sg["power0"])
+            if sg["branch"] == 2:   # power < 0.001 (:476)
+                P("Detected very weak signal - applying aggressive filtering")
+                P("Enhancing weak signal: Signal %d" % k)
+                P("Removed DC bias: %.6f + %.6fi" % (sg["dc_re"], sg["dc_im"]))
+                for lo, hi in ((57.5, 62.5), (117.5, 122.5), (975000.0, 1000000.0), (100.0, 40000.0)):   # :446-448, :457
+                    P(bp % (lo, hi, 2000000.0))
+            else:
+                P("Standard signal processing")
+                P("Removed DC bias: %.6f + %.6fi" % (sg["dc_re"], sg["dc_im"]))
+                P(bp % (500.0, 50000.0, 2000000.0))   # :489
+            if sg["power1"] > 0:   # :338-340, :349
+                P("Normalized signal power: %.6f → 1.000000" % sg["power1"])
+        P("\n--- Time Domain Correlation ---")
+        P("Performing time domain correlation")
+        tl, sl = min(sig1["n"], sig2["n"]), max(sig1["n"], sig2["n"])
+        P("Template: %d samples, Signal: %d samples" % (tl, sl))
+        n_lags = max(1, min(max_lag, sl - tl))   # :668-675
+        P("Using coherent integration with %d-sample blocks" % block)
+        # :729-731: every 2000th delay, carriage return instead of a new line
+        progress = "".join("Time domain progress: %d/%d (coherent blocks: %d)\r" % (d, n_lags, pk["n_blocks"])
+                           for d in range(0, n_lags, 2000))
+        P(progress + "\nTime domain correlation: %.6f at delay %d samples" % (pk["corr"], pk["lag"]))
+        P("\n--- Result: Time Domain with Preprocessing ---")
+        P("Correlation: %.6f at delay %d samples" % (pk["corr"], pk["lag"]))
+
     # -- processor.go:739-929; in MODE_BINARY every stdout line of the shipped binary
     def process_tdoa(self, dat_files: List[str]):
         if len(dat_files) < 3:
@@ -204,27 +243,28 @@ class TDOAProcessor:
                 n = self.load_iq_data(slot, fn, S)
             except RuntimeError as exc:
                 raise RuntimeError(f"failed to load data from {fn}: {exc}") from exc
-            if binary:
-                b = n // 3  # processor.go:211-236, :244-265
-                n_ref, n_tgt = (n, n) if n < 3 else (2 * b, b)   # fewer than 3 samples: returned unchanged
-                P("Extracting reference signal from dual-frequency data")
-                if n < 3:
-                    P("Warning: Data too small for dual-frequency extraction")
-                else:
-                    P("Total samples: %d, block size: %d" % (n, b))
-                    P("Extracted %d reference samples from blocks 1 and 3" % (2 * b))
-                P("Extracting target signal from dual-frequency data")
-                if n < 3:
-                    P("Warning: Data too small for dual-frequency extraction")
-                else:
-                    P("Total samples: %d, block size: %d" % (n, b))
-                    P("Extracted %d target samples from block 2" % b)
-                chunk = 1_000_000  # processor.go:772-780 with the shipped binary's chunk (the engine's chunk_samples)
-                if n_ref > chunk:
-                    P("Using test chunk: %d samples (%.1f ms)" % (chunk, chunk / 2e6 * 1000))
-                if n_tgt > chunk:
-                    P("Using target test chunk: %d samples (%.1f ms)" % (chunk, chunk / 2e6 * 1000))
-                P("Coherent integration time: 500 ms (expecting ~10.0 dB processing gain)")
+            b = n // 3  # processor.go:211-236, :244-265
+            n_ref, n_tgt = (n, n) if n < 3 else (2 * b, b)   # fewer than 3 samples: returned unchanged
+            P("Extracting reference signal from dual-frequency data")
+            if n < 3:
+                P("Warning: Data too small for dual-frequency extraction")
+            else:
+                P("Total samples: %d, block size: %d" % (n, b))
+                P("Extracted %d reference samples from blocks 1 and 3" % (2 * b))
+            P("Extracting target signal from dual-frequency data")
+            if n < 3:
+                P("Warning: Data too small for dual-frequency extraction")
+            else:
+                P("Total samples: %d, block size: %d" % (n, b))
+                P("Extracted %d target samples from block 2" % b)
+            # processor.go:772-783 (testChunkSize 2 000 000; the shipped binary: 1 000 000) = the engine's chunk_samples
+            chunk = eng.cfg.chunk_samples
+            if n_ref > chunk:
+                P("Using test chunk: %d samples (%.1f ms)" % (chunk, chunk / 2e6 * 1000))
+            if n_tgt > chunk:
+                P("Using target test chunk: %d samples (%.1f ms)" % (chunk, chunk / 2e6 * 1000))
+            P("Coherent integration time: %.0f ms (expecting ~%.1f dB processing gain)"
+              % (chunk / 2e6 * 1000, 10 * math.log10(chunk / 100000)))
             stations.append(st)
             P("Loaded collector: %s at %.6f°, %.6f°, %.1fm" % (st.name, st.latitude, st.longitude, st.elevation))
         llh = np.array([s.llh for s in stations], np.float64)
@@ -242,14 +282,15 @@ class TDOAProcessor:
         for kind, label in ((N.KIND_REF, "REF"), (N.KIND_TGT, "TGT")):
             if kind == N.KIND_REF:
                 P("\n=== REFERENCE SIGNAL CORRELATION TEST ===")
-                if binary:
-                    P("Testing weak %.1f MHz NOAA weather signal:" % (self.reference_freq / 1e6))
+                # processor.go:813 prints the frequency as a literal; the shipped binary formats it
+                P("Testing weak %.1f MHz NOAA weather signal:" % (self.reference_freq / 1e6) if binary
+                  else "Testing weak 162.4 MHz NOAA weather signal:")
             else:
                 P("\n=== TARGET SIGNAL CORRELATION TEST ===")
-                if binary:
-                    P("Testing strong %.1f MHz FM broadcast signal:" % (self.target_freq / 1e6))
+                P("Testing strong %.1f MHz FM broadcast signal:" % (self.target_freq / 1e6) if binary
+                  else "Testing strong 92.3 MHz FM broadcast signal:")   # processor.go:833
             peaks = done["ref" if kind == N.KIND_REF else "tgt"]
-            info, first = eng.xcorr_info(kind) if binary else (None, None)
+            info, first = eng.xcorr_info(kind)
             tds = []
             for p_idx, ((i, j), pk) in enumerate(zip(pairs, peaks)):
                 td = float(pk["lag"]) / fs
@@ -257,12 +298,18 @@ class TDOAProcessor:
                 if binary:
                     self._print_pair_binary(info[i], info[j], pk, float(first[p_idx]), fs, eng.cfg.max_lag,
                                             eng.cfg.block_size, eng.cfg.sanity_lag)
+                else:
+                    self._print_pair_source(info[i], info[j], pk, eng.cfg.max_lag, eng.cfg.block_size)
                 P("%s %s - %s: delay=%d samples (%.3f μs), correlation=%.6f"
                   % (label, stations[i].name, stations[j].name, pk["lag"], td * 1e6, pk["corr"]))
             results[label] = (peaks, tds)
         ref_td, tgt_td = results["REF"][1], results["TGT"][1]
         if not binary:
             tds = tgt_td  # processor.go:853: target differences only
+            P("\n=== CORRELATION COMPARISON ===")   # :855-858
+            P("Reference signal (162.4 MHz): Generally weaker correlation")
+            P("Target signal (92.3 MHz): Should show stronger correlation")
+            P("Using target signal for TDOA calculation")
         else:
             # shipped binary: corrected = target - reference, pair by pair
             P("\n=== REFERENCE SIGNAL SYNCHRONIZATION ===")
@@ -279,15 +326,14 @@ class TDOAProcessor:
             P("Target signal (%.1f MHz): Corrected with reference timing offsets" % (self.target_freq / 1e6))
             P("Using corrected target signal for TDOA calculation")
         rds = [td * SPEED_OF_LIGHT for td in tds]  # :899-903
-        if binary:
-            P("\nTDOA triangulation:")
-            # the binary prints the first three here, whatever the number of pairs
-            P("Corrected time differences: " + ", ".join("%.3f μs" % (td * 1e6) for td in tds[:3]))
-            P("Corrected distance differences: " + ", ".join("%.1f m" % rd for rd in rds[:3]))
-            P("\nDiagnostic test with example delays:")  # processor.go:885-889
-            P("Simulating 10 μs, 5 μs, -3 μs delays...")
-            for k, us in enumerate((10.0, 5.0, -3.0)):
-                P("Test delay %d: %.1f μs → %.1f m" % (k + 1, us, us * 1e-6 * SPEED_OF_LIGHT))
+        P("\nTDOA triangulation:")
+        # both revisions print the first three here, whatever the number of pairs (:869-879)
+        P(("Corrected time differences: " if binary else "Time differences: ") + ", ".join("%.3f μs" % (td * 1e6) for td in tds[:3]))
+        P(("Corrected distance differences: " if binary else "Distance differences: ") + ", ".join("%.1f m" % rd for rd in rds[:3]))
+        P("\nDiagnostic test with example delays:")  # processor.go:882-889
+        P("Simulating 10 μs, 5 μs, -3 μs delays...")
+        for k, us in enumerate((10.0, 5.0, -3.0)):
+            P("Test delay %d: %.1f μs → %.1f m" % (k + 1, us, us * 1e-6 * SPEED_OF_LIGHT))
         P("\n=== TDOA GEOLOCATION ===")
         P("Time differences (μs): " + "".join("%.3f " % (td * 1e6) for td in tds))
         P("Range differences (m): " + "".join("%.1f " % rd for rd in rds))
@@ -340,8 +386,14 @@ class TDOAProcessor:
             if conv:
                 P("Converged after %d iterations" % n_iter)
             done = dict(done, position=pos, status=0)
-        if done["status"] != 0:
-            raise RuntimeError("TDOA solution failed: singular Jacobian matrix")  # processor.go:997-999, :920
+        else:
+            # processor.go:957, :971, :998, :1013 (solveTDOA ran inside tdoa_process; fix_iters = the
+            # iteration it stopped at: converged, singular, or 10 = all ten steps taken)
+            m = llh[:3].sum(axis=0) / 3.0
+            P("Initial guess: %.6f°, %.6f°, %.1fm" % (m[0], m[1], m[2]))
+            if done["status"] != 0:
+                raise RuntimeError("TDOA solution failed: singular Jacobian matrix at iteration %d" % done["iters"])
+            P("Converged after %d iterations" % done["iters"] if done["iters"] < 10 else "Maximum iterations reached")
         lat, lon, elev = (float(x) for x in done["position"])
         P("\n*** CALCULATED TRANSMITTER LOCATION ***")
         P("Latitude:  %.6f°" % lat)

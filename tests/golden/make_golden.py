@@ -162,6 +162,33 @@ def case_fm_truncated(B=1_050_000):
     return out
 
 
+def _simulators():
+    sys.path.insert(0, str(ROOT / "tools"))
+    import simulators
+    return simulators
+
+
+def case_sim_perfect(B=200_000):
+    """simulator.go's own content (tools/simulators.py restates simulateStation, :100-177), with its
+    usage example's arguments (:229: 41.20 -96.00 400 1000) and 200 000-sample blocks instead of
+    20 000 000: literal tones + uniform noise, power ~2e-4 -> the weak branch on every signal, periodic
+    peaks.  Regenerated from the seed (torch CPU generator), SHA-256 checked."""
+    S = _simulators()
+    caps, _ = S.simulate_perfect(list(S.STATIONS.values()), (41.20, -96.00, 400.0), 92300000.0, 1000.0, B, seed=100)
+    return {name: c.numpy() for name, c in zip(STATIONS, caps)}
+
+
+def case_sim_weak(B=200_000):
+    """weak_signal_simulator.go's own content (tools/simulators.py restates simulateWeakSignalStation,
+    :141-247) with its usage example's arguments (:298: ref_power 10, tgt_power 1000): the reference
+    blocks carry 7e-5 ... 3e-4 of amplitude, under half a quantisation step, so every byte is 127, the
+    signal after removeDCBias has (nearly) no power and the REF records are (0, 0.000000); the target
+    blocks are a 1-3 count tone.  Regenerated from the seed, SHA-256 checked."""
+    S = _simulators()
+    caps, _ = S.simulate_weak(list(S.STATIONS.values()), (41.20, -96.00, 400.0), 92300000.0, 10.0, 1000.0, B, seed=300)
+    return {name: c.numpy() for name, c in zip(STATIONS, caps)}
+
+
 def _degenerate_third(third: np.ndarray):
     caps = case_fm_strong(B=20000)
     caps[STATIONS[2]] = third
@@ -285,7 +312,7 @@ CASE_CSV = {   # case -> (file name under tests/golden/, contents)
 }
 
 # cases whose captures are regenerated from their seeds instead of being stored
-REGENERATED = {"fm_truncated"}
+REGENERATED = {"fm_truncated", "sim_perfect", "sim_weak"}
 
 CASES = {
     "fm_strong": case_fm_strong,
@@ -306,6 +333,8 @@ CASES = {
     "tiny_third": case_tiny_third,
     "three_sample_third": case_three_sample_third,
     "empty_third": case_empty_third,
+    "sim_perfect": case_sim_perfect,
+    "sim_weak": case_sim_weak,
 }
 
 PAIR_RE = re.compile(r"^(REF|TGT) (\S+) - (\S+): delay=(-?\d+) samples \((-?[\d.]+) μs\), correlation=(-?[\d.]+)")

@@ -18,6 +18,9 @@ GOLDEN_TABLE_CASES = ["twin_stations", "back_stations", "close_stations"]
 GOLDEN_DEGENERATE_CASES = ["tiny_third", "three_sample_third", "empty_third"]
 # golden records whose captures are regenerated from their seeds (18 MB: not stored); 1 M-sample chunk
 GOLDEN_LONG_CASES = ["fm_truncated"]
+# the reference's own simulators' content (simulator.go, weak_signal_simulator.go restated in
+# tools/simulators.py) at 200 000-sample blocks, regenerated from the seeds and SHA-checked
+GOLDEN_SIM_CASES = ["sim_perfect", "sim_weak"]
 FS = 2e6
 
 # lat-lon-table.csv rows of the three collectors (tests/golden/stations.csv)

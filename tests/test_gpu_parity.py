@@ -1,11 +1,13 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden
 vectors of the reference's shipped binary.  Tolerances (BASELINE.json north_star):
 integer lag of every correlation peak bit-exact; sub-sample TDOA within 1e-3 samples;
-position within 1 m.  Float intermediates: the f32 DC bias is computed from an exactly
-rounded sum instead of the reference's sequential f32 accumulator, so preprocessed
-samples may differ in the last bits (<= 2e-6 abs on unit-power signals) and printed
-correlations by <= 1e-6."""
+position within 1 m.  Float intermediates: the f32 DC bias is the reference's sequential
+f32 accumulator bit for bit (seqsum.cu) up to seq_dc_limit samples -- everything the
+reference can reach -- and an exactly rounded sum beyond; the f64 power sums use a fixed
+tree instead of the reference's running sum (<= 1e-15 relative), so a preprocessed sample
+may differ in its last bit with probability ~1e-8 and a printed correlation by <= 1e-6."""
 import io
+import sys
 import re
 
 import numpy as np
@@ -13,11 +15,12 @@ import pytest
 
 import tdoa_b200 as T
 from oracle import oracle
-from helpers import GOLDEN, GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, GOLDEN_ORDER_CASES, GOLDEN_TABLE_CASES, STATION_LLH, fm_capture, load_golden, quantise
+from helpers import GOLDEN, GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, GOLDEN_SIM_CASES, GOLDEN_ORDER_CASES, GOLDEN_TABLE_CASES, STATION_LLH, fm_capture, load_golden, quantise
 
 pytestmark = pytest.mark.gpu
 
 CORR_TOL = 1e-6
+SOURCE_TOL = 2e-4   # SOURCE mode, relative (see test_source_mode_pairs)
 SAMPLE_TOL = 2e-6
 
 
@@ -206,6 +209,39 @@ def test_source_mode_unequal_lengths(eng_source):
     assert abs(pk.corr - c) <= 2e-4 * max(1.0, abs(c))
 
 
+@pytest.mark.parametrize("case", ["fm_strong", "weak_noise", "fm_uneven"])
+def test_source_command_prints_what_processor_go_prints(tmp_path, case):
+    """`processor_b200 --source` and the Python mirror in MODE_SOURCE against processor.go's print
+    statements restated in the oracle (oracle.source_stdout: ProcessTDOA :739-929, preprocessSignal
+    :469-499, enhanceWeakSignal :437-466, timeDomainCorrelation :646-736, solveTDOA :957-1013), line
+    for line -- the standard and the weak chain, equal and unequal lengths (progress lines, lags
+    beyond 0).  The source cannot run here: the expected text is the oracle's, "parity unpinned"."""
+    import subprocess
+    raws, _ = load_golden(case)
+    names = ["kx0u", "n3pay", "kf0mtl"]
+    files = []
+    for name, raw in zip(names, raws):
+        f = tmp_path / f"sim-{name}-1.dat"
+        raw.tofile(f)
+        files.append(str(f))
+    csv_file = str(GOLDEN / "stations.csv")
+    want, err = oracle.source_stdout(files, names, [tuple(r) for r in STATION_LLH], raws,
+                                     ("162400000", 41.25703803095629, -95.95512763589404, 349.07), 92300000.0, 5)
+    assert err is None
+    exe = GOLDEN.parent.parent / "tdoa-geolocation_b200" / "processor_b200"
+    out = subprocess.run([str(exe), "--source", "162400000", "92300000", csv_file, *files], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    buf = io.StringIO()
+    p = T.TDOAProcessor(162400000.0, 92300000.0, csv_file, mode=T.MODE_SOURCE, out=buf)
+    p.process_tdoa(files)
+    p.close()
+    for who, text in (("processor_b200 --source", out.stdout), ("python mirror", buf.getvalue())):
+        ours, gold = text.split("\n"), want.split("\n")
+        assert len(ours) == len(gold), (who, text[-1500:])
+        for k, (a, b) in enumerate(zip(ours, gold)):
+            assert _same_line(a, b, tol=SOURCE_TOL), f"{who}, line {k}: ours {a!r} != oracle {b!r}"
+
+
 # ------------------------------------------------------------------ windows
 def test_windows_equal_single_calls(eng_binary):
     raws = fm_capture(120000, (0, 3, 8), (0, 20, 41), seed=7)
@@ -273,6 +309,50 @@ def test_extended_wide_lags_use_the_big_transform():
     oracle.set_seq_dc_limit(-1)
     assert [int(g["lag"]) for g in got] == [-2500 + 3100, -2500, -3100]
     assert [int(g["lag"]) for g in ref] == [-400, 1300, 1700]
+
+
+def test_extended_weak_branch_wide_boxcar():
+    """EXTENDED mode on the reference simulators' content (every signal on the weak branch): the
+    1001-tap high-pass takes its window sums from an f64 prefix sum (k_boxcar_slide) instead of
+    1001 f32 additions per sample.  Against the oracle's statement of that arithmetic
+    (orc_set_wide_boxcar_f64): samples equal to the f32 bit on all but a handful, lags identical,
+    correlation <= 1e-6; against the reference's own f32 tap walk (what BINARY mode reproduces): the
+    difference is that chain's rounding, < 1e-4 of the signal's RMS."""
+    sys.path.insert(0, str(GOLDEN.parent.parent / "tools"))
+    import simulators as S
+    L, W = 300, 60000
+    st = list(S.STATIONS.values())
+    caps, _ = S.simulate_perfect(st, (41.20, -96.00, 400.0), 92300000.0, 1000.0, 70000, seed=500)
+    raws = [c.numpy() for c in caps]
+    oracle.set_seq_dc_limit(0)
+    try:
+        with T.Engine(T.MODE_EXTENDED, max_lag=L) as e:
+            load_all(e, raws)
+            got = e.xcorr(T.KIND_TGT, 500, W, 1, 0)[0]
+            ys_ref, ys = [], []
+            for k in range(3):
+                x = split(raws[k])[1][500:500 + W]
+                out, p0, br = e.preprocess(k, T.KIND_TGT, 500, W)
+                assert br == 2
+                oracle.set_wide_boxcar_f64(0)
+                y_ref, wbr = oracle.preprocess_binary(x)          # the reference's f32 tap walk
+                oracle.set_wide_boxcar_f64(33)
+                y, _ = oracle.preprocess_binary(x)                # EXTENDED's statement
+                assert wbr == 2
+                assert np.count_nonzero(out != y) <= W // 1000, np.count_nonzero(out != y)
+                assert np.max(np.abs(out - y)) <= 2e-6
+                rms = float(np.sqrt(np.mean(np.abs(y_ref) ** 2)))
+                assert np.max(np.abs(out - y_ref)) <= 1e-4 * rms
+                ys.append(y)
+            for p, (i, j) in enumerate([(0, 1), (0, 2), (1, 2)]):
+                c = oracle.xcorr_two_sided(ys[i], ys[j], L)
+                idx, frac, val = oracle.peak_parabolic(c)
+                assert int(got[p]["lag"]) == idx - L
+                assert abs(float(got[p]["frac"]) - frac) <= 1e-3
+                assert abs(float(got[p]["corr"]) - val) <= CORR_TOL
+    finally:
+        oracle.set_seq_dc_limit(-1)
+        oracle.set_wide_boxcar_f64(0)
 
 
 @pytest.mark.parametrize("D", [4, 8])
@@ -475,13 +555,14 @@ def test_cpp_host_mirror_stdout_is_the_shipped_binarys(tmp_path, case):
         assert _same_line(a, b), f"line {k}: ours {a!r} != reference {b!r}"
 
 
-@pytest.mark.parametrize("case", GOLDEN_LONG_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_ORDER_CASES + GOLDEN_TABLE_CASES)
+@pytest.mark.parametrize("case", GOLDEN_LONG_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_ORDER_CASES + GOLDEN_TABLE_CASES + GOLDEN_SIM_CASES)
 def test_blocks_longer_than_the_test_chunk(tmp_path, case):
     """Blocks of 1 050 000 samples: the shipped binary cuts REF and TGT to their first 1 000 000
     samples before the pair loops (processor.go:772-780).  Degenerate cases: a third capture of 2
     samples (returned unchanged as REF and TGT), of 3 samples (one-sample blocks), empty
     (crossCorrelate warns and returns (0, 0.0)).  Captures given in another order, and four
-    collectors: pairs i < j in the order of the arguments.  Station tables with coincident or
+    collectors: pairs i < j in the order of the arguments.  The reference's own simulators' content
+    (sim_perfect, sim_weak: weak branch on every signal).  Station tables with coincident or
     close stations: the solver's single-equation fall-back and poor-geometry warning.  Records against what the binary
     printed (bit-exact lags, correlation to the printed 6 decimals), and the C++ command's
     stdout against the binary's, line for line."""

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from helpers import GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, GOLDEN_ORDER_CASES, GOLDEN_TABLE_CASES, STATION_LLH, load_golden
+from helpers import GOLDEN_CASES, GOLDEN_DEGENERATE_CASES, GOLDEN_LONG_CASES, GOLDEN_SIM_CASES, GOLDEN_ORDER_CASES, GOLDEN_TABLE_CASES, STATION_LLH, load_golden
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
@@ -18,6 +18,22 @@ def test_binary_pairs_match_reference_stdout(case):
         assert kind == want["kind"]
         assert delay == want["delay"], (case, want)
         # the reference prints %.6f
+        assert abs(corr - want["corr"]) <= 0.51e-6, (case, corr, want)
+
+
+@pytest.mark.parametrize("case", GOLDEN_SIM_CASES)
+def test_binary_on_the_reference_simulators_content(case):
+    """simulator.go / weak_signal_simulator.go content (BASELINE configs[0] and configs[3] name them;
+    restated in tools/simulators.py): every signal takes the weak branch (1001-tap high-pass, 5-tap
+    low-pass), the tones give periodic peaks and sanity re-searches, the weak simulator's reference
+    blocks quantise to a constant.  Records as the binary printed them."""
+    raws, meta = load_golden(case)
+    assert set(meta["branch"]) == {2}
+    ref, tgt = oracle.process_capture_binary(raws)
+    got = [("REF",) + r for r in ref] + [("TGT",) + r for r in tgt]
+    assert len(got) == len(meta["pairs"]) == 6
+    for (kind, delay, corr, _), want in zip(got, meta["pairs"]):
+        assert (kind, delay) == (want["kind"], want["delay"]), (case, want)
         assert abs(corr - want["corr"]) <= 0.51e-6, (case, corr, want)
 
 
@@ -85,7 +101,7 @@ def _golden_solver_inputs(case):
     return meta, llh, rd, (GOLDEN / f"{case}.stdout.txt").read_text()
 
 
-ALL_GOLDEN = GOLDEN_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_LONG_CASES + GOLDEN_ORDER_CASES + GOLDEN_TABLE_CASES
+ALL_GOLDEN = GOLDEN_CASES + GOLDEN_DEGENERATE_CASES + GOLDEN_LONG_CASES + GOLDEN_ORDER_CASES + GOLDEN_TABLE_CASES + GOLDEN_SIM_CASES
 
 
 def check_binary_solver_against_stdout(llh, rd, text, returncode, err):
