@@ -113,7 +113,13 @@ typedef struct {
                               the REF pair loop (their kernels share the SMs); 1 = one stream, one
                               kernel at a time (what the per-kernel timings of tdoa_get_stats
                               need to mean anything)                                        */
-    int32_t reserved[2];
+    int32_t n_devices;     /* 0 or 1: one GPU (`device`).  N > 1: this ONE process drives the N GPUs
+                              device .. device + N - 1: every capture is loaded to each of them and
+                              tdoa_xcorr over >= 2 windows deals the windows round-robin over them
+                              (processor.go:816-850 is the loop being sharded), the peak records
+                              meeting in one NCCL all-gather over NVLink; every other call runs on
+                              `device`.  One process per GPU instead: tdoa_comm_init            */
+    int32_t reserved[1];
 } tdoa_config;
 
 /* Fill *cfg with the reference-matching defaults of `mode`. */
@@ -170,6 +176,23 @@ TDOA_API int tdoa_xcorr(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t
 /* Same, peaks left in device memory (e.g. an NCCL send buffer); d_out[n_windows*P]. */
 TDOA_API int tdoa_xcorr_device(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
                                int32_t n_windows, int64_t hop, tdoa_peak *d_out);
+
+/* ---- more than one GPU, one process per GPU (torchrun, MPI, ...).  Rank 0 asks for an id
+ * (ncclGetUniqueId), the launcher hands its 128 bytes to every rank, every rank joins with its own
+ * engine (ncclCommInitRank on the engine's device).  From then on tdoa_xcorr / tdoa_xcorr_device
+ * over >= 2 windows are COLLECTIVE: every rank makes the same call; rank r correlates the windows w
+ * with (cursor + w) % world == r -- all pairs of a window on one GPU, so no data-path exchange --
+ * its peak kernel writes the records straight into the gather buffer, one ncclAllGather
+ * completes the table on every rank, and every rank returns all n_windows * P records.  cursor
+ * starts at 0 and advances by n_windows after every sharded call.  Each rank loads the captures it
+ * correlates (all of them, or -- tdoa_load_u8_pinned -- only the bytes its windows need).
+ * tdoa_xcorr_info afterwards describes the first window this rank processed. */
+TDOA_API int tdoa_comm_unique_id(uint8_t id[128]);
+TDOA_API int tdoa_comm_init(tdoa_engine *e, const uint8_t id[128], int32_t rank, int32_t world);
+TDOA_API int tdoa_comm_rank(tdoa_engine *e, int32_t *rank, int32_t *world);
+/* The dealing rule itself (host arithmetic, no GPU): rank's first window and how many it gets. */
+TDOA_API int tdoa_shard_windows(int32_t n_windows, int32_t rank, int32_t world, int32_t cursor, int32_t *first,
+                                int32_t *count);
 
 /* ProcessTDOA from the pair loops to the fix as ONE call (processor.go:816-929 on window 0
  * with the config's chunk): the REF pair loop, the TGT pair loop, dt = delay / fs, the

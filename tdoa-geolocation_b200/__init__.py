@@ -20,6 +20,7 @@ from ._native import (  # noqa: F401
     library_path,
     load_library,
     host_alloc,
+    comm_unique_id,
 )
 from .processor import Station, TDOAProcessor  # noqa: F401
 from . import sharding  # noqa: F401
@@ -27,5 +28,5 @@ from . import analyzer  # noqa: F401
 
 __all__ = [
     "Engine", "TdoaError", "Peak", "MODE_SOURCE", "MODE_BINARY", "MODE_EXTENDED", "KIND_REF", "KIND_TGT",
-    "default_config", "library_path", "load_library", "host_alloc", "Station", "TDOAProcessor", "sharding", "analyzer",
+    "default_config", "library_path", "load_library", "host_alloc", "comm_unique_id", "Station", "TDOAProcessor", "sharding", "analyzer",
 ]

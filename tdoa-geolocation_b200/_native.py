@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "tdoa_load_u8", "tdoa_load_file", "tdoa_load_u8_pinned", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_process", "tdoa_xcorr_info", "tdoa_analyze",
     "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_solve_binary", "tdoa_solve_ls", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
     "tdoa_set_stream", "tdoa_synchronize", "tdoa_selftest",
+    "tdoa_comm_unique_id", "tdoa_comm_init", "tdoa_comm_rank", "tdoa_shard_windows",
 ]
 
 
@@ -41,7 +42,7 @@ class Config(C.Structure):
         ("sample_rate", C.c_double), ("mode", C.c_int32), ("n_stations", C.c_int32),
         ("chunk_samples", C.c_int32), ("max_lag", C.c_int32), ("block_size", C.c_int32),
         ("sanity_lag", C.c_int32), ("fast_demod", C.c_int32), ("use_fft", C.c_int32),
-        ("device", C.c_int32), ("seq_dc_limit", C.c_int32), ("copy_chunk", C.c_int32), ("guard_samples", C.c_int32), ("decimate", C.c_int32), ("serial_kinds", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("device", C.c_int32), ("seq_dc_limit", C.c_int32), ("copy_chunk", C.c_int32), ("guard_samples", C.c_int32), ("decimate", C.c_int32), ("serial_kinds", C.c_int32), ("n_devices", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -154,6 +155,10 @@ def load_library():
     L.tdoa_set_stream.argtypes = [vp, vp]
     L.tdoa_synchronize.argtypes = [vp]
     L.tdoa_selftest.argtypes = [vp, i32, C.POINTER(C.c_int64)]
+    L.tdoa_comm_unique_id.argtypes = [vp]
+    L.tdoa_comm_init.argtypes = [vp, vp, i32, i32]
+    L.tdoa_comm_rank.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.tdoa_shard_windows.argtypes = [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     _lib = L
     return L
 
@@ -168,6 +173,25 @@ def default_config(mode: int, **overrides) -> Config:
             raise AttributeError(k)
         setattr(cfg, k, v)
     return cfg
+
+
+def comm_unique_id() -> bytes:
+    """tdoa_comm_unique_id: rank 0 makes the 128-byte id every rank passes to Engine.comm_init."""
+    buf = (C.c_uint8 * 128)()
+    L = load_library()
+    rc = L.tdoa_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc:
+        raise TdoaError(rc, (L.tdoa_last_error(None) or b"").decode())
+    return bytes(buf)
+
+
+def shard_windows_rule(n_windows: int, rank: int, world: int, cursor: int = 0):
+    """tdoa_shard_windows (host arithmetic, no GPU): (first, count) -- rank's windows are first, first + world, ..."""
+    first, count = C.c_int32(), C.c_int32()
+    rc = load_library().tdoa_shard_windows(n_windows, rank, world, cursor, C.byref(first), C.byref(count))
+    if rc:
+        raise ValueError(f"bad rank {rank} of {world} (cursor {cursor}, {n_windows} windows)")
+    return first.value, count.value
 
 
 class PinnedBuffer:
@@ -255,6 +279,16 @@ class Engine:
 
     def synchronize(self):
         self._check(self._lib.tdoa_synchronize(self._h))
+
+    # -- more than one GPU, one process per GPU (tdoa_comm_init): xcorr over >= 2 windows becomes collective
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.tdoa_comm_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+
+    def comm_rank(self):
+        r, w = C.c_int32(), C.c_int32()
+        self._check(self._lib.tdoa_comm_rank(self._h, C.byref(r), C.byref(w)))
+        return r.value, w.value
 
     def selftest(self, which: int = 0) -> int:
         bad = C.c_int64(-1)

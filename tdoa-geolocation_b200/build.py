@@ -33,6 +33,8 @@ UNITS = [
     ("xcorr_big.cu", []),
     ("xcorr_spec.cu", []),
     ("engine.cu", []),
+    ("engine_pipeline.cu", []),
+    ("engine_multi.cu", []),
 ]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -85,7 +87,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
             if res.returncode:
                 raise RuntimeError(f"nvcc failed on {src}")
     if force or _stale(OUT, objs):
-        cmd = [nvcc(), *ARCH, "-shared", "-o", str(OUT), *map(str, objs), "-cudart", "static"]
+        cmd = [nvcc(), *ARCH, "-shared", "-o", str(OUT), *map(str, objs), "-cudart", "static", "-ldl", "-lpthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode:
             sys.stderr.write(res.stderr)

@@ -15,14 +15,32 @@ from typing import List, Sequence, Tuple
 
 import numpy as np
 
-from ._native import PEAK_DTYPE
+from ._native import PEAK_DTYPE, comm_unique_id, shard_windows_rule
 
 
-def shard_windows(n_windows: int, rank: int, world: int) -> List[int]:
-    """Window indices owned by `rank` (round-robin: balances a trailing partial group)."""
+def shard_windows(n_windows: int, rank: int, world: int, cursor: int = 0) -> List[int]:
+    """Window indices owned by `rank`: window w belongs to rank (cursor + w) % world (round-robin:
+    balances a trailing partial group).  The rule is the engine's own (tdoa_shard_windows), the
+    one its in-library sharded tdoa_xcorr applies."""
     if world < 1 or not (0 <= rank < world):
         raise ValueError(f"bad rank {rank} of {world}")
-    return list(range(rank, n_windows, world))
+    first, count = shard_windows_rule(n_windows, rank, world, cursor)
+    return list(range(first, first + count * world, world))
+
+
+def init_engine_comm(engine, group=None) -> None:
+    """One process per GPU under torch.distributed: rank 0 makes the NCCL id (tdoa_comm_unique_id),
+    the process group carries its 128 bytes to the others, every rank joins (tdoa_comm_init).  From
+    then on engine.xcorr over >= 2 windows is sharded and gathered inside the library."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t = torch.tensor(list(comm_unique_id()), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, 0, group=group)
+    engine.comm_init(bytes(t.cpu().tolist()), rank, world)
 
 
 def window_runs(windows: Sequence[int]) -> List[Tuple[int, int, int]]:

@@ -26,6 +26,29 @@ def test_window_partition_covers_everything_once():
         S.shard_windows(4, 2, 2)
 
 
+def test_rotating_cursor_balances_back_to_back_calls():
+    """The engine's rule (tdoa_shard_windows, host arithmetic of libtdoa_b200.so): window w belongs to
+    rank (cursor + w) % world and the cursor advances by the windows of every sharded call, so that
+    66 REF windows followed by 33 TGT windows over 8 ranks (BASELINE config 4) leave every rank
+    with 12 or 13 windows instead of 9 + 5 on rank 0."""
+    world, cursor, load = 8, 0, [0] * 8
+    for n in (66, 33):
+        seen = []
+        for r in range(world):
+            ws = S.shard_windows(n, r, world, cursor)
+            assert all((cursor + w) % world == r for w in ws)
+            load[r] += len(ws)
+            seen += ws
+        assert sorted(seen) == list(range(n))
+        cursor = (cursor + n) % world
+    assert sorted(set(load)) == [12, 13] and sum(load) == 99
+    first, count = N.shard_windows_rule(5, 3, 4, 2)   # rank 3 of 4, window 0 belongs to rank 2
+    assert (first, count) == (1, 1)
+    assert N.shard_windows_rule(2, 1, 8, 6) == (3, 0)  # nothing for this rank
+    with pytest.raises(ValueError):
+        N.shard_windows_rule(4, 2, 2, 0)
+
+
 def test_window_runs_reconstruct_the_windows():
     for ws in ([], [5], [0, 2, 4, 6], [1, 9, 17], [0, 1, 2, 10, 20, 30, 31]):
         out = []
