@@ -19,6 +19,16 @@ and device->host read of the peak records and the fix inside the timed region.
 
 N > 1 (torchrun): every rank processes its own capture set (weak scaling, no data-path
 collective); the peak records are gathered with one NCCL all_gather.
+
+Beside the headline the line carries
+  parity_check.oracle_at_size  the CPU oracle (reference arithmetic) on the benchmark's own full-length captures:
+                               every one of the six pairs at the reported peak lag +- 5 -- the lag must be
+                               the oracle's arg-max and the correlation equal to 1e-6; a mismatch fails the run
+  sharded                      BASELINE configs[3] (weak_signal_simulator content, 16 stations = 120 pairs, 66 REF +
+                               33 TGT windows of 1 s) as ONE job dealt over the N GPUs inside the library
+                               (tdoa_comm_init, in-place ncclAllGather of the peak records): fixed work, strong scaling
+  cpu_restatement              BASELINE.md section 3, items 2-3: the C restatement of the binary's path on one host
+                               thread and on all host cores ("restatement, not the reference build")
 """
 from __future__ import annotations
 
@@ -197,6 +207,191 @@ def cpu_baseline(block: int = 250_000, n_proc: int = 1):
             "ok": ok}
 
 
+
+# ----------------------------------------------------------------------------- oracle at size (checker, never timed)
+def _oracle_signals(raws, block, kinds=(0, 1), workers=6):
+    """The reference's preprocessing (oracle/tdoa_oracle.c: unpack, power, discriminator, DC, 11-tap
+    box-car, normalise) of every station's REF (kind 0) / TGT (kind 1) signal, whole length, on host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+
+    def prep(job):
+        k, kind = job
+        raw = raws[k]
+        if kind == 0:   # blocks 1 and 3 (processor.go:224-236)
+            s = np.concatenate([oracle.unpack_u8(raw[:2 * block]), oracle.unpack_u8(raw[4 * block:6 * block])])
+        else:           # block 2 (:258-263)
+            s = oracle.unpack_u8(raw[2 * block:4 * block])
+        y, branch = oracle.preprocess_binary(s)
+        return job, y, branch
+
+    jobs = [(k, kind) for kind in kinds for k in range(len(raws))]
+    with ThreadPoolExecutor(max_workers=min(workers, len(jobs), os.cpu_count() or 1)) as pool:
+        return {job: (y, br) for job, y, br in pool.map(prep, jobs)}
+
+
+def oracle_check_at_size(raws, block, ref_pk, tgt_pk, max_lag=2000, span=5, tol=1e-6):
+    """Config 2 at its full length against the oracle: for each of the 3 REF + 3 TGT pairs the
+    reference's block-averaged correlation (binary_lag, ELF 0x49e027) at the engine's peak lag +- span.
+    Asserts nothing itself; returns what bench.py puts into parity_check (and fails the run on)."""
+    from oracle import oracle
+    t0 = time.perf_counter()
+    oracle.set_seq_dc_limit(4194304)   # beyond the reference's reach the engine's DC sum is exactly rounded (DESIGN.md 5)
+    try:
+        sig = _oracle_signals(raws, block)
+    finally:
+        oracle.set_seq_dc_limit(-1)
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    out, ok, worst = [], True, 0.0
+    for kind, pk in ((0, ref_pk), (1, tgt_pk)):
+        for p, (i, j) in enumerate(pairs):
+            yi, yj = sig[(i, kind)][0], sig[(j, kind)][0]
+            lag = int(pk[p]["lag"])
+            d0, d1 = max(0, lag - span), min(max_lag - 1, lag + span)
+            vals = oracle.tdcorr_binary_lags_mt(yi, yj[d0:], yi.size - max_lag, d1 - d0 + 1)   # equal lengths: template shortened by max_lag
+            best = int(np.argmax(np.abs(vals)))   # first maximum, as the reference's strict `>` scan
+            diff = abs(float(vals[lag - d0]) - float(pk[p]["corr"]))
+            worst = max(worst, diff)
+            good = best + d0 == lag and diff <= tol and sig[(i, kind)][1] == 0 and sig[(j, kind)][1] == 0
+            ok &= good
+            out.append({"kind": "REF" if kind == 0 else "TGT", "pair": [i, j], "engine_lag": lag, "oracle_argmax": best + d0,
+                        "oracle_corr": float(vals[lag - d0]), "engine_corr": float(pk[p]["corr"]), "ok": bool(good)})
+    return {"ok": bool(ok), "pairs": out, "lags_per_pair": 2 * span + 1, "max_abs_corr_diff": worst, "tolerance": tol,
+            "samples_per_pair": [2 * block, block], "seconds": time.perf_counter() - t0,
+            "what": "oracle/tdoa_oracle.c (the reference's arithmetic) on the benchmark's own full-length captures, "
+                    "peak lag +- %d of all six pairs" % span}
+
+
+def cpu_restatement(budget_block_st: int = 400_000, budget_block_mt: int = 6_000_000):
+    """the C restatement of the shipped binary's path (oracle/tdoa_oracle.c) on
+    whole signals -- no 1 000 000-sample truncation -- one host thread, then all host cores (OpenMP over lags,
+    threads over signals).  Restatement, not the reference build; bounded samples of the workload."""
+    from oracle import oracle
+    res = {}
+    for name, block, mt in (("single_thread", budget_block_st, False), ("all_cores", budget_block_mt, True)):
+        raws, _ = synth_captures_cpu(block)
+        t0 = time.perf_counter()
+        sig = _oracle_signals(raws, block, workers=6 if mt else 1)
+        n_lags, lag_found = 2000, []
+        for kind in (0, 1):
+            for i, j in ((0, 1), (0, 2), (1, 2)):
+                yi, yj = sig[(i, kind)][0], sig[(j, kind)][0]
+                if mt:
+                    vals = oracle.tdcorr_binary_lags_mt(yi, yj, yi.size - n_lags, n_lags)
+                    lag_found.append(int(np.argmax(np.abs(vals))))
+                else:
+                    lag_found.append(oracle.tdcorr_binary(yi, yj)[0])
+        wall = time.perf_counter() - t0
+        res[name] = {"value": 9 * block / wall / 1e6, "unit": "pair-Msamples/s", "cores": (os.cpu_count() or 1) if mt else 1,
+                     "kind": "port", "wall_s": wall, "lags": lag_found,
+                     "sample": f"3 stations x {3 * block} samples, whole-signal correlation of 3 REF ({2 * block}) + 3 TGT ({block}) "
+                               f"pairs x {n_lags} lags, C restatement of the binary's path (restatement, not the reference build)"}
+    return res
+
+
+# ----------------------------------------------------------------------------- BASELINE configs[3], dealt over the GPUs
+SHARD_W = 2_000_000
+
+
+def sharded_block(args, torch, dist, T, device, local, rank, world):
+    """weak_signal_simulator.go content (tools/simulators.py), 16 stations = 120 pairs, 1 s windows over the
+    whole 100 s capture: 66 REF + 33 TGT windows x 120 pairs per step, EXTENDED mode (+-2000 lags, sub-sample
+    vertex).  ONE job: the windows are dealt over the ranks inside tdoa_xcorr, all pairs of a window stay on one
+    GPU, the records meet in one in-place ncclAllGather per call.  Strong scaling: the work does not grow with N."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import simulators as S
+    block = args.shard_block
+    stations = S.ring_stations(16)
+    caps, _ = S.simulate_weak(stations, tuple(TX_LLH), 92300000.0, 10.0, 1000.0, block, seed=4242, device=device)
+    eng = T.Engine(T.MODE_EXTENDED, n_stations=16, max_lag=2000, device=local)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    for k in range(16):
+        eng.load_u8_device(k, caps[k].data_ptr(), caps[k].numel(), keep=caps[k])
+    if world > 1:
+        T.sharding.init_engine_comm(eng)
+    nw_t, nw_r = block // SHARD_W, 2 * block // SHARD_W
+
+    def step():
+        r = eng.xcorr(T.KIND_REF, 0, SHARD_W, nw_r, SHARD_W)
+        t = eng.xcorr(T.KIND_TGT, 0, SHARD_W, nw_t, SHARD_W)
+        return r, t
+
+    steps, warm = max(1, min(args.steps, 5)), 3
+    for _ in range(warm):
+        r, t = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.stats()["launches_total"]
+    e0.record()
+    for _ in range(steps):
+        r, t = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device, dtype=torch.float64)
+    launches = eng.stats()["launches_total"] - l0
+    # every rank must hold the same table
+    digest = torch.tensor([float(np.frombuffer(r.tobytes() + t.tobytes(), np.uint8).astype(np.int64).sum())], device=device,
+                          dtype=torch.float64)
+    same = True
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        lo, hi = digest.clone(), digest.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(lo.item() == hi.item())
+    out = None
+    if rank == 0:
+        sec = float(ms.item()) * 1e-3
+        units = (nw_r + nw_t) * 120
+        # the oracle's statement of EXTENDED mode on one sampled TGT window, two pairs (CPU: seconds)
+        verdict = sharded_oracle_sample(caps, block, t, nw_t) if world == 1 or args.shard_check else None
+        out = {"workload": "configs[3]: weak_signal_simulator.go content (ref_power 10, tgt_power 1000; tools/simulators.py), 16 stations "
+                           f"(120 pairs), {nw_r} REF + {nw_t} TGT windows of {SHARD_W} samples per step, EXTENDED mode, +-2000 lags",
+               "scaling": "strong", "n_gpus": world, "ms_per_step": sec * 1e3, "value": units * SHARD_W / sec / 1e6,
+               "unit": "pair-Msamples/s", "fixes_per_s": nw_t / sec, "window_pairs_per_step": units, "steps": steps, "warmup": warm,
+               "gpu_launches_rank0": int(launches), "all_ranks_hold_the_same_table": same,
+               "collective": "one in-place ncclAllGather of 32-byte peak records per tdoa_xcorr call (inside the library)"
+                             if world > 1 else "none (one rank)",
+               "windows_on_busiest_rank": -(-nw_r // world) + -(-nw_t // world) if world > 1 else nw_r + nw_t,
+               "oracle_sample": verdict}
+    eng.close()
+    del caps
+    torch.cuda.empty_cache()
+    return out
+
+
+def sharded_oracle_sample(caps, block, tgt_table, nw_t, window=7, pairs=((0, 1), (3, 9))):
+    from oracle import oracle
+    t0 = time.perf_counter()
+    w = min(window, nw_t - 1)
+    oracle.set_seq_dc_limit(0)
+    oracle.set_wide_boxcar_f64(33)
+    try:
+        ys = {}
+        for k in sorted({s for pr in pairs for s in pr}):
+            raw = caps[k][2 * block + 2 * w * SHARD_W:2 * block + 2 * (w + 1) * SHARD_W].cpu().numpy()
+            ys[k] = oracle.preprocess_binary(oracle.unpack_u8(raw))
+        res, ok = [], True
+        all_pairs = [(i, j) for i in range(16) for j in range(i + 1, 16)]
+        for i, j in pairs:
+            c = oracle.xcorr_two_sided(ys[i][0], ys[j][0], 2000)
+            idx, frac, val = oracle.peak_parabolic(c)
+            got = tgt_table[w][all_pairs.index((i, j))]
+            good = int(got["lag"]) == idx - 2000 and abs(float(got["frac"]) - frac) <= 1e-3 and abs(float(got["corr"]) - val) <= 1e-6
+            ok &= good
+            res.append({"pair": [i, j], "engine": [int(got["lag"]), float(got["frac"]), float(got["corr"])],
+                        "oracle": [idx - 2000, float(frac), float(val)], "branches": [ys[i][1], ys[j][1]], "ok": bool(good)})
+    finally:
+        oracle.set_seq_dc_limit(-1)
+        oracle.set_wide_boxcar_f64(0)
+    return {"ok": bool(ok), "window": w, "pairs": res, "seconds": time.perf_counter() - t0,
+            "what": "orc_preprocess_binary (EXTENDED arithmetic) + orc_xcorr_two_sided + orc_peak_parabolic on one TGT window"}
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -206,6 +401,8 @@ def main_reference(args):
     walls = []
     for i in range(args.warmup + args.steps):
         cb = cpu_baseline(block, n_proc)
+        if not cb["ok"]:
+            raise SystemExit("bench.py --impl reference: the reference binary did not print its six pair records")
         if i >= args.warmup:
             walls.append(3 * 3 * block * n_proc / (cb["value"] * 1e6))
     t = float(np.mean(walls))
@@ -214,7 +411,12 @@ def main_reference(args):
         "impl": "reference", "metric": "station-pair xcorr throughput", "value": value, "unit": "pair-Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": WORKLOAD_CONFIG,
+        # the workload is configs[1]; what this arm can run of it is a bounded sample (the binary truncates every
+        # signal to 1 000 000 samples, processor.go:772-780 with the shipped chunk): the rate per pair-sample is
+        # comparable (2000 lags on either side), the sizes are not -- both are stated
+        "config": dict(WORKLOAD_CONFIG, samples_per_station=3 * block,
+                       sample=f"each step: {n_proc} concurrent runs of the reference binary on 3 x {3 * block}-sample captures "
+                              f"(blocks of {block}); the GPU arm runs 3 x 200 000 000-sample captures per step"),
         "cpu_baseline": {"value": value, "unit": "pair-Msamples/s", "cores": n_proc, "kind": cb["kind"],
                          "sample": cb["sample"]},
         "e2e": {"value": value, "unit": "pair-Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -340,6 +542,10 @@ def main_ours(args):
     got_r, got_t = [int(x) for x in ref["lag"]], [int(x) for x in tgt["lag"]]
     clamp = [max(w, 0) for w in want]  # the reference searches non-negative lags only
     lags_ok = got_r == clamp and got_t == clamp
+    # the reference's own arithmetic (CPU oracle) on these very captures, at their full length
+    oracle_verdict = None
+    if rank == 0 and world == 1 and not args.no_oracle_check:
+        oracle_verdict = oracle_check_at_size([pb.array for pb in pinned], block, ref, tgt)
 
     # the same peaks through the engine's least-squares fix (all three range differences,
     # elevation held): the reference's own solver stops after ten half steps wherever it is
@@ -388,9 +594,11 @@ def main_ours(args):
     line = None
     if rank == 0:
         st = eng.stats()
-        # per-kernel roofline: ALGORITHMIC bytes per launch (distinct input +
-        # output bytes per unit x units of the launch) / device time of the launch (CUDA
-        # events recorded by the engine around the launch, on its own stream)
+        # per-kernel roofline: ALGORITHMIC bytes per launch = DISTINCT input + output bytes, each counted once
+        # (SURVEY.md 8d's rule) / device time of the launch (CUDA events recorded by the
+        # engine around the launch, on its own stream).  The correlation kernels read station planes that
+        # several pairs share: 3 stations serve 3 pairs, so a pair-sample stands for 4 distinct bytes (one f32
+        # of one plane), not the 8 a pair alone would read -- round 1 counted 8 and reported 0.42 / 1.23.
         traffic_db = {}
         tpath = ROOT / "profiles" / "traffic.json"
         if tpath.exists():
@@ -404,15 +612,16 @@ def main_ours(args):
             ms = stage[ms_key] / n
             ach = alg / (ms * 1e-3) / 1e9
             return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic_db.get(name), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                    "traffic": traffic_db.get(name), "traffic_source": traffic_db.get("_source") if traffic_db.get(name) else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                     "kernel_ms_per_launch": ms, "share_of_step": stage[ms_key] / (ms_serial if ms_serial > 0 else 1.0),
                     "measured": "CUDA events around each launch, %d serial steps (serial_kinds=1) of the same workload" % args.steps}
 
         kernels = [k for k in (
             kernel_line("k_demod_lean", 6.0, "demod_samples", "ms_demod", "demod_launches"),
             kernel_line("k_boxcar_small", 8.0, "boxcar_samples", "ms_boxcar", "boxcar_launches"),
-            kernel_line("k_fft_tiles", 8.0, "fft_pair_samples", "ms_fft_seg", "fft_launches"),
-            kernel_line("k_corr_candidates", 8.0, "cand_pair_samples", "ms_cand", "cand_launches"),
+            kernel_line("k_fft_tiles", 4.0, "fft_pair_samples", "ms_fft_seg", "fft_launches"),
+            kernel_line("k_corr_candidates", 4.0, "cand_pair_samples", "ms_cand", "cand_launches"),
         ) if k]
         if not kernels:  # FFT path disabled: the exact every-lag correlator carries the step
             k_ms = stage["ms_exact"] / max(1, args.steps)
@@ -423,6 +632,8 @@ def main_ours(args):
                         "share_of_step": 1.0}]
         dominant = max(kernels, key=lambda k: k["share_of_step"])
         cb = cpu_baseline() if world == 1 else None
+        if cb is not None and not cb["ok"]:
+            raise SystemExit("bench.py: the reference binary did not print its six pair records (cpu_baseline)")
         line = {
             "metric": "station-pair xcorr throughput", "value": value, "unit": "pair-Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
@@ -436,7 +647,9 @@ def main_ours(args):
                     # (llh, status, iterations), the per-signal statistics and first-pass correlations
                     "d2h_bytes_per_step": 2 * 3 * 32 + 2 * 3 * 8 + 3 * 8 + 4 + 4 + 2 * 3 * 8 * 8 + 2 * 3 * 8,
                     "ms_per_step": t_e2e * 1e3,
-                    "fixes_per_s": world / t_e2e},
+                    "fixes_per_s": world / t_e2e,
+                    # what the host path gives each GPU when all N pull at once (the copies are the step's floor)
+                    "h2d_gbps_per_gpu": 3 * nbytes / t_e2e / 1e9},
             "gpu_launches": launches,
             "host_affinity": numa,
             "clocks": clocks.summary(),
@@ -451,17 +664,38 @@ def main_ours(args):
                              "fix_note": "fix_llh is solveTDOA as the reference states it (its 10th half step, Z frozen); "
                                          "ls_fix_llh is tdoa_solve_ls on the same lags",
                              "ls_fix_llh": [float(x) for x in ls_pos], "ls_fix_error_m": ls_err, "ls_fix_rms_m": float(ls_rms),
-                             "ls_fix_status": int(ls_status)},
+                             "ls_fix_status": int(ls_status), "oracle_at_size": oracle_verdict},
             "cpu_baseline": {k: v for k, v in cb.items() if k != "ok"} if cb else None,
         }
+    eng.close()
+    eng_serial.close()
+    del caps, pinned
+    torch.cuda.empty_cache()
+    # BASELINE configs[3] as one job over the N GPUs (every rank takes part)
+    shard = None
+    if not args.no_sharded:
+        shard = sharded_block(args, torch, dist, T, device, local, rank, world)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    rc = 0
     if line is not None:
+        line["sharded"] = shard
+        if world == 1 and not args.no_cpu_restatement:
+            line["cpu_restatement"] = cpu_restatement()
+        bad = []
+        if not lags_ok:
+            bad.append("the benchmarked path did not recover the injected delays")
+        if oracle_verdict is not None and not oracle_verdict["ok"]:
+            bad.append("the benchmarked path disagrees with the CPU oracle at full size")
+        if shard and (not shard["all_ranks_hold_the_same_table"] or (shard["oracle_sample"] and not shard["oracle_sample"]["ok"])):
+            bad.append("the sharded configs[3] run failed its checks")
+        if bad:   # a throughput of wrong results is not a result
+            line["error"] = "; ".join(bad)
+            line["value"] = None
+            rc = 1
         OUT.emit(json.dumps(line))
-    eng.close()
-    eng_serial.close()
-    return 0
+    return rc
 
 
 class OnlyJsonOnStdout:
@@ -497,6 +731,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--block", type=int, default=66_666_666, help="samples per block (default: 100 s capture)")
+    ap.add_argument("--shard-block", type=int, default=66_666_666, help="samples per block of the sharded configs[3] job")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded configs[3] block")
+    ap.add_argument("--shard-check", action="store_true", help="run the oracle sample of the sharded block at N > 1 too")
+    ap.add_argument("--no-oracle-check", action="store_true", help="skip the CPU oracle at full size (parity_check.oracle_at_size)")
+    ap.add_argument("--no-cpu-restatement", action="store_true", help="skip the C restatement baselines (cpu_restatement)")
     args = ap.parse_args()
     with OnlyJsonOnStdout() as OUT:
         if args.impl == "reference":

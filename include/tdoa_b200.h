@@ -85,7 +85,9 @@ typedef struct {
     int32_t block_size;    /* 1000 source (processor.go:682), 10000 binary           */
     int32_t sanity_lag;    /* 120 (binary re-search window); 0 disables              */
     int32_t fast_demod;    /* 0: f64 products + f64 atan2 as the reference;
-                              1: f32 discriminator (<= 2 ulp), EXTENDED only default */
+                              1: f32 discriminator (<= 2 ulp), EXTENDED only default;
+                              2: as 0, every sample through the full-accuracy arctangent
+                                 (no fast path; a test switch)                        */
     int32_t use_fft;       /* 1: FFT candidate search + exact re-evaluation (2 x 2 station
                               tiles; station spectra parked once per segment for >= 10
                               pairs per window; a 2^21-point transform for >= 8192 lags);
@@ -319,8 +321,12 @@ TDOA_API int tdoa_get_stats(tdoa_engine *e, tdoa_stats *out);
 /* Device self-tests of arithmetic shortcuts the kernels rely on.  which = 0: the
  * box-car's constant-divisor division equals a correctly rounded f32 divide for every
  * float input (exhaustive, ~10 ms); *mismatches = 0 means proven.  which = 1: the
- * production FM discriminator against the reference statement of it over all 2^32
- * (previous, current) byte quads; the differing quads are listed in tdoa_last_error. */
+ * production FM discriminator (fast arctangent + full-accuracy fall-back where the f32
+ * rounding is not decided) against the reference statement of it over all 2^32
+ * (previous, current) byte quads; tdoa_last_error then carries the counts and the
+ * differing quads.  which = 2: *mismatches = how many of the 2^32 quads take the
+ * fall-back.  which = 3: as 1 for the full-accuracy arctangent on every sample
+ * (fast_demod = 2). */
 TDOA_API int tdoa_selftest(tdoa_engine *e, int32_t which, int64_t *mismatches);
 
 /* Raw CUDA stream of the engine (cudaStream_t as void*), for callers that time or

@@ -738,17 +738,20 @@ int tdoa_selftest(tdoa_engine *e, int32_t which, int64_t *mismatches)
     if (!e || !mismatches) return TDOA_E_INVALID;
     int rc = begin_call(e);
     if (rc) return rc;
-    if (which != 0 && which != 1) return fail(e, TDOA_E_INVALID, "tdoa_selftest: unknown test %d", which);
+    if (which < 0 || which > 3) return fail(e, TDOA_E_INVALID, "tdoa_selftest: unknown test %d", which);
     unsigned first_bad[64] = {0};
-    const long long bad = which == 0 ? div_selftest(e->stream) : demod_selftest(e->stream, first_bad);
-    if (which == 1 && bad > 0) {
+    long long extra[2] = {0, 0};
+    const long long bad = which == 0 ? div_selftest(e->stream) : demod_selftest(e->stream, first_bad, which == 3 ? 3 : 1, extra);
+    if (bad < 0) return fail(e, TDOA_E_CUDA, "tdoa_selftest: kernel failed");
+    if (which == 2) { *mismatches = extra[0]; return TDOA_OK; }   // fall-backs taken over the 2^32 quads
+    if (which != 0) {
         char buf[400];
-        int off = snprintf(buf, sizeof(buf), "demod selftest: %lld differing quads, first:", bad);
+        int off = snprintf(buf, sizeof(buf), "demod selftest: %lld differing quads, %lld fall-backs to the full-accuracy arctangent "
+                           "(%lld of them changed the value)%s", bad, extra[0], extra[1], bad ? "; first:" : "");
         for (unsigned k = 0; k < first_bad[0] && k < 12 && off < (int)sizeof(buf) - 12; k++)
             off += snprintf(buf + off, sizeof(buf) - off, " %08x", first_bad[1 + k]);
         e->error = buf;
     }
-    if (bad < 0) return fail(e, TDOA_E_CUDA, "tdoa_selftest: kernel failed");
     *mismatches = bad;
     return TDOA_OK;
 }

@@ -25,6 +25,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -35,7 +36,25 @@ using namespace tdoa;
 
 namespace tdoa {
 
+// one process, several devices: the host threads meet here before the gather, so that a device which
+// failed on the way (and will never launch its part of the collective) does not leave the others waiting
+struct Rendezvous {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 0, arrived = 0, failed = 0;
+    bool arrive(bool ok)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        arrived++;
+        if (!ok) failed++;
+        if (arrived == n) cv.notify_all();
+        else cv.wait(lk, [&] { return arrived == n; });
+        return failed == 0;
+    }
+};
+
 struct MultiState {
+    Rendezvous *rdv = nullptr;            // set for the duration of a multi-device call
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
     int cursor = 0;                       // rank that owns window 0 of the next sharded call
@@ -102,15 +121,22 @@ int sharded_rank(tdoa_engine *e, int32_t kind, int64_t win_start, const std::vec
     int32_t first = 0, count = 0;
     tdoa_shard_windows(n_windows, M.rank, world, M.cursor, &first, &count);
     int rc;
-    PeakRec *d_gather = nullptr, *d_table = nullptr;
-    if ((rc = alloc_t(e, &d_gather, (size_t)world * n_max * P))) return rc;
-    if (out_is_device) d_table = reinterpret_cast<PeakRec *>(out);
-    else if ((rc = alloc_t(e, &d_table, (size_t)n_windows * P))) return rc;
-    PeakRec *mine = d_gather + (size_t)M.rank * n_max * P;
-    CU(cudaMemsetAsync(mine, 0, (size_t)n_max * P * sizeof(PeakRec), e->stream));
-    stats_reset(e);
-    cudaEventRecord(e->ev[0], e->stream);
-    if (count > 0 && (rc = xcorr_core(e, kind, win_start + (i64)first * hop, len, count, hop * world, mine, nullptr))) return rc;
+    PeakRec *d_gather = nullptr, *d_table = nullptr, *mine = nullptr;
+    auto before_the_gather = [&]() -> int {
+        if ((rc = alloc_t(e, &d_gather, (size_t)world * n_max * P))) return rc;
+        if (out_is_device) d_table = reinterpret_cast<PeakRec *>(out);
+        else if ((rc = alloc_t(e, &d_table, (size_t)n_windows * P))) return rc;
+        mine = d_gather + (size_t)M.rank * n_max * P;
+        CU(cudaMemsetAsync(mine, 0, (size_t)n_max * P * sizeof(PeakRec), e->stream));
+        stats_reset(e);
+        cudaEventRecord(e->ev[0], e->stream);
+        if (count > 0 && (rc = xcorr_core(e, kind, win_start + (i64)first * hop, len, count, hop * world, mine, nullptr))) return rc;
+        return TDOA_OK;
+    };
+    rc = before_the_gather();
+    if (M.rdv && !M.rdv->arrive(rc == TDOA_OK))
+        return rc ? rc : fail(e, TDOA_E_STATE, "another device of this engine failed before the gather");
+    if (rc) return rc;
     const ncclResult_t nr = N.AllGather(mine, d_gather, (size_t)n_max * P * sizeof(PeakRec), ncclUint8, M.comm, e->stream);
     if (nr != ncclSuccess) return fail(e, TDOA_E_CUDA, "ncclAllGather failed: %s", N.GetErrorString(nr));
     k_window_order<<<(n_windows * P + 255) / 256, 256, 0, e->stream>>>(d_gather, d_table, n_windows, P, world, M.cursor, n_max);
@@ -147,6 +173,9 @@ int xcorr_sharded(tdoa_engine *e, int32_t kind, int64_t win_start, const std::ve
     const int n = (int)M.peers.size();
     std::vector<int> rcs(n, TDOA_OK);
     std::vector<std::thread> threads;
+    Rendezvous rdv;
+    rdv.n = n;
+    for (int r = 0; r < n; r++) M.peers[r]->multi->rdv = &rdv;
     for (int r = 1; r < n; r++)
         threads.emplace_back([&, r] {
             tdoa_engine *p = M.peers[r];
@@ -154,11 +183,13 @@ int xcorr_sharded(tdoa_engine *e, int32_t kind, int64_t win_start, const std::ve
             std::vector<i64> plen;
             const i64 wl = len.empty() ? 0 : len[0];
             if (!rc) rc = window_lengths(p, kind, win_start, wl, n_windows, hop, plen);
-            if (!rc) rc = sharded_rank(p, kind, win_start, plen, n_windows, hop, nullptr, false);
+            if (rc) rdv.arrive(false);
+            else rc = sharded_rank(p, kind, win_start, plen, n_windows, hop, nullptr, false);
             rcs[r] = rc;
         });
     rcs[0] = sharded_rank(e, kind, win_start, len, n_windows, hop, out, out_is_device);
     for (auto &t : threads) t.join();
+    for (int r = 0; r < n; r++) M.peers[r]->multi->rdv = nullptr;
     cudaSetDevice(e->device);
     for (int r = 1; r < n; r++)
         if (rcs[r]) return fail(e, rcs[r], "device %d: %s", M.peers[r]->device, M.peers[r]->error.c_str());

@@ -770,6 +770,7 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
         S.neighbours = J.variant == CORR_EXTENDED; S.max_cand = kMaxCand;
         S.tol = 2e-5f;
         S.cand = d_cand; S.n_cand = d_ncand; S.approx_max = d_amax;
+        S.t_stats = J.t_stats; S.s_stats = J.s_stats;
         CandJob &C = cjobs[p];
         C.cand = d_cand; C.n_cand = d_ncand; C.max_cand = kMaxCand; C.approx = d_approx; C.blocksums = J.blocksums;
         pjobs[p] = J;

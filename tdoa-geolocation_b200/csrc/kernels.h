@@ -135,7 +135,7 @@ long long div_selftest(cudaStream_t st);  // mismatches of the constant-divisor 
 int demod_setup(cudaStream_t st);         // tables + shared-memory opt-in of the lean discriminator; 0 ok
 // lean discriminator against the reference statement over all 2^32 (previous, current) byte quads;
 // first_bad: [0] = count stored, [1..63] = offending quads (prev I, prev Q, cur I, cur Q from the low byte up)
-long long demod_selftest(cudaStream_t st, unsigned *first_bad);
+long long demod_selftest(cudaStream_t st, unsigned *first_bad, int which, long long *extra);
 int fast_grid_x(i64 n);
 
 // ---- xcorr_exact.cu

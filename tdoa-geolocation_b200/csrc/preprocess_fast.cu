@@ -407,6 +407,262 @@ __global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean(const SigJob *jo
     }
 }
 
+
+// ---------------------------------------------------------------- lean discriminator, second generation
+// Measured per-SM rates of this part (tools/micro/pipes.cu, profiles/r2_pipe_rates.txt): FP64 and
+// LOP/SHF/PRMT/SEL issue every 2nd cycle per scheduler, MUFU (f32 or RCP64H) and the f64 -> f32
+// conversion every 8th, the f32 -> f64 conversion is nearly free, and all of them overlap -- so the
+// kernel is bound by ISSUE SLOTS first (round 1: 69 per sample, ncu).  This version spends ~46:
+//   - the f64 products are rounded to f32 by the conversion instruction (1 slot instead of 6 integer
+//     ones); with the f32 values at hand the octant logic is f32 min/max/compare (|.| is an operand
+//     modifier) and the table index comes from one MUFU.RCP + FFMA;
+//   - FAST PATH: atan(mn/mx) = atan(k/64) + atan(z), z = (mn - c mx)/(mx + c mn) from ONE Newton step on
+//     the RCP64H seed and a two-term series -- relative error < 2^-43 -- which decides the f32 rounding
+//     unless the f64 result sits within 2^-38 (relative) of an f32 rounding boundary: 2^-14 of the samples;
+//   - those samples (a thread with any of its 8) are redone with the full-accuracy arctangent of
+//     round 1 (atan2_lean), so the output equals it everywhere: tdoa_selftest(1) runs THIS function
+//     against demod_one<false> over all 2^32 byte quads and counts the fall-backs.
+struct __align__(16) OctEntry {
+    double base;   // B(case) + sigma(case) * atan(k / 64)
+    double c;      // k / 64
+};
+
+struct LeanSmem2 {
+    LeanEntry tab[256][16];                       // 64 KB
+    OctEntry oct[4][kOctStride];                  // 8 KB
+    double oct_exact[4][kOctStride];              // round-1 table for the exact fall-back (4 KB)
+    unsigned stage[2][kLeanWords][kLeanThreads];  // cp.async landing zone, double buffered
+    double scratch[32];
+    int last;
+};
+
+__device__ __forceinline__ void lean2_fill(LeanSmem2 &S, const double *__restrict__ atab_g)
+{
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+        const float v = unpack_byte((unsigned)(i >> 4));
+        LeanEntry e;
+        e.v = (double)v; e.sq = __fmul_rn(v, v); e.vf = v;
+        S.tab[i >> 4][i & 15] = e;
+    }
+    for (int i = threadIdx.x; i < 4 * kOctStride; i += blockDim.x) {
+        const int oc = i / kOctStride, k = i % kOctStride;
+        const int kk = k <= kAtanK ? k : kAtanK;
+        const double a = atab_g[kk];
+        const double pio2 = 1.57079632679489661923, pi = 3.14159265358979323846;
+        const double b = oc == 0 ? a : (oc == 1 ? pio2 - a : (oc == 2 ? pi - a : pio2 + a));
+        S.oct[oc][k].base = b;
+        S.oct[oc][k].c = (double)kk / (double)kAtanK;
+        S.oct_exact[oc][k] = b;
+    }
+}
+
+// fast discriminator value for X = Re p, Y = Im p (f64, before their rounding to f32); `unsafe` is
+// raised when the f32 rounding of the result is not decided by the fast path's accuracy
+__device__ __forceinline__ float lean2_fast(double X, double Y, unsigned oct_base, unsigned &unsafe)
+{
+    const float xf = (float)X, yf = (float)Y;                     // the reference's float32(...) of the products
+    const float ax = fabsf(xf), ay = fabsf(yf);
+    const bool sw = ay > ax;
+    const float mxf = fmaxf(ax, ay), mnf = fminf(ax, ay);
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(mxf));
+    const float kf = fmaf(mnf * rf, (float)kAtanK, 12582912.0f);   // 1.5 * 2^23: round(64 q) in the low mantissa bits
+    const unsigned kb = __float_as_uint(kf) & 0x7fu;
+    const unsigned xneg = __float_as_uint(xf) >> 31;
+    const unsigned addr = oct_base + (((xneg * 2u + (sw ? 1u : 0u)) * (unsigned)kOctStride + kb) << 4);
+    double base, c;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(base), "=d"(c) : "r"(addr));
+    const double mx = (double)mxf, mn = (double)mnf;              // exact
+    const double num = fma(-c, mx, mn), den = fma(c, mn, mx);
+    double r = rcp_seed(den);
+    r = fma(r, fma(-den, r, 1.0), r);
+    const double z = num * r;
+    const double w = z * z;
+    const double az = fma(z * w, fma(w, 0.2, -1.0 / 3.0), z);     // |z| <= ~1/127: the next term is < 2^-44 relative
+    // atan(z) enters with a minus sign when exactly one of {swap, x < 0} holds
+    const unsigned flip = ((sw ? 1u : 0u) ^ xneg) << 31;
+    const double a = base + hilo((unsigned)__double2hiint(az) ^ flip, (unsigned)__double2loint(az));
+    // f64 -> f32 keeps 24 of the 53 mantissa bits: rounding boundary at 2^28 in the low word's 29 bits
+    const unsigned t = ((unsigned)__double2loint(a) - 0x0FFFC000u) & 0x1FFFFFFFu;
+    unsafe |= t < 0x8000u ? 1u : 0u;
+    const float o = (float)a;
+    return __uint_as_float(__float_as_uint(o) | (__float_as_uint(yf) & 0x80000000u));
+}
+
+__global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean2(const SigJob *jobs, const double *__restrict__ atab_g)
+{
+    extern __shared__ __align__(16) unsigned char lean_raw[];
+    LeanSmem2 &S = *reinterpret_cast<LeanSmem2 *>(lean_raw);
+    const SigJob &J = jobs[blockIdx.y];
+    const int tid = threadIdx.x;
+    lean2_fill(S, atab_g);
+    __syncthreads();
+    const i64 n = J.n;
+    const i64 i_begin = J.i_begin, i_end = J.i_end > 0 ? J.i_end : n;
+    const uint8_t *__restrict__ rawb = J.src.raw;
+    float *__restrict__ out = J.p_re;
+    const i64 run0 = J.src.run0_len;
+    const unsigned slot16 = (unsigned)(tid & 15) * 16u;
+    const unsigned tab_base = (unsigned)__cvta_generic_to_shared(&S.tab[0][0]);
+    const unsigned oct_base = (unsigned)__cvta_generic_to_shared(&S.oct[0][0]);
+    const unsigned octx_base = (unsigned)__cvta_generic_to_shared(&S.oct_exact[0][0]);
+    double pw = 0.0, sr = 0.0;
+    auto fast_tile = [&](i64 t0) {
+        const bool in0 = t0 + kLeanTile + 2 <= run0, in1 = t0 - 1 >= run0 && t0 + kLeanTile + 2 <= n;
+        return t0 > 0 && t0 + kLeanTile <= i_end && (in0 || in1);
+    };
+    auto tile_addr = [&](i64 t0) { return rawb + 2 * (raw_index(J.src, t0) + (i64)kLeanPer * tid); };
+    auto stage_tile = [&](i64 t0, int buf) {
+        if (fast_tile(t0)) {
+            const uint8_t *ap = tile_addr(t0);
+            const unsigned *wp = reinterpret_cast<const unsigned *>(ap - (reinterpret_cast<uintptr_t>(ap) & 2u)) - 1;
+#pragma unroll
+            for (int k = 0; k < kLeanWords; k++) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&S.stage[buf][k][tid]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(wp + k) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const i64 step = (i64)gridDim.x * kLeanTile;
+    int buf = 0;
+    stage_tile(i_begin + (i64)blockIdx.x * kLeanTile, 0);
+    for (i64 i0 = i_begin + (i64)blockIdx.x * kLeanTile; i0 < i_end; i0 += step, buf ^= 1) {
+        stage_tile(i0 + step, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (fast_tile(i0)) {
+            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(tile_addr(i0)) & 2u) * 8u;
+            const unsigned wm = S.stage[buf][0][tid], w0 = S.stage[buf][1][tid], w1 = S.stage[buf][2][tid],
+                           w2 = S.stage[buf][3][tid], w3 = S.stage[buf][4][tid], w4 = S.stage[buf][5][tid];
+            const unsigned pv = __funnelshift_r(wm, w0, sh);
+            unsigned w[4];
+            w[0] = __funnelshift_r(w0, w1, sh); w[1] = __funnelshift_r(w1, w2, sh);
+            w[2] = __funnelshift_r(w2, w3, sh); w[3] = __funnelshift_r(w3, w4, sh);
+            double pr, pi;
+            float sq_i, sq_q;
+            lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5524), pr, sq_i);
+            lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5534), pi, sq_q);
+            const double pr0 = pr, pi0 = pi;
+            float o[kLeanPer];
+            unsigned unsafe = 0u;
+            double srt = 0.0;
+#pragma unroll
+            for (int s = 0; s < kLeanPer; s++) {
+                const unsigned ww = w[s >> 1];
+                double cr, ci;
+                lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5524 : 0x5504), cr, sq_i);
+                lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5534 : 0x5514), ci, sq_q);
+                pw += (double)__fadd_rn(sq_i, sq_q);   // processor.go:328, f32 re*re + im*im
+                const double X = fma(pr, cr, __dmul_rn(pi, ci)), Y = fma(ci, pr, -__dmul_rn(pi, cr));
+                o[s] = lean2_fast(X, Y, oct_base, unsafe);
+                srt += (double)o[s];
+                pr = cr; pi = ci;
+            }
+            if (unsafe) {
+                // ~2^-14 of the samples: the thread's eight again, with the full-accuracy arctangent
+                pr = pr0; pi = pi0;
+                srt = 0.0;
+#pragma unroll
+                for (int s = 0; s < kLeanPer; s++) {
+                    const unsigned ww = w[s >> 1];
+                    double cr, ci;
+                    lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5524 : 0x5504), cr, sq_i);
+                    lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5534 : 0x5514), ci, sq_q);
+                    o[s] = lean_one(pr, pi, cr, ci, octx_base);
+                    srt += (double)o[s];
+                    pr = cr; pi = ci;
+                }
+            }
+            sr += srt;
+            float4 *op = reinterpret_cast<float4 *>(out + i0 + (i64)kLeanPer * tid);
+            op[0] = make_float4(o[0], o[1], o[2], o[3]);
+            op[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+            // edges (signal start, the block-1/block-3 joint, the tail): the reference's
+            // own statement of the discriminator, sample by sample, gates included
+            for (int u = 0; u < kLeanPer; u++) {
+                const i64 i = i0 + tid + (i64)kLeanThreads * u;
+                if (i >= i_end) break;
+                const i64 k = i == 0 ? 1 : i;  // out[0] = out[1]
+                const uchar2 cur = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k)];
+                const uchar2 prv = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k - 1)];
+                const uchar2 me = i == 0 ? prv : cur;  // initial power is of sample i itself
+                pw += (double)__fadd_rn(S.tab[me.x][0].sq, S.tab[me.y][0].sq);
+                const double pr = S.tab[prv.x][0].v, pi = S.tab[prv.y][0].v, cr = S.tab[cur.x][0].v, ci = S.tab[cur.y][0].v;
+                const double re = fma(pr, cr, __dmul_rn(ci, pi)), im = fma(ci, pr, -__dmul_rn(pi, cr));
+                const float fre = (float)re, fim = (float)im;
+                const float m = __fadd_rn(__fmul_rn(fre, fre), __fmul_rn(fim, fim));
+                float y = 0.f;
+                if (m > 1e-10f) y = (float)atan2_lean((double)fim, (double)fre, octx_base);
+                out[i] = y;
+                sr += (double)y;
+            }
+        }
+    }
+    double part[2], total[2];
+    part[0] = block_sum(pw, S.scratch);
+    part[1] = block_sum(sr, S.scratch);
+    if (grid_sum_last_dyn<2>(part, J.partials, J.counter, gridDim.x, blockIdx.x, S.scratch, &S.last, total)) {
+        if (J.chunk_out) {
+            J.chunk_out[0] = total[0];
+            J.chunk_out[1] = total[1];
+            return;
+        }
+        J.stats[ST_POWER0] = n > 0 ? total[0] / (double)n : 0.0;
+        J.stats[ST_SUM_RE] = total[1];
+        J.stats[ST_SUM_IM] = 0.0;
+        J.stats[ST_DC_RE] = n > 0 ? (double)dc_from_sum(total[1], n) : 0.0;
+        J.stats[ST_DC_IM] = 0.0;
+    }
+}
+
+// every (previous, current) byte quad: the production path (fast value, exact fall-back when flagged)
+// against demod_one<false>; also counts the fall-backs and the fast values that would have been wrong
+// without their flag
+__global__ void __launch_bounds__(256) k_demod_selftest2(const double *__restrict__ atab_g, unsigned long long *counts,
+                                                         unsigned *first_bad)
+{
+    extern __shared__ __align__(16) unsigned char lean_raw[];
+    LeanSmem2 &S = *reinterpret_cast<LeanSmem2 *>(lean_raw);
+    __shared__ DemodLuts L;
+    lean2_fill(S, atab_g);
+    {
+        const float v = unpack_byte((unsigned)threadIdx.x);
+        L.lutf[threadIdx.x] = v;
+        L.lut[threadIdx.x] = (double)v;
+        if (threadIdx.x < 9) { L.atan_d[threadIdx.x] = atan_k8(threadIdx.x); L.atan_f[threadIdx.x] = (float)atan_k8(threadIdx.x); }
+    }
+    __syncthreads();
+    const unsigned oct_base = (unsigned)__cvta_generic_to_shared(&S.oct[0][0]);
+    const unsigned octx_base = (unsigned)__cvta_generic_to_shared(&S.oct_exact[0][0]);
+    const int slot = threadIdx.x & 15;
+    unsigned bad = 0, flagged = 0, saved = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * 256 + threadIdx.x; q < (1ull << 32); q += stride) {
+        const uchar2 prv = make_uchar2((unsigned char)(q & 255), (unsigned char)(q >> 8 & 255));
+        const uchar2 cur = make_uchar2((unsigned char)(q >> 16 & 255), (unsigned char)(q >> 24 & 255));
+        const float want = demod_one<false>(L, prv, cur);
+        const double pr = S.tab[prv.x][slot].v, pi = S.tab[prv.y][slot].v, cr = S.tab[cur.x][slot].v, ci = S.tab[cur.y][slot].v;
+        const double X = fma(pr, cr, __dmul_rn(pi, ci)), Y = fma(ci, pr, -__dmul_rn(pi, cr));
+        unsigned unsafe = 0u;
+        float got = lean2_fast(X, Y, oct_base, unsafe);
+        if (unsafe) {
+            flagged++;
+            const float exact = lean_one(pr, pi, cr, ci, octx_base);
+            if (__float_as_uint(exact) != __float_as_uint(got)) saved++;
+            got = exact;
+        }
+        if (__float_as_uint(want) != __float_as_uint(got)) {
+            bad++;
+            const unsigned at = atomicAdd(first_bad, 1u);
+            if (at < 63) first_bad[1 + at] = (unsigned)q;
+        }
+    }
+    if (bad) atomicAdd(counts, (unsigned long long)bad);
+    if (flagged) atomicAdd(counts + 1, (unsigned long long)flagged);
+    if (saved) atomicAdd(counts + 2, (unsigned long long)saved);
+}
+
 // statistics of a signal whose discriminator ran in chunks (fixed order: chunk 0, 1, ...)
 __global__ void k_demod_finish(const double *__restrict__ chunk_sums, int n_chunks, i64 n, double *stats)
 {
@@ -630,19 +886,38 @@ int fast_grid_x(i64 n)
 }
 
 // atan(k / 64) for the lean discriminator, correctly rounded by the host's libm
-static double *g_atab = nullptr;
+// (one table per device: an engine with n_devices > 1 has peers on other GPUs of this process)
+constexpr int kMaxDevices = 64;
+static double *g_atab_dev[kMaxDevices] = {nullptr};
+
+static double *atab_here()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? g_atab_dev[dev] : nullptr;
+}
 
 int demod_setup(cudaStream_t st)
 {
-    if (g_atab) return 0;
-    double h[kAtanK + 2];
-    for (int k = 0; k <= kAtanK + 1; k++) h[k] = atan((double)k / (double)kAtanK);
-    if (cudaMalloc(&g_atab, sizeof(h)) != cudaSuccess) return -1;
-    if (cudaMemcpyAsync(g_atab, h, sizeof(h), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
-    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    if (!g_atab_dev[dev]) {
+        double h[kAtanK + 2];
+        for (int k = 0; k <= kAtanK + 1; k++) h[k] = atan((double)k / (double)kAtanK);
+        double *d = nullptr;
+        if (cudaMalloc(&d, sizeof(h)) != cudaSuccess) return -1;
+        if (cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+        g_atab_dev[dev] = d;
+    }
     if (cudaFuncSetAttribute(k_demod_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) != cudaSuccess)
         return -1;
     if (cudaFuncSetAttribute(k_demod_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) !=
+        cudaSuccess)
+        return -1;
+    if (cudaFuncSetAttribute(k_demod_lean2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2)) != cudaSuccess)
+        return -1;
+    if (cudaFuncSetAttribute(k_demod_selftest2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2)) !=
         cudaSuccess)
         return -1;
     return 0;
@@ -658,10 +933,12 @@ int lean_grid_x(i64 n, int n_jobs)
 
 void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, cudaStream_t st)
 {
-    if (fast) {
+    if (fast == 2) {   // test switch: the round-1 kernel (every sample through the full-accuracy arctangent)
+        k_demod_lean<<<dim3(lean_grid_x(max_n, n_jobs), n_jobs), kLeanThreads, sizeof(LeanSmem), st>>>(d_jobs, atab_here());
+    } else if (fast) {
         k_demod_fused<true><<<dim3(fast_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
     } else {
-        k_demod_lean<<<dim3(lean_grid_x(max_n, n_jobs), n_jobs), kLeanThreads, sizeof(LeanSmem), st>>>(d_jobs, g_atab);
+        k_demod_lean2<<<dim3(lean_grid_x(max_n, n_jobs), n_jobs), kLeanThreads, sizeof(LeanSmem2), st>>>(d_jobs, atab_here());
     }
 }
 
@@ -670,21 +947,26 @@ void launch_demod_finish(const double *chunk_sums, int n_chunks, i64 n, double *
     k_demod_finish<<<1, 32, 0, st>>>(chunk_sums, n_chunks, n, stats);
 }
 
-long long demod_selftest(cudaStream_t st, unsigned *first_bad_out)
+// which = 1: the production discriminator (fast value + exact fall-back); which = 3: the round-1 kernel's
+// arithmetic (every sample through the full-accuracy arctangent).  extra[0] = fall-backs taken, extra[1] =
+// fall-backs whose fast value would have been wrong (which = 1 only).
+long long demod_selftest(cudaStream_t st, unsigned *first_bad_out, int which, long long *extra)
 {
-    unsigned long long *d_bad = nullptr, h_bad = ~0ull;
+    unsigned long long *d_cnt = nullptr, h_cnt[3] = {~0ull, 0, 0};
     unsigned *d_first = nullptr;
-    if (cudaMalloc(&d_bad, sizeof(*d_bad)) != cudaSuccess) return -1;
-    if (cudaMalloc(&d_first, 64 * sizeof(unsigned)) != cudaSuccess) { cudaFree(d_bad); return -1; }
-    cudaMemsetAsync(d_bad, 0, sizeof(*d_bad), st);
+    if (cudaMalloc(&d_cnt, sizeof(h_cnt)) != cudaSuccess) return -1;
+    if (cudaMalloc(&d_first, 64 * sizeof(unsigned)) != cudaSuccess) { cudaFree(d_cnt); return -1; }
+    cudaMemsetAsync(d_cnt, 0, sizeof(h_cnt), st);
     cudaMemsetAsync(d_first, 0, 64 * sizeof(unsigned), st);
-    k_demod_selftest<<<148 * 2, 256, sizeof(LeanSmem), st>>>(g_atab, d_bad, d_first);
-    cudaMemcpyAsync(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, st);
+    if (which == 3) k_demod_selftest<<<148 * 2, 256, sizeof(LeanSmem), st>>>(atab_here(), d_cnt, d_first);
+    else k_demod_selftest2<<<148 * 2, 256, sizeof(LeanSmem2), st>>>(atab_here(), d_cnt, d_first);
+    cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
     if (first_bad_out) cudaMemcpyAsync(first_bad_out, d_first, 64 * sizeof(unsigned), cudaMemcpyDeviceToHost, st);
     const cudaError_t err = cudaStreamSynchronize(st);
-    cudaFree(d_bad);
+    cudaFree(d_cnt);
     cudaFree(d_first);
-    return err == cudaSuccess ? (long long)h_bad : -1;
+    if (extra) { extra[0] = (long long)h_cnt[1]; extra[1] = (long long)h_cnt[2]; }
+    return err == cudaSuccess ? (long long)h_cnt[0] : -1;
 }
 
 void launch_boxcar_small(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)

@@ -214,6 +214,14 @@ __global__ void __launch_bounds__(256) k_select_candidates(const SelJob *jobs)
     for (int o = 128; o > 0; o >>= 1) { if (tid < o) s_red[tid] = fmaxf(s_red[tid], s_red[tid + o]); __syncthreads(); }
     m2 = s_red[0];
     __syncthreads();
+    // A signal whose power before normalisation is zero is identically zero (the weak simulator's
+    // reference blocks quantise to a constant byte): every product is +-0, every lag's correlation
+    // is exactly 0, and the reference's strict `>` keeps its initial (first lag, 0.0).  One
+    // candidate says the same; without this the flat surface makes every lag a candidate.
+    if (m1 == 0.f && ((J.t_stats && J.t_stats[ST_POWER1] == 0.0) || (J.s_stats && J.s_stats[ST_POWER1] == 0.0))) {
+        if (tid == 0) { J.cand[0] = 0; *J.n_cand = 1; *J.approx_max = 0.f; }
+        return;
+    }
     const float thr1 = m1 - J.tol, thr2 = m2 - J.tol;
     // candidates are few: collect them with a shared-memory ticket, then order them by rank
     // (ascending lag, as the reference scans).  More than 256 means overflow anyway.

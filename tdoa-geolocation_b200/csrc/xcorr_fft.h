@@ -47,6 +47,7 @@ struct SelJob {
     int *cand;            // [max_cand] ascending lag indices
     int *n_cand;          // candidates found (may exceed max_cand: overflow)
     float *approx_max;
+    const double *t_stats, *s_stats;   // per-signal statistics (ST_POWER1): a signal without power is identically zero
 };
 
 struct CandJob {
