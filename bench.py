@@ -472,6 +472,15 @@ def main_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
+    if args.only_sharded:   # profiling aid: the sharded configs[3] block alone
+        shard = sharded_block(args, torch, dist, T, device, local, rank, world)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0:
+            OUT.emit(json.dumps({"sharded": shard}))
+        return 0
+
     block = args.block
     n_samp = 3 * block
     caps, delays = synth_captures_gpu(torch, device, block, seed=rank)
@@ -733,6 +742,7 @@ def main():
     ap.add_argument("--block", type=int, default=66_666_666, help="samples per block (default: 100 s capture)")
     ap.add_argument("--shard-block", type=int, default=66_666_666, help="samples per block of the sharded configs[3] job")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded configs[3] block")
+    ap.add_argument("--only-sharded", action="store_true", help="run the sharded configs[3] block alone (profiling aid)")
     ap.add_argument("--shard-check", action="store_true", help="run the oracle sample of the sharded block at N > 1 too")
     ap.add_argument("--no-oracle-check", action="store_true", help="skip the CPU oracle at full size (parity_check.oracle_at_size)")
     ap.add_argument("--no-cpu-restatement", action="store_true", help="skip the C restatement baselines (cpu_restatement)")

@@ -9,6 +9,7 @@
 //
 // Both keep the reference's arithmetic: f32 unpack via table, f64 products rounded once
 // to f32, f64 arctangent rounded to f32, sequential f32 tap sums in ascending order.
+#include <cstdlib>
 #include "atan2_core.cuh"
 #include "kernels.h"
 
@@ -427,16 +428,19 @@ struct __align__(16) OctEntry {
     double c;      // k / 64
 };
 
-struct LeanSmem2 {
+template <int THREADS>
+struct LeanSmem2T {
     LeanEntry tab[256][16];                       // 64 KB
     OctEntry oct[4][kOctStride];                  // 8 KB
     double oct_exact[4][kOctStride];              // round-1 table for the exact fall-back (4 KB)
-    unsigned stage[2][kLeanWords][kLeanThreads];  // cp.async landing zone, double buffered
+    unsigned stage[2][kLeanWords][THREADS];       // cp.async landing zone, double buffered
     double scratch[32];
     int last;
 };
+typedef LeanSmem2T<kLeanThreads> LeanSmem2;
 
-__device__ __forceinline__ void lean2_fill(LeanSmem2 &S, const double *__restrict__ atab_g)
+template <class SM>
+__device__ __forceinline__ void lean2_fill(SM &S, const double *__restrict__ atab_g)
 {
     for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
         const float v = unpack_byte((unsigned)(i >> 4));
@@ -489,10 +493,13 @@ __device__ __forceinline__ float lean2_fast(double X, double Y, unsigned oct_bas
     return __uint_as_float(__float_as_uint(o) | (__float_as_uint(yf) & 0x80000000u));
 }
 
-__global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean2(const SigJob *jobs, const double *__restrict__ atab_g)
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_demod_lean2(const SigJob *jobs, const double *__restrict__ atab_g)
 {
+    constexpr int kLeanThreads = THREADS;
+    constexpr int kLeanTile = THREADS * kLeanPer;
     extern __shared__ __align__(16) unsigned char lean_raw[];
-    LeanSmem2 &S = *reinterpret_cast<LeanSmem2 *>(lean_raw);
+    LeanSmem2T<THREADS> &S = *reinterpret_cast<LeanSmem2T<THREADS> *>(lean_raw);
     const SigJob &J = jobs[blockIdx.y];
     const int tid = threadIdx.x;
     lean2_fill(S, atab_g);
@@ -915,7 +922,11 @@ int demod_setup(cudaStream_t st)
     if (cudaFuncSetAttribute(k_demod_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) !=
         cudaSuccess)
         return -1;
-    if (cudaFuncSetAttribute(k_demod_lean2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2)) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_demod_lean2<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2T<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_lean2<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2T<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_lean2<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2T<256>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_lean2<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2T<384>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_lean2<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2T<256>)) != cudaSuccess)
         return -1;
     if (cudaFuncSetAttribute(k_demod_selftest2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2)) !=
         cudaSuccess)
@@ -938,7 +949,20 @@ void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, c
     } else if (fast) {
         k_demod_fused<true><<<dim3(fast_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
     } else {
-        k_demod_lean2<<<dim3(lean_grid_x(max_n, n_jobs), n_jobs), kLeanThreads, sizeof(LeanSmem2), st>>>(d_jobs, atab_here());
+        static const int variant = getenv("TDOA_DEMOD_VARIANT") ? atoi(getenv("TDOA_DEMOD_VARIANT")) : 0;   // experiment switch
+        auto gx = [&](int threads, int per_sm) {
+            const i64 tiles = (max_n + (i64)threads * kLeanPer - 1) / ((i64)threads * kLeanPer);
+            i64 cap = (i64)(per_sm * 148) / (n_jobs > 0 ? n_jobs : 1);
+            if (cap < 1) cap = 1;
+            return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
+        };
+        switch (variant) {
+            case 1: k_demod_lean2<512, 1><<<dim3(gx(512, 1), n_jobs), 512, sizeof(LeanSmem2T<512>), st>>>(d_jobs, atab_here()); break;
+            case 2: k_demod_lean2<256, 2><<<dim3(gx(256, 2), n_jobs), 256, sizeof(LeanSmem2T<256>), st>>>(d_jobs, atab_here()); break;
+            case 3: k_demod_lean2<384, 2><<<dim3(gx(384, 2), n_jobs), 384, sizeof(LeanSmem2T<384>), st>>>(d_jobs, atab_here()); break;
+            case 4: k_demod_lean2<256, 1><<<dim3(gx(256, 1), n_jobs), 256, sizeof(LeanSmem2T<256>), st>>>(d_jobs, atab_here()); break;
+            default: k_demod_lean2<512, 2><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem2T<512>), st>>>(d_jobs, atab_here()); break;
+        }
     }
 }
 

@@ -148,25 +148,31 @@ __global__ void k_solve_binary(const double *llh, const double *rd, int n_rd, do
             if (fabs(res1) < 1.0 && fabs(res2) < 1.0) { converged = 1; break; }
             const double det = J22 * J11 - J21 * J12;
             n_iter = it + 1;
-            double tr_local[5];
-            double *tr = trace ? trace + 5 * it : tr_local;   // trace may be NULL (tdoa_b200.h)
-            tr[0] = det; tr[1] = res1; tr[2] = res2; tr[3] = 0.0; tr[4] = 0.0;
+            double t_step = 0.0, t_code = 0.0;
+            // trace may be NULL (tdoa_b200.h): one guarded store per iteration
+            auto record = [&]() {
+                if (trace) {
+                    double *tr = trace + 5 * it;
+                    tr[0] = det; tr[1] = res1; tr[2] = res2; tr[3] = t_step; tr[4] = t_code;
+                }
+            };
             if (fabs(det) < 1e-12) {
                 double d = 0.0;
-                if (fabs(J11) > fabs(J21) && fabs(J12) > 1e-10) { d = -res1 / J11; tr[4] = 2.0; }
-                else if (fabs(J21) > 1e-10) { d = -res2 / J21; tr[4] = 3.0; }
-                else { status = 3; break; }
+                if (fabs(J11) > fabs(J21) && fabs(J12) > 1e-10) { d = -res1 / J11; t_code = 2.0; }
+                else if (fabs(J21) > 1e-10) { d = -res2 / J21; t_code = 3.0; }
+                else { status = 3; record(); break; }
                 x[0] += d * 0.1;
             } else {
                 const double dx = (-res1 * J22 + J12 * res2) / det;
                 const double dy = (res1 * J21 - J11 * res2) / det;
                 const double step = sqrt(dx * dx + dy * dy);
                 double scale = 0.7;
-                if (step > 1000.0) { scale = 1000.0 / step * 0.7; tr[4] = 1.0; }
-                tr[3] = step;
+                if (step > 1000.0) { scale = 1000.0 / step * 0.7; t_code = 1.0; }
+                t_step = step;
                 x[0] += dx * scale;
                 x[1] += dy * scale;
             }
+            record();
         }
         if (status == 0) ecef_to_llh(x[0], x[1], x[2], o);
     }
