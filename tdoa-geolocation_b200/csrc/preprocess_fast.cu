@@ -670,6 +670,750 @@ __global__ void __launch_bounds__(256) k_demod_selftest2(const double *__restric
     if (saved) atomicAdd(counts + 2, (unsigned long long)saved);
 }
 
+// ---------------------------------------------------------------- lean discriminator, third generation
+// ncu of the second generation (profiles/r2f_full.md): 76 instructions per sample of which NINE run on the
+// 16-lane XU pipe (three f64->f32 and four f32->f64 conversions, MUFU.RCP, MUFU.RCP64H) -- 72 XU cycles per
+// warp-sample against a 34-cycle HBM budget.  The conversions exist because the fast path mixed f32 and f64.
+// This version keeps the arctangent in f32 DOUBLE-FLOAT arithmetic (value = hi + lo, two f32), issued
+// two samples at a time with Blackwell's packed FFMA2 / FADD2 / FMUL2 (one issue slot for two samples):
+//   - X, Y: the reference's f64 products (DMUL + DFMA), rounded to f32 by the conversion instruction:
+//     the only two conversions of the arctangent;
+//   - octant by FMNMX / FSETP on |x|, |y|; c = k/128 from a magic-number add on mn * rcp(mx);
+//   - rotation  y' = mn - c mx  (exact in f32: the leading bits cancel),  x' = mx + c mn  as hi + lo
+//     (three FMAs), u = y'/x' from one MUFU.RCP seed and an exact-residual correction (error < 2^-44),
+//     atan(u) = u - u^3/3 + u^5/5 with |u| <= 2^-8 (the terms after u ride in the low word);
+//   - B(case) +- atan(k/128) from a table of double-float pairs, added by a Fast2Sum;
+//   - the f32 result is RN(hi + lo), evaluated TWICE as fma(lo, 1 +- 2^-14, hi): when the two differ, hi + lo
+//     sits within 2^-38 (relative) of a rounding boundary and the fast path's accuracy (< 2^-40) does not
+//     decide the rounding -- 2^-13 of the samples.  A thread with such a sample among its eight redoes them
+//     with the full-accuracy f64 arctangent of round 1.
+// tdoa_selftest(1) runs THIS path (fast value, exact fall-back when flagged) against the reference statement
+// demod_one<false> over all 2^32 byte quads.
+constexpr int kAtanK3 = 128;
+constexpr int kOct3Stride = 256;   // entries per octant case
+
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float rcp_f32(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#define TDOA_PK2(x) ((((unsigned long long)(x)) << 32) | (unsigned long long)(x))
+
+template <int THREADS>
+struct LeanSmem3T {
+    LeanEntry tab[256][16];                       // 64 KB
+    float octh[4 * kOct3Stride];                  // B(case) + sigma(case) * atan(k / 128), high word ...
+    float octl[4 * kOct3Stride];                  // ... and low word of the double-float pair (4 + 4 KB)
+    double oct_exact[4][kOctStride];              // round-1 table for the exact fall-back (4 KB)
+    unsigned stage[2][kLeanWords][THREADS];       // cp.async landing zone, double buffered
+    double scratch[32];
+    int last;
+};
+
+// atab3_g: atan(k / 128), k = 0..128; atab_g: atan(k / 64) (fall-back)
+template <class SM>
+__device__ __forceinline__ void lean3_fill(SM &S, const double *__restrict__ atab_g, const double *__restrict__ atab3_g)
+{
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+        const float v = unpack_byte((unsigned)(i >> 4));
+        LeanEntry e;
+        e.v = (double)v; e.sq = __fmul_rn(v, v); e.vf = v;
+        S.tab[i >> 4][i & 15] = e;
+    }
+    const double pio2 = 1.57079632679489661923, pi = 3.14159265358979323846;
+    for (int i = threadIdx.x; i < 4 * kOct3Stride; i += blockDim.x) {
+        const int oc = i / kOct3Stride, k = i % kOct3Stride;
+        const double a = atab3_g[k <= kAtanK3 ? k : kAtanK3];
+        const double b = oc == 0 ? a : (oc == 1 ? pio2 - a : (oc == 2 ? pi - a : pio2 + a));
+        const float bh = (float)b;
+        S.octh[i] = bh;
+        S.octl[i] = (float)(b - (double)bh);
+    }
+    for (int i = threadIdx.x; i < 4 * kOctStride; i += blockDim.x) {
+        const int oc = i / kOctStride, k = i % kOctStride;
+        const double a = atab_g[k <= kAtanK ? k : kAtanK];
+        S.oct_exact[oc][k] = oc == 0 ? a : (oc == 1 ? pio2 - a : (oc == 2 ? pi - a : pio2 + a));
+    }
+}
+
+// table entry of a byte: the address is (byte << 8 | slot << 4) from one PRMT; the table base is CTA-uniform
+__device__ __forceinline__ void lean3_lookup(const LeanEntry *tab, unsigned off, double &v, float &sq)
+{
+    const double2 t = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(tab) + off);
+    v = t.x;
+    sq = __int_as_float(__double2loint(t.y));
+}
+
+// f32 -> f64 without the conversion pipe: the bit pattern moved into the f64 fields is the value times
+// 2^-896, exactly (normal f32 or zero); sums of such terms are scaled back once per CTA
+__device__ __forceinline__ double widen_scaled_pos(float g)
+{
+    const unsigned b = __float_as_uint(g);
+    return hilo(b >> 3, b << 29);
+}
+__device__ __forceinline__ double widen_scaled(float o)
+{
+    const unsigned b = __float_as_uint(o);
+    return hilo((unsigned)((int)b >> 3) & 0x8FFFFFFFu, b << 29);
+}
+
+// two discriminator values at once from the f64 products X = Re p, Y = Im p of two samples; `diff` collects
+// (o1 ^ o2) of every sample: nonzero = some rounding undecided
+template <class SM>
+__device__ __forceinline__ void lean3_pair(const SM &S, double XA, double YA, double XB, double YB,
+                                           float &oA, float &oB, unsigned &diff)
+{
+    const float xA = (float)XA, yA = (float)YA, xB = (float)XB, yB = (float)YB;   // the reference's float32(...) of the products
+    const float mxA = fmaxf(fabsf(xA), fabsf(yA)), mnA = fminf(fabsf(xA), fabsf(yA));
+    const float mxB = fmaxf(fabsf(xB), fabsf(yB)), mnB = fminf(fabsf(xB), fabsf(yB));
+    const bool swA = fabsf(yA) > fabsf(xA), swB = fabsf(yB) > fabsf(xB);
+    const unsigned xbA = __float_as_uint(xA), xbB = __float_as_uint(xB);
+    const f32x2 MX = pk(mxA, mxB), MN = pk(mnA, mnB);
+    const f32x2 kMagic = TDOA_PK2(0x47C00000u);     // 98304 = 1.5 * 2^16: ulp 2^-7
+    const f32x2 kMinus1 = TDOA_PK2(0xBF800000u);
+    const f32x2 T = fma2(MN, pk(rcp_f32(mxA), rcp_f32(mxB)), kMagic);   // q + magic: k = round(128 q) in the low mantissa bits
+    const f32x2 C = fma2(kMagic, kMinus1, T);                   // T - magic =  c = k / 128, exact
+    const f32x2 NC = fma2(T, kMinus1, kMagic);                  // -c
+    float tA, tB;
+    upk(T, tA, tB);
+    // table entry: case = swap + 2 * (x < 0)
+    const unsigned ixA = (__float_as_uint(tA) & 0x1FFu) + (swA ? (unsigned)kOct3Stride : 0u) + ((xbA >> 31) << 9);
+    const unsigned ixB = (__float_as_uint(tB) & 0x1FFu) + (swB ? (unsigned)kOct3Stride : 0u) + ((xbB >> 31) << 9);
+    const f32x2 BH = pk(S.octh[ixA], S.octh[ixB]), BL = pk(S.octl[ixA], S.octl[ixB]);
+    const f32x2 Y1 = fma2(NC, MX, MN);                          // mn - c mx (exact)
+    const f32x2 XH = fma2(C, MN, MX);                           // mx + c mn, rounded
+    const f32x2 D = fma2(XH, kMinus1, MX);                      // mx - xh (exact)
+    const f32x2 XL = fma2(C, MN, D);                            // (mx + c mn) - xh (exact)
+    float xhA, xhB;
+    upk(XH, xhA, xhB);
+    const f32x2 NR = pk(rcp_f32(-xhA), rcp_f32(-xhB));          // -1 / xh
+    const f32x2 NUH = mul2(Y1, NR);                             // -u, high part
+    const f32x2 E = fma2(NUH, XH, Y1);                          // y' - uh xh
+    const f32x2 E2 = fma2(NUH, XL, E);                          // y' - uh (xh + xl)
+    const f32x2 NUL = mul2(E2, NR);                             // -u, low part
+    const f32x2 W = mul2(NUH, NUH);
+    const f32x2 P = fma2(W, TDOA_PK2(0x3E4CCCCDu), TDOA_PK2(0xBEAAAAABu));   // w / 5 - 1 / 3
+    const f32x2 CORR = fma2(mul2(NUH, W), P, NUL);              // atan(-u) - (-uh)
+    // atan(u) enters with a minus sign when exactly one of {swap, x < 0} holds; we carry -u, so sigma' = -sigma
+    const unsigned sgA = (swA ? 0x3F800000u : 0xBF800000u) ^ (xbA & 0x80000000u);
+    const unsigned sgB = (swB ? 0x3F800000u : 0xBF800000u) ^ (xbB & 0x80000000u);
+    const f32x2 SIG = pk(__uint_as_float(sgA), __uint_as_float(sgB));
+    const f32x2 SH = fma2(SIG, NUH, BH);                        // Fast2Sum: |bh| >= |uh| or bh == 0
+    const f32x2 T2 = fma2(SH, kMinus1, BH);                     // bh - sh
+    const f32x2 ERR = fma2(SIG, NUH, T2);
+    const f32x2 LO = add2(ERR, fma2(SIG, CORR, BL));
+    // hi + lo is not normalised (for k = 0 the low word carries all of u^3/3 ...): round, take the exact
+    // remainder r (|r| <= half an ulp of o), and ask whether r (1 + 2^-14) still rounds to o
+    const f32x2 O = add2(SH, LO);
+    const f32x2 R = add2(fma2(O, kMinus1, SH), LO);             // (sh - o) + lo, both steps exact
+    const f32x2 O1 = fma2(R, TDOA_PK2(0x3F800200u), O);         // 1 + 2^-14
+    float o1A, o1B, o2A, o2B;
+    upk(O1, o1A, o1B);
+    upk(O, o2A, o2B);
+    diff |= (__float_as_uint(o1A) ^ __float_as_uint(o2A)) | (__float_as_uint(o1B) ^ __float_as_uint(o2B));
+    oA = __uint_as_float(__float_as_uint(o2A) | (__float_as_uint(yA) & 0x80000000u));
+    oB = __uint_as_float(__float_as_uint(o2B) | (__float_as_uint(yB) & 0x80000000u));
+}
+
+// lean3_pair with the octant table as (hi, lo) pairs: one 64-bit load per sample.  Two discriminator values at once from the f64 products X = Re p, Y = Im p of two samples; `diff` collects
+// (o1 ^ o2) of every sample: nonzero = some rounding undecided
+template <class SM>
+__device__ __forceinline__ void lean4_pair(const SM &S, double XA, double YA, double XB, double YB,
+                                           float &oA, float &oB, unsigned &diff)
+{
+    const float xA = (float)XA, yA = (float)YA, xB = (float)XB, yB = (float)YB;   // the reference's float32(...) of the products
+    const float mxA = fmaxf(fabsf(xA), fabsf(yA)), mnA = fminf(fabsf(xA), fabsf(yA));
+    const float mxB = fmaxf(fabsf(xB), fabsf(yB)), mnB = fminf(fabsf(xB), fabsf(yB));
+    const bool swA = fabsf(yA) > fabsf(xA), swB = fabsf(yB) > fabsf(xB);
+    const unsigned xbA = __float_as_uint(xA), xbB = __float_as_uint(xB);
+    const f32x2 MX = pk(mxA, mxB), MN = pk(mnA, mnB);
+    const f32x2 kMagic = TDOA_PK2(0x47C00000u);     // 98304 = 1.5 * 2^16: ulp 2^-7
+    const f32x2 kMinus1 = TDOA_PK2(0xBF800000u);
+    const f32x2 T = fma2(MN, pk(rcp_f32(mxA), rcp_f32(mxB)), kMagic);   // q + magic: k = round(128 q) in the low mantissa bits
+    const f32x2 C = fma2(kMagic, kMinus1, T);                   // T - magic =  c = k / 128, exact
+    const f32x2 NC = fma2(T, kMinus1, kMagic);                  // -c
+    float tA, tB;
+    upk(T, tA, tB);
+    // table entry: case = swap + 2 * (x < 0)
+    const unsigned ixA = (__float_as_uint(tA) & 0x1FFu) + (swA ? (unsigned)kOct3Stride : 0u) + ((xbA >> 31) << 9);
+    const unsigned ixB = (__float_as_uint(tB) & 0x1FFu) + (swB ? (unsigned)kOct3Stride : 0u) + ((xbB >> 31) << 9);
+    const float2 eA = S.oct[ixA], eB = S.oct[ixB];
+    const f32x2 BH = pk(eA.x, eB.x), BL = pk(eA.y, eB.y);
+    const f32x2 Y1 = fma2(NC, MX, MN);                          // mn - c mx (exact)
+    const f32x2 XH = fma2(C, MN, MX);                           // mx + c mn, rounded
+    const f32x2 D = fma2(XH, kMinus1, MX);                      // mx - xh (exact)
+    const f32x2 XL = fma2(C, MN, D);                            // (mx + c mn) - xh (exact)
+    float xhA, xhB;
+    upk(XH, xhA, xhB);
+    const f32x2 NR = pk(rcp_f32(-xhA), rcp_f32(-xhB));          // -1 / xh
+    const f32x2 NUH = mul2(Y1, NR);                             // -u, high part
+    const f32x2 E = fma2(NUH, XH, Y1);                          // y' - uh xh
+    const f32x2 E2 = fma2(NUH, XL, E);                          // y' - uh (xh + xl)
+    const f32x2 NUL = mul2(E2, NR);                             // -u, low part
+    const f32x2 W = mul2(NUH, NUH);
+    const f32x2 P = fma2(W, TDOA_PK2(0x3E4CCCCDu), TDOA_PK2(0xBEAAAAABu));   // w / 5 - 1 / 3
+    const f32x2 CORR = fma2(mul2(NUH, W), P, NUL);              // atan(-u) - (-uh)
+    // atan(u) enters with a minus sign when exactly one of {swap, x < 0} holds; we carry -u, so sigma' = -sigma
+    const unsigned sgA = (swA ? 0x3F800000u : 0xBF800000u) ^ (xbA & 0x80000000u);
+    const unsigned sgB = (swB ? 0x3F800000u : 0xBF800000u) ^ (xbB & 0x80000000u);
+    const f32x2 SIG = pk(__uint_as_float(sgA), __uint_as_float(sgB));
+    const f32x2 SH = fma2(SIG, NUH, BH);                        // Fast2Sum: |bh| >= |uh| or bh == 0
+    const f32x2 T2 = fma2(SH, kMinus1, BH);                     // bh - sh
+    const f32x2 ERR = fma2(SIG, NUH, T2);
+    const f32x2 LO = add2(ERR, fma2(SIG, CORR, BL));
+    // hi + lo is not normalised (for k = 0 the low word carries all of u^3/3 ...): round, take the exact
+    // remainder r (|r| <= half an ulp of o), and ask whether r (1 + 2^-14) still rounds to o
+    const f32x2 O = add2(SH, LO);
+    const f32x2 R = add2(fma2(O, kMinus1, SH), LO);             // (sh - o) + lo, both steps exact
+    const f32x2 O1 = fma2(R, TDOA_PK2(0x3F800200u), O);         // 1 + 2^-14
+    float o1A, o1B, o2A, o2B;
+    upk(O1, o1A, o1B);
+    upk(O, o2A, o2B);
+    diff |= (__float_as_uint(o1A) ^ __float_as_uint(o2A)) | (__float_as_uint(o1B) ^ __float_as_uint(o2B));
+    oA = __uint_as_float(__float_as_uint(o2A) | (__float_as_uint(yA) & 0x80000000u));
+    oB = __uint_as_float(__float_as_uint(o2B) | (__float_as_uint(yB) & 0x80000000u));
+}
+
+// SUMS: 0 = the two sums' f32 -> f64 conversions on the conversion pipe, 1 = by integer moves (widen_scaled)
+template <int THREADS, int MINB, int SUMS>
+__global__ void __launch_bounds__(THREADS, MINB) k_demod_lean3(const SigJob *jobs, const double *__restrict__ atab_g,
+                                                               const double *__restrict__ atab3_g)
+{
+    constexpr int kLeanTile = THREADS * kLeanPer;
+    extern __shared__ __align__(16) unsigned char lean_raw[];
+    LeanSmem3T<THREADS> &S = *reinterpret_cast<LeanSmem3T<THREADS> *>(lean_raw);
+    const SigJob &J = jobs[blockIdx.y];
+    const int tid = threadIdx.x;
+    lean3_fill(S, atab_g, atab3_g);
+    __syncthreads();
+    const i64 n = J.n;
+    const i64 i_begin = J.i_begin, i_end = J.i_end > 0 ? J.i_end : n;
+    const uint8_t *__restrict__ rawb = J.src.raw;
+    float *__restrict__ out = J.p_re;
+    const i64 run0 = J.src.run0_len;
+    const unsigned slot16 = (unsigned)(tid & 15) * 16u;
+    const LeanEntry *tab = &S.tab[0][0];
+    const unsigned tab_base = (unsigned)__cvta_generic_to_shared(&S.tab[0][0]);
+    const unsigned octx_base = (unsigned)__cvta_generic_to_shared(&S.oct_exact[0][0]);
+    double pw = 0.0, sr = 0.0;       // plain sums (edges, fall-backs)
+    double pws = 0.0, srs = 0.0;     // sums of terms scaled by 2^-896 (SUMS == 1)
+    auto fast_tile = [&](i64 t0) {
+        const bool in0 = t0 + kLeanTile + 2 <= run0, in1 = t0 - 1 >= run0 && t0 + kLeanTile + 2 <= n;
+        return t0 > 0 && t0 + kLeanTile <= i_end && (in0 || in1);
+    };
+    auto tile_addr = [&](i64 t0) { return rawb + 2 * (raw_index(J.src, t0) + (i64)kLeanPer * tid); };
+    auto stage_tile = [&](i64 t0, int buf) {
+        if (fast_tile(t0)) {
+            const uint8_t *ap = tile_addr(t0);
+            const unsigned *wp = reinterpret_cast<const unsigned *>(ap - (reinterpret_cast<uintptr_t>(ap) & 2u)) - 1;
+#pragma unroll
+            for (int k = 0; k < kLeanWords; k++) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&S.stage[buf][k][tid]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(wp + k) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const i64 step = (i64)gridDim.x * kLeanTile;
+    int buf = 0;
+    stage_tile(i_begin + (i64)blockIdx.x * kLeanTile, 0);
+    for (i64 i0 = i_begin + (i64)blockIdx.x * kLeanTile; i0 < i_end; i0 += step, buf ^= 1) {
+        stage_tile(i0 + step, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (fast_tile(i0)) {
+            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(tile_addr(i0)) & 2u) * 8u;
+            unsigned w[4];
+            double pr, pi;
+            {
+                const unsigned wm = S.stage[buf][0][tid], w0 = S.stage[buf][1][tid], w1 = S.stage[buf][2][tid],
+                               w2 = S.stage[buf][3][tid], w3 = S.stage[buf][4][tid], w4 = S.stage[buf][5][tid];
+                const unsigned pv = __funnelshift_r(wm, w0, sh);
+                w[0] = __funnelshift_r(w0, w1, sh); w[1] = __funnelshift_r(w1, w2, sh);
+                w[2] = __funnelshift_r(w2, w3, sh); w[3] = __funnelshift_r(w3, w4, sh);
+                float sq_i, sq_q;
+                lean3_lookup(tab, __byte_perm(pv, slot16, 0x5524), pr, sq_i);
+                lean3_lookup(tab, __byte_perm(pv, slot16, 0x5534), pi, sq_q);
+            }
+            float o[kLeanPer];
+            unsigned diff = 0u;
+            double srt = 0.0;
+#pragma unroll
+            for (int s = 0; s < kLeanPer; s += 2) {
+                const unsigned ww = w[s >> 1];
+                double crA, ciA, crB, ciB;
+                float sqiA, sqqA, sqiB, sqqB;
+                lean3_lookup(tab, __byte_perm(ww, slot16, 0x5504), crA, sqiA);
+                lean3_lookup(tab, __byte_perm(ww, slot16, 0x5514), ciA, sqqA);
+                lean3_lookup(tab, __byte_perm(ww, slot16, 0x5524), crB, sqiB);
+                lean3_lookup(tab, __byte_perm(ww, slot16, 0x5534), ciB, sqqB);
+                float gA, gB;
+                upk(add2(pk(sqiA, sqiB), pk(sqqA, sqqB)), gA, gB);   // processor.go:328, f32 re*re + im*im
+                if (SUMS) { pws += widen_scaled_pos(gA); pws += widen_scaled_pos(gB); }
+                else { pw += (double)gA; pw += (double)gB; }
+                const double XA = fma(pr, crA, __dmul_rn(pi, ciA)), YA = fma(ciA, pr, -__dmul_rn(pi, crA));
+                const double XB = fma(crA, crB, __dmul_rn(ciA, ciB)), YB = fma(ciB, crA, -__dmul_rn(ciA, crB));
+                lean3_pair(S, XA, YA, XB, YB, o[s], o[s + 1], diff);
+                if (SUMS) { srt += widen_scaled(o[s]); srt += widen_scaled(o[s + 1]); }
+                else { srt += (double)o[s]; srt += (double)o[s + 1]; }
+                pr = crB; pi = ciB;
+            }
+            if (diff) {
+                // ~2^-13 of the samples: the thread's eight again, with the full-accuracy arctangent
+                const unsigned wm = S.stage[buf][0][tid], w0 = S.stage[buf][1][tid];
+                const unsigned pv = __funnelshift_r(wm, w0, sh);
+                float sq_i, sq_q;
+                lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5524), pr, sq_i);
+                lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5534), pi, sq_q);
+                srt = 0.0;
+#pragma unroll
+                for (int s = 0; s < kLeanPer; s++) {
+                    const unsigned ww = w[s >> 1];
+                    double cr, ci;
+                    lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5524 : 0x5504), cr, sq_i);
+                    lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5534 : 0x5514), ci, sq_q);
+                    o[s] = lean_one(pr, pi, cr, ci, octx_base);
+                    srt += (double)o[s];
+                    pr = cr; pi = ci;
+                }
+                sr += srt;
+            } else if (SUMS) {
+                srs += srt;
+            } else {
+                sr += srt;
+            }
+            float4 *op = reinterpret_cast<float4 *>(out + i0 + (i64)kLeanPer * tid);
+            op[0] = make_float4(o[0], o[1], o[2], o[3]);
+            op[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+            // edges (signal start, the block-1/block-3 joint, the tail): the reference's
+            // own statement of the discriminator, sample by sample, gates included
+            for (int u = 0; u < kLeanPer; u++) {
+                const i64 i = i0 + tid + (i64)THREADS * u;
+                if (i >= i_end) break;
+                const i64 k = i == 0 ? 1 : i;  // out[0] = out[1]
+                const uchar2 cur = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k)];
+                const uchar2 prv = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k - 1)];
+                const uchar2 me = i == 0 ? prv : cur;  // initial power is of sample i itself
+                pw += (double)__fadd_rn(S.tab[me.x][0].sq, S.tab[me.y][0].sq);
+                const double pr = S.tab[prv.x][0].v, pi = S.tab[prv.y][0].v, cr = S.tab[cur.x][0].v, ci = S.tab[cur.y][0].v;
+                const double re = fma(pr, cr, __dmul_rn(ci, pi)), im = fma(ci, pr, -__dmul_rn(pi, cr));
+                const float fre = (float)re, fim = (float)im;
+                const float m = __fadd_rn(__fmul_rn(fre, fre), __fmul_rn(fim, fim));
+                float y = 0.f;
+                if (m > 1e-10f) y = (float)atan2_lean((double)fim, (double)fre, octx_base);
+                out[i] = y;
+                sr += (double)y;
+            }
+        }
+    }
+    if (SUMS) {
+        // 2^896: the scaled terms are exact multiples, so is their sum until the one rounding of each addition,
+        // which the scaling (a power of two, no underflow: the smallest term is 2^-959) does not change
+        const double k2p896 = hilo(0x77F00000u, 0u);
+        pw += pws * k2p896;
+        sr += srs * k2p896;
+    }
+    double part[2], total[2];
+    part[0] = block_sum(pw, S.scratch);
+    part[1] = block_sum(sr, S.scratch);
+    if (grid_sum_last_dyn<2>(part, J.partials, J.counter, gridDim.x, blockIdx.x, S.scratch, &S.last, total)) {
+        if (J.chunk_out) {
+            J.chunk_out[0] = total[0];
+            J.chunk_out[1] = total[1];
+            return;
+        }
+        J.stats[ST_POWER0] = n > 0 ? total[0] / (double)n : 0.0;
+        J.stats[ST_SUM_RE] = total[1];
+        J.stats[ST_SUM_IM] = 0.0;
+        J.stats[ST_DC_RE] = n > 0 ? (double)dc_from_sum(total[1], n) : 0.0;
+        J.stats[ST_DC_IM] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------- third generation, tiles staged by TMA
+// ncu of k_demod_lean3 (profiles/r2h): the LSU data pipe is 91 % busy -- 28 wavefronts per warp-sample, of
+// which 6 belong to the six 4-byte cp.async per thread (16-byte lane stride: four cache lines per
+// instruction) and their bank conflicts.  Here one thread issues ONE bulk copy (cp.async.bulk, the TMA
+// engine) per CTA tile: (THREADS + 1) 16-byte chunks from the 16-byte-aligned address below the tile's
+// previous sample, two tiles ahead, completion on an mbarrier.  A thread then reads its two chunks with two
+// LDS.128 and cuts its 18 bytes out with funnel shifts (the misalignment is uniform over the tile).
+template <int THREADS>
+struct __align__(128) LeanSmem4T {
+    LeanEntry tab[256][16];                       // 64 KB
+    float2 oct[4 * kOct3Stride];                  // double-float B(case) + sigma(case) * atan(k / 128): 8 KB
+    double oct_exact[4][kOctStride];              // round-1 table for the exact fall-back (4 KB)
+    __align__(128) uint4 stage[2][THREADS + THREADS / 32 + 8];   // landing zone of the bulk copies, double buffered (STAGE 0); or
+                                                  // per warp w: chunks [33 w, 33 w + 33) (STAGE 1)
+    unsigned long long full[2];                   // mbarriers
+    double scratch[32];
+    int last;
+};
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+// one bulk copy global -> this CTA's shared memory; src, dst 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_bulk(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+
+// the 5 words starting at word m4 of the 8 staged ones, each shifted right by `s` bits into its successor
+template <int M4>
+__device__ __forceinline__ void cut_words(const unsigned (&W)[8], unsigned s, unsigned (&V)[5])
+{
+#pragma unroll
+    for (int j = 0; j < 5; j++) V[j] = __funnelshift_r(W[M4 + j], M4 + j + 1 < 8 ? W[M4 + j + 1] : 0u, s);
+}
+
+template <class SM>
+__device__ __forceinline__ void lean4_fill(SM &S, const double *__restrict__ atab_g, const double *__restrict__ atab3_g)
+{
+    const int tid = threadIdx.x, THREADS = blockDim.x;
+    // tables (lean3_fill's, with the octant table as float2)
+    for (int i = tid; i < 256 * 16; i += THREADS) {
+        const float v = unpack_byte((unsigned)(i >> 4));
+        LeanEntry e;
+        e.v = (double)v; e.sq = __fmul_rn(v, v); e.vf = v;
+        S.tab[i >> 4][i & 15] = e;
+    }
+    {
+        const double pio2 = 1.57079632679489661923, pi = 3.14159265358979323846;
+        for (int i = tid; i < 4 * kOct3Stride; i += THREADS) {
+            const int oc = i / kOct3Stride, k = i % kOct3Stride;
+            const double a = atab3_g[k <= kAtanK3 ? k : kAtanK3];
+            const double b = oc == 0 ? a : (oc == 1 ? pio2 - a : (oc == 2 ? pi - a : pio2 + a));
+            const float bh = (float)b;
+            S.oct[i] = make_float2(bh, (float)(b - (double)bh));
+        }
+        for (int i = tid; i < 4 * kOctStride; i += THREADS) {
+            const int oc = i / kOctStride, k = i % kOctStride;
+            const double a = atab_g[k <= kAtanK ? k : kAtanK];
+            S.oct_exact[oc][k] = oc == 0 ? a : (oc == 1 ? pio2 - a : (oc == 2 ? pi - a : pio2 + a));
+        }
+    }
+}
+
+// a thread's eight samples with the full-accuracy arctangent (rare: kept out of line so that its registers
+// do not weigh on the fast path); v0..v4 as cut_words leaves them; stores the eight values, returns their sum
+__device__ __noinline__ double demod_exact8(unsigned v0, unsigned v1, unsigned v2, unsigned v3, unsigned v4, unsigned slot16,
+                                            unsigned tab_base, unsigned octx_base, float4 *op)
+{
+    const unsigned V[5] = {v0, v1, v2, v3, v4};
+    double pr, pi;
+    float sq_i, sq_q, o[kLeanPer];
+    lean_lookup(tab_base + __byte_perm(V[0], slot16, 0x5504), pr, sq_i);
+    lean_lookup(tab_base + __byte_perm(V[0], slot16, 0x5514), pi, sq_q);
+    double srt = 0.0;
+#pragma unroll
+    for (int s = 0; s < kLeanPer; s++) {
+        const unsigned ww = V[(s + 1) >> 1];
+        double cr, ci;
+        lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5504 : 0x5524), cr, sq_i);
+        lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5514 : 0x5534), ci, sq_q);
+        o[s] = lean_one(pr, pi, cr, ci, octx_base);
+        srt += (double)o[s];
+        pr = cr; pi = ci;
+    }
+    op[0] = make_float4(o[0], o[1], o[2], o[3]);
+    op[1] = make_float4(o[4], o[5], o[6], o[7]);
+    return srt;
+}
+
+// STAGE: 0 = one bulk copy (TMA) per CTA tile, mbarrier + one CTA barrier per tile; 1 = every warp stages its
+// own 33 chunks with 16-byte cp.async (no barrier wider than the warp)
+template <int THREADS, int MINB, int SUMS, int STAGE>
+__global__ void __launch_bounds__(THREADS, MINB) k_demod_tma(const SigJob *jobs, const double *__restrict__ atab_g,
+                                                             const double *__restrict__ atab3_g)
+{
+    constexpr int kLeanTile = THREADS * kLeanPer;
+    constexpr unsigned kStageBytes = (THREADS + 1) * 16;
+    extern __shared__ __align__(128) unsigned char lean_raw[];
+    LeanSmem4T<THREADS> &S = *reinterpret_cast<LeanSmem4T<THREADS> *>(lean_raw);
+    const SigJob &J = jobs[blockIdx.y];
+    const int tid = threadIdx.x;
+    lean4_fill(S, atab_g, atab3_g);
+    if (tid == 0) {
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const i64 n = J.n;
+    const i64 i_begin = J.i_begin, i_end = J.i_end > 0 ? J.i_end : n;
+    const uint8_t *__restrict__ rawb = J.src.raw;
+    float *__restrict__ out = J.p_re;
+    const i64 run0 = J.src.run0_len;
+    const unsigned slot16 = (unsigned)(tid & 15) * 16u;
+    const LeanEntry *tab = &S.tab[0][0];
+    const unsigned tab_base = (unsigned)__cvta_generic_to_shared(&S.tab[0][0]);
+    const unsigned octx_base = (unsigned)__cvta_generic_to_shared(&S.oct_exact[0][0]);
+    double pw = 0.0, sr = 0.0;       // plain sums (edges, fall-backs)
+    double pws = 0.0, srs = 0.0;     // sums of terms scaled by 2^-896 (SUMS == 1)
+    // Tile j covers samples [i_begin + j T, + T).  It takes the fast path when it, the 8 samples before it and the
+    // 8 after it lie inside one run of the capture (the staged copy starts up to 14 bytes before the tile's
+    // previous sample and ends up to 16 after its last): two ranges of tile indices, worked out once.
+    constexpr i64 T = kLeanTile;
+    const int n_tiles = (int)((i_end - i_begin + T - 1) / T);
+    auto ceil_div = [](i64 a, i64 b) { return a <= 0 ? (i64)0 : (a + b - 1) / b; };
+    auto tiles_below = [&](i64 limit) {   // number of tiles j with i_begin + j T + T <= limit
+        const i64 room = limit - i_begin;
+        return room < T ? (i64)0 : room / T;
+    };
+    auto clampi = [&](i64 v) { return (int)(v < 0 ? 0 : (v > n_tiles ? n_tiles : v)); };
+    const i64 end0 = (run0 - 8 < i_end ? run0 - 8 : i_end), end1 = (n - 8 < i_end ? n - 8 : i_end);
+    const int jA0 = clampi(ceil_div(8 - i_begin, T)), jB0 = clampi(tiles_below(end0));
+    const int jA1 = clampi(ceil_div(run0 + 8 - i_begin, T)), jB1 = clampi(tiles_below(end1));
+    auto fast_tile = [&](int j) { return (j >= jA0 && j < jB0) || (j >= jA1 && j < jB1); };
+    // address of tile j's previous sample, per run
+    const uintptr_t base0 = reinterpret_cast<uintptr_t>(rawb) + 2 * (uintptr_t)(J.src.run0_start + i_begin) - 2;
+    const uintptr_t base1 = reinterpret_cast<uintptr_t>(rawb) + 2 * (uintptr_t)(J.src.run1_start + i_begin - run0) - 2;
+    auto prev_addr = [&](int j) { return (j < jB0 ? base0 : base1) + (uintptr_t)j * (uintptr_t)(2 * T); };
+    auto issue = [&](int j, int buf) {
+        if (j < n_tiles && fast_tile(j))
+            tma_load_bulk(&S.stage[buf][0], reinterpret_cast<const void *>(prev_addr(j) & ~(uintptr_t)15), kStageBytes, &S.full[buf]);
+    };
+    const int jstep = (int)gridDim.x;
+    const int jfirst = (int)blockIdx.x;
+    // STAGE 1: warp w keeps its 33 chunks at stage[buf][33 w .. 33 w + 32]
+    const int lane = tid & 31, wrp = tid >> 5;
+    const unsigned wstage0 = (unsigned)__cvta_generic_to_shared(&S.stage[0][0] + 33 * wrp + lane);
+    constexpr unsigned kBufStride = (unsigned)sizeof(S.stage[0]);
+    auto issue_w = [&](int j, int b) {
+        if (j < n_tiles && fast_tile(j)) {
+            const char *src = reinterpret_cast<const char *>(prev_addr(j) & ~(uintptr_t)15) + 16 * tid;
+            const unsigned dst = wstage0 + (unsigned)b * kBufStride;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            if (lane == 0)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 32 * 16), "l"(src + 32 * 16) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (STAGE == 0) {
+        if (tid == 0) { issue(jfirst, 0); issue(jfirst + jstep, 1); }
+    } else {
+        issue_w(jfirst, 0);
+    }
+    unsigned phase[2] = {0u, 0u};
+    int buf = 0;
+    for (int j = jfirst; j < n_tiles; j += jstep, buf ^= 1) {
+        const bool fast = fast_tile(j);
+        const i64 i0 = i_begin + (i64)j * T;
+        unsigned W[8];
+        if (STAGE == 0) {
+            if (fast) {
+                mbar_wait(&S.full[buf], phase[buf]);
+                phase[buf] ^= 1u;
+                const uint4 a = S.stage[buf][tid], b = S.stage[buf][tid + 1];
+                W[0] = a.x; W[1] = a.y; W[2] = a.z; W[3] = a.w; W[4] = b.x; W[5] = b.y; W[6] = b.z; W[7] = b.w;
+            }
+            __syncthreads();                                   // every thread holds its words: the buffer is free
+            if (tid == 0) issue(j + 2 * jstep, buf);
+        } else {
+            __syncwarp();                                      // the warp is done reading the other buffer
+            issue_w(j + jstep, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();                                      // ... and every lane's copies of this one have landed
+            if (fast) {
+                uint4 a, b;
+                const unsigned src = wstage0 + (unsigned)buf * kBufStride;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(src));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(src));
+                W[0] = a.x; W[1] = a.y; W[2] = a.z; W[3] = a.w; W[4] = b.x; W[5] = b.y; W[6] = b.z; W[7] = b.w;
+            }
+        }
+        if (fast) {
+            const unsigned mis = (unsigned)(prev_addr(j) & 15);  // even, uniform over the tile
+            const unsigned sb = (mis & 2u) * 8u;
+            unsigned V[5];   // V0 = [previous | s0], V1 = [s1 | s2], V2 = [s3 | s4], V3 = [s5 | s6], V4 = [s7 | -]
+            switch (mis >> 2) {
+                case 0: cut_words<0>(W, sb, V); break;
+                case 1: cut_words<1>(W, sb, V); break;
+                case 2: cut_words<2>(W, sb, V); break;
+                default: cut_words<3>(W, sb, V); break;
+            }
+            double pr, pi;
+            {
+                float sq_i, sq_q;
+                lean3_lookup(tab, __byte_perm(V[0], slot16, 0x5504), pr, sq_i);
+                lean3_lookup(tab, __byte_perm(V[0], slot16, 0x5514), pi, sq_q);
+            }
+            float4 *op = reinterpret_cast<float4 *>(out + i0 + (i64)kLeanPer * tid);
+            float o[4];
+            unsigned diff = 0u;
+            double srt = 0.0;
+#pragma unroll
+            for (int s = 0; s < kLeanPer; s += 2) {
+                const unsigned wa = V[s >> 1], wb = V[(s >> 1) + 1];   // sample s in the high half of wa, s + 1 in the low half of wb
+                double crA, ciA, crB, ciB;
+                float sqiA, sqqA, sqiB, sqqB;
+                lean3_lookup(tab, __byte_perm(wa, slot16, 0x5524), crA, sqiA);
+                lean3_lookup(tab, __byte_perm(wa, slot16, 0x5534), ciA, sqqA);
+                lean3_lookup(tab, __byte_perm(wb, slot16, 0x5504), crB, sqiB);
+                lean3_lookup(tab, __byte_perm(wb, slot16, 0x5514), ciB, sqqB);
+                const float gA = __fadd_rn(sqiA, sqqA), gB = __fadd_rn(sqiB, sqqB);   // processor.go:328, f32 re*re + im*im
+                if (SUMS) { pws += widen_scaled_pos(gA); pws += widen_scaled_pos(gB); }
+                else { pw += (double)gA; pw += (double)gB; }
+                const double XA = fma(pr, crA, __dmul_rn(pi, ciA)), YA = fma(ciA, pr, -__dmul_rn(pi, crA));
+                const double XB = fma(crA, crB, __dmul_rn(ciA, ciB)), YB = fma(ciB, crA, -__dmul_rn(ciA, crB));
+                lean4_pair(S, XA, YA, XB, YB, o[s & 2], o[(s & 2) + 1], diff);
+                if (SUMS) { srt += widen_scaled(o[s & 2]); srt += widen_scaled(o[(s & 2) + 1]); }
+                else { srt += (double)o[s & 2]; srt += (double)o[(s & 2) + 1]; }
+                if (s & 2) op[s >> 2] = make_float4(o[0], o[1], o[2], o[3]);
+                pr = crB; pi = ciB;
+            }
+            if (diff) {
+                // ~2^-13 of the samples: the thread's eight again, with the full-accuracy arctangent
+                sr += demod_exact8(V[0], V[1], V[2], V[3], V[4], slot16, tab_base, octx_base, op);
+            } else if (SUMS) {
+                srs += srt;
+            } else {
+                sr += srt;
+            }
+        } else {
+            // edges (signal start, the block-1/block-3 joint, the tail): the reference's
+            // own statement of the discriminator, sample by sample, gates included
+            for (int u = 0; u < kLeanPer; u++) {
+                const i64 i = i0 + tid + (i64)THREADS * u;
+                if (i >= i_end) break;
+                const i64 k = i == 0 ? 1 : i;  // out[0] = out[1]
+                const uchar2 cur = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k)];
+                const uchar2 prv = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k - 1)];
+                const uchar2 me = i == 0 ? prv : cur;  // initial power is of sample i itself
+                pw += (double)__fadd_rn(S.tab[me.x][0].sq, S.tab[me.y][0].sq);
+                const double pr = S.tab[prv.x][0].v, pi = S.tab[prv.y][0].v, cr = S.tab[cur.x][0].v, ci = S.tab[cur.y][0].v;
+                const double re = fma(pr, cr, __dmul_rn(ci, pi)), im = fma(ci, pr, -__dmul_rn(pi, cr));
+                const float fre = (float)re, fim = (float)im;
+                const float m = __fadd_rn(__fmul_rn(fre, fre), __fmul_rn(fim, fim));
+                float y = 0.f;
+                if (m > 1e-10f) y = (float)atan2_lean((double)fim, (double)fre, octx_base);
+                out[i] = y;
+                sr += (double)y;
+            }
+        }
+    }
+    if (SUMS) {
+        const double k2p896 = hilo(0x77F00000u, 0u);
+        pw += pws * k2p896;
+        sr += srs * k2p896;
+    }
+    double part[2], total[2];
+    part[0] = block_sum(pw, S.scratch);
+    part[1] = block_sum(sr, S.scratch);
+    if (grid_sum_last_dyn<2>(part, J.partials, J.counter, gridDim.x, blockIdx.x, S.scratch, &S.last, total)) {
+        if (J.chunk_out) {
+            J.chunk_out[0] = total[0];
+            J.chunk_out[1] = total[1];
+            return;
+        }
+        J.stats[ST_POWER0] = n > 0 ? total[0] / (double)n : 0.0;
+        J.stats[ST_SUM_RE] = total[1];
+        J.stats[ST_SUM_IM] = 0.0;
+        J.stats[ST_DC_RE] = n > 0 ? (double)dc_from_sum(total[1], n) : 0.0;
+        J.stats[ST_DC_IM] = 0.0;
+    }
+}
+
+// every (previous, current) byte quad, two at a time: the third-generation path (fast value, exact fall-back
+// when flagged) against demod_one<false>; counts as k_demod_selftest2
+__global__ void __launch_bounds__(256) k_demod_selftest3(const double *__restrict__ atab_g, const double *__restrict__ atab3_g,
+                                                         unsigned long long *counts, unsigned *first_bad)
+{
+    extern __shared__ __align__(16) unsigned char lean_raw[];
+    LeanSmem4T<kLeanThreads> &S = *reinterpret_cast<LeanSmem4T<kLeanThreads> *>(lean_raw);
+    __shared__ DemodLuts L;
+    lean4_fill(S, atab_g, atab3_g);
+    {
+        const float v = unpack_byte((unsigned)threadIdx.x);
+        L.lutf[threadIdx.x] = v;
+        L.lut[threadIdx.x] = (double)v;
+        if (threadIdx.x < 9) { L.atan_d[threadIdx.x] = atan_k8(threadIdx.x); L.atan_f[threadIdx.x] = (float)atan_k8(threadIdx.x); }
+    }
+    __syncthreads();
+    const unsigned octx_base = (unsigned)__cvta_generic_to_shared(&S.oct_exact[0][0]);
+    const int slot = threadIdx.x & 15;
+    unsigned bad = 0, flagged = 0, saved = 0;
+    const unsigned long long half = 1ull << 31;
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+    for (unsigned long long q0 = (unsigned long long)blockIdx.x * 256 + threadIdx.x; q0 < half; q0 += stride) {
+        unsigned long long qq[2] = {q0, q0 + half};
+        double pr[2], pi[2], cr[2], ci[2], X[2], Y[2];
+        float want[2], got[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const unsigned long long q = qq[j];
+            const uchar2 prv = make_uchar2((unsigned char)(q & 255), (unsigned char)(q >> 8 & 255));
+            const uchar2 cur = make_uchar2((unsigned char)(q >> 16 & 255), (unsigned char)(q >> 24 & 255));
+            want[j] = demod_one<false>(L, prv, cur);
+            pr[j] = S.tab[prv.x][slot].v; pi[j] = S.tab[prv.y][slot].v; cr[j] = S.tab[cur.x][slot].v; ci[j] = S.tab[cur.y][slot].v;
+            X[j] = fma(pr[j], cr[j], __dmul_rn(pi[j], ci[j]));
+            Y[j] = fma(ci[j], pr[j], -__dmul_rn(pi[j], cr[j]));
+        }
+        unsigned diff = 0u;
+        lean4_pair(S, X[0], Y[0], X[1], Y[1], got[0], got[1], diff);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            // the production kernel redoes all eight samples of a flagged thread: here the pair
+            if (diff) {
+                flagged++;
+                const float exact = lean_one(pr[j], pi[j], cr[j], ci[j], octx_base);
+                if (__float_as_uint(exact) != __float_as_uint(got[j])) saved++;
+                got[j] = exact;
+            }
+            if (__float_as_uint(want[j]) != __float_as_uint(got[j])) {
+                bad++;
+                const unsigned at = atomicAdd(first_bad, 1u);
+                if (at < 63) first_bad[1 + at] = (unsigned)qq[j];
+            }
+        }
+    }
+    if (bad) atomicAdd(counts, (unsigned long long)bad);
+    if (flagged) atomicAdd(counts + 1, (unsigned long long)flagged);
+    if (saved) atomicAdd(counts + 2, (unsigned long long)saved);
+}
+
 // statistics of a signal whose discriminator ran in chunks (fixed order: chunk 0, 1, ...)
 __global__ void k_demod_finish(const double *__restrict__ chunk_sums, int n_chunks, i64 n, double *stats)
 {
@@ -896,12 +1640,20 @@ int fast_grid_x(i64 n)
 // (one table per device: an engine with n_devices > 1 has peers on other GPUs of this process)
 constexpr int kMaxDevices = 64;
 static double *g_atab_dev[kMaxDevices] = {nullptr};
+static double *g_atab3_dev[kMaxDevices] = {nullptr};   // atan(k / 128), third-generation discriminator
 
 static double *atab_here()
 {
     int dev = 0;
     cudaGetDevice(&dev);
     return dev >= 0 && dev < kMaxDevices ? g_atab_dev[dev] : nullptr;
+}
+
+static double *atab3_here()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? g_atab3_dev[dev] : nullptr;
 }
 
 int demod_setup(cudaStream_t st)
@@ -917,6 +1669,29 @@ int demod_setup(cudaStream_t st)
         if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
         g_atab_dev[dev] = d;
     }
+    if (!g_atab3_dev[dev]) {
+        double h[kAtanK3 + 2];
+        for (int k = 0; k <= kAtanK3 + 1; k++) h[k] = atan((double)k / (double)kAtanK3);
+        double *d = nullptr;
+        if (cudaMalloc(&d, sizeof(h)) != cudaSuccess) return -1;
+        if (cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+        g_atab3_dev[dev] = d;
+    }
+    if (cudaFuncSetAttribute(k_demod_lean3<512, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem3T<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_lean3<512, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem3T<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_lean3<512, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem3T<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_lean3<256, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem3T<256>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_lean3<256, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem3T<256>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_tma<512, 2, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_tma<512, 2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_tma<512, 2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_tma<512, 2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_tma<384, 2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<384>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_tma<384, 2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<384>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_tma<256, 2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<256>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_selftest3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<kLeanThreads>)) != cudaSuccess)
+        return -1;
     if (cudaFuncSetAttribute(k_demod_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) != cudaSuccess)
         return -1;
     if (cudaFuncSetAttribute(k_demod_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) !=
@@ -957,11 +1732,23 @@ void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, c
             return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
         };
         switch (variant) {
+            case 20: k_demod_tma<512, 2, 1, 0><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem4T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 21: k_demod_tma<512, 2, 0, 0><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem4T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 22: k_demod_tma<512, 2, 0, 1><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem4T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 23: k_demod_tma<512, 2, 1, 1><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem4T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 24: k_demod_tma<384, 2, 1, 1><<<dim3(gx(384, 2), n_jobs), 384, sizeof(LeanSmem4T<384>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 25: k_demod_tma<384, 2, 0, 1><<<dim3(gx(384, 2), n_jobs), 384, sizeof(LeanSmem4T<384>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 26: k_demod_tma<256, 2, 1, 1><<<dim3(gx(256, 2), n_jobs), 256, sizeof(LeanSmem4T<256>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 10: k_demod_lean2<512, 2><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem2T<512>), st>>>(d_jobs, atab_here()); break;
+            case 11: k_demod_lean3<512, 1, 1><<<dim3(gx(512, 1), n_jobs), 512, sizeof(LeanSmem3T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 12: k_demod_lean3<256, 2, 1><<<dim3(gx(256, 2), n_jobs), 256, sizeof(LeanSmem3T<256>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 13: k_demod_lean3<256, 3, 1><<<dim3(gx(256, 3), n_jobs), 256, sizeof(LeanSmem3T<256>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 14: k_demod_lean3<512, 2, 0><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem3T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
             case 1: k_demod_lean2<512, 1><<<dim3(gx(512, 1), n_jobs), 512, sizeof(LeanSmem2T<512>), st>>>(d_jobs, atab_here()); break;
             case 2: k_demod_lean2<256, 2><<<dim3(gx(256, 2), n_jobs), 256, sizeof(LeanSmem2T<256>), st>>>(d_jobs, atab_here()); break;
             case 3: k_demod_lean2<384, 2><<<dim3(gx(384, 2), n_jobs), 384, sizeof(LeanSmem2T<384>), st>>>(d_jobs, atab_here()); break;
             case 4: k_demod_lean2<256, 1><<<dim3(gx(256, 1), n_jobs), 256, sizeof(LeanSmem2T<256>), st>>>(d_jobs, atab_here()); break;
-            default: k_demod_lean2<512, 2><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem2T<512>), st>>>(d_jobs, atab_here()); break;
+            default: k_demod_lean3<512, 2, 1><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem3T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
         }
     }
 }
@@ -983,7 +1770,8 @@ long long demod_selftest(cudaStream_t st, unsigned *first_bad_out, int which, lo
     cudaMemsetAsync(d_cnt, 0, sizeof(h_cnt), st);
     cudaMemsetAsync(d_first, 0, 64 * sizeof(unsigned), st);
     if (which == 3) k_demod_selftest<<<148 * 2, 256, sizeof(LeanSmem), st>>>(atab_here(), d_cnt, d_first);
-    else k_demod_selftest2<<<148 * 2, 256, sizeof(LeanSmem2), st>>>(atab_here(), d_cnt, d_first);
+    else if (which == 2) k_demod_selftest2<<<148 * 2, 256, sizeof(LeanSmem2), st>>>(atab_here(), d_cnt, d_first);
+    else k_demod_selftest3<<<148 * 2, 256, sizeof(LeanSmem4T<kLeanThreads>), st>>>(atab_here(), atab3_here(), d_cnt, d_first);
     cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
     if (first_bad_out) cudaMemcpyAsync(first_bad_out, d_first, 64 * sizeof(unsigned), cudaMemcpyDeviceToHost, st);
     const cudaError_t err = cudaStreamSynchronize(st);
