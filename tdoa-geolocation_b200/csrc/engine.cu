@@ -738,10 +738,10 @@ int tdoa_selftest(tdoa_engine *e, int32_t which, int64_t *mismatches)
     if (!e || !mismatches) return TDOA_E_INVALID;
     int rc = begin_call(e);
     if (rc) return rc;
-    if (which < 0 || which > 4) return fail(e, TDOA_E_INVALID, "tdoa_selftest: unknown test %d", which);
+    if (which < 0 || which > 3) return fail(e, TDOA_E_INVALID, "tdoa_selftest: unknown test %d", which);
     unsigned first_bad[64] = {0};
     long long extra[2] = {0, 0};
-    const long long bad = which == 0 ? div_selftest(e->stream) : demod_selftest(e->stream, first_bad, which == 3 ? 3 : (which == 4 ? 2 : 1), extra);
+    const long long bad = which == 0 ? div_selftest(e->stream) : demod_selftest(e->stream, first_bad, which == 3 ? 3 : 1, extra);
     if (bad < 0) return fail(e, TDOA_E_CUDA, "tdoa_selftest: kernel failed");
     if (which == 2) { *mismatches = extra[0]; return TDOA_OK; }   // fall-backs taken over the 2^32 quads
     if (which != 0) {

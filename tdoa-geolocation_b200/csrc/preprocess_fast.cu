@@ -299,7 +299,7 @@ __device__ __forceinline__ bool grid_sum_last_dyn(const double (&part)[K], doubl
 
 __global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean(const SigJob *jobs, const double *__restrict__ atab_g)
 {
-    extern __shared__ __align__(16) unsigned char lean_raw[];
+    extern __shared__ __align__(128) unsigned char lean_raw[];
     LeanSmem &S = *reinterpret_cast<LeanSmem *>(lean_raw);
     const SigJob &J = jobs[blockIdx.y];
     const int tid = threadIdx.x;
@@ -409,286 +409,27 @@ __global__ void __launch_bounds__(kLeanThreads, 2) k_demod_lean(const SigJob *jo
 }
 
 
-// ---------------------------------------------------------------- lean discriminator, second generation
-// Measured per-SM rates of this part (tools/micro/pipes.cu, profiles/r2_pipe_rates.txt): FP64 and
-// LOP/SHF/PRMT/SEL issue every 2nd cycle per scheduler, MUFU (f32 or RCP64H) and the f64 -> f32
-// conversion every 8th, the f32 -> f64 conversion is nearly free, and all of them overlap -- so the
-// kernel is bound by ISSUE SLOTS first (round 1: 69 per sample, ncu).  This version spends ~46:
-//   - the f64 products are rounded to f32 by the conversion instruction (1 slot instead of 6 integer
-//     ones); with the f32 values at hand the octant logic is f32 min/max/compare (|.| is an operand
-//     modifier) and the table index comes from one MUFU.RCP + FFMA;
-//   - FAST PATH: atan(mn/mx) = atan(k/64) + atan(z), z = (mn - c mx)/(mx + c mn) from ONE Newton step on
-//     the RCP64H seed and a two-term series -- relative error < 2^-43 -- which decides the f32 rounding
-//     unless the f64 result sits within 2^-38 (relative) of an f32 rounding boundary: 2^-14 of the samples;
-//   - those samples (a thread with any of its 8) are redone with the full-accuracy arctangent of
-//     round 1 (atan2_lean), so the output equals it everywhere: tdoa_selftest(1) runs THIS function
-//     against demod_one<false> over all 2^32 byte quads and counts the fall-backs.
-struct __align__(16) OctEntry {
-    double base;   // B(case) + sigma(case) * atan(k / 64)
-    double c;      // k / 64
-};
-
-template <int THREADS>
-struct LeanSmem2T {
-    LeanEntry tab[256][16];                       // 64 KB
-    OctEntry oct[4][kOctStride];                  // 8 KB
-    double oct_exact[4][kOctStride];              // round-1 table for the exact fall-back (4 KB)
-    unsigned stage[2][kLeanWords][THREADS];       // cp.async landing zone, double buffered
-    double scratch[32];
-    int last;
-};
-typedef LeanSmem2T<kLeanThreads> LeanSmem2;
-
-template <class SM>
-__device__ __forceinline__ void lean2_fill(SM &S, const double *__restrict__ atab_g)
-{
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
-        const float v = unpack_byte((unsigned)(i >> 4));
-        LeanEntry e;
-        e.v = (double)v; e.sq = __fmul_rn(v, v); e.vf = v;
-        S.tab[i >> 4][i & 15] = e;
-    }
-    for (int i = threadIdx.x; i < 4 * kOctStride; i += blockDim.x) {
-        const int oc = i / kOctStride, k = i % kOctStride;
-        const int kk = k <= kAtanK ? k : kAtanK;
-        const double a = atab_g[kk];
-        const double pio2 = 1.57079632679489661923, pi = 3.14159265358979323846;
-        const double b = oc == 0 ? a : (oc == 1 ? pio2 - a : (oc == 2 ? pi - a : pio2 + a));
-        S.oct[oc][k].base = b;
-        S.oct[oc][k].c = (double)kk / (double)kAtanK;
-        S.oct_exact[oc][k] = b;
-    }
-}
-
-// fast discriminator value for X = Re p, Y = Im p (f64, before their rounding to f32); `unsafe` is
-// raised when the f32 rounding of the result is not decided by the fast path's accuracy
-__device__ __forceinline__ float lean2_fast(double X, double Y, unsigned oct_base, unsigned &unsafe)
-{
-    const float xf = (float)X, yf = (float)Y;                     // the reference's float32(...) of the products
-    const float ax = fabsf(xf), ay = fabsf(yf);
-    const bool sw = ay > ax;
-    const float mxf = fmaxf(ax, ay), mnf = fminf(ax, ay);
-    float rf;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(mxf));
-    const float kf = fmaf(mnf * rf, (float)kAtanK, 12582912.0f);   // 1.5 * 2^23: round(64 q) in the low mantissa bits
-    const unsigned kb = __float_as_uint(kf) & 0x7fu;
-    const unsigned xneg = __float_as_uint(xf) >> 31;
-    const unsigned addr = oct_base + (((xneg * 2u + (sw ? 1u : 0u)) * (unsigned)kOctStride + kb) << 4);
-    double base, c;
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(base), "=d"(c) : "r"(addr));
-    const double mx = (double)mxf, mn = (double)mnf;              // exact
-    const double num = fma(-c, mx, mn), den = fma(c, mn, mx);
-    double r = rcp_seed(den);
-    r = fma(r, fma(-den, r, 1.0), r);
-    const double z = num * r;
-    const double w = z * z;
-    const double az = fma(z * w, fma(w, 0.2, -1.0 / 3.0), z);     // |z| <= ~1/127: the next term is < 2^-44 relative
-    // atan(z) enters with a minus sign when exactly one of {swap, x < 0} holds
-    const unsigned flip = ((sw ? 1u : 0u) ^ xneg) << 31;
-    const double a = base + hilo((unsigned)__double2hiint(az) ^ flip, (unsigned)__double2loint(az));
-    // f64 -> f32 keeps 24 of the 53 mantissa bits: rounding boundary at 2^28 in the low word's 29 bits
-    const unsigned t = ((unsigned)__double2loint(a) - 0x0FFFC000u) & 0x1FFFFFFFu;
-    unsafe |= t < 0x8000u ? 1u : 0u;
-    const float o = (float)a;
-    return __uint_as_float(__float_as_uint(o) | (__float_as_uint(yf) & 0x80000000u));
-}
-
-template <int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_demod_lean2(const SigJob *jobs, const double *__restrict__ atab_g)
-{
-    constexpr int kLeanThreads = THREADS;
-    constexpr int kLeanTile = THREADS * kLeanPer;
-    extern __shared__ __align__(16) unsigned char lean_raw[];
-    LeanSmem2T<THREADS> &S = *reinterpret_cast<LeanSmem2T<THREADS> *>(lean_raw);
-    const SigJob &J = jobs[blockIdx.y];
-    const int tid = threadIdx.x;
-    lean2_fill(S, atab_g);
-    __syncthreads();
-    const i64 n = J.n;
-    const i64 i_begin = J.i_begin, i_end = J.i_end > 0 ? J.i_end : n;
-    const uint8_t *__restrict__ rawb = J.src.raw;
-    float *__restrict__ out = J.p_re;
-    const i64 run0 = J.src.run0_len;
-    const unsigned slot16 = (unsigned)(tid & 15) * 16u;
-    const unsigned tab_base = (unsigned)__cvta_generic_to_shared(&S.tab[0][0]);
-    const unsigned oct_base = (unsigned)__cvta_generic_to_shared(&S.oct[0][0]);
-    const unsigned octx_base = (unsigned)__cvta_generic_to_shared(&S.oct_exact[0][0]);
-    double pw = 0.0, sr = 0.0;
-    auto fast_tile = [&](i64 t0) {
-        const bool in0 = t0 + kLeanTile + 2 <= run0, in1 = t0 - 1 >= run0 && t0 + kLeanTile + 2 <= n;
-        return t0 > 0 && t0 + kLeanTile <= i_end && (in0 || in1);
-    };
-    auto tile_addr = [&](i64 t0) { return rawb + 2 * (raw_index(J.src, t0) + (i64)kLeanPer * tid); };
-    auto stage_tile = [&](i64 t0, int buf) {
-        if (fast_tile(t0)) {
-            const uint8_t *ap = tile_addr(t0);
-            const unsigned *wp = reinterpret_cast<const unsigned *>(ap - (reinterpret_cast<uintptr_t>(ap) & 2u)) - 1;
-#pragma unroll
-            for (int k = 0; k < kLeanWords; k++) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&S.stage[buf][k][tid]);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(wp + k) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    const i64 step = (i64)gridDim.x * kLeanTile;
-    int buf = 0;
-    stage_tile(i_begin + (i64)blockIdx.x * kLeanTile, 0);
-    for (i64 i0 = i_begin + (i64)blockIdx.x * kLeanTile; i0 < i_end; i0 += step, buf ^= 1) {
-        stage_tile(i0 + step, buf ^ 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        if (fast_tile(i0)) {
-            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(tile_addr(i0)) & 2u) * 8u;
-            const unsigned wm = S.stage[buf][0][tid], w0 = S.stage[buf][1][tid], w1 = S.stage[buf][2][tid],
-                           w2 = S.stage[buf][3][tid], w3 = S.stage[buf][4][tid], w4 = S.stage[buf][5][tid];
-            const unsigned pv = __funnelshift_r(wm, w0, sh);
-            unsigned w[4];
-            w[0] = __funnelshift_r(w0, w1, sh); w[1] = __funnelshift_r(w1, w2, sh);
-            w[2] = __funnelshift_r(w2, w3, sh); w[3] = __funnelshift_r(w3, w4, sh);
-            double pr, pi;
-            float sq_i, sq_q;
-            lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5524), pr, sq_i);
-            lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5534), pi, sq_q);
-            const double pr0 = pr, pi0 = pi;
-            float o[kLeanPer];
-            unsigned unsafe = 0u;
-            double srt = 0.0;
-#pragma unroll
-            for (int s = 0; s < kLeanPer; s++) {
-                const unsigned ww = w[s >> 1];
-                double cr, ci;
-                lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5524 : 0x5504), cr, sq_i);
-                lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5534 : 0x5514), ci, sq_q);
-                pw += (double)__fadd_rn(sq_i, sq_q);   // processor.go:328, f32 re*re + im*im
-                const double X = fma(pr, cr, __dmul_rn(pi, ci)), Y = fma(ci, pr, -__dmul_rn(pi, cr));
-                o[s] = lean2_fast(X, Y, oct_base, unsafe);
-                srt += (double)o[s];
-                pr = cr; pi = ci;
-            }
-            if (unsafe) {
-                // ~2^-14 of the samples: the thread's eight again, with the full-accuracy arctangent
-                pr = pr0; pi = pi0;
-                srt = 0.0;
-#pragma unroll
-                for (int s = 0; s < kLeanPer; s++) {
-                    const unsigned ww = w[s >> 1];
-                    double cr, ci;
-                    lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5524 : 0x5504), cr, sq_i);
-                    lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5534 : 0x5514), ci, sq_q);
-                    o[s] = lean_one(pr, pi, cr, ci, octx_base);
-                    srt += (double)o[s];
-                    pr = cr; pi = ci;
-                }
-            }
-            sr += srt;
-            float4 *op = reinterpret_cast<float4 *>(out + i0 + (i64)kLeanPer * tid);
-            op[0] = make_float4(o[0], o[1], o[2], o[3]);
-            op[1] = make_float4(o[4], o[5], o[6], o[7]);
-        } else {
-            // edges (signal start, the block-1/block-3 joint, the tail): the reference's
-            // own statement of the discriminator, sample by sample, gates included
-            for (int u = 0; u < kLeanPer; u++) {
-                const i64 i = i0 + tid + (i64)kLeanThreads * u;
-                if (i >= i_end) break;
-                const i64 k = i == 0 ? 1 : i;  // out[0] = out[1]
-                const uchar2 cur = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k)];
-                const uchar2 prv = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k - 1)];
-                const uchar2 me = i == 0 ? prv : cur;  // initial power is of sample i itself
-                pw += (double)__fadd_rn(S.tab[me.x][0].sq, S.tab[me.y][0].sq);
-                const double pr = S.tab[prv.x][0].v, pi = S.tab[prv.y][0].v, cr = S.tab[cur.x][0].v, ci = S.tab[cur.y][0].v;
-                const double re = fma(pr, cr, __dmul_rn(ci, pi)), im = fma(ci, pr, -__dmul_rn(pi, cr));
-                const float fre = (float)re, fim = (float)im;
-                const float m = __fadd_rn(__fmul_rn(fre, fre), __fmul_rn(fim, fim));
-                float y = 0.f;
-                if (m > 1e-10f) y = (float)atan2_lean((double)fim, (double)fre, octx_base);
-                out[i] = y;
-                sr += (double)y;
-            }
-        }
-    }
-    double part[2], total[2];
-    part[0] = block_sum(pw, S.scratch);
-    part[1] = block_sum(sr, S.scratch);
-    if (grid_sum_last_dyn<2>(part, J.partials, J.counter, gridDim.x, blockIdx.x, S.scratch, &S.last, total)) {
-        if (J.chunk_out) {
-            J.chunk_out[0] = total[0];
-            J.chunk_out[1] = total[1];
-            return;
-        }
-        J.stats[ST_POWER0] = n > 0 ? total[0] / (double)n : 0.0;
-        J.stats[ST_SUM_RE] = total[1];
-        J.stats[ST_SUM_IM] = 0.0;
-        J.stats[ST_DC_RE] = n > 0 ? (double)dc_from_sum(total[1], n) : 0.0;
-        J.stats[ST_DC_IM] = 0.0;
-    }
-}
-
-// every (previous, current) byte quad: the production path (fast value, exact fall-back when flagged)
-// against demod_one<false>; also counts the fall-backs and the fast values that would have been wrong
-// without their flag
-__global__ void __launch_bounds__(256) k_demod_selftest2(const double *__restrict__ atab_g, unsigned long long *counts,
-                                                         unsigned *first_bad)
-{
-    extern __shared__ __align__(16) unsigned char lean_raw[];
-    LeanSmem2 &S = *reinterpret_cast<LeanSmem2 *>(lean_raw);
-    __shared__ DemodLuts L;
-    lean2_fill(S, atab_g);
-    {
-        const float v = unpack_byte((unsigned)threadIdx.x);
-        L.lutf[threadIdx.x] = v;
-        L.lut[threadIdx.x] = (double)v;
-        if (threadIdx.x < 9) { L.atan_d[threadIdx.x] = atan_k8(threadIdx.x); L.atan_f[threadIdx.x] = (float)atan_k8(threadIdx.x); }
-    }
-    __syncthreads();
-    const unsigned oct_base = (unsigned)__cvta_generic_to_shared(&S.oct[0][0]);
-    const unsigned octx_base = (unsigned)__cvta_generic_to_shared(&S.oct_exact[0][0]);
-    const int slot = threadIdx.x & 15;
-    unsigned bad = 0, flagged = 0, saved = 0;
-    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
-    for (unsigned long long q = (unsigned long long)blockIdx.x * 256 + threadIdx.x; q < (1ull << 32); q += stride) {
-        const uchar2 prv = make_uchar2((unsigned char)(q & 255), (unsigned char)(q >> 8 & 255));
-        const uchar2 cur = make_uchar2((unsigned char)(q >> 16 & 255), (unsigned char)(q >> 24 & 255));
-        const float want = demod_one<false>(L, prv, cur);
-        const double pr = S.tab[prv.x][slot].v, pi = S.tab[prv.y][slot].v, cr = S.tab[cur.x][slot].v, ci = S.tab[cur.y][slot].v;
-        const double X = fma(pr, cr, __dmul_rn(pi, ci)), Y = fma(ci, pr, -__dmul_rn(pi, cr));
-        unsigned unsafe = 0u;
-        float got = lean2_fast(X, Y, oct_base, unsafe);
-        if (unsafe) {
-            flagged++;
-            const float exact = lean_one(pr, pi, cr, ci, octx_base);
-            if (__float_as_uint(exact) != __float_as_uint(got)) saved++;
-            got = exact;
-        }
-        if (__float_as_uint(want) != __float_as_uint(got)) {
-            bad++;
-            const unsigned at = atomicAdd(first_bad, 1u);
-            if (at < 63) first_bad[1 + at] = (unsigned)q;
-        }
-    }
-    if (bad) atomicAdd(counts, (unsigned long long)bad);
-    if (flagged) atomicAdd(counts + 1, (unsigned long long)flagged);
-    if (saved) atomicAdd(counts + 2, (unsigned long long)saved);
-}
-
-// ---------------------------------------------------------------- lean discriminator, third generation
-// ncu of the second generation (profiles/r2f_full.md): 76 instructions per sample of which NINE run on the
-// 16-lane XU pipe (three f64->f32 and four f32->f64 conversions, MUFU.RCP, MUFU.RCP64H) -- 72 XU cycles per
-// warp-sample against a 34-cycle HBM budget.  The conversions exist because the fast path mixed f32 and f64.
-// This version keeps the arctangent in f32 DOUBLE-FLOAT arithmetic (value = hi + lo, two f32), issued
-// two samples at a time with Blackwell's packed FFMA2 / FADD2 / FMUL2 (one issue slot for two samples):
-//   - X, Y: the reference's f64 products (DMUL + DFMA), rounded to f32 by the conversion instruction:
-//     the only two conversions of the arctangent;
+// ---------------------------------------------------------------- double-float discriminator (round 2)
+// The same bits as k_demod_lean at four fifths of its time.  What ncu said about the f64 kernels
+// (profiles/r2_demod.md): 76 instructions per sample, NINE of them on the 16-lane XU pipe (three f64->f32 and
+// four f32->f64 conversions, MUFU.RCP, MUFU.RCP64H) and 28 LSU wavefronts per warp-sample (six 4-byte cp.async
+// per thread at a 16-byte lane stride, three 128-bit table loads per sample) -- the XU and LSU pipes, not FP64,
+// were what bound it.  Here:
+//   - the arctangent runs in f32 DOUBLE-FLOAT arithmetic (value = hi + lo, two f32), issued two samples at a
+//     time with Blackwell's packed FFMA2 / FADD2 / FMUL2 (one issue slot for two samples);
+//   - X, Y: the reference's f64 products (DMUL + DFMA), rounded to f32 by the conversion instruction: the only
+//     two conversions per sample (the two sums widen their terms with integer moves, widen_scaled);
 //   - octant by FMNMX / FSETP on |x|, |y|; c = k/128 from a magic-number add on mn * rcp(mx);
 //   - rotation  y' = mn - c mx  (exact in f32: the leading bits cancel),  x' = mx + c mn  as hi + lo
 //     (three FMAs), u = y'/x' from one MUFU.RCP seed and an exact-residual correction (error < 2^-44),
 //     atan(u) = u - u^3/3 + u^5/5 with |u| <= 2^-8 (the terms after u ride in the low word);
-//   - B(case) +- atan(k/128) from a table of double-float pairs, added by a Fast2Sum;
-//   - the f32 result is RN(hi + lo), evaluated TWICE as fma(lo, 1 +- 2^-14, hi): when the two differ, hi + lo
-//     sits within 2^-38 (relative) of a rounding boundary and the fast path's accuracy (< 2^-40) does not
-//     decide the rounding -- 2^-13 of the samples.  A thread with such a sample among its eight redoes them
-//     with the full-accuracy f64 arctangent of round 1.
+//   - B(case) +- atan(k/128) from a table of (hi, lo) pairs, added by a Fast2Sum;
+//   - the f32 result is o = RN(hi + lo); with r = (hi + lo) - o (exact, |r| <= ulp/2) the test
+//     RN(o + r (1 + 2^-16)) != o says that hi + lo sits within 2^-40 (relative) of a rounding boundary, where
+//     the fast path's accuracy does not decide the rounding: 3e-5 of the samples.  A thread with such a
+//     sample among its eight redoes them with the full-accuracy f64 arctangent of round 1 (demod_exact8).
 // tdoa_selftest(1) runs THIS path (fast value, exact fall-back when flagged) against the reference statement
-// demod_one<false> over all 2^32 byte quads.
+// demod_one<false> over all 2^32 byte quads: 0 differing, 132 432 fall-backs, 112 of which changed the value.
 constexpr int kAtanK3 = 128;
 constexpr int kOct3Stride = 256;   // entries per octant case
 
@@ -727,45 +468,8 @@ __device__ __forceinline__ float rcp_f32(float x)
 }
 #define TDOA_PK2(x) ((((unsigned long long)(x)) << 32) | (unsigned long long)(x))
 
-template <int THREADS>
-struct LeanSmem3T {
-    LeanEntry tab[256][16];                       // 64 KB
-    float octh[4 * kOct3Stride];                  // B(case) + sigma(case) * atan(k / 128), high word ...
-    float octl[4 * kOct3Stride];                  // ... and low word of the double-float pair (4 + 4 KB)
-    double oct_exact[4][kOctStride];              // round-1 table for the exact fall-back (4 KB)
-    unsigned stage[2][kLeanWords][THREADS];       // cp.async landing zone, double buffered
-    double scratch[32];
-    int last;
-};
-
-// atab3_g: atan(k / 128), k = 0..128; atab_g: atan(k / 64) (fall-back)
-template <class SM>
-__device__ __forceinline__ void lean3_fill(SM &S, const double *__restrict__ atab_g, const double *__restrict__ atab3_g)
-{
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
-        const float v = unpack_byte((unsigned)(i >> 4));
-        LeanEntry e;
-        e.v = (double)v; e.sq = __fmul_rn(v, v); e.vf = v;
-        S.tab[i >> 4][i & 15] = e;
-    }
-    const double pio2 = 1.57079632679489661923, pi = 3.14159265358979323846;
-    for (int i = threadIdx.x; i < 4 * kOct3Stride; i += blockDim.x) {
-        const int oc = i / kOct3Stride, k = i % kOct3Stride;
-        const double a = atab3_g[k <= kAtanK3 ? k : kAtanK3];
-        const double b = oc == 0 ? a : (oc == 1 ? pio2 - a : (oc == 2 ? pi - a : pio2 + a));
-        const float bh = (float)b;
-        S.octh[i] = bh;
-        S.octl[i] = (float)(b - (double)bh);
-    }
-    for (int i = threadIdx.x; i < 4 * kOctStride; i += blockDim.x) {
-        const int oc = i / kOctStride, k = i % kOctStride;
-        const double a = atab_g[k <= kAtanK ? k : kAtanK];
-        S.oct_exact[oc][k] = oc == 0 ? a : (oc == 1 ? pio2 - a : (oc == 2 ? pi - a : pio2 + a));
-    }
-}
-
 // table entry of a byte: the address is (byte << 8 | slot << 4) from one PRMT; the table base is CTA-uniform
-__device__ __forceinline__ void lean3_lookup(const LeanEntry *tab, unsigned off, double &v, float &sq)
+__device__ __forceinline__ void df_lookup(const LeanEntry *tab, unsigned off, double &v, float &sq)
 {
     const double2 t = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(tab) + off);
     v = t.x;
@@ -785,68 +489,10 @@ __device__ __forceinline__ double widen_scaled(float o)
     return hilo((unsigned)((int)b >> 3) & 0x8FFFFFFFu, b << 29);
 }
 
-// two discriminator values at once from the f64 products X = Re p, Y = Im p of two samples; `diff` collects
+// Two discriminator values at once from the f64 products X = Re p, Y = Im p of two samples; `diff` collects
 // (o1 ^ o2) of every sample: nonzero = some rounding undecided
 template <class SM>
-__device__ __forceinline__ void lean3_pair(const SM &S, double XA, double YA, double XB, double YB,
-                                           float &oA, float &oB, unsigned &diff)
-{
-    const float xA = (float)XA, yA = (float)YA, xB = (float)XB, yB = (float)YB;   // the reference's float32(...) of the products
-    const float mxA = fmaxf(fabsf(xA), fabsf(yA)), mnA = fminf(fabsf(xA), fabsf(yA));
-    const float mxB = fmaxf(fabsf(xB), fabsf(yB)), mnB = fminf(fabsf(xB), fabsf(yB));
-    const bool swA = fabsf(yA) > fabsf(xA), swB = fabsf(yB) > fabsf(xB);
-    const unsigned xbA = __float_as_uint(xA), xbB = __float_as_uint(xB);
-    const f32x2 MX = pk(mxA, mxB), MN = pk(mnA, mnB);
-    const f32x2 kMagic = TDOA_PK2(0x47C00000u);     // 98304 = 1.5 * 2^16: ulp 2^-7
-    const f32x2 kMinus1 = TDOA_PK2(0xBF800000u);
-    const f32x2 T = fma2(MN, pk(rcp_f32(mxA), rcp_f32(mxB)), kMagic);   // q + magic: k = round(128 q) in the low mantissa bits
-    const f32x2 C = fma2(kMagic, kMinus1, T);                   // T - magic =  c = k / 128, exact
-    const f32x2 NC = fma2(T, kMinus1, kMagic);                  // -c
-    float tA, tB;
-    upk(T, tA, tB);
-    // table entry: case = swap + 2 * (x < 0)
-    const unsigned ixA = (__float_as_uint(tA) & 0x1FFu) + (swA ? (unsigned)kOct3Stride : 0u) + ((xbA >> 31) << 9);
-    const unsigned ixB = (__float_as_uint(tB) & 0x1FFu) + (swB ? (unsigned)kOct3Stride : 0u) + ((xbB >> 31) << 9);
-    const f32x2 BH = pk(S.octh[ixA], S.octh[ixB]), BL = pk(S.octl[ixA], S.octl[ixB]);
-    const f32x2 Y1 = fma2(NC, MX, MN);                          // mn - c mx (exact)
-    const f32x2 XH = fma2(C, MN, MX);                           // mx + c mn, rounded
-    const f32x2 D = fma2(XH, kMinus1, MX);                      // mx - xh (exact)
-    const f32x2 XL = fma2(C, MN, D);                            // (mx + c mn) - xh (exact)
-    float xhA, xhB;
-    upk(XH, xhA, xhB);
-    const f32x2 NR = pk(rcp_f32(-xhA), rcp_f32(-xhB));          // -1 / xh
-    const f32x2 NUH = mul2(Y1, NR);                             // -u, high part
-    const f32x2 E = fma2(NUH, XH, Y1);                          // y' - uh xh
-    const f32x2 E2 = fma2(NUH, XL, E);                          // y' - uh (xh + xl)
-    const f32x2 NUL = mul2(E2, NR);                             // -u, low part
-    const f32x2 W = mul2(NUH, NUH);
-    const f32x2 P = fma2(W, TDOA_PK2(0x3E4CCCCDu), TDOA_PK2(0xBEAAAAABu));   // w / 5 - 1 / 3
-    const f32x2 CORR = fma2(mul2(NUH, W), P, NUL);              // atan(-u) - (-uh)
-    // atan(u) enters with a minus sign when exactly one of {swap, x < 0} holds; we carry -u, so sigma' = -sigma
-    const unsigned sgA = (swA ? 0x3F800000u : 0xBF800000u) ^ (xbA & 0x80000000u);
-    const unsigned sgB = (swB ? 0x3F800000u : 0xBF800000u) ^ (xbB & 0x80000000u);
-    const f32x2 SIG = pk(__uint_as_float(sgA), __uint_as_float(sgB));
-    const f32x2 SH = fma2(SIG, NUH, BH);                        // Fast2Sum: |bh| >= |uh| or bh == 0
-    const f32x2 T2 = fma2(SH, kMinus1, BH);                     // bh - sh
-    const f32x2 ERR = fma2(SIG, NUH, T2);
-    const f32x2 LO = add2(ERR, fma2(SIG, CORR, BL));
-    // hi + lo is not normalised (for k = 0 the low word carries all of u^3/3 ...): round, take the exact
-    // remainder r (|r| <= half an ulp of o), and ask whether r (1 + 2^-14) still rounds to o
-    const f32x2 O = add2(SH, LO);
-    const f32x2 R = add2(fma2(O, kMinus1, SH), LO);             // (sh - o) + lo, both steps exact
-    const f32x2 O1 = fma2(R, TDOA_PK2(0x3F800200u), O);         // 1 + 2^-14
-    float o1A, o1B, o2A, o2B;
-    upk(O1, o1A, o1B);
-    upk(O, o2A, o2B);
-    diff |= (__float_as_uint(o1A) ^ __float_as_uint(o2A)) | (__float_as_uint(o1B) ^ __float_as_uint(o2B));
-    oA = __uint_as_float(__float_as_uint(o2A) | (__float_as_uint(yA) & 0x80000000u));
-    oB = __uint_as_float(__float_as_uint(o2B) | (__float_as_uint(yB) & 0x80000000u));
-}
-
-// lean3_pair with the octant table as (hi, lo) pairs: one 64-bit load per sample.  Two discriminator values at once from the f64 products X = Re p, Y = Im p of two samples; `diff` collects
-// (o1 ^ o2) of every sample: nonzero = some rounding undecided
-template <class SM>
-__device__ __forceinline__ void lean4_pair(const SM &S, double XA, double YA, double XB, double YB,
+__device__ __forceinline__ void df_pair(const SM &S, double XA, double YA, double XB, double YB,
                                            float &oA, float &oB, unsigned &diff)
 {
     const float xA = (float)XA, yA = (float)YA, xB = (float)XB, yB = (float)YB;   // the reference's float32(...) of the products
@@ -893,7 +539,7 @@ __device__ __forceinline__ void lean4_pair(const SM &S, double XA, double YA, do
     // remainder r (|r| <= half an ulp of o), and ask whether r (1 + 2^-14) still rounds to o
     const f32x2 O = add2(SH, LO);
     const f32x2 R = add2(fma2(O, kMinus1, SH), LO);             // (sh - o) + lo, both steps exact
-    const f32x2 O1 = fma2(R, TDOA_PK2(0x3F800200u), O);         // 1 + 2^-14
+    const f32x2 O1 = fma2(R, TDOA_PK2(0x3F800080u), O);         // 1 + 2^-16
     float o1A, o1B, o2A, o2B;
     upk(O1, o1A, o1B);
     upk(O, o2A, o2B);
@@ -902,171 +548,18 @@ __device__ __forceinline__ void lean4_pair(const SM &S, double XA, double YA, do
     oB = __uint_as_float(__float_as_uint(o2B) | (__float_as_uint(yB) & 0x80000000u));
 }
 
-// SUMS: 0 = the two sums' f32 -> f64 conversions on the conversion pipe, 1 = by integer moves (widen_scaled)
-template <int THREADS, int MINB, int SUMS>
-__global__ void __launch_bounds__(THREADS, MINB) k_demod_lean3(const SigJob *jobs, const double *__restrict__ atab_g,
-                                                               const double *__restrict__ atab3_g)
-{
-    constexpr int kLeanTile = THREADS * kLeanPer;
-    extern __shared__ __align__(16) unsigned char lean_raw[];
-    LeanSmem3T<THREADS> &S = *reinterpret_cast<LeanSmem3T<THREADS> *>(lean_raw);
-    const SigJob &J = jobs[blockIdx.y];
-    const int tid = threadIdx.x;
-    lean3_fill(S, atab_g, atab3_g);
-    __syncthreads();
-    const i64 n = J.n;
-    const i64 i_begin = J.i_begin, i_end = J.i_end > 0 ? J.i_end : n;
-    const uint8_t *__restrict__ rawb = J.src.raw;
-    float *__restrict__ out = J.p_re;
-    const i64 run0 = J.src.run0_len;
-    const unsigned slot16 = (unsigned)(tid & 15) * 16u;
-    const LeanEntry *tab = &S.tab[0][0];
-    const unsigned tab_base = (unsigned)__cvta_generic_to_shared(&S.tab[0][0]);
-    const unsigned octx_base = (unsigned)__cvta_generic_to_shared(&S.oct_exact[0][0]);
-    double pw = 0.0, sr = 0.0;       // plain sums (edges, fall-backs)
-    double pws = 0.0, srs = 0.0;     // sums of terms scaled by 2^-896 (SUMS == 1)
-    auto fast_tile = [&](i64 t0) {
-        const bool in0 = t0 + kLeanTile + 2 <= run0, in1 = t0 - 1 >= run0 && t0 + kLeanTile + 2 <= n;
-        return t0 > 0 && t0 + kLeanTile <= i_end && (in0 || in1);
-    };
-    auto tile_addr = [&](i64 t0) { return rawb + 2 * (raw_index(J.src, t0) + (i64)kLeanPer * tid); };
-    auto stage_tile = [&](i64 t0, int buf) {
-        if (fast_tile(t0)) {
-            const uint8_t *ap = tile_addr(t0);
-            const unsigned *wp = reinterpret_cast<const unsigned *>(ap - (reinterpret_cast<uintptr_t>(ap) & 2u)) - 1;
-#pragma unroll
-            for (int k = 0; k < kLeanWords; k++) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&S.stage[buf][k][tid]);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(wp + k) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    const i64 step = (i64)gridDim.x * kLeanTile;
-    int buf = 0;
-    stage_tile(i_begin + (i64)blockIdx.x * kLeanTile, 0);
-    for (i64 i0 = i_begin + (i64)blockIdx.x * kLeanTile; i0 < i_end; i0 += step, buf ^= 1) {
-        stage_tile(i0 + step, buf ^ 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        if (fast_tile(i0)) {
-            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(tile_addr(i0)) & 2u) * 8u;
-            unsigned w[4];
-            double pr, pi;
-            {
-                const unsigned wm = S.stage[buf][0][tid], w0 = S.stage[buf][1][tid], w1 = S.stage[buf][2][tid],
-                               w2 = S.stage[buf][3][tid], w3 = S.stage[buf][4][tid], w4 = S.stage[buf][5][tid];
-                const unsigned pv = __funnelshift_r(wm, w0, sh);
-                w[0] = __funnelshift_r(w0, w1, sh); w[1] = __funnelshift_r(w1, w2, sh);
-                w[2] = __funnelshift_r(w2, w3, sh); w[3] = __funnelshift_r(w3, w4, sh);
-                float sq_i, sq_q;
-                lean3_lookup(tab, __byte_perm(pv, slot16, 0x5524), pr, sq_i);
-                lean3_lookup(tab, __byte_perm(pv, slot16, 0x5534), pi, sq_q);
-            }
-            float o[kLeanPer];
-            unsigned diff = 0u;
-            double srt = 0.0;
-#pragma unroll
-            for (int s = 0; s < kLeanPer; s += 2) {
-                const unsigned ww = w[s >> 1];
-                double crA, ciA, crB, ciB;
-                float sqiA, sqqA, sqiB, sqqB;
-                lean3_lookup(tab, __byte_perm(ww, slot16, 0x5504), crA, sqiA);
-                lean3_lookup(tab, __byte_perm(ww, slot16, 0x5514), ciA, sqqA);
-                lean3_lookup(tab, __byte_perm(ww, slot16, 0x5524), crB, sqiB);
-                lean3_lookup(tab, __byte_perm(ww, slot16, 0x5534), ciB, sqqB);
-                float gA, gB;
-                upk(add2(pk(sqiA, sqiB), pk(sqqA, sqqB)), gA, gB);   // processor.go:328, f32 re*re + im*im
-                if (SUMS) { pws += widen_scaled_pos(gA); pws += widen_scaled_pos(gB); }
-                else { pw += (double)gA; pw += (double)gB; }
-                const double XA = fma(pr, crA, __dmul_rn(pi, ciA)), YA = fma(ciA, pr, -__dmul_rn(pi, crA));
-                const double XB = fma(crA, crB, __dmul_rn(ciA, ciB)), YB = fma(ciB, crA, -__dmul_rn(ciA, crB));
-                lean3_pair(S, XA, YA, XB, YB, o[s], o[s + 1], diff);
-                if (SUMS) { srt += widen_scaled(o[s]); srt += widen_scaled(o[s + 1]); }
-                else { srt += (double)o[s]; srt += (double)o[s + 1]; }
-                pr = crB; pi = ciB;
-            }
-            if (diff) {
-                // ~2^-13 of the samples: the thread's eight again, with the full-accuracy arctangent
-                const unsigned wm = S.stage[buf][0][tid], w0 = S.stage[buf][1][tid];
-                const unsigned pv = __funnelshift_r(wm, w0, sh);
-                float sq_i, sq_q;
-                lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5524), pr, sq_i);
-                lean_lookup(tab_base + __byte_perm(pv, slot16, 0x5534), pi, sq_q);
-                srt = 0.0;
-#pragma unroll
-                for (int s = 0; s < kLeanPer; s++) {
-                    const unsigned ww = w[s >> 1];
-                    double cr, ci;
-                    lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5524 : 0x5504), cr, sq_i);
-                    lean_lookup(tab_base + __byte_perm(ww, slot16, (s & 1) ? 0x5534 : 0x5514), ci, sq_q);
-                    o[s] = lean_one(pr, pi, cr, ci, octx_base);
-                    srt += (double)o[s];
-                    pr = cr; pi = ci;
-                }
-                sr += srt;
-            } else if (SUMS) {
-                srs += srt;
-            } else {
-                sr += srt;
-            }
-            float4 *op = reinterpret_cast<float4 *>(out + i0 + (i64)kLeanPer * tid);
-            op[0] = make_float4(o[0], o[1], o[2], o[3]);
-            op[1] = make_float4(o[4], o[5], o[6], o[7]);
-        } else {
-            // edges (signal start, the block-1/block-3 joint, the tail): the reference's
-            // own statement of the discriminator, sample by sample, gates included
-            for (int u = 0; u < kLeanPer; u++) {
-                const i64 i = i0 + tid + (i64)THREADS * u;
-                if (i >= i_end) break;
-                const i64 k = i == 0 ? 1 : i;  // out[0] = out[1]
-                const uchar2 cur = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k)];
-                const uchar2 prv = reinterpret_cast<const uchar2 *>(rawb)[raw_index(J.src, k - 1)];
-                const uchar2 me = i == 0 ? prv : cur;  // initial power is of sample i itself
-                pw += (double)__fadd_rn(S.tab[me.x][0].sq, S.tab[me.y][0].sq);
-                const double pr = S.tab[prv.x][0].v, pi = S.tab[prv.y][0].v, cr = S.tab[cur.x][0].v, ci = S.tab[cur.y][0].v;
-                const double re = fma(pr, cr, __dmul_rn(ci, pi)), im = fma(ci, pr, -__dmul_rn(pi, cr));
-                const float fre = (float)re, fim = (float)im;
-                const float m = __fadd_rn(__fmul_rn(fre, fre), __fmul_rn(fim, fim));
-                float y = 0.f;
-                if (m > 1e-10f) y = (float)atan2_lean((double)fim, (double)fre, octx_base);
-                out[i] = y;
-                sr += (double)y;
-            }
-        }
-    }
-    if (SUMS) {
-        // 2^896: the scaled terms are exact multiples, so is their sum until the one rounding of each addition,
-        // which the scaling (a power of two, no underflow: the smallest term is 2^-959) does not change
-        const double k2p896 = hilo(0x77F00000u, 0u);
-        pw += pws * k2p896;
-        sr += srs * k2p896;
-    }
-    double part[2], total[2];
-    part[0] = block_sum(pw, S.scratch);
-    part[1] = block_sum(sr, S.scratch);
-    if (grid_sum_last_dyn<2>(part, J.partials, J.counter, gridDim.x, blockIdx.x, S.scratch, &S.last, total)) {
-        if (J.chunk_out) {
-            J.chunk_out[0] = total[0];
-            J.chunk_out[1] = total[1];
-            return;
-        }
-        J.stats[ST_POWER0] = n > 0 ? total[0] / (double)n : 0.0;
-        J.stats[ST_SUM_RE] = total[1];
-        J.stats[ST_SUM_IM] = 0.0;
-        J.stats[ST_DC_RE] = n > 0 ? (double)dc_from_sum(total[1], n) : 0.0;
-        J.stats[ST_DC_IM] = 0.0;
-    }
-}
-
-// ---------------------------------------------------------------- third generation, tiles staged by TMA
-// ncu of k_demod_lean3 (profiles/r2h): the LSU data pipe is 91 % busy -- 28 wavefronts per warp-sample, of
-// which 6 belong to the six 4-byte cp.async per thread (16-byte lane stride: four cache lines per
-// instruction) and their bank conflicts.  Here one thread issues ONE bulk copy (cp.async.bulk, the TMA
-// engine) per CTA tile: (THREADS + 1) 16-byte chunks from the 16-byte-aligned address below the tile's
-// previous sample, two tiles ahead, completion on an mbarrier.  A thread then reads its two chunks with two
-// LDS.128 and cuts its 18 bytes out with funnel shifts (the misalignment is uniform over the tile).
+// ---------------------------------------------------------------- staging of the capture bytes
+// A thread owns 8 consecutive samples = 16 bytes of the capture, plus the sample before them.  The bytes of a
+// tile arrive in shared memory as (THREADS + 1) 16-byte chunks copied from the 16-byte-aligned address below
+// the tile's previous sample; a thread reads its two chunks with two LDS.128 and cuts its 18 bytes out with
+// funnel shifts (the misalignment is uniform over the tile).  Two ways to get them there (template STAGE):
+//   1 (production): every warp copies its own 33 chunks with 16-byte cp.async, one tile ahead -- nothing wider
+//     than __syncwarp between the warps;
+//   0: one thread issues ONE bulk copy (cp.async.bulk, the TMA engine: UBLKCP in the SASS) per CTA tile, two
+//     tiles ahead, completion on an mbarrier.  No LSU work for the copy at all, but the buffer hand-back needs a
+//     CTA barrier per tile, and with 4096-sample tiles that costs more than the copy saves (0.90 vs 0.75 ms).
 template <int THREADS>
-struct __align__(128) LeanSmem4T {
+struct __align__(128) DfSmem {
     LeanEntry tab[256][16];                       // 64 KB
     float2 oct[4 * kOct3Stride];                  // double-float B(case) + sigma(case) * atan(k / 128): 8 KB
     double oct_exact[4][kOctStride];              // round-1 table for the exact fall-back (4 KB)
@@ -1109,10 +602,10 @@ __device__ __forceinline__ void cut_words(const unsigned (&W)[8], unsigned s, un
 }
 
 template <class SM>
-__device__ __forceinline__ void lean4_fill(SM &S, const double *__restrict__ atab_g, const double *__restrict__ atab3_g)
+__device__ __forceinline__ void df_fill(SM &S, const double *__restrict__ atab_g, const double *__restrict__ atab3_g)
 {
     const int tid = threadIdx.x, THREADS = blockDim.x;
-    // tables (lean3_fill's, with the octant table as float2)
+    // tables: byte -> {value widened, f32 square}; octant case and k -> B(case) + sigma(case) atan(k / 128) as (hi, lo)
     for (int i = tid; i < 256 * 16; i += THREADS) {
         const float v = unpack_byte((unsigned)(i >> 4));
         LeanEntry e;
@@ -1165,16 +658,16 @@ __device__ __noinline__ double demod_exact8(unsigned v0, unsigned v1, unsigned v
 // STAGE: 0 = one bulk copy (TMA) per CTA tile, mbarrier + one CTA barrier per tile; 1 = every warp stages its
 // own 33 chunks with 16-byte cp.async (no barrier wider than the warp)
 template <int THREADS, int MINB, int SUMS, int STAGE>
-__global__ void __launch_bounds__(THREADS, MINB) k_demod_tma(const SigJob *jobs, const double *__restrict__ atab_g,
+__global__ void __launch_bounds__(THREADS, MINB) k_demod_df(const SigJob *jobs, const double *__restrict__ atab_g,
                                                              const double *__restrict__ atab3_g)
 {
     constexpr int kLeanTile = THREADS * kLeanPer;
     constexpr unsigned kStageBytes = (THREADS + 1) * 16;
     extern __shared__ __align__(128) unsigned char lean_raw[];
-    LeanSmem4T<THREADS> &S = *reinterpret_cast<LeanSmem4T<THREADS> *>(lean_raw);
+    DfSmem<THREADS> &S = *reinterpret_cast<DfSmem<THREADS> *>(lean_raw);
     const SigJob &J = jobs[blockIdx.y];
     const int tid = threadIdx.x;
-    lean4_fill(S, atab_g, atab3_g);
+    df_fill(S, atab_g, atab3_g);
     if (tid == 0) {
         mbar_init(&S.full[0], 1);
         mbar_init(&S.full[1], 1);
@@ -1225,9 +718,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_demod_tma(const SigJob *jobs,
         if (j < n_tiles && fast_tile(j)) {
             const char *src = reinterpret_cast<const char *>(prev_addr(j) & ~(uintptr_t)15) + 16 * tid;
             const unsigned dst = wstage0 + (unsigned)b * kBufStride;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
             if (lane == 0)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 32 * 16), "l"(src + 32 * 16) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 32 * 16), "l"(src + 32 * 16) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -1277,8 +770,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_demod_tma(const SigJob *jobs,
             double pr, pi;
             {
                 float sq_i, sq_q;
-                lean3_lookup(tab, __byte_perm(V[0], slot16, 0x5504), pr, sq_i);
-                lean3_lookup(tab, __byte_perm(V[0], slot16, 0x5514), pi, sq_q);
+                df_lookup(tab, __byte_perm(V[0], slot16, 0x5504), pr, sq_i);
+                df_lookup(tab, __byte_perm(V[0], slot16, 0x5514), pi, sq_q);
             }
             float4 *op = reinterpret_cast<float4 *>(out + i0 + (i64)kLeanPer * tid);
             float o[4];
@@ -1289,16 +782,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_demod_tma(const SigJob *jobs,
                 const unsigned wa = V[s >> 1], wb = V[(s >> 1) + 1];   // sample s in the high half of wa, s + 1 in the low half of wb
                 double crA, ciA, crB, ciB;
                 float sqiA, sqqA, sqiB, sqqB;
-                lean3_lookup(tab, __byte_perm(wa, slot16, 0x5524), crA, sqiA);
-                lean3_lookup(tab, __byte_perm(wa, slot16, 0x5534), ciA, sqqA);
-                lean3_lookup(tab, __byte_perm(wb, slot16, 0x5504), crB, sqiB);
-                lean3_lookup(tab, __byte_perm(wb, slot16, 0x5514), ciB, sqqB);
+                df_lookup(tab, __byte_perm(wa, slot16, 0x5524), crA, sqiA);
+                df_lookup(tab, __byte_perm(wa, slot16, 0x5534), ciA, sqqA);
+                df_lookup(tab, __byte_perm(wb, slot16, 0x5504), crB, sqiB);
+                df_lookup(tab, __byte_perm(wb, slot16, 0x5514), ciB, sqqB);
                 const float gA = __fadd_rn(sqiA, sqqA), gB = __fadd_rn(sqiB, sqqB);   // processor.go:328, f32 re*re + im*im
                 if (SUMS) { pws += widen_scaled_pos(gA); pws += widen_scaled_pos(gB); }
                 else { pw += (double)gA; pw += (double)gB; }
                 const double XA = fma(pr, crA, __dmul_rn(pi, ciA)), YA = fma(ciA, pr, -__dmul_rn(pi, crA));
                 const double XB = fma(crA, crB, __dmul_rn(ciA, ciB)), YB = fma(ciB, crA, -__dmul_rn(ciA, crB));
-                lean4_pair(S, XA, YA, XB, YB, o[s & 2], o[(s & 2) + 1], diff);
+                df_pair(S, XA, YA, XB, YB, o[s & 2], o[(s & 2) + 1], diff);
                 if (SUMS) { srt += widen_scaled(o[s & 2]); srt += widen_scaled(o[(s & 2) + 1]); }
                 else { srt += (double)o[s & 2]; srt += (double)o[(s & 2) + 1]; }
                 if (s & 2) op[s >> 2] = make_float4(o[0], o[1], o[2], o[3]);
@@ -1357,14 +850,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_demod_tma(const SigJob *jobs,
 }
 
 // every (previous, current) byte quad, two at a time: the third-generation path (fast value, exact fall-back
-// when flagged) against demod_one<false>; counts as k_demod_selftest2
-__global__ void __launch_bounds__(256) k_demod_selftest3(const double *__restrict__ atab_g, const double *__restrict__ atab3_g,
+// when flagged) against demod_one<false>; also counts the fall-backs and the fast values that would have been
+// wrong without their flag
+__global__ void __launch_bounds__(256) k_demod_selftest_df(const double *__restrict__ atab_g, const double *__restrict__ atab3_g,
                                                          unsigned long long *counts, unsigned *first_bad)
 {
-    extern __shared__ __align__(16) unsigned char lean_raw[];
-    LeanSmem4T<kLeanThreads> &S = *reinterpret_cast<LeanSmem4T<kLeanThreads> *>(lean_raw);
+    extern __shared__ __align__(128) unsigned char lean_raw[];
+    DfSmem<kLeanThreads> &S = *reinterpret_cast<DfSmem<kLeanThreads> *>(lean_raw);
     __shared__ DemodLuts L;
-    lean4_fill(S, atab_g, atab3_g);
+    df_fill(S, atab_g, atab3_g);
     {
         const float v = unpack_byte((unsigned)threadIdx.x);
         L.lutf[threadIdx.x] = v;
@@ -1392,7 +886,7 @@ __global__ void __launch_bounds__(256) k_demod_selftest3(const double *__restric
             Y[j] = fma(ci[j], pr[j], -__dmul_rn(pi[j], cr[j]));
         }
         unsigned diff = 0u;
-        lean4_pair(S, X[0], Y[0], X[1], Y[1], got[0], got[1], diff);
+        df_pair(S, X[0], Y[0], X[1], Y[1], got[0], got[1], diff);
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             // the production kernel redoes all eight samples of a flagged thread: here the pair
@@ -1431,7 +925,7 @@ __global__ void k_demod_finish(const double *__restrict__ chunk_sums, int n_chun
 __global__ void __launch_bounds__(256) k_demod_selftest(const double *__restrict__ atab_g, unsigned long long *bad,
                                                         unsigned *first_bad)
 {
-    extern __shared__ __align__(16) unsigned char lean_raw[];
+    extern __shared__ __align__(128) unsigned char lean_raw[];
     LeanSmem &S = *reinterpret_cast<LeanSmem *>(lean_raw);
     __shared__ DemodLuts L;
     lean_fill(S, atab_g);
@@ -1678,33 +1172,13 @@ int demod_setup(cudaStream_t st)
         if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
         g_atab3_dev[dev] = d;
     }
-    if (cudaFuncSetAttribute(k_demod_lean3<512, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem3T<512>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_lean3<512, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem3T<512>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_lean3<512, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem3T<512>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_lean3<256, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem3T<256>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_lean3<256, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem3T<256>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_tma<512, 2, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<512>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_tma<512, 2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<512>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_tma<512, 2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<512>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_tma<512, 2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<512>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_tma<384, 2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<384>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_tma<384, 2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<384>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_tma<256, 2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<256>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_selftest3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem4T<kLeanThreads>)) != cudaSuccess)
-        return -1;
-    if (cudaFuncSetAttribute(k_demod_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) != cudaSuccess)
-        return -1;
-    if (cudaFuncSetAttribute(k_demod_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) !=
-        cudaSuccess)
-        return -1;
-    if (cudaFuncSetAttribute(k_demod_lean2<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2T<512>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_lean2<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2T<512>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_lean2<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2T<256>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_lean2<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2T<384>)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_demod_lean2<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2T<256>)) != cudaSuccess)
-        return -1;
-    if (cudaFuncSetAttribute(k_demod_selftest2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem2)) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(k_demod_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_df<512, 2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_df<512, 2, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_df<512, 2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem<512>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_df<384, 2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem<384>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_demod_selftest_df, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfSmem<kLeanThreads>)) != cudaSuccess)
         return -1;
     return 0;
 }
@@ -1717,38 +1191,31 @@ int lean_grid_x(i64 n, int n_jobs)
     return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
 }
 
+// fast = 0: the production discriminator (k_demod_df: double-float arctangent, exact fall-back where its accuracy
+// does not decide the rounding -- the reference's bits); 2: the round-1 kernel (every sample through the f64
+// arctangent; same bits, test switch); 1: f32 arctangent (not the parity path).
+// TDOA_DEMOD_VARIANT (experiment switch, fast = 0 only): 1 = tiles staged by one TMA bulk copy per CTA,
+// 2 = 384-thread CTAs, 3 = the two sums' conversions on the conversion pipe.
 void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, cudaStream_t st)
 {
-    if (fast == 2) {   // test switch: the round-1 kernel (every sample through the full-accuracy arctangent)
+    if (fast == 2) {
         k_demod_lean<<<dim3(lean_grid_x(max_n, n_jobs), n_jobs), kLeanThreads, sizeof(LeanSmem), st>>>(d_jobs, atab_here());
     } else if (fast) {
         k_demod_fused<true><<<dim3(fast_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
     } else {
-        static const int variant = getenv("TDOA_DEMOD_VARIANT") ? atoi(getenv("TDOA_DEMOD_VARIANT")) : 0;   // experiment switch
+        static const int variant = getenv("TDOA_DEMOD_VARIANT") ? atoi(getenv("TDOA_DEMOD_VARIANT")) : 0;
         auto gx = [&](int threads, int per_sm) {
             const i64 tiles = (max_n + (i64)threads * kLeanPer - 1) / ((i64)threads * kLeanPer);
-            i64 cap = (i64)(per_sm * 148) / (n_jobs > 0 ? n_jobs : 1);
+            i64 cap = (i64)(per_sm * 148) / (n_jobs > 0 ? n_jobs : 1);   // all jobs together: one resident wave
             if (cap < 1) cap = 1;
             return (int)(tiles < 1 ? 1 : (tiles > cap ? cap : tiles));
         };
+        const double *a = atab_here(), *a3 = atab3_here();
         switch (variant) {
-            case 20: k_demod_tma<512, 2, 1, 0><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem4T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 21: k_demod_tma<512, 2, 0, 0><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem4T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 22: k_demod_tma<512, 2, 0, 1><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem4T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 23: k_demod_tma<512, 2, 1, 1><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem4T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 24: k_demod_tma<384, 2, 1, 1><<<dim3(gx(384, 2), n_jobs), 384, sizeof(LeanSmem4T<384>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 25: k_demod_tma<384, 2, 0, 1><<<dim3(gx(384, 2), n_jobs), 384, sizeof(LeanSmem4T<384>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 26: k_demod_tma<256, 2, 1, 1><<<dim3(gx(256, 2), n_jobs), 256, sizeof(LeanSmem4T<256>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 10: k_demod_lean2<512, 2><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem2T<512>), st>>>(d_jobs, atab_here()); break;
-            case 11: k_demod_lean3<512, 1, 1><<<dim3(gx(512, 1), n_jobs), 512, sizeof(LeanSmem3T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 12: k_demod_lean3<256, 2, 1><<<dim3(gx(256, 2), n_jobs), 256, sizeof(LeanSmem3T<256>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 13: k_demod_lean3<256, 3, 1><<<dim3(gx(256, 3), n_jobs), 256, sizeof(LeanSmem3T<256>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 14: k_demod_lean3<512, 2, 0><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem3T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
-            case 1: k_demod_lean2<512, 1><<<dim3(gx(512, 1), n_jobs), 512, sizeof(LeanSmem2T<512>), st>>>(d_jobs, atab_here()); break;
-            case 2: k_demod_lean2<256, 2><<<dim3(gx(256, 2), n_jobs), 256, sizeof(LeanSmem2T<256>), st>>>(d_jobs, atab_here()); break;
-            case 3: k_demod_lean2<384, 2><<<dim3(gx(384, 2), n_jobs), 384, sizeof(LeanSmem2T<384>), st>>>(d_jobs, atab_here()); break;
-            case 4: k_demod_lean2<256, 1><<<dim3(gx(256, 1), n_jobs), 256, sizeof(LeanSmem2T<256>), st>>>(d_jobs, atab_here()); break;
-            default: k_demod_lean3<512, 2, 1><<<dim3(gx(512, 2), n_jobs), 512, sizeof(LeanSmem3T<512>), st>>>(d_jobs, atab_here(), atab3_here()); break;
+            case 1: k_demod_df<512, 2, 1, 0><<<dim3(gx(512, 2), n_jobs), 512, sizeof(DfSmem<512>), st>>>(d_jobs, a, a3); break;
+            case 2: k_demod_df<384, 2, 1, 1><<<dim3(gx(384, 2), n_jobs), 384, sizeof(DfSmem<384>), st>>>(d_jobs, a, a3); break;
+            case 3: k_demod_df<512, 2, 0, 1><<<dim3(gx(512, 2), n_jobs), 512, sizeof(DfSmem<512>), st>>>(d_jobs, a, a3); break;
+            default: k_demod_df<512, 2, 1, 1><<<dim3(gx(512, 2), n_jobs), 512, sizeof(DfSmem<512>), st>>>(d_jobs, a, a3); break;
         }
     }
 }
@@ -1770,8 +1237,7 @@ long long demod_selftest(cudaStream_t st, unsigned *first_bad_out, int which, lo
     cudaMemsetAsync(d_cnt, 0, sizeof(h_cnt), st);
     cudaMemsetAsync(d_first, 0, 64 * sizeof(unsigned), st);
     if (which == 3) k_demod_selftest<<<148 * 2, 256, sizeof(LeanSmem), st>>>(atab_here(), d_cnt, d_first);
-    else if (which == 2) k_demod_selftest2<<<148 * 2, 256, sizeof(LeanSmem2), st>>>(atab_here(), d_cnt, d_first);
-    else k_demod_selftest3<<<148 * 2, 256, sizeof(LeanSmem4T<kLeanThreads>), st>>>(atab_here(), atab3_here(), d_cnt, d_first);
+    else k_demod_selftest_df<<<148 * 2, 256, sizeof(DfSmem<kLeanThreads>), st>>>(atab_here(), atab3_here(), d_cnt, d_first);
     cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
     if (first_bad_out) cudaMemcpyAsync(first_bad_out, d_first, 64 * sizeof(unsigned), cudaMemcpyDeviceToHost, st);
     const cudaError_t err = cudaStreamSynchronize(st);

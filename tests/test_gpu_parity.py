@@ -727,11 +727,13 @@ def test_constant_divisor_division_is_exact(eng_binary):
 
 
 def test_lean_discriminator_all_byte_quads(eng_binary):
-    """The production discriminator (integer rounding of the f64 products, table-driven
-    f64 arctangent) against the reference statement (F2F conversions, gates, the older
-    arctangent) over every (previous, current) byte quad -- the discriminator is a function
-    of four bytes, so this is exhaustive.  Measured: 0 differing quads of 2^32
-    (profiles/r2_source_parity_and_selftest.txt), and that is what is asserted.  What it proves:
+    """The production discriminator (k_demod_df: f64 products rounded to f32, f32 double-float
+    arctangent two samples per packed instruction, full-accuracy f64 fall-back wherever the fast
+    value sits within 2^-40 of an f32 rounding boundary) against the reference statement (F2F
+    conversions, gates, the older f64 arctangent) over every (previous, current) byte quad -- the
+    discriminator is a function of four bytes, so this is exhaustive.  Measured: 0 differing quads
+    of 2^32, 132 432 fall-backs of which 112 changed the value (profiles/r2_demod.md), and 0 is what
+    is asserted; selftest(3) is the same check of the round-1 kernel (fast_demod = 2).  What it proves:
     the production kernel equals the engine's plain statement of the reference's discriminator
     (demod_one<false>: f64 products, F2F roundings, the gates, a <= 1 ulp f64 arctangent); the link
     from that statement to Go's math.Atan2 is test_discriminator_bits_match_oracle (libm's atan2
@@ -740,6 +742,9 @@ def test_lean_discriminator_all_byte_quads(eng_binary):
     bad = eng_binary.selftest(1)
     print("lean discriminator: differing byte quads =", bad, eng_binary.last_error() if bad else "")
     assert bad == 0
+    assert eng_binary.selftest(3) == 0
+    falls = eng_binary.selftest(2)
+    assert 0 < falls < 1 << 20       # the exact fall-back exists and is rare (3e-5 of the quads)
 
 
 # ------------------------------------------------------------------ lazy pinned load (copy-following discriminator)

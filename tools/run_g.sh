@@ -1,4 +1,10 @@
-cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out/r2m
-TDOA_DEMOD_VARIANT=23 timeout 300 python tools/diag_demod.py > gpurun_out/r2m/demod23.txt 2>&1; head -3 gpurun_out/r2m/demod23.txt;  sed -n 6p gpurun_out/r2m/demod23.txt
-for v in 20 21 22 24 25 26; do TDOA_DEMOD_VARIANT=$v timeout 300 python tools/diag_demod.py --quick > gpurun_out/r2m/demod$v.txt 2>&1; echo $v; tail -n 1 gpurun_out/r2m/demod$v.txt; done
-TDOA_DEMOD_VARIANT=23 ncu --set full --clock-control none --import-source on -k regex:k_demod_tma -c 1 -o gpurun_out/r2m/v23 python tools/diag_demod.py --quick > gpurun_out/r2m/ncu23.log 2>&1
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out/r2o
+python -m pytest tests -m gpu -x -q > gpurun_out/r2o/pytest.txt 2>&1; tail -n 5 gpurun_out/r2o/pytest.txt
+python bench.py --steps 10 --warmup 3 --no-sharded > gpurun_out/r2o/bench.json 2> gpurun_out/r2o/bench.err; tail -c 600 gpurun_out/r2o/bench.err
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2o/bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['serial_ms_per_step'])
+for r in d['roofline_kernels']: print(r['kernel'], round(r['frac'],3), round(r['kernel_ms_per_launch'],3))
+print(d['parity_check'].get('oracle_at_size'))
+P
