@@ -627,7 +627,7 @@ def main_ours(args):
                     "measured": "CUDA events around each launch, %d serial steps (serial_kinds=1) of the same workload" % args.steps}
 
         kernels = [k for k in (
-            kernel_line("k_demod_lean", 6.0, "demod_samples", "ms_demod", "demod_launches"),
+            kernel_line("k_demod_df", 6.0, "demod_samples", "ms_demod", "demod_launches"),
             kernel_line("k_boxcar_small", 8.0, "boxcar_samples", "ms_boxcar", "boxcar_launches"),
             kernel_line("k_fft_tiles", 4.0, "fft_pair_samples", "ms_fft_seg", "fft_launches"),
             kernel_line("k_corr_candidates", 4.0, "cand_pair_samples", "ms_cand", "cand_launches"),

@@ -1,9 +1,13 @@
 #!/usr/bin/env python
 """Times the BASELINE.json configs other than the headline one (bench.py measures
-configs[1]) and checks size-independent properties on them: injected integer delays are
+configs[1]), on BOTH kinds of content -- the Mode-B FM generator with injected integer delays, and the
+reference's own simulators' content (simulator.go / weak_signal_simulator.go restated in
+tools/simulators.py) -- and gives each line an oracle verdict: the CPU restatement of the
+reference (oracle/) run on the same bytes, whole capture for config 1, one sampled window
+(peak lag +- 5) for the windowed configs.  Size-independent properties ride along: injected delays
 recovered, every window agrees, the grid arg-min lands on the transmitter cell.
 
-    python tools/configs_bench.py [--quick]      -> one JSON line per config
+    python tools/configs_bench.py [--quick]      -> one JSON line per config and content
 """
 import argparse
 import json
@@ -21,6 +25,11 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 import tdoa_b200 as T  # noqa: E402
+sys.path.insert(0, str(ROOT / "tools"))
+import simulators as S  # noqa: E402
+from oracle import oracle  # noqa: E402  (the checker; never on the measured path)
+
+PEAK_HBM = bench.measured_peaks()[0] if hasattr(bench, "measured_peaks") else 6557.4
 
 FS, C = 2e6, 299792458.0
 
@@ -83,21 +92,100 @@ def timed(fn, reps=3):
     return (time.perf_counter() - t0) / reps, out
 
 
+
+def stage_ms(e):
+    st = e.stats()
+    return {k: round(float(st[k]), 4) for k in ("ms_preprocess", "ms_fft", "ms_exact", "ms_total")}
+
+
+def oracle_capture_verdict(caps, mode, ref_pk, tgt_pk, chunk):
+    """Config 1: the whole chunked run of the reference (oracle.process_capture_*) on the same bytes."""
+    t0 = time.perf_counter()
+    # the reference truncates each signal to `chunk` samples (blocks >= chunk here): block 1 / block 2 heads suffice
+    block = caps[0].numel() // 6
+    m = min(chunk, block)
+    raws = [torch.cat([c[:2 * m], c[2 * block:2 * block + 2 * m], c[4 * block:4 * block + 2 * m]]).cpu().numpy() for c in caps]
+    fn = oracle.process_capture_binary if mode == T.MODE_BINARY else oracle.process_capture_source
+    want_ref, want_tgt = fn(raws, chunk=chunk)
+    ok, worst = True, 0.0
+    for want, pk in ((want_ref, ref_pk), (want_tgt, tgt_pk)):
+        for p, rec in enumerate(want):
+            lag, corr = int(rec[0]), float(rec[1])
+            d = abs(float(pk[p]["corr"]) - corr)
+            worst = max(worst, d / max(1.0, abs(corr)))
+            ok &= int(pk[p]["lag"]) == lag and d <= 1e-6 * max(1.0, abs(corr))
+    return {"ok": bool(ok), "max_rel_corr_diff": worst, "seconds": round(time.perf_counter() - t0, 2),
+            "what": "oracle.process_capture_%s on the same captures: all 6 (lag, correlation) records" %
+                    ("binary" if mode == T.MODE_BINARY else "source")}
+
+
+def oracle_window_verdict(caps, first_byte, W, L, table_row, pairs, all_pairs, span=5):
+    """EXTENDED mode on one window: the oracle's preprocessing of the window of every station of `pairs`, then
+    c(l) = mean_i y1[i] y2[i + l] over i in [L, W - L) in f64 (orc_xcorr_two_sided's definition) at the engine's
+    peak lag +- span: arg-max, value (1e-6) and parabolic vertex (1e-3 samples)."""
+    t0 = time.perf_counter()
+    oracle.set_seq_dc_limit(0)
+    oracle.set_wide_boxcar_f64(33)
+    try:
+        ys = {}
+        for k in sorted({s for pr in pairs for s in pr}):
+            raw = caps[k][first_byte:first_byte + 2 * W].cpu().numpy()
+            ys[k] = oracle.preprocess_binary(oracle.unpack_u8(raw))
+    finally:
+        oracle.set_seq_dc_limit(-1)
+        oracle.set_wide_boxcar_f64(0)
+    ok, res = True, []
+    for i, j in pairs:
+        got = table_row[all_pairs.index((i, j))]
+        lag = int(got["lag"])
+        a = np.ascontiguousarray(ys[i][0].real[L:W - L]).astype(np.float64)
+        lags = [l for l in range(lag - span, lag + span + 1) if -L <= l <= L]
+        vals = np.array([float(np.dot(a, ys[j][0].real[L + l:W - L + l].astype(np.float64))) / a.size for l in lags])
+        b = int(np.argmax(np.abs(vals)))
+        frac = 0.0
+        if 0 < b < len(vals) - 1:
+            x, y, z = abs(vals[b - 1]), abs(vals[b]), abs(vals[b + 1])
+            den = x - 2 * y + z
+            frac = 0.5 * (x - z) / den if den != 0 else 0.0
+        good = lags[b] == lag and abs(vals[b] - float(got["corr"])) <= 1e-6 and abs(frac - float(got["frac"])) <= 1e-3
+        ok &= good
+        res.append({"pair": [i, j], "engine": [lag, float(got["frac"]), float(got["corr"])],
+                    "oracle": [lags[b], float(frac), float(vals[b])], "branches": [ys[i][1], ys[j][1]], "ok": bool(good)})
+    return {"ok": bool(ok), "pairs": res, "seconds": round(time.perf_counter() - t0, 2),
+            "what": "orc_preprocess_binary (EXTENDED arithmetic) of one window + the two-sided f64 correlation at the "
+                    "engine's peak lag +- %d" % span}
+
+
 def cfg1(args, dev, res):
-    # ---- config 1: 3-station 10 s capture, the reference's own chunked run (binary + source arithmetic)
+    # ---- config 1: 3-station 10 s capture, the reference's own chunked run (binary + source arithmetic),
+    # Mode-B FM content (strong branch) and simulator.go's own content (Mode A: literal tones -> weak branch)
     block = 2_000_000 if args.quick else 20_000_000
     delays, _ = delays_for(bench.STATION_LLH)
-    caps = synth(dev, 3, block, delays)
     want = [int(delays[j] - delays[i]) for i in range(3) for j in range(i + 1, 3)]
-    for mode, name in ((T.MODE_BINARY, "binary"), (T.MODE_SOURCE, "source")):
-        with T.Engine(mode) as e:
-            for k in range(3):
-                e.load_u8_device(k, caps[k].data_ptr(), caps[k].numel(), keep=caps[k])
-            dt, (r, t) = timed(lambda: (e.xcorr(T.KIND_REF)[0], e.xcorr(T.KIND_TGT)[0]))
-            chunk = e.cfg.chunk_samples
-        ok = [int(x) for x in t["lag"]] == (want if mode == T.MODE_BINARY else [0, 0, 0])
-        res.append({"config": f"1 ({name} arithmetic, chunk {chunk})", "ms": dt * 1e3,
-                    "pair_msamples_per_s": 6 * chunk / dt / 1e6, "lags": [int(x) for x in t["lag"]], "ok": bool(ok)})
+    contents = (("Mode B FM", lambda: synth(dev, 3, block, delays)),
+                ("Mode A simulator.go", lambda: S.simulate_perfect([tuple(x) for x in bench.STATION_LLH], tuple(bench.TX_LLH),
+                                                                   92300000.0, 1000.0, block, seed=1, device=dev)[0]))
+    for cname, make in contents:
+        caps = make()
+        for mode, name in ((T.MODE_BINARY, "binary"), (T.MODE_SOURCE, "source")):
+            with T.Engine(mode) as e:
+                for k in range(3):
+                    e.load_u8_device(k, caps[k].data_ptr(), caps[k].numel(), keep=caps[k])
+                dt, (r, t) = timed(lambda: (e.xcorr(T.KIND_REF)[0], e.xcorr(T.KIND_TGT)[0]))
+                chunk = e.cfg.chunk_samples
+                info = e.xcorr_info(T.KIND_TGT)[0] if hasattr(e, "xcorr_info") else None
+                stages = stage_ms(e)
+            verdict = oracle_capture_verdict(caps, mode, r, t, chunk)
+            line = {"config": f"1 ({name} arithmetic, chunk {chunk})", "content": cname, "ms": dt * 1e3,
+                    "pair_msamples_per_s": 6 * chunk / dt / 1e6, "lags": [int(x) for x in t["lag"]],
+                    "branches": [int(x["branch"]) for x in info] if info is not None else None,
+                    "stage_ms_last_call": stages, "oracle": verdict}
+            if cname.startswith("Mode B"):
+                line["ok"] = bool([int(x) for x in t["lag"]] == (want if mode == T.MODE_BINARY else [0, 0, 0]) and verdict["ok"])
+            else:
+                line["ok"] = bool(verdict["ok"])
+            res.append(line)
+        del caps
 
 
 def cfg2x(args, dev, res):
@@ -125,7 +213,7 @@ def cfg3(args, dev, res):
     caps = synth(dev, 3, block, delays)
     W, L = 2_000_000, 50_000
     nw = block // W
-    with T.Engine(T.MODE_EXTENDED, max_lag=L, fast_demod=1) as e:
+    with T.Engine(T.MODE_EXTENDED, max_lag=L) as e:
         for k in range(3):
             e.load_u8_device(k, caps[k].data_ptr(), caps[k].numel(), keep=caps[k])
 
@@ -136,28 +224,72 @@ def cfg3(args, dev, res):
             return pk, pos
 
         dt, (pk, pos) = timed(run3, reps=args.reps)
+        stages = stage_ms(e)
     ok = all([int(x) for x in pk[w]["lag"]] == want for w in range(nw))
-    res.append({"config": f"3 (EXTENDED, {nw} windows x 3 pairs, W=2e6, +-{L} lags)", "ms": dt * 1e3,
-                "pair_msamples_per_s": nw * 3 * W / dt / 1e6, "fixes_per_s": nw / dt, "ok": bool(ok),
-                "max_abs_frac": float(np.abs(pk["frac"]).max())})
+    w_s = min(7, nw - 1)
+    pairs3 = [(0, 1), (0, 2), (1, 2)]
+    verdict = oracle_window_verdict(caps, 2 * block + 2 * w_s * W, W, L, pk[w_s], pairs3, pairs3)
+    # SURVEY 8d, two-pass regime: 32 MiB (S + P) per window = 201 MB at S = 3, P = 3 (four 8 MiB passes per station
+    # transform, four per pair inverse); distinct input bytes of the windows (three planes, once) beside it
+    fft_bytes = nw * 32.0 * 1048576 * 6
+    distinct = nw * 3 * W * 4.0
+    fft_s = min(stages["ms_fft"], dt * 1e3) * 1e-3   # stage time is summed over the engine's two streams: cap at the wall
+    res.append({"config": f"3 (EXTENDED, {nw} windows x 3 pairs, W=2e6, +-{L} lags)", "content": "Mode B FM", "ms": dt * 1e3,
+                "pair_msamples_per_s": nw * 3 * W / dt / 1e6, "fixes_per_s": nw / dt, "ok": bool(ok and verdict["ok"]),
+                "max_abs_frac": float(np.abs(pk["frac"]).max()), "stage_ms_last_call": stages,
+                "roofline_stage": {"stage": "ms_fft (k_big_cols / k_big_rows / k_big_cross / k_big_out)", "bound": "hbm",
+                                   "algorithmic_bytes": fft_bytes, "achieved_gbs": fft_bytes / fft_s / 1e9,
+                                   "peak_gbs": PEAK_HBM, "frac": fft_bytes / fft_s / 1e9 / PEAK_HBM,
+                                   "distinct_input_bytes": distinct, "frac_distinct": distinct / fft_s / 1e9 / PEAK_HBM,
+                                   "note": "SURVEY 8d's two-pass figure (201 MB per window); the engine packs two stations per "
+                                           "transform and two pairs per inverse, so it moves less than that"},
+                "oracle": verdict})
 
 
 def cfg4(args, dev, res):
-    # ---- config 4: 16 stations (120 pairs), windowed
+    # ---- config 4: 16 stations (120 pairs), windowed: Mode-B FM content and weak_signal_simulator.go's own
     W = 2_000_000
     st16 = ring_stations(16)
     d16, _ = delays_for(st16)
     block = 4_000_000 if args.quick else 66_666_666
-    caps = synth(dev, 16, block, d16)
     nw = block // W
     want16 = [int(d16[j] - d16[i]) for i in range(16) for j in range(i + 1, 16)]
-    with T.Engine(T.MODE_EXTENDED, n_stations=16, max_lag=2000, fast_demod=1) as e:
-        for k in range(16):
-            e.load_u8_device(k, caps[k].data_ptr(), caps[k].numel(), keep=caps[k])
-        dt, pk = timed(lambda: e.xcorr(T.KIND_TGT, 0, W, nw, W), reps=args.reps)
-    ok = all([int(x) for x in pk[w]["lag"]] == want16 for w in range(nw))
-    res.append({"config": f"4 (EXTENDED, 16 stations, {nw} windows x 120 pairs, +-2000 lags)", "ms": dt * 1e3,
-                "pair_msamples_per_s": nw * 120 * W / dt / 1e6, "fixes_per_s": nw / dt, "ok": bool(ok)})
+    all_pairs = [(i, j) for i in range(16) for j in range(i + 1, 16)]
+    contents = (("Mode B FM", lambda: synth(dev, 16, block, d16)),
+                ("weak_signal_simulator.go (ref_power 10, tgt_power 1000)",
+                 lambda: S.simulate_weak([tuple(x) for x in st16], tuple(bench.TX_LLH), 92300000.0, 10.0, 1000.0, block,
+                                         seed=4242, device=dev)[0]))
+    for cname, make in contents:
+        caps = make()
+        with T.Engine(T.MODE_EXTENDED, n_stations=16, max_lag=2000) as e:
+            for k in range(16):
+                e.load_u8_device(k, caps[k].data_ptr(), caps[k].numel(), keep=caps[k])
+            dt, pk = timed(lambda: e.xcorr(T.KIND_TGT, 0, W, nw, W), reps=args.reps)
+            stages = stage_ms(e)
+            info = e.xcorr_info(T.KIND_TGT)[0]
+        w_s = min(7, nw - 1)
+        verdict = oracle_window_verdict(caps, 2 * block + 2 * w_s * W, W, 2000, pk[w_s], [(0, 1), (3, 9)], all_pairs)
+        line = {"config": f"4 (EXTENDED, 16 stations, {nw} windows x 120 pairs, +-2000 lags)", "content": cname, "ms": dt * 1e3,
+                "pair_msamples_per_s": nw * 120 * W / dt / 1e6, "fixes_per_s": nw / dt,
+                "branches_window0": sorted({int(x["branch"]) for x in info}), "stage_ms_last_call": stages, "oracle": verdict}
+        if cname.startswith("Mode B"):
+            line["ok"] = bool(all([int(x) for x in pk[w]["lag"]] == want16 for w in range(nw)) and verdict["ok"])
+        else:
+            line["ok"] = bool(verdict["ok"])
+        # SURVEY 8d, in-smem regime: 8 B per pair-sample; distinct bytes (16 station planes per window, once) beside it
+        fft_bytes = nw * 120 * W * 8.0
+        distinct = nw * 16 * W * 4.0
+        fft_s = min(stages["ms_fft"], dt * 1e3) * 1e-3
+        line["roofline_stage"] = {"stage": "ms_fft (k_spec_fft + k_spec_acc + inverse)", "bound": "hbm", "algorithmic_bytes": fft_bytes,
+                                  "achieved_gbs": fft_bytes / fft_s / 1e9, "peak_gbs": PEAK_HBM,
+                                  "frac": fft_bytes / fft_s / 1e9 / PEAK_HBM, "distinct_input_bytes": distinct,
+                                  "frac_distinct": distinct / fft_s / 1e9 / PEAK_HBM,
+                                  "note": "every station-segment is transformed once and shared by its 15 pairs, so the per-pair "
+                                          "figure of SURVEY 8d overstates the traffic 30-fold; the parked spectra (1 MB per "
+                                          "segment) are written and re-read on top of the distinct bytes"}
+        res.append(line)
+        del caps
+        torch.cuda.empty_cache()
 
 
 def cfg5(args, dev, res):
@@ -181,6 +313,11 @@ def cfg5(args, dev, res):
     res.append({"config": f"5 (grid 1000x1000, 16 stations, {sets} sets)", "ms": dt * 1e3,
                 "cell_sets_per_s": 1e6 * sets / dt, "fixes_per_s": sets / dt, "median_err_m": float(np.median(err_m)),
                 "ls_refine_ms": dt_ls * 1e3, "ls_median_err_m": float(np.median(err_ls)), "ls_median_rms_m": float(np.median(rms)),
+                "roofline_stage": {"stage": "k_grid_cost", "bound": "fp64 alu (no HBM traffic to speak of: 24 B per cell-set out)",
+                                   "flop_per_cell_set": 16 * 33.0, "achieved_tflops": 1e6 * sets * 16 * 33.0 / dt / 1e12,
+                                   "peak_tflops": 37.0, "frac": 1e6 * sets * 16 * 33.0 / dt / 1e12 / 37.0,
+                                   "note": "16 stations x (3 sub, 3 mul-add, sqrt ~ 20) per cell + 120 pair residuals; peak = "
+                                           "148 SMs x 64 FP64 lanes x 2 x 1.965 GHz"},
                 "ok": bool(np.median(err_m) < 60.0 and int(status.max()) == 0)})
 
 
