@@ -632,6 +632,17 @@ def main_ours(args):
             kernel_line("k_fft_tiles", 4.0, "fft_pair_samples", "ms_fft_seg", "fft_launches"),
             kernel_line("k_corr_candidates", 4.0, "cand_pair_samples", "ms_cand", "cand_launches"),
         ) if k]
+        for k in kernels:
+            if k["kernel"] == "k_fft_tiles":
+                # the tile FFT is bound by FP32 issue, not by HBM (FFT is not a dense contraction: CUDA cores only).
+                # Work per 6144-sample segment of a 3-station tile: two 8192-point complex transforms (5 N log2 N flop
+                # each) + three cross-spectrum accumulations (4097 bins x 8 multiply-adds + the split of the packed spectra)
+                seg = k["algorithmic_bytes_per_launch"] / 4.0 / 3.0 / 6144.0
+                flop = seg * (2 * 5.0 * 8192 * 13 + 3 * 4097 * 2 * 8.0 + 4097 * 16.0)
+                peak_tf = 148 * 128 * 2 * 1.965e9 / 1e12
+                k["compute"] = {"bound": "fp32 (CUDA cores)", "flop_per_launch": flop, "achieved_tflops": flop / (k["kernel_ms_per_launch"] * 1e-3) / 1e12,
+                                "peak_tflops": peak_tf, "frac": flop / (k["kernel_ms_per_launch"] * 1e-3) / 1e12 / peak_tf,
+                                "note": "peak = 148 SMs x 128 FP32 lanes x 2 x 1.965 GHz; DESIGN.md section 4 has the instruction budget"}
         if not kernels:  # FFT path disabled: the exact every-lag correlator carries the step
             k_ms = stage["ms_exact"] / max(1, args.steps)
             ach = 8.0 * pair_samples / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0

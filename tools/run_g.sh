@@ -1,7 +1,6 @@
-cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out/r2r
-timeout 1500 python tools/configs_bench.py > gpurun_out/r2r/configs.jsonl 2> gpurun_out/r2r/configs.err; echo rc=$?; tail -c 800 gpurun_out/r2r/configs.err
-python - <<'P'
-import json
-for l in open('gpurun_out/r2r/configs.jsonl'):
-    d=json.loads(l); print(d['config'][:44], '|', (d.get('content') or '')[:24], '|', round(d['ms'],2), 'ok', d['ok'], 'oracle', d.get('oracle',{}).get('ok'), d.get('stage_ms_last_call'), (d.get('roofline_stage') or {}).get('frac'))
-P
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out/r2s
+python bench.py --steps 20 --warmup 3 > gpurun_out/r2s/bench.json 2> gpurun_out/r2s/bench.err; echo bench rc=$?; tail -c 300 gpurun_out/r2s/bench.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2s/bench_ref.json 2> gpurun_out/r2s/bench_ref.err; echo ref rc=$?
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2s/launches.csv python bench.py --steps 2 --warmup 1 --no-sharded --no-oracle-check --no-cpu-restatement > gpurun_out/r2s/ncu_launch.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_demod_df|k_fft_tiles|k_boxcar_small|k_corr_candidates" -c 8 -o gpurun_out/r2s/prof python bench.py --steps 1 --warmup 1 --no-sharded --no-oracle-check --no-cpu-restatement > gpurun_out/r2s/ncu_full.log 2>&1
+ls -la gpurun_out/r2s
