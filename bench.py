@@ -312,9 +312,8 @@ def sharded_block(args, torch, dist, T, device, local, rank, world):
     nw_t, nw_r = block // SHARD_W, 2 * block // SHARD_W
 
     def step():
-        r = eng.xcorr(T.KIND_REF, 0, SHARD_W, nw_r, SHARD_W)
-        t = eng.xcorr(T.KIND_TGT, 0, SHARD_W, nw_t, SHARD_W)
-        return r, t
+        # both pair loops in one call: the windows of both kinds are dealt over the ranks as one list (tdoa_xcorr_windows)
+        return eng.xcorr_windows(0, SHARD_W, nw_r, nw_t, SHARD_W)
 
     steps, warm = max(1, min(args.steps, 5)), 3
     for _ in range(warm):
@@ -354,9 +353,10 @@ def sharded_block(args, torch, dist, T, device, local, rank, world):
                "scaling": "strong", "n_gpus": world, "ms_per_step": sec * 1e3, "value": units * SHARD_W / sec / 1e6,
                "unit": "pair-Msamples/s", "fixes_per_s": nw_t / sec, "window_pairs_per_step": units, "steps": steps, "warmup": warm,
                "gpu_launches_rank0": int(launches), "all_ranks_hold_the_same_table": same,
-               "collective": "one in-place ncclAllGather of 32-byte peak records per tdoa_xcorr call (inside the library)"
+               "collective": "two in-place ncclAllGather of 32-byte peak records (REF table, TGT table) at the end of the one "
+                             "tdoa_xcorr_windows call (inside the library); the ranks meet once per step"
                              if world > 1 else "none (one rank)",
-               "windows_on_busiest_rank": -(-nw_r // world) + -(-nw_t // world) if world > 1 else nw_r + nw_t,
+               "windows_on_busiest_rank": -(-(nw_r + nw_t) // world),
                "oracle_sample": verdict}
     eng.close()
     del caps

@@ -179,6 +179,16 @@ TDOA_API int tdoa_xcorr(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t
 TDOA_API int tdoa_xcorr_device(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t win_len,
                                int32_t n_windows, int64_t hop, tdoa_peak *d_out);
 
+/* Both pair loops of ProcessTDOA over windows in ONE call (processor.go:816-830 REF, then :836-850 TGT):
+ * ref_out[n_ref_windows * P], tgt_out[n_tgt_windows * P] as tdoa_xcorr(TDOA_KIND_REF, ...) followed by
+ * tdoa_xcorr(TDOA_KIND_TGT, ...) would fill them (same win_start / win_len / hop for both kinds; either
+ * count may be 0).  On one GPU it is exactly those two calls.  On a multi-GPU engine (n_devices > 1 or
+ * tdoa_comm_init) the windows of BOTH kinds are dealt over the ranks as one list and correlated before the
+ * first gather, so the ranks meet once per call instead of once per kind -- with 66 + 33 windows on 8 GPUs
+ * the busiest rank works 13 window times instead of 9 + 5. */
+TDOA_API int tdoa_xcorr_windows(tdoa_engine *e, int64_t win_start, int64_t win_len, int32_t n_ref_windows,
+                                int32_t n_tgt_windows, int64_t hop, tdoa_peak *ref_out, tdoa_peak *tgt_out);
+
 /* ---- more than one GPU, one process per GPU (torchrun, MPI, ...).  Rank 0 asks for an id
  * (ncclGetUniqueId), the launcher hands its 128 bytes to every rank, every rank joins with its own
  * engine (ncclCommInitRank on the engine's device).  From then on tdoa_xcorr / tdoa_xcorr_device

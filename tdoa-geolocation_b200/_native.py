@@ -23,7 +23,7 @@ ERRORS = {-1: "TDOA_E_INVALID", -2: "TDOA_E_NODEVICE", -3: "TDOA_E_CUDA", -4: "T
 # every symbol include/tdoa_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "tdoa_default_config", "tdoa_create", "tdoa_destroy", "tdoa_last_error", "tdoa_host_alloc", "tdoa_host_free",
-    "tdoa_load_u8", "tdoa_load_file", "tdoa_load_u8_pinned", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_process", "tdoa_xcorr_info", "tdoa_analyze",
+    "tdoa_load_u8", "tdoa_load_file", "tdoa_load_u8_pinned", "tdoa_load_u8_device", "tdoa_unpack", "tdoa_preprocess", "tdoa_xcorr", "tdoa_xcorr_device", "tdoa_xcorr_windows", "tdoa_process", "tdoa_xcorr_info", "tdoa_analyze",
     "tdoa_cross_correlate", "tdoa_baselines", "tdoa_solve", "tdoa_solve_binary", "tdoa_solve_ls", "tdoa_grid", "tdoa_get_stats", "tdoa_stream",
     "tdoa_set_stream", "tdoa_synchronize", "tdoa_selftest",
     "tdoa_comm_unique_id", "tdoa_comm_init", "tdoa_comm_rank", "tdoa_shard_windows",
@@ -143,6 +143,7 @@ def load_library():
     L.tdoa_process.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.tdoa_analyze.argtypes = [vp, i32, i32, vp, vp]
     L.tdoa_xcorr_device.argtypes = [vp, i32, i64, i64, i32, i64, vp]
+    L.tdoa_xcorr_windows.argtypes = [vp, i64, i64, i32, i32, i64, vp, vp]
     L.tdoa_cross_correlate.argtypes = [vp, vp, i64, vp, i64, C.POINTER(PeakStruct)]
     L.tdoa_baselines.argtypes = [vp, vp, i32, vp]
     L.tdoa_solve.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
@@ -353,6 +354,15 @@ class Engine:
         out = np.zeros((n_windows, self.n_pairs), PEAK_DTYPE)
         self._check(self._lib.tdoa_xcorr(self._h, kind, win_start, win_len, n_windows, hop, _ptr(out)))
         return out
+
+    def xcorr_windows(self, win_start: int, win_len: int, n_ref_windows: int, n_tgt_windows: int, hop: int):
+        """Both pair loops over windows in one call (tdoa_xcorr_windows): (ref, tgt) tables.  On a multi-GPU
+        engine the windows of both kinds are dealt as one list and the ranks meet once."""
+        ref = np.zeros((n_ref_windows, self.n_pairs), PEAK_DTYPE)
+        tgt = np.zeros((n_tgt_windows, self.n_pairs), PEAK_DTYPE)
+        self._check(self._lib.tdoa_xcorr_windows(self._h, win_start, win_len, n_ref_windows, n_tgt_windows, hop,
+                                                 _ptr(ref), _ptr(tgt)))
+        return ref, tgt
 
     def xcorr_info(self, kind: int):
         """(signals, first_corr) of window 0 of the last xcorr(kind): what the reference prints while it

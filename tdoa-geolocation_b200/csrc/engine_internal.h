@@ -182,6 +182,17 @@ int xcorr_core(tdoa_engine *e, int32_t kind, int64_t win_start, const std::vecto
 bool multi_wants(const tdoa_engine *e, int32_t n_windows);
 int xcorr_sharded(tdoa_engine *e, int32_t kind, int64_t win_start, const std::vector<i64> &len, int32_t n_windows, int64_t hop,
                   tdoa_peak *out, bool out_is_device);
+// several signal kinds' windows in one collective call (tdoa_xcorr_windows): one meeting of the ranks
+struct ShardPart {
+    int32_t kind = 0;
+    int64_t win_start = 0;
+    std::vector<i64> len;       // per-station window lengths (window_lengths)
+    int32_t n_windows = 0;
+    int64_t hop = 0;
+    tdoa_peak *out = nullptr;   // host or device table of n_windows * P records, or nullptr
+    bool out_is_device = false;
+};
+int xcorr_sharded(tdoa_engine *e, const std::vector<ShardPart> &parts);
 void multi_destroy(tdoa_engine *e);
 int multi_create_peers(tdoa_engine *e, const tdoa_config *cfg);   // tdoa_create with n_devices > 1
 // which: 0 tdoa_load_u8, 1 tdoa_load_u8_pinned, 2 tdoa_load_file (p = path)

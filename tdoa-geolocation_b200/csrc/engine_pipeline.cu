@@ -1472,6 +1472,34 @@ int tdoa_xcorr_device(tdoa_engine *e, int32_t kind, int64_t win_start, int64_t w
     return xcorr_impl(e, kind, win_start, win_len, n_windows, hop, d_out, true);
 }
 
+int tdoa_xcorr_windows(tdoa_engine *e, int64_t win_start, int64_t win_len, int32_t n_ref_windows, int32_t n_tgt_windows,
+                       int64_t hop, tdoa_peak *ref_out, tdoa_peak *tgt_out)
+{
+    if (!e) return TDOA_E_INVALID;
+    if (n_ref_windows < 0 || n_tgt_windows < 0 || (n_ref_windows && !ref_out) || (n_tgt_windows && !tgt_out))
+        return fail(e, TDOA_E_INVALID, "tdoa_xcorr_windows: a table is NULL");
+    const bool sharded = multi_wants(e, n_ref_windows + n_tgt_windows);
+    if (!sharded) {   // one GPU: the two pair loops one after the other (processor.go:816-830, then :836-850)
+        int rc = TDOA_OK;
+        if (n_ref_windows) rc = xcorr_impl(e, TDOA_KIND_REF, win_start, win_len, n_ref_windows, hop, ref_out, false);
+        if (!rc && n_tgt_windows) rc = xcorr_impl(e, TDOA_KIND_TGT, win_start, win_len, n_tgt_windows, hop, tgt_out, false);
+        return rc;
+    }
+    int rc = begin_call(e);
+    if (rc) return rc;
+    std::vector<ShardPart> parts;
+    for (int kind = 0; kind < 2; kind++) {
+        const int32_t nw = kind == TDOA_KIND_REF ? n_ref_windows : n_tgt_windows;
+        if (!nw) continue;
+        ShardPart Q;
+        Q.kind = kind; Q.win_start = win_start; Q.n_windows = nw; Q.hop = hop;
+        Q.out = kind == TDOA_KIND_REF ? ref_out : tgt_out;
+        if ((rc = window_lengths(e, kind, win_start, win_len, nw, hop, Q.len))) return rc;
+        parts.push_back(Q);
+    }
+    return xcorr_sharded(e, parts);
+}
+
 int tdoa_process(tdoa_engine *e, const double *stations_llh, tdoa_peak *ref_out, tdoa_peak *tgt_out, double *time_diffs,
                  double *range_diffs, double *fix_llh, int32_t *fix_status, int32_t *fix_iters)
 {

@@ -71,6 +71,26 @@ def test_one_rank_communicator_takes_the_sharded_path():
             e.comm_init(T.comm_unique_id(), 0, 1)   # one communicator per engine
 
 
+def test_xcorr_windows_is_the_two_pair_loops():
+    """tdoa_xcorr_windows: both pair loops over windows in one call.  On one GPU it is tdoa_xcorr(REF) followed
+    by tdoa_xcorr(TGT); behind a communicator (one rank here) the windows of both kinds are dealt as one list and
+    gathered at the end -- the same records either way, unequal window counts and a zero count included."""
+    raws = captures()
+    want_r, want_t = reference_table(raws, T.KIND_REF), reference_table(raws, T.KIND_TGT)
+    with T.Engine(T.MODE_EXTENDED, max_lag=L) as e:
+        load_all(e, raws)
+        r, t = e.xcorr_windows(1000, W, NW, NW - 2, HOP)
+        same_records(r, want_r)
+        same_records(t, want_t[:NW - 2])
+        e.comm_init(T.comm_unique_id(), 0, 1)
+        r, t = e.xcorr_windows(1000, W, NW, NW - 2, HOP)
+        same_records(r, want_r)
+        same_records(t, want_t[:NW - 2])
+        r, t = e.xcorr_windows(1000, W, 0, NW, HOP)
+        assert r.shape[0] == 0
+        same_records(t, want_t)
+
+
 def test_n_devices_beyond_the_box_is_refused():
     n = torch.cuda.device_count()
     with pytest.raises(T.TdoaError, match="n_devices"):
@@ -88,6 +108,9 @@ def test_one_process_two_devices():
             same_records(e.xcorr(kind, 1000, W, NW, HOP), reference_table(raws, kind))
         one = e.xcorr(T.KIND_TGT, 1000, W, 1, 0)               # a single window runs on device 0
         same_records(one, reference_table(raws, T.KIND_TGT)[:1])
+        r, t = e.xcorr_windows(1000, W, NW, NW - 2, HOP)       # 7 + 5 windows dealt as one list of 12
+        same_records(r, reference_table(raws, T.KIND_REF))
+        same_records(t, reference_table(raws, T.KIND_TGT)[:NW - 2])
 
 
 def _rank_main(rank, world, id_path, q):
@@ -107,7 +130,8 @@ def _rank_main(rank, world, id_path, q):
         load_all(e, raws)
         e.comm_init(uid, rank, world)
         out = [e.xcorr(kind, 1000, W, NW, HOP) for kind in (T.KIND_TGT, T.KIND_REF)]
-        q.put((rank, [o.tobytes() for o in out]))
+        r2, t2 = e.xcorr_windows(1000, W, NW, NW, HOP)
+        q.put((rank, [o.tobytes() for o in out + [t2, r2]]))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
@@ -127,5 +151,5 @@ def test_one_process_per_gpu_two_ranks():
             p.join(timeout=60)
             assert p.exitcode == 0
     for r in range(2):
-        for got, w in zip(res[r], want):
+        for got, w in zip(res[r], want + want):   # tdoa_xcorr per kind, then tdoa_xcorr_windows: the same tables
             same_records(np.frombuffer(got, T.sharding.PEAK_DTYPE).reshape(NW, 3), w)
