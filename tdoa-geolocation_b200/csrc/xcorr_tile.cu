@@ -82,13 +82,13 @@ __device__ __forceinline__ void load_rows(const float *__restrict__ x0, const fl
         const float *__restrict__ p0 = x0 + base + t;
         const float *__restrict__ p1 = x1 + base + t;
 #pragma unroll
-        for (int r = 0; r < 32; r++) v[r] = r < CNT ? make_float2(p0[256 * r], p1[256 * r]) : make_float2(0.f, 0.f);
+        for (int r = 0; r < 32; r++) v[r] = r < CNT ? make_float2(__ldg(p0 + 256 * r), __ldg(p1 + 256 * r)) : make_float2(0.f, 0.f);
     } else {
 #pragma unroll
         for (int r = 0; r < 32; r++) {
             const i64 m = t + 256 * r;
             const bool ok = r < CNT && m >= lo && m < hi;
-            v[r] = ok ? make_float2(x0[base + m], x1[base + m]) : make_float2(0.f, 0.f);
+            v[r] = ok ? make_float2(__ldg(x0 + base + m), __ldg(x1 + base + m)) : make_float2(0.f, 0.f);
         }
     }
 }
