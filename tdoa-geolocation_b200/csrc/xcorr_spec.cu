@@ -81,9 +81,24 @@ __global__ void __launch_bounds__(kT, 2) k_spec_fft(const SpecFftJob *jobs, cons
 }
 
 // ---------------------------------------------------------------- pair accumulation
+// Round 1: the next segment's spectrum values fetched into registers one segment ahead, two CTA barriers
+// per segment, and per pair two byte loads (which template, which signal), a bounds test and the address
+// arithmetic around four FMAs -- 10 000 cycles per segment and CTA.  Round 2:
+//   - a thread's <= 16 (template row, signal row) pairs are packed into eight registers before the segment
+//     loop (one PRMT per use); pairs beyond the list point at row 0 and their sums are never stored, so the
+//     inner loop has no predicate;
+//   - the reads run kSpecStages - 1 = 3 segments ahead through cp.async into a shared-memory ring (a thread
+//     copies and later unpacks only its own items: no barrier for the ring);
+//   - the unpacked station spectra are double buffered: one barrier per segment.
+constexpr int kSpecStages = 4;
+constexpr int kItems = kSpecMaxPacked * kAccBins / kAccThreads;   // 2 (Z[k], Z[N-k]) pairs per thread and segment
+constexpr int kAccSmem = kSpecStages * kItems * 2 * kAccThreads * (int)sizeof(float2);   // 64 KB
+constexpr int kRowBytes = kAccBins * (int)sizeof(float2);          // one station's 64 bins: 512 B
+
 __global__ void __launch_bounds__(kAccThreads, 2) k_spec_acc(const SpecAccJob *jobs)
 {
-    __shared__ float2 s_st[2 * kSpecMaxPacked][kAccBins];   // unpacked station spectra of the CTA's bins
+    extern __shared__ __align__(16) float2 ring[];           // [stage][item][k / N-k][thread]
+    __shared__ __align__(16) float2 s_st[2][2 * kSpecMaxPacked][kAccBins];  // unpacked station spectra, double buffered
     const SpecAccJob &J = jobs[blockIdx.y];
     const int k0 = blockIdx.x * kAccBins;
     const int nb = min(kAccBins, kN / 2 + 1 - k0);
@@ -91,60 +106,84 @@ __global__ void __launch_bounds__(kAccThreads, 2) k_spec_acc(const SpecAccJob *j
     const int tid = threadIdx.x, b = tid & (kAccBins - 1), g = tid >> 6;
     const int n_pk = J.n_pk_t + J.n_pk_s;
     const int per = (J.n_pairs + kAccGroups - 1) / kAccGroups;   // pairs per thread group, <= kAccPer
-    __shared__ unsigned char s_pt[kSpecMaxPairs], s_ps[kSpecMaxPairs];
-    if (tid < kSpecMaxPairs) { s_pt[tid] = J.pair_t[tid]; s_ps[tid] = J.pair_s[tid]; }
     const int n_pairs = J.n_pairs, sig0 = 2 * J.n_pk_t, n_seg = J.n_seg;
+    // this thread's pairs: template rows in rows_t[0..3], signal rows in rows_s[0..3], one byte each
+    unsigned rows_t[kAccPer / 4], rows_s[kAccPer / 4];
+#pragma unroll
+    for (int w = 0; w < kAccPer / 4; w++) {
+        rows_t[w] = rows_s[w] = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int q = 4 * w + c, p = g * per + q;
+            const bool ok = q < per && p < n_pairs;
+            // twice the row number: one PRMT (byte c into byte 1 of the result) then gives row * 512 bytes
+            rows_t[w] |= (ok ? 2u * (unsigned)J.pair_t[p] : 0u) << (8 * c);
+            rows_s[w] |= (ok ? 2u * (unsigned)(sig0 + J.pair_s[p]) : 0u) << (8 * c);
+        }
+    }
     float2 acc[kAccPer];
 #pragma unroll
     for (int q = 0; q < kAccPer; q++) acc[q] = make_float2(0.f, 0.f);
-    // software pipeline: the next segment's spectrum values (2 (Z[k], Z[N-k]) pairs per thread)
-    // travel in registers while this segment's pairs are accumulated
-    constexpr int kItems = kSpecMaxPacked * kAccBins / kAccThreads;   // 2
-    float2 ra[kItems], rc[kItems];
-    auto fetch = [&](int seg) {
-        const float2 *__restrict__ sp = J.spec + (size_t)seg * n_pk * kN;
-#pragma unroll
-        for (int u = 0; u < kItems; u++) {
-            const int item = tid + u * kAccThreads;
-            const int m = item >> 6, bb = item & (kAccBins - 1);
-            if (m < n_pk && bb < nb) {
-                const int k = k0 + bb;
-                ra[u] = sp[(size_t)m * kN + k];
-                rc[u] = sp[(size_t)m * kN + ((kN - k) & (kN - 1))];
-            }
-        }
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring);
+    const unsigned st_base = (unsigned)__cvta_generic_to_shared(&s_st[0][0][0]) + (unsigned)b * (unsigned)sizeof(float2);
+    auto slot = [&](int stage, int u, int which) {
+        return ring_base + (unsigned)((((stage * kItems + u) * 2 + which) * kAccThreads + tid) * sizeof(float2));
     };
-    fetch(0);
-    for (int seg = 0; seg < n_seg; seg++) {
-        __syncthreads();   // the previous segment's station spectra have been consumed
+    auto issue = [&](int seg) {
+        if (seg < n_seg) {
+            const float2 *__restrict__ sp = J.spec + (size_t)seg * n_pk * kN;
+            const int stage = seg % kSpecStages;
 #pragma unroll
-        for (int u = 0; u < kItems; u++) {
-            const int item = tid + u * kAccThreads;
-            const int m = item >> 6, bb = item & (kAccBins - 1);
-            if (m < n_pk && bb < nb) {
-                const float2 a = ra[u], c = rc[u];
-                // Z = FFT(x0 + i x1): X0[k] = (Z[k] + conj Z[N-k]) / 2, X1[k] = (Z[k] - conj Z[N-k]) / (2i)
-                s_st[2 * m][bb] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
-                s_st[2 * m + 1][bb] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
-            }
-        }
-        if (seg + 1 < n_seg) fetch(seg + 1);
-        __syncthreads();
-        if (b < nb) {
-            int last_i = -1;
-            float2 ti = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < kAccPer; q++) {
-                const int p = g * per + q;
-                if (q < per && p < n_pairs) {
-                    const int i = s_pt[p], j = s_ps[p];
-                    if (i != last_i) { ti = s_st[i][b]; last_i = i; }
-                    const float2 sj = s_st[sig0 + j][b];
-                    // conj(T) S
-                    acc[q].x = fmaf(ti.x, sj.x, fmaf(ti.y, sj.y, acc[q].x));
-                    acc[q].y = fmaf(ti.x, sj.y, fmaf(-ti.y, sj.x, acc[q].y));
+            for (int u = 0; u < kItems; u++) {
+                const int item = tid + u * kAccThreads;
+                const int m = item >> 6, bb = item & (kAccBins - 1);
+                if (m < n_pk && bb < nb) {
+                    const int k = k0 + bb;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot(stage, u, 0)), "l"(sp + (size_t)m * kN + k) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot(stage, u, 1)),
+                                 "l"(sp + (size_t)m * kN + ((kN - k) & (kN - 1))) : "memory");
                 }
             }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto lds2 = [](unsigned addr) {
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+        return v;
+    };
+#pragma unroll
+    for (int p = 0; p < kSpecStages - 1; p++) issue(p);
+    for (int seg = 0; seg < n_seg; seg++) {
+        issue(seg + kSpecStages - 1);   // into the stage whose items this thread unpacked one segment ago
+        asm volatile("cp.async.wait_group %0;" ::"n"(kSpecStages - 1) : "memory");
+        const int stage = seg % kSpecStages, half = seg & 1;
+#pragma unroll
+        for (int u = 0; u < kItems; u++) {
+            const int item = tid + u * kAccThreads;
+            const int m = item >> 6, bb = item & (kAccBins - 1);
+            if (m < n_pk && bb < nb) {
+                const float2 a = lds2(slot(stage, u, 0)), c = lds2(slot(stage, u, 1));
+                // Z = FFT(x0 + i x1): X0[k] = (Z[k] + conj Z[N-k]) / 2, X1[k] = (Z[k] - conj Z[N-k]) / (2i)
+                s_st[half][2 * m][bb] = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+                s_st[half][2 * m + 1][bb] = make_float2(0.5f * (a.y + c.y), 0.5f * (c.x - a.x));
+            }
+        }
+        __syncthreads();   // this segment's station spectra are complete; the other buffer was consumed before the previous barrier
+        const unsigned base = st_base + (unsigned)half * (unsigned)(2 * kSpecMaxPacked * kRowBytes);
+        unsigned last = 0xffffffffu;
+        float2 ti = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < kAccPer; q++) {
+            // volatile: kept inside the loop (hoisted, the 32 row offsets would not fit the 64 registers)
+            unsigned it, js;
+            asm volatile("prmt.b32 %0, %1, 0, %2;" : "=r"(it) : "r"(rows_t[q >> 2]), "r"(0x4404 | ((q & 3) << 4)));
+            asm volatile("prmt.b32 %0, %1, 0, %2;" : "=r"(js) : "r"(rows_s[q >> 2]), "r"(0x4404 | ((q & 3) << 4)));
+            if (it != last) { ti = lds2(base + it); last = it; }   // pairs are listed template by template
+            const float2 sj = lds2(base + js);
+            // conj(T) S
+            acc[q].x = fmaf(ti.x, sj.x, fmaf(ti.y, sj.y, acc[q].x));
+            acc[q].y = fmaf(ti.x, sj.y, fmaf(-ti.y, sj.x, acc[q].y));
         }
     }
     if (b < nb) {
@@ -160,7 +199,9 @@ __global__ void __launch_bounds__(kAccThreads, 2) k_spec_acc(const SpecAccJob *j
 
 int spec_setup()
 {
-    return cudaFuncSetAttribute(k_spec_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem) == cudaSuccess ? 0 : -1;
+    return cudaFuncSetAttribute(k_spec_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem) == cudaSuccess &&
+                   cudaFuncSetAttribute(k_spec_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, kAccSmem) == cudaSuccess
+               ? 0 : -1;
 }
 
 void launch_spec_fft(const SpecFftJob *d_jobs, int n_jobs, int max_seg, const float2 *d_tw, cudaStream_t st)
@@ -172,7 +213,7 @@ void launch_spec_fft(const SpecFftJob *d_jobs, int n_jobs, int max_seg, const fl
 void launch_spec_acc(const SpecAccJob *d_jobs, int n_jobs, cudaStream_t st)
 {
     if (n_jobs <= 0) return;
-    k_spec_acc<<<dim3((kN / 2 + 1 + kAccBins - 1) / kAccBins, n_jobs), kAccThreads, 0, st>>>(d_jobs);
+    k_spec_acc<<<dim3((kN / 2 + 1 + kAccBins - 1) / kAccBins, n_jobs), kAccThreads, kAccSmem, st>>>(d_jobs);
 }
 
 }  // namespace tdoa

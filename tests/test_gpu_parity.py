@@ -188,6 +188,35 @@ def test_fft_path_equals_every_lag_path(case):
     assert np.max(np.abs(brute["corr"] - fft["corr"])) <= 1e-12
 
 
+@pytest.mark.parametrize("seed,noise,mode", [(31, 0.35, "BINARY"), (32, 0.6, "BINARY"), (33, 1.0, "BINARY"), (34, 1.5, "BINARY"),
+                                             (35, 0.6, "EXTENDED"), (36, 1.2, "EXTENDED")])
+def test_fft_ranking_survives_low_snr(seed, noise, mode):
+    """Low-SNR stress of the FFT ranking (every path: BINARY one-sided lags, EXTENDED two-sided lags with the
+    parabolic vertex, full windows and ragged ones): with noise up to 3 x the signal amplitude the correlation
+    peak stands only a few per cent above its neighbours, so an f32 transform error beyond the ranking
+    tolerance would drop the true maximum from the candidates.  The exhaustive every-lag path (use_fft = 0) is
+    the reference's own loop; both must return the same records."""
+    block = 90000 + 137 * seed
+    raws = fm_capture(block, (0, 7, 19), (0, 23, 41), seed=seed, noise=noise)
+    kw = dict(max_lag=500) if mode == "EXTENDED" else {}
+    res = []
+    for use_fft in (0, 1):
+        with T.Engine(getattr(T, "MODE_" + mode), use_fft=use_fft, **kw) as e:
+            load_all(e, raws)
+            out = [e.xcorr(T.KIND_REF)[0], e.xcorr(T.KIND_TGT)[0]]
+            if mode == "EXTENDED":
+                out.append(e.xcorr(T.KIND_TGT, 1234, 20000, 3, 17001).reshape(-1))   # windows that straddle nothing round
+            res.append(np.concatenate(out))
+    brute, fft = res
+    assert np.array_equal(brute["lag"], fft["lag"])
+    assert np.array_equal(brute["first_lag"], fft["first_lag"])
+    assert np.max(np.abs(brute["corr"] - fft["corr"])) <= 1e-12
+    assert np.max(np.abs(brute["frac"] - fft["frac"])) <= 1e-9
+    # the stress is real: the peak is small (noise dominates) in the noisiest cases
+    if noise >= 1.0:
+        assert np.max(np.abs(brute["corr"])) < 0.5
+
+
 # ------------------------------------------------------------------ source mode (processor.go as committed)
 def test_source_mode_pairs(eng_source):
     raws, _ = load_golden("fm_strong")
