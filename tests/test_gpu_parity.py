@@ -776,6 +776,34 @@ def test_lean_discriminator_all_byte_quads(eng_binary):
     assert 0 < falls < 1 << 20       # the exact fall-back exists and is rare (3e-5 of the quads)
 
 
+def test_production_discriminator_on_random_windows():
+    """k_demod_df stages 16-byte chunks from the 16-byte-aligned address below a tile's previous sample and
+    takes the fast path only for tiles that lie, with 8 samples of margin on both sides, inside one run of the
+    capture; everything else goes sample by sample.  Random (start, length) views -- every 16-byte
+    misalignment class, lengths below one tile, REF views across the block-1 / block-3 joint, views ending at
+    the capture's last sample -- must preprocess to the bits of the round-1 kernel (fast_demod = 2: the f64
+    arctangent on every sample, staged word by word), power and DC included."""
+    rng = np.random.default_rng(77)
+    block = 61003                      # odd block length: the joint and the tail sit at odd byte offsets
+    raws = fm_capture(block, (0, 5, 11), (0, 17, 30), seed=23)
+    cases = [(T.KIND_REF, 0, 2 * block), (T.KIND_TGT, 0, block), (T.KIND_REF, block - 4100, 8300), (T.KIND_TGT, block - 5000, 5000)]
+    for _ in range(36):
+        kind = int(rng.integers(0, 2))
+        n = (2 if kind == T.KIND_REF else 1) * block
+        length = int(rng.choice([3, 17, 4095, 4096, 4097, 9000, 20000, 40000]))
+        start = int(rng.integers(0, n - length + 1))
+        cases.append((kind, start, length))
+    with T.Engine(T.MODE_BINARY, chunk_samples=0) as new, T.Engine(T.MODE_BINARY, chunk_samples=0, fast_demod=2) as old:
+        load_all(new, raws)
+        load_all(old, raws)
+        for kind, start, length in cases:
+            a, pa, ba = new.preprocess(1, kind, start, length)
+            b, pb, bb = old.preprocess(1, kind, start, length)
+            assert ba == bb == 0, (kind, start, length)
+            assert abs(pa - pb) <= 4e-16 * abs(pb), (kind, start, length, pa, pb)   # the same terms, another (fixed) order
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (kind, start, length)
+
+
 # ------------------------------------------------------------------ lazy pinned load (copy-following discriminator)
 @pytest.mark.parametrize("copy_chunk", [0, 65536, 8192])
 def test_pinned_lazy_load_equals_synchronous_load(copy_chunk):
