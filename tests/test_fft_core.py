@@ -38,6 +38,19 @@ def test_tile_fft_phases_and_cross_spectra(tmp_path):
 
 
 @pytest.mark.skipif(shutil.which("nvcc") is None, reason="needs nvcc (host compile only)")
+def test_tile16_fft_phases_match_direct_dft(tmp_path):
+    """csrc/fft_tile16_core.cuh (512 threads x 16 points: 16 x 16 x 32 with the radix-32 step taken by pairs of
+    lanes through a shuffle), emulated thread by thread on the host against a direct DFT in double precision."""
+    exe = tmp_path / "fft_tile16_emul"
+    subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I",
+                    str(ROOT / "tdoa-geolocation_b200" / "csrc"), "-o", str(exe),
+                    str(ROOT / "tests" / "native" / "fft_tile16_emul.cu")], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    assert float(res.stdout.split()[1]) < 1e-6
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="needs nvcc (host compile only)")
 def test_chunk_parallel_sequential_sum_is_exact(tmp_path):
     """csrc/seqsum_core.cuh: the reference's sequential f32 accumulator (processor.go:304-309) evaluated
     chunk by chunk in integer arithmetic, against the plain loop, bit for bit, on 49 signals (noise,
