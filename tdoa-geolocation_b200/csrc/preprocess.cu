@@ -256,12 +256,21 @@ __global__ void __launch_bounds__(kThreads) k_boxcar(const SigJob *jobs)
 // difference of two entries of an f64 prefix sum over the staged tile: the same taps, the same edge
 // normalisation (divisor = taps in range), one rounding to f32 at the divide.  It differs from the
 // reference's chain by that chain's own f32 rounding (~1e-6 relative), which the mode does not promise.
-__global__ void __launch_bounds__(kThreads) k_boxcar_slide(const SigJob *jobs)
+// Tiles of 6144 outputs (round 1: 2048, where the 1000-sample halo was half of what a CTA staged and scanned:
+// 0.22 of the HBM roofline), 512 threads, the staged samples and their prefix sums in 86 KB of dynamic shared memory.
+constexpr int kSlideTile = 6144;
+constexpr int kSlideThreads = 512;
+constexpr int kSlideLen = kSlideTile + 2 * kBoxHalfMax;
+constexpr int kSlideSmem = kSlideLen * (int)(sizeof(float) + sizeof(double));
+
+__global__ void __launch_bounds__(kSlideThreads, 2) k_boxcar_slide(const SigJob *jobs)
 {
-    constexpr int kLen = kBoxTile + 2 * kBoxHalfMax;
-    constexpr int kPer = (kLen + kThreads - 1) / kThreads;   // 12 consecutive entries per thread
-    __shared__ float s_x[kLen];
-    __shared__ double s_p[kLen];      // inclusive prefix sums of s_x
+    constexpr int kBoxTile = kSlideTile, kThreads = kSlideThreads;   // this kernel's own tile and CTA size
+    constexpr int kLen = kSlideLen;
+    constexpr int kPer = (kLen + kThreads - 1) / kThreads;   // 14 consecutive entries per thread
+    extern __shared__ __align__(16) unsigned char slide_raw[];
+    double *s_p = reinterpret_cast<double *>(slide_raw);      // inclusive prefix sums of s_x
+    float *s_x = reinterpret_cast<float *>(s_p + kLen);
     __shared__ double s_w[kThreads / 32];
     __shared__ double scratch[32];
     const SigJob &J = jobs[blockIdx.y];
@@ -458,7 +467,15 @@ void launch_boxcar(const SigJob *d_jobs, int n_jobs, i64 max_n, int max_window, 
 }
 void launch_boxcar_slide(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)
 {
-    k_boxcar_slide<<<dim3(boxcar_grid_x(max_n), n_jobs), kThreads, 0, st>>>(d_jobs);
+    static bool opted_in[64] = {false};   // per device: more than 48 KB of dynamic shared memory
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !opted_in[dev]) {
+        cudaFuncSetAttribute(k_boxcar_slide, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlideSmem);
+        opted_in[dev] = true;
+    }
+    const i64 g = (max_n + kSlideTile - 1) / kSlideTile;   // <= boxcar_grid_x(max_n): the partial-sum slots suffice
+    k_boxcar_slide<<<dim3((unsigned)(g < 1 ? 1 : g), n_jobs), kSlideThreads, kSlideSmem, st>>>(d_jobs);
 }
 void launch_notch_combine(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)
 {
