@@ -94,7 +94,8 @@ typedef struct {
                               0: evaluate every lag in the time domain;
                               test switches: 2 one transform per pair, 3 no 2^21-point
                               transform, 4 no parked spectra, 5 plain one-add-at-a-
-                              time walk for the sequential DC sum                    */
+                              time walk for the sequential DC sum, 6 EXTENDED weak
+                              branch as four kernels over planes (not the fused pass) */
     int32_t device;        /* CUDA device ordinal                                    */
     int32_t seq_dc_limit;  /* removeDCBias (processor.go:299-319): signals of up to this many
                               samples get the reference's sequential f32 accumulator,

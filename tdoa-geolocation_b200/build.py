@@ -24,6 +24,7 @@ OBJ = HERE / "build"
 UNITS = [
     ("preprocess.cu", ["-fmad=false"]),
     ("preprocess_fast.cu", []),
+    ("preprocess_weak.cu", ["-fmad=false"]),
     ("seqsum.cu", ["-fmad=false"]),
     ("xcorr_exact.cu", ["-fmad=false"]),
     ("solve.cu", ["-fmad=false"]),

@@ -250,13 +250,14 @@ int tdoa_create(tdoa_engine **out, const tdoa_config *cfg)
         tdoa_destroy(e);
         return TDOA_E_CUDA;
     }
-    const int bad = unpack_selftest(e->stream);
+    int bad = unpack_selftest(e->stream);
+    if (bad == 0 && e->cfg.mode == TDOA_MODE_EXTENDED) bad = weak_unpack_selftest(e->stream);   // k_weak_fused's divide-free unpack
     if (bad != 0) {
         g_create_error = "tdoa_create: device unpack self-test failed (kernel image not runnable on this GPU?)";
         tdoa_destroy(e);
         return TDOA_E_CUDA;
     }
-    e->st.launches_total = 1;
+    e->st.launches_total = e->cfg.mode == TDOA_MODE_EXTENDED ? 2 : 1;
     if (cfg->n_devices > 1) {
         e->cfg.n_devices = cfg->n_devices;
         const int rc = multi_create_peers(e, cfg);

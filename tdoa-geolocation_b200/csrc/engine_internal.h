@@ -59,6 +59,8 @@ struct Sig {
     i64 q0 = 0;           // first sample of the view within that station's REF / TGT signal
     bool fused = false;   // stage 0 ran the fused power + discriminator kernel
     bool deferred = false;  // branch 0 was assumed without reading the power back; the caller verifies
+    bool raw_sums = false;  // the power pass was k_raw_stats: ST_SUM_* / ST_DC_* of the raw signal are in place
+    bool need_im = false;   // a consumer reads out_im of a BINARY / EXTENDED signal (the tdoa_preprocess probe)
 };
 
 struct Pair {

@@ -181,7 +181,7 @@ int ensure_plane(tdoa_engine *e, Sig &s, int idx, bool cplx)
     return TDOA_OK;
 }
 
-enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_SEQSUM, K_BOXCAR, K_BOXCAR_SMALL, K_BOXCAR_SLIDE, K_NOTCH, K_DECIMATE };
+enum Kern { K_UNPACK, K_DEMOD, K_ENVELOPE, K_SEQSUM, K_BOXCAR, K_BOXCAR_SMALL, K_BOXCAR_SLIDE, K_NOTCH, K_DECIMATE, K_WEAK_FUSED };
 
 // queue of (stage, kernel) steps: step k of every signal that runs the same kernel at
 // that stage is batched into one launch; stages run in order
@@ -289,6 +289,7 @@ int run_pipeline(tdoa_engine *e, Pipeline &pl)
                 case K_BOXCAR_SLIDE: launch_boxcar_slide(d_jobs, nj, st.max_n, e->stream); break;
                 case K_NOTCH: launch_notch_combine(d_jobs, nj, st.max_n, e->stream); break;
                 case K_DECIMATE: launch_decimate(d_jobs, nj, st.max_n, e->stream); break;
+                case K_WEAK_FUSED: launch_weak_fused(d_jobs, nj, st.max_n, e->stream); break;
             }
             count_launch(e);
         }
@@ -319,13 +320,13 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs, bool allow_defer = false)
     unsigned *d_counters = nullptr;
     int rc;
     if ((rc = alloc_t(e, &d_stats, (size_t)ns * ST_COUNT))) return rc;
-    if ((rc = alloc_t(e, &d_partials, (size_t)ns * 2 * gmax))) return rc;
+    if ((rc = alloc_t(e, &d_partials, (size_t)ns * 3 * gmax))) return rc;   // k_raw_stats reduces three sums
     if ((rc = alloc_t(e, &d_counters, (size_t)ns))) return rc;
     CU(cudaMemsetAsync(d_stats, 0, (size_t)ns * ST_COUNT * sizeof(double), e->stream));
     CU(cudaMemsetAsync(d_counters, 0, (size_t)ns * sizeof(unsigned), e->stream));
     for (int i = 0; i < ns; i++) {
         sigs[i].stats = d_stats + (size_t)i * ST_COUNT;
-        sigs[i].partials = d_partials + (size_t)i * 2 * gmax;
+        sigs[i].partials = d_partials + (size_t)i * 3 * gmax;
         sigs[i].counter = d_counters + i;
     }
     // ---- initial power (selects the branch).  In the shipped binary's modes a capture
@@ -336,6 +337,7 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs, bool allow_defer = false)
     (void)gmax2;
     {
         std::vector<SigJob> pjobs, fjobs;
+        const bool mode_raw_stats = e->cfg.mode == TDOA_MODE_EXTENDED && e->cfg.use_fft != 6;   // 6: test switch, the four-kernel chain
         // signals whose capture is still arriving (tdoa_load_u8_pinned): the discriminator
         // follows the copy chunk by chunk, every launch waiting for one chunk only
         struct Follow { SigJob job; cudaEvent_t wait; i64 len; int sig; bool last; int n_sub; double *sums; };
@@ -379,6 +381,7 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs, bool allow_defer = false)
             } else {
                 if (arriving && (rc = wait_kind(e, *stn, s.kind))) return rc;
                 pjobs.push_back(base_job(s));
+                s.raw_sums = mode_raw_stats;
             }
         }
         if (!follow.empty()) {
@@ -403,7 +406,10 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs, bool allow_defer = false)
         if (!pjobs.empty()) {
             const SigJob *d_jobs = nullptr;
             if ((rc = upload(e, pjobs, &d_jobs))) return rc;
-            launch_power(d_jobs, (int)pjobs.size(), max_n, gx, e->stream);
+            // EXTENDED: power and both DC sums from one vectorised read of the bytes (k_weak_fused then needs
+            // no unpacked planes); the other modes keep k_power, whose partition the golden digits were taken with
+            if (mode_raw_stats) launch_raw_stats(d_jobs, (int)pjobs.size(), max_n, e->stream);
+            else launch_power(d_jobs, (int)pjobs.size(), max_n, gx, e->stream);
             count_launch(e);
         }
         if (!fjobs.empty()) {
@@ -497,6 +503,20 @@ int preprocess(tdoa_engine *e, std::vector<Sig> &sigs, bool allow_defer = false)
                 pl.add(g++, K_BOXCAR, box_job(s, 0, 1, false, 1, BOX_LP, true, true));
                 s.out_re = s.plane[1][0]; s.out_im = nullptr;
             } else {
+                const int w_hp = cutoff_window(100.0), w_lp = cutoff_window(200000.0);
+                if (mode == TDOA_MODE_EXTENDED && s.raw_sums && s.src.raw && !wants_seq_dc(e, s.n) && w_hp >= 3 && w_lp >= 3 &&
+                    w_hp / 2 <= weak_fused_max_half_wide() && w_lp / 2 <= weak_fused_max_half_small()) {
+                    // the whole chain in one pass over the bytes (preprocess_weak.cu); the imaginary plane only
+                    // where somebody reads it (the correlators of this revision take real parts only)
+                    const bool im = s.need_im || decimation(e) > 1;
+                    if ((rc = ensure_plane(e, s, 0, im))) return rc;
+                    SigJob u = base_job(s);
+                    u.p_re = s.plane[0][0]; u.p_im = im ? s.plane[0][1] : nullptr;
+                    u.window = w_hp; u.window2 = w_lp;
+                    pl.add(g++, K_WEAK_FUSED, u);
+                    s.out_re = s.plane[0][0]; s.out_im = u.p_im;
+                    continue;
+                }
                 if ((rc = ensure_plane(e, s, 0, true)) || (rc = ensure_plane(e, s, 1, true))) return rc;
                 SigJob u = base_job(s);
                 u.p_re = s.plane[0][0]; u.p_im = s.plane[0][1];
@@ -1435,6 +1455,8 @@ int tdoa_preprocess(tdoa_engine *e, int32_t station, int32_t kind, int64_t start
     sigs[0].n = len;
     sigs[0].src = make_view(s, kind, start, len, e->cfg.guard_samples);
     sigs[0].station = station; sigs[0].kind = kind; sigs[0].q0 = start;
+    sigs[0].need_im = true;   // the probe returns complex samples
+    sigs[0].memo = station * 2 + kind;   // a branch seen before is not guessed again
     if ((rc = queue_lazy_copies(e, kind))) return rc;
     if ((rc = preprocess(e, sigs))) return rc;
     if (power) *power = sigs[0].power0;

@@ -37,6 +37,7 @@ struct SigJob {
     double *partials;  // >= 2 * grid.x doubles of scratch for this job
     unsigned *counter; // zeroed ticket counter for this job
     int window;        // box-car window size (processor.go:270)
+    int window2;       // k_weak_fused only: the low-pass window that follows the high-pass of `window`
     int mode;          // BOX_LP / BOX_HP
     int sub_dc;        // subtract ST_DC_* from the input while loading
     int want_power;    // accumulate ST_POWER1 / ST_SCALE of the output
@@ -124,6 +125,14 @@ void launch_deinterleave(const float *c64, i64 n, float *re, float *im, cudaStre
 int boxcar_grid_x(i64 n);
 int stream_grid_x(i64 n);
 int unpack_selftest(cudaStream_t st);  // 0 ok: arithmetic unpack == host LUT for all 256 codes
+
+// ---- preprocess_weak.cu (EXTENDED mode, weak branch: two passes over the capture bytes)
+void launch_raw_stats(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);    // ST_POWER0 + ST_SUM_* + ST_DC_*
+void launch_weak_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st);   // bytes -> DC, HP(window), LP(window2), power
+int raw_stats_grid_x(i64 n);
+int weak_fused_max_half_wide();
+int weak_fused_max_half_small();
+int weak_unpack_selftest(cudaStream_t st);  // 0 ok: divide-free unpack == unpack_byte for all 256 codes
 
 // ---- preprocess_fast.cu
 void launch_demod_fused(const SigJob *d_jobs, int n_jobs, i64 max_n, int fast, cudaStream_t st);

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kCorrThreads) k_corr_brute(const PairJob *jobs
                 const double tv = (double)s_t[i];
 #pragma unroll
                 for (int k = 0; k < kLagsPerThread; k++)
-                    acc[k] = __dadd_rn(acc[k], __dmul_rn(tv, (double)s_s[i + threadIdx.x + k * kCorrThreads]));
+                    acc[k] = __fma_rn(tv, (double)s_s[i + threadIdx.x + k * kCorrThreads], acc[k]);   // the product is exact: one rounding either way
             }
         }
     }

@@ -260,6 +260,11 @@ constexpr int kCandChunk = 2048;   // template samples staged per step
 constexpr int kCandSpan = 2048;    // lag span served from shared memory
 constexpr int kCandGroup = 8;      // candidates evaluated per sweep
 
+// f32 x f32 widened to f64 is an exact product (48 significant bits), so one fused multiply-add rounds
+// exactly as the separate multiply and add of the statement (acc + (double)t * (double)s) would: bit-identical,
+// and one FP64-pipe instruction per (sample, candidate) instead of two.
+__device__ __forceinline__ double fma_exact(float t, float s, double acc) { return __fma_rn((double)t, (double)s, acc); }
+
 // Inner sweep over one staged chunk for NG candidates (NG = 1, 2, 4, 8: no wasted lanes
 // of FP64 work when the peak is sharp and only one lag needs the exact treatment).
 template <int NG, bool STAGED, bool F64>
@@ -277,7 +282,7 @@ __device__ __forceinline__ void cand_sweep(const float *s_t, const float *s_s, c
                 const i64 q = sbase + i + off[c];
                 sv = (q >= 0 && q < J.sl) ? __fmul_rn(J.s_re[q], sc_s) : 0.f;
             }
-            if (F64) acc[c] = __dadd_rn(acc[c], __dmul_rn((double)tv, (double)sv));
+            if (F64) acc[c] = fma_exact(tv, sv, acc[c]);
             else acc[c] = __dadd_rn(acc[c], (double)__fmul_rn(tv, sv));
         }
     }
@@ -320,7 +325,7 @@ __device__ __forceinline__ void cand_sweep_vec(const float *__restrict__ tp, con
         for (int k = 0; k < 4; k++) {
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                if (F64) acc[c] = __dadd_rn(acc[c], __dmul_rn((double)tv[k], (double)w[A + k + c]));
+                if (F64) acc[c] = fma_exact(tv[k], w[A + k + c], acc[c]);
                 else acc[c] = __dadd_rn(acc[c], (double)__fmul_rn(tv[k], w[A + k + c]));
             }
         }
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(kCandThreads) k_corr_candidates(const PairJob 
                 const float t = __fmul_rn(tp[i], sc_t);
                 for (int c = 0; c < ng; c++) {
                     const float q = __fmul_rn(sp[i + c], sc_s);
-                    acc[c] = exact_f64 ? __dadd_rn(acc[c], __dmul_rn((double)t, (double)q)) : __dadd_rn(acc[c], (double)__fmul_rn(t, q));
+                    acc[c] = exact_f64 ? fma_exact(t, q, acc[c]) : __dadd_rn(acc[c], (double)__fmul_rn(t, q));
                 }
             }
         } else if (ng <= 2 && s_first >= 0 && s_first + blk_len + span <= J.sl) {
@@ -439,8 +444,8 @@ __global__ void __launch_bounds__(kCandThreads) k_corr_candidates(const PairJob 
                 for (int u = 0; u < 4; u++) {
                     const float t = __fmul_rn(tv[u], sc_t), a = __fmul_rn(s0[u], sc_s), bb = __fmul_rn(s1[u], sc_s);
                     if (exact_f64) {
-                        acc[0] = __dadd_rn(acc[0], __dmul_rn((double)t, (double)a));
-                        if (ng == 2) acc[1] = __dadd_rn(acc[1], __dmul_rn((double)t, (double)bb));
+                        acc[0] = fma_exact(t, a, acc[0]);
+                        if (ng == 2) acc[1] = fma_exact(t, bb, acc[1]);
                     } else {
                         acc[0] = __dadd_rn(acc[0], (double)__fmul_rn(t, a));
                         if (ng == 2) acc[1] = __dadd_rn(acc[1], (double)__fmul_rn(t, bb));
@@ -451,8 +456,8 @@ __global__ void __launch_bounds__(kCandThreads) k_corr_candidates(const PairJob 
                 const float t = __fmul_rn(tp[i], sc_t), a = __fmul_rn(sp[i], sc_s);
                 const float bb = ng == 2 ? __fmul_rn(sp[i + o1], sc_s) : 0.f;
                 if (exact_f64) {
-                    acc[0] = __dadd_rn(acc[0], __dmul_rn((double)t, (double)a));
-                    if (ng == 2) acc[1] = __dadd_rn(acc[1], __dmul_rn((double)t, (double)bb));
+                    acc[0] = fma_exact(t, a, acc[0]);
+                    if (ng == 2) acc[1] = fma_exact(t, bb, acc[1]);
                 } else {
                     acc[0] = __dadd_rn(acc[0], (double)__fmul_rn(t, a));
                     if (ng == 2) acc[1] = __dadd_rn(acc[1], (double)__fmul_rn(t, bb));

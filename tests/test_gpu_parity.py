@@ -385,6 +385,58 @@ def test_extended_weak_branch_wide_boxcar():
         oracle.set_wide_boxcar_f64(0)
 
 
+def _weak_capture(block, seed):
+    """A capture whose every block is on the weak branch (power <= 0.001): small tones + noise around a DC offset."""
+    g = np.random.default_rng(seed)
+    n = 3 * block
+    t = np.arange(n)
+    x = 0.012 * np.exp(2j * np.pi * 0.013 * t) + 0.006 * (g.standard_normal(n) + 1j * g.standard_normal(n)) + (0.004 - 0.003j)
+    return quantise(x)
+
+
+@pytest.mark.parametrize("kind,start,W", [(0, 0, 70001), (0, 46000, 9000), (1, 0, 50000), (1, 137, 6144), (1, 49000, 1000),
+                                           (0, 49990, 20), (1, 5, 3), (1, 0, 12289)])
+def test_extended_weak_fused_pass_equals_the_four_kernel_chain(kind, start, W):
+    """EXTENDED mode, weak branch: k_raw_stats + k_weak_fused (two passes over the capture bytes, preprocess_weak.cu)
+    against the four kernels over complex planes they replace (use_fft = 6: k_power, k_unpack, k_boxcar_slide,
+    k_boxcar) and against the oracle's statement of the chain.  Views of both kinds: across the joint of the REF
+    signal's two blocks (50 000), ragged lengths, windows shorter than the filter, a tile boundary (6144)."""
+    block = 50000
+    raws = [_weak_capture(block, 900 + k) for k in range(3)]
+    oracle.set_seq_dc_limit(0)
+    oracle.set_wide_boxcar_f64(33)
+    try:
+        with T.Engine(T.MODE_EXTENDED, max_lag=8) as e, T.Engine(T.MODE_EXTENDED, max_lag=8, use_fft=6) as e4:
+            load_all(e, raws)
+            load_all(e4, raws)
+            for k in range(3):
+                e.preprocess(k, kind, start, W)    # the first call of a (station, kind) guesses "strong FM"; the
+                e4.preprocess(k, kind, start, W)   # branch is remembered from then on
+                l0, l4 = e.stats()["launches_total"], e4.stats()["launches_total"]
+                a, pa, ba = e.preprocess(k, kind, start, W)
+                b, pb, bb = e4.preprocess(k, kind, start, W)
+                assert ba == 2 and bb == 2
+                assert e.stats()["launches_total"] - l0 == e4.stats()["launches_total"] - l4 - 2   # two kernels instead of four
+                assert abs(pa - pb) <= 1e-15 * abs(pb)
+                # the window sums come from prefix sums of different tiles: a sample may differ in its last f32 bit
+                assert np.count_nonzero(a != b) <= max(1, W // 1000), np.count_nonzero(a != b)
+                assert np.max(np.abs(a - b)) <= 2e-6
+                sig = split(raws[k])[0 if kind == 0 else 1][start:start + W]
+                y, br = oracle.preprocess_binary(sig)
+                assert br == 2
+                assert np.count_nonzero(a != y) <= max(1, W // 1000), np.count_nonzero(a != y)
+                assert np.max(np.abs(a - y)) <= 2e-6
+            if W > 64:
+                ra = e.xcorr(kind, start, W, 1, 0)[0]
+                rb = e4.xcorr(kind, start, W, 1, 0)[0]
+                assert [int(x) for x in ra["lag"]] == [int(x) for x in rb["lag"]]
+                assert np.max(np.abs(ra["corr"] - rb["corr"])) <= CORR_TOL
+                assert sorted({int(x["branch"]) for x in e.xcorr_info(kind)[0]}) == [2]
+    finally:
+        oracle.set_seq_dc_limit(-1)
+        oracle.set_wide_boxcar_f64(0)
+
+
 @pytest.mark.parametrize("D", [4, 8])
 def test_extended_decimating_boxcar(D):
     """decimate = D (EXTENDED only, engine-defined): the binary's chain, then the mean of D

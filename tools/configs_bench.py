@@ -251,7 +251,7 @@ def cfg4(args, dev, res):
     W = 2_000_000
     st16 = ring_stations(16)
     d16, _ = delays_for(st16)
-    block = 4_000_000 if args.quick else 66_666_666
+    block = args.block or (4_000_000 if args.quick else 66_666_666)
     nw = block // W
     want16 = [int(d16[j] - d16[i]) for i in range(16) for j in range(i + 1, 16)]
     all_pairs = [(i, j) for i in range(16) for j in range(i + 1, 16)]
@@ -260,6 +260,8 @@ def cfg4(args, dev, res):
                  lambda: S.simulate_weak([tuple(x) for x in st16], tuple(bench.TX_LLH), 92300000.0, 10.0, 1000.0, block,
                                          seed=4242, device=dev)[0]))
     for cname, make in contents:
+        if args.content and args.content not in cname:
+            continue
         caps = make()
         with T.Engine(T.MODE_EXTENDED, n_stations=16, max_lag=2000) as e:
             for k in range(16):
@@ -326,6 +328,8 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", type=int, default=0, help="run one config only (1, 2, 3, 4 or 5)")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--content", default="", help="config 4: only the content whose name contains this (e.g. weak)")
+    ap.add_argument("--block", type=int, default=0, help="config 4: samples per capture block (default 66 666 666)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     res = []
