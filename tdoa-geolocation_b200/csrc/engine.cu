@@ -617,9 +617,39 @@ int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_stations, co
     CU(cudaMemcpyAsync(d_llh, stations_llh, (size_t)3 * n_stations * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(d_desc, grid_desc, 7 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(d_rd, range_diffs, (size_t)n_sets * rd_stride * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    launch_grid_cells(d_llh, n_stations, d_desc, nlat, nlon, d_rd, n_sets, rd_stride, d_cost, d_idx, d_out, d_scratch,
-                      e->stream);
-    count_launch(e, 2);
+    bool exhaustive = e->cfg.use_fft == 0;   // every cell by the statement (SOURCE mode's default; the fall-back below)
+    if (!exhaustive) {
+        // ranked: the expanded cost (16 FMA per cell and set) finds the cells that can hold the minimum, the
+        // statement settles them (solve.cu); the host's share is the table of c_k per set
+        const int T = grid_rank_tab_doubles();
+        std::vector<double> tab((size_t)n_sets * T);
+        for (int s = 0; s < n_sets; s++) grid_rank_row(range_diffs + (size_t)s * rd_stride, n_stations, tab.data() + (size_t)s * T);
+        double *d_tab = nullptr;
+        int *d_count = nullptr;
+        const int chunk = grid_rank_max_sets();
+        const int n_chunks = (n_sets + chunk - 1) / chunk;
+        void *d_rscratch = nullptr;
+        if ((rc = alloc_t(e, &d_tab, tab.size())) || (rc = alloc_t(e, &d_count, (size_t)n_chunks)) ||
+            (rc = alloc(e, &d_rscratch, grid_rank_scratch_bytes(nlat, nlon, std::min(n_sets, chunk)))))
+            return rc;
+        CU(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        std::vector<int> h_count((size_t)n_chunks, 0);
+        for (int c = 0; c < n_chunks; c++) {
+            const int s0 = c * chunk, ns = std::min(chunk, n_sets - s0);
+            launch_grid_ranked(d_llh, n_stations, d_desc, nlat, nlon, d_tab + (size_t)s0 * T, d_rd + (size_t)s0 * rd_stride, ns,
+                               rd_stride, d_cost + s0, d_idx + s0, d_out + 3 * s0, d_rscratch, d_count + c, e->stream);
+            count_launch(e, 5);
+        }
+        CU(cudaMemcpyAsync(h_count.data(), d_count, (size_t)n_chunks * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));   // tab and h_count are this frame's
+        for (int c = 0; c < n_chunks; c++)
+            if (h_count[c] > grid_rank_cand_cap(std::min(chunk, n_sets - c * chunk))) exhaustive = true;   // a plateau of ties
+    }
+    if (exhaustive) {
+        launch_grid_cells(d_llh, n_stations, d_desc, nlat, nlon, d_rd, n_sets, rd_stride, d_cost, d_idx, d_out, d_scratch,
+                          e->stream);
+        count_launch(e, 2);
+    }
     CU(cudaMemcpyAsync(out_llh, d_out, (size_t)3 * n_sets * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     if (out_cost) CU(cudaMemcpyAsync(out_cost, d_cost, (size_t)n_sets * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     if (out_index) CU(cudaMemcpyAsync(out_index, d_idx, (size_t)n_sets * sizeof(i64), cudaMemcpyDeviceToHost, e->stream));

@@ -183,5 +183,14 @@ void launch_grid_cells(const double *d_llh, int n_st, const double *d_grid_desc,
                        const double *d_rd, int n_sets, int rd_stride, double *d_best_cost, i64 *d_best_idx,
                        double *d_out_llh, void *d_scratch, cudaStream_t st);
 size_t grid_scratch_bytes(int n_st, int nlat, int nlon, int n_sets);
+// the same arg-min, ranked by the expanded cost (16 FMA per cell and set) and settled by the statement on the survivors
+void launch_grid_ranked(const double *d_llh, int n_st, const double *d_grid_desc, int nlat, int nlon, const double *d_tab,
+                        const double *d_rd, int n_sets, int rd_stride, double *d_best_cost, i64 *d_best_idx,
+                        double *d_out_llh, void *d_scratch, int *d_count, cudaStream_t st);
+size_t grid_rank_scratch_bytes(int nlat, int nlon, int n_sets);
+void grid_rank_row(const double *rd, int n_st, double *row);   // host: one set's row of d_tab
+int grid_rank_tab_doubles();
+int grid_rank_max_sets();
+int grid_rank_cand_cap(int n_sets);
 
 }  // namespace tdoa

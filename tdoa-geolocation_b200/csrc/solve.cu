@@ -504,6 +504,334 @@ void launch_solve_ls(const double *d_llh, int n_st, const double *d_rd, int n_se
                                                                        d_out_llh, d_rms, d_status, d_iters);
 }
 
+// ---------------------------------------------------------------- grid multilateration, ranked
+// The cost above spends 4 f64 operations per (cell, set, pair): 480 per cell and set at 16 stations.  Expanded
+// around q_k = r_k - r_0 (the cost only sees differences of ranges) it separates into a part of the cell, a
+// part of the set and ONE dot product that couples them:
+//     cost = [S sum q_k^2 - (sum q_k)^2]  -  2 sum_k q_k c_k  +  sum_p rd_p^2 ,
+//     c_k  = sum_{i<k} rd_ik - sum_{j>k} rd_kj      (S = stations; c_k and sum rd^2 come from the host, per set)
+// i.e. 16 fused multiply-adds per cell and set.  That form only RANKS cells (it cancels ~1e11 m^2 down to the
+// cost): its rounding error is bounded by tol = kGridKappa * (2 S sum q^2 + 4 max|q| sum|rd| + sum rd^2), so the
+// statement's arg-min x* satisfies f(x*) - tol(x*) <= min_x (f(x) + tol(x)) =: U.  k_grid_rank leaves per CTA and
+// set the minima of f - tol and f + tol; k_grid_bound takes U; k_grid_refine revisits only the CTAs that can
+// hold a cell under U and lists those cells (normally one per set); k_grid_exact evaluates the listed cells by the
+// statement itself -- pair by pair in its order -- and k_grid_pick runs the statement's selection (strict <,
+// lowest index on ties) on them.  The
+// index and the cost are the statement's, bit for bit; config 5 (10^6 cells x 64 sets) 7.5 ms -> see DESIGN.md.
+constexpr int kRankThreads = 128;
+constexpr int kRankCells = 2;                    // cells per thread
+constexpr int kRankSpan = kRankThreads * kRankCells;
+constexpr int kRankTab = 20;                     // doubles per set: c[16], sum rd^2, 2 sum |rd|, pad
+constexpr double kGridKappa = 4e-13;             // ~3600 ulp of the largest partial result: far above the ~200 roundings
+constexpr int kRankMaxSets = 512;                // per launch (shared memory: 64 B per set)
+
+struct RankCell {
+    double q[kMaxStations];
+    double a;      // S sum q^2 - (sum q)^2
+    double t0;     // 2 S sum q^2
+    double qmax;
+    bool live;
+};
+
+__device__ __forceinline__ void rank_cell(const GridDesc &G, const double *s_st, int n_st, i64 cell, i64 n_cells,
+                                          RankCell &c, double *r_out)
+{
+    c.live = cell < n_cells;
+    double r[kMaxStations];
+    if (c.live) {
+        const int a = (int)(cell / G.nlon), b = (int)(cell % G.nlon);
+        double x[3];
+        llh_to_ecef(G.lat0 + a * G.dlat, G.lon0 + b * G.dlon, G.elev, x);
+#pragma unroll
+        for (int k = 0; k < kMaxStations; k++) {
+            if (k < n_st) {
+                const double dx = x[0] - s_st[3 * k], dy = x[1] - s_st[3 * k + 1], dz = x[2] - s_st[3 * k + 2];
+                r[k] = sqrt(dx * dx + dy * dy + dz * dz);
+            } else {
+                r[k] = 0.0;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kMaxStations; k++) r[k] = 0.0;
+    }
+    double sq = 0.0, sl = 0.0, qm = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxStations; k++) {
+        const double q = k < n_st ? r[k] - r[0] : 0.0;
+        c.q[k] = q;
+        sq = __fma_rn(q, q, sq);
+        sl += q;
+        qm = fmax(qm, fabs(q));
+    }
+    c.a = (double)n_st * sq - sl * sl;
+    c.t0 = 2.0 * (double)n_st * sq;
+    c.qmax = qm;
+    if (r_out) {
+#pragma unroll
+        for (int k = 0; k < kMaxStations; k++) r_out[k] = r[k];
+    }
+}
+
+// f and tol of one cell for one set; tab = the set's row (c[16], B, C1)
+__device__ __forceinline__ void rank_eval(const RankCell &c, const double2 *__restrict__ tab, double &lo, double &hi)
+{
+    double mid = 0.0;
+#pragma unroll
+    for (int m = 0; m < kMaxStations / 2; m++) {
+        const double2 cc = __ldg(tab + m);
+        mid = __fma_rn(c.q[2 * m], cc.x, mid);
+        mid = __fma_rn(c.q[2 * m + 1], cc.y, mid);
+    }
+    const double2 bc = __ldg(tab + kMaxStations / 2);   // (sum rd^2, 2 sum |rd|)
+    const double f = __fma_rn(-2.0, mid, c.a + bc.x);
+    const double tol = kGridKappa * (c.t0 + __fma_rn(2.0 * c.qmax, bc.y, bc.x));
+    lo = f - tol;
+    hi = f + tol;
+}
+
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(kRankThreads) k_grid_rank(const double *llh, int n_st, const double *gdesc,
+                                                            const double *tab, int n_sets, double *cta_lo, double *cta_hi)
+{
+    extern __shared__ double sm[];   // [3 * 16] station ECEF, then [n_sets][4 warps] lo, [n_sets][4 warps] hi
+    double *s_st = sm;
+    double *s_lo = sm + 3 * kMaxStations;
+    double *s_hi = s_lo + (size_t)n_sets * (kRankThreads / 32);
+    const GridDesc G = read_desc(gdesc);
+    if (threadIdx.x < n_st) llh_to_ecef(llh[3 * threadIdx.x], llh[3 * threadIdx.x + 1], llh[3 * threadIdx.x + 2],
+                                        s_st + 3 * threadIdx.x);
+    __syncthreads();
+    const i64 n_cells = (i64)G.nlat * G.nlon;
+    const i64 base = (i64)blockIdx.x * kRankSpan + threadIdx.x;
+    RankCell c0, c1;
+    rank_cell(G, s_st, n_st, base, n_cells, c0, nullptr);
+    rank_cell(G, s_st, n_st, base + kRankThreads, n_cells, c1, nullptr);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    for (int set = 0; set < n_sets; set++) {
+        const double2 *row = reinterpret_cast<const double2 *>(tab + (size_t)set * kRankTab);
+        double lo0, hi0, lo1, hi1;
+        rank_eval(c0, row, lo0, hi0);
+        rank_eval(c1, row, lo1, hi1);
+        double lo = fmin(c0.live ? lo0 : inf, c1.live ? lo1 : inf);
+        double hi = fmin(c0.live ? hi0 : inf, c1.live ? hi1 : inf);
+        lo = warp_min(lo);
+        hi = warp_min(hi);
+        if (lane == 0) { s_lo[set * (kRankThreads / 32) + wid] = lo; s_hi[set * (kRankThreads / 32) + wid] = hi; }
+    }
+    __syncthreads();
+    for (int set = threadIdx.x; set < n_sets; set += kRankThreads) {
+        double lo = inf, hi = inf;
+#pragma unroll
+        for (int w = 0; w < kRankThreads / 32; w++) {
+            lo = fmin(lo, s_lo[set * (kRankThreads / 32) + w]);
+            hi = fmin(hi, s_hi[set * (kRankThreads / 32) + w]);
+        }
+        cta_lo[(size_t)set * gridDim.x + blockIdx.x] = lo;
+        cta_hi[(size_t)set * gridDim.x + blockIdx.x] = hi;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_grid_bound(const double *cta_hi, int n_cta, double *bound)
+{
+    __shared__ double s_m[8];
+    const int set = blockIdx.x;
+    double m = __longlong_as_double(0x7ff0000000000000ll);
+    for (int i = threadIdx.x; i < n_cta; i += 256) m = fmin(m, cta_hi[(size_t)set * n_cta + i]);
+    m = warp_min(m);
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; w++) m = fmin(m, s_m[w]);
+        bound[set] = m;
+    }
+}
+
+struct GridCand { i64 cell; double cost; int set; int pad; };
+
+__global__ void __launch_bounds__(kRankThreads) k_grid_refine(const double *llh, int n_st, const double *gdesc,
+                                                              const double *tab, const double *rd_all, int n_sets,
+                                                              int rd_stride, const double *cta_lo, const double *bound,
+                                                              GridCand *cands, int cap, int *n_cand)
+{
+    __shared__ double s_st[3 * kMaxStations];
+    __shared__ int s_sets[kRankMaxSets];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int set = threadIdx.x; set < n_sets; set += kRankThreads)
+        if (cta_lo[(size_t)set * gridDim.x + blockIdx.x] <= bound[set]) s_sets[atomicAdd(&s_n, 1)] = set;
+    __syncthreads();
+    const int ns = s_n;
+    if (ns == 0) return;   // nearly every CTA
+    const GridDesc G = read_desc(gdesc);
+    if (threadIdx.x < n_st) llh_to_ecef(llh[3 * threadIdx.x], llh[3 * threadIdx.x + 1], llh[3 * threadIdx.x + 2],
+                                        s_st + 3 * threadIdx.x);
+    __syncthreads();
+    const i64 n_cells = (i64)G.nlat * G.nlon;
+    for (int h = 0; h < kRankCells; h++) {
+        const i64 cell = (i64)blockIdx.x * kRankSpan + h * kRankThreads + threadIdx.x;
+        RankCell c;
+        rank_cell(G, s_st, n_st, cell, n_cells, c, nullptr);
+        if (!c.live) continue;
+        for (int u = 0; u < ns; u++) {
+            const int set = s_sets[u];
+            double lo, hi;
+            rank_eval(c, reinterpret_cast<const double2 *>(tab + (size_t)set * kRankTab), lo, hi);
+            if (!(lo <= bound[set])) continue;
+            const int slot = atomicAdd(n_cand, 1);
+            if (slot < cap) cands[slot] = GridCand{cell, 0.0, set, 0};
+        }
+    }
+}
+
+// The statement itself (k_grid_cost / orc_grid_solve) on the surviving (cell, set) pairs, one thread each: pair by
+// pair, in order, no contraction.  (Inside k_grid_refine the survivors of all sets sit in two or three
+// neighbouring cells, i.e. in one warp, and their 120-term chains ran one after the other: 0.41 ms of 0.75.)
+__global__ void __launch_bounds__(kRankThreads) k_grid_exact(const double *llh, int n_st, const double *gdesc,
+                                                             const double *rd_all, int rd_stride, GridCand *cands, int cap,
+                                                             const int *n_cand)
+{
+    __shared__ double s_st[3 * kMaxStations];
+    const int n = min(*n_cand, cap);
+    if ((int)(blockIdx.x * kRankThreads) >= n) return;
+    const GridDesc G = read_desc(gdesc);
+    if (threadIdx.x < n_st) llh_to_ecef(llh[3 * threadIdx.x], llh[3 * threadIdx.x + 1], llh[3 * threadIdx.x + 2],
+                                        s_st + 3 * threadIdx.x);
+    __syncthreads();
+    const int i = blockIdx.x * kRankThreads + threadIdx.x;
+    if (i >= n) return;
+    const GridCand g = cands[i];
+    RankCell c;
+    double r[kMaxStations];
+    rank_cell(G, s_st, n_st, g.cell, (i64)G.nlat * G.nlon, c, r);
+    const double *rd = rd_all + (size_t)g.set * rd_stride;
+    double cost = 0.0;
+    int p = 0;
+#pragma unroll
+    for (int a = 0; a < kMaxStations; a++) {
+#pragma unroll
+        for (int b = a + 1; b < kMaxStations; b++) {
+            if (b < n_st) {
+                const double e = (r[b] - r[a]) - rd[p];
+                cost = __dadd_rn(cost, __dmul_rn(e, e));
+                p++;
+            }
+        }
+    }
+    cands[i].cost = cost;
+}
+
+__global__ void __launch_bounds__(128) k_grid_pick(const double *gdesc, const GridCand *cands, int cap, const int *n_cand,
+                                                  double *best_cost, i64 *best_idx, double *out_llh)
+{
+    __shared__ double s_cost[128];
+    __shared__ i64 s_idx[128];
+    const int set = blockIdx.x;
+    const int n = min(*n_cand, cap);
+    double c = 0.0;
+    i64 ix = -1;
+    for (int i = threadIdx.x; i < n; i += 128) {
+        const GridCand g = cands[i];
+        if (g.set == set && (ix < 0 || g.cost < c || (g.cost == c && g.cell < ix))) { c = g.cost; ix = g.cell; }
+    }
+    s_cost[threadIdx.x] = c;
+    s_idx[threadIdx.x] = ix;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const i64 ia = s_idx[threadIdx.x], ib = s_idx[threadIdx.x + o];
+            const double ca = s_cost[threadIdx.x], cb = s_cost[threadIdx.x + o];
+            if (ib >= 0 && (ia < 0 || cb < ca || (cb == ca && ib < ia))) { s_cost[threadIdx.x] = cb; s_idx[threadIdx.x] = ib; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const GridDesc G = read_desc(gdesc);
+        const i64 bi = s_idx[0];
+        best_cost[set] = s_cost[0];
+        best_idx[set] = bi;
+        if (bi >= 0) {
+            out_llh[3 * set] = G.lat0 + (double)(bi / G.nlon) * G.dlat;
+            out_llh[3 * set + 1] = G.lon0 + (double)(bi % G.nlon) * G.dlon;
+            out_llh[3 * set + 2] = G.elev;
+        }
+    }
+}
+
+int grid_rank_tab_doubles() { return kRankTab; }
+int grid_rank_max_sets() { return kRankMaxSets; }
+int grid_rank_cand_cap(int n_sets) { return 64 * n_sets + 1024; }
+
+static int rank_n_cta(int nlat, int nlon)
+{
+    const i64 cells = (i64)nlat * nlon;
+    return (int)((cells + kRankSpan - 1) / kRankSpan);
+}
+
+// scratch: [n_sets][n_cta] lo, [n_sets][n_cta] hi, [n_sets] bound, candidates, counter
+size_t grid_rank_scratch_bytes(int nlat, int nlon, int n_sets)
+{
+    const size_t n_cta = (size_t)rank_n_cta(nlat, nlon);
+    return (2 * n_cta * (size_t)n_sets + (size_t)n_sets) * sizeof(double) +
+           (size_t)grid_rank_cand_cap(n_sets) * sizeof(GridCand) + 64;
+}
+
+// Host part of the expansion: the set's row of the table (c_k, sum rd^2, sum |c_k|) from its range differences.
+void grid_rank_row(const double *rd, int n_st, double *row)
+{
+    double c[kMaxStations] = {0.0};
+    double b = 0.0;
+    int p = 0;
+    for (int i = 0; i < n_st; i++)
+        for (int j = i + 1; j < n_st; j++, p++) {
+            c[j] += rd[p];
+            c[i] -= rd[p];
+            b += rd[p] * rd[p];
+        }
+    // the bound takes sum |rd| over the terms of every c_k (not sum |c_k|: a c_k that cancels keeps its rounding)
+    double c1 = 0.0;
+    p = 0;
+    for (int i = 0; i < n_st; i++)
+        for (int j = i + 1; j < n_st; j++, p++) c1 += 2.0 * (rd[p] < 0 ? -rd[p] : rd[p]);
+    for (int k = 0; k < kMaxStations; k++) row[k] = c[k];
+    row[16] = b;
+    row[17] = c1;
+    row[18] = row[19] = 0.0;
+}
+
+// n_sets <= grid_rank_max_sets().  d_count: one int, read back by the caller after the stream has drained --
+// more than grid_rank_cand_cap(n_sets) candidates means the table is incomplete (launch_grid_cells then).
+void launch_grid_ranked(const double *d_llh, int n_st, const double *d_grid_desc, int nlat, int nlon, const double *d_tab,
+                        const double *d_rd, int n_sets, int rd_stride, double *d_best_cost, i64 *d_best_idx,
+                        double *d_out_llh, void *d_scratch, int *d_count, cudaStream_t st)
+{
+    const int n_cta = rank_n_cta(nlat, nlon);
+    if (n_cta <= 0 || n_sets <= 0) return;
+    double *cta_lo = reinterpret_cast<double *>(d_scratch);
+    double *cta_hi = cta_lo + (size_t)n_cta * n_sets;
+    double *bound = cta_hi + (size_t)n_cta * n_sets;
+    GridCand *cands = reinterpret_cast<GridCand *>(bound + n_sets);
+    const int cap = grid_rank_cand_cap(n_sets);
+    cudaMemsetAsync(d_count, 0, sizeof(int), st);
+    const size_t smem = (3 * kMaxStations + 2 * (size_t)n_sets * (kRankThreads / 32)) * sizeof(double);
+    k_grid_rank<<<n_cta, kRankThreads, smem, st>>>(d_llh, n_st, d_grid_desc, d_tab, n_sets, cta_lo, cta_hi);
+    k_grid_bound<<<n_sets, 256, 0, st>>>(cta_hi, n_cta, bound);
+    k_grid_refine<<<n_cta, kRankThreads, 0, st>>>(d_llh, n_st, d_grid_desc, d_tab, d_rd, n_sets, rd_stride, cta_lo, bound, cands,
+                                                cap, d_count);
+    k_grid_exact<<<(cap + kRankThreads - 1) / kRankThreads, kRankThreads, 0, st>>>(d_llh, n_st, d_grid_desc, d_rd, rd_stride, cands,
+                                                                                   cap, d_count);
+    k_grid_pick<<<n_sets, 128, 0, st>>>(d_grid_desc, cands, cap, d_count, d_best_cost, d_best_idx, d_out_llh);
+}
+
 static int grid_n_cta(int nlat, int nlon)
 {
     const i64 cells = (i64)nlat * nlon;

@@ -533,6 +533,39 @@ def test_grid_multilateration(eng_binary):
         assert np.allclose(out[k], wl, atol=1e-12)
 
 
+@pytest.mark.parametrize("n_st,n_sets,nlat,nlon,dlat", [(3, 4, 90, 110, 0.002), (5, 7, 257, 129, 0.001), (16, 9, 300, 300, 0.0015),
+                                                        (16, 3, 64, 500, 0.0), (9, 700, 40, 37, 0.003), (2, 2, 50, 50, 0.002)])
+def test_grid_ranked_equals_exhaustive(n_st, n_sets, nlat, nlon, dlat):
+    """tdoa_grid ranks the cells by the expanded cost (16 FMA per cell and set, solve.cu) and lets the statement
+    settle the survivors; use_fft = 0 evaluates every cell by the statement.  Same index and the same cost, bit
+    for bit: noisy sets, noiseless sets (cost ~ 0 at the minimum), a grid of identical rows (dlat = 0: every
+    cell ties with nlat - 1 others and the lowest index has to win), more sets than one launch takes (512)."""
+    rng = np.random.default_rng(100 * n_st + n_sets)
+    st = np.array([[41.26 + rng.uniform(-0.2, 0.2), -96.02 + rng.uniform(-0.25, 0.25), rng.uniform(300, 400)] for _ in range(n_st)])
+    desc = [41.26 - 0.5 * nlat * dlat, -96.02 - 0.5 * nlon * 0.002, dlat, 0.002, nlat, nlon, 350.0]
+    rds = []
+    for k in range(n_sets):
+        tx = np.array([41.26 + rng.uniform(-0.05, 0.05), -96.02 + rng.uniform(-0.08, 0.08), 350.0])
+        r = [np.linalg.norm(oracle.llh_to_ecef(*tx) - oracle.llh_to_ecef(*s)) for s in st]
+        rd = np.array([r[j] - r[i] for i in range(n_st) for j in range(i + 1, n_st)])
+        rds.append(rd + rng.normal(0, [0.0, 15.0, 150.0][k % 3], rd.size))
+    rds = np.stack(rds)
+    with T.Engine(T.MODE_BINARY) as e, T.Engine(T.MODE_BINARY, use_fft=0) as ex:
+        l0, l1 = e.stats()["launches_total"], ex.stats()["launches_total"]
+        out, cost, idx = e.grid(st, desc, rds)
+        out0, cost0, idx0 = ex.grid(st, desc, rds)
+        launches = e.stats()["launches_total"] - l0, ex.stats()["launches_total"] - l1
+    assert launches == (5 * ((n_sets + 511) // 512), 2)   # ranked (five kernels per 512 sets), exhaustive (two)
+    assert idx.tolist() == idx0.tolist()
+    assert cost.view(np.uint64).tolist() == cost0.view(np.uint64).tolist()
+    assert np.array_equal(out, out0)
+    if dlat == 0.0:
+        assert all(int(i) < nlon for i in idx)   # first row wins the ties
+    k = 1
+    wi, wc, wl = oracle.grid_solve(st, rds[k], *desc[:4], int(desc[4]), int(desc[5]), desc[6])
+    assert idx[k] == wi and cost[k] == pytest.approx(wc, rel=1e-9)
+
+
 # ------------------------------------------------------------------ the reference-interface mirror
 def test_processor_mirror_stdout(tmp_path):
     raws, meta = load_golden("fm_strong")

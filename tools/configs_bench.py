@@ -303,24 +303,39 @@ def cfg5(args, dev, res):
     sets = 8 if args.quick else 64
     rds = rd[None, :] + rng.normal(0, 50e-9 * C, (sets, rd.size))
     desc = [41.26 - 0.25, -96.02 - 0.25, 0.0005, 0.0005, 1000, 1000, 400.0]
-    with T.Engine(T.MODE_BINARY) as e:
-        dt, (out, cost, idx) = timed(lambda: e.grid(st16, desc, rds), reps=args.reps)
+    with T.Engine(T.MODE_BINARY) as e, T.Engine(T.MODE_BINARY, use_fft=0) as ex:
+        dt, (out, cost, idx) = timed(lambda: e.grid(st16, desc, rds), reps=max(args.reps, 5))
+        dt_ex, (out_x, cost_x, idx_x) = timed(lambda: ex.grid(st16, desc, rds), reps=args.reps)   # every cell by the statement
         e.solve_ls(st16, rds, init_llh=out, dims=2)   # first call loads the kernel
         t0 = time.perf_counter()
         fine, rms, status, iters = e.solve_ls(st16, rds, init_llh=out, dims=2)
         dt_ls = time.perf_counter() - t0
+    same = bool(idx.tolist() == idx_x.tolist() and cost.view(np.uint64).tolist() == cost_x.view(np.uint64).tolist())
+    # the oracle's own arg-min in the 11 x 11 cells around the engine's cell, three sets
+    orc_ok = True
+    for k in (0, sets // 2, sets - 1):
+        a, b = divmod(int(idx[k]), 1000)
+        a0, b0 = max(a - 5, 0), max(b - 5, 0)
+        wi, wc, _ = oracle.grid_solve(st16, rds[k], desc[0] + a0 * desc[2], desc[1] + b0 * desc[3], desc[2], desc[3], 11, 11, desc[6])
+        orc_ok = orc_ok and (a0 + wi // 11, b0 + wi % 11) == (a, b) and abs(cost[k] - wc) <= 1e-9 * abs(wc)
     err_m = [float(np.linalg.norm(bench.llh_to_ecef(*o) - bench.llh_to_ecef(*bench.TX_LLH))) for o in out]
     err_ls = [float(np.linalg.norm(bench.llh_to_ecef(o[0], o[1], bench.TX_LLH[2]) - bench.llh_to_ecef(*bench.TX_LLH)))
               for o in fine]
+    fp64_peak = 148 * 64 * 1.965e9   # FP64 instructions per second (an FMA counts once)
     res.append({"config": f"5 (grid 1000x1000, 16 stations, {sets} sets)", "ms": dt * 1e3,
                 "cell_sets_per_s": 1e6 * sets / dt, "fixes_per_s": sets / dt, "median_err_m": float(np.median(err_m)),
+                "exhaustive_ms": dt_ex * 1e3, "same_index_and_cost_as_exhaustive": same,
+                "oracle": {"ok": bool(orc_ok), "what": "orc_grid_solve on the 11 x 11 cells around the engine's cell, sets 0, n/2, n-1: same cell, cost within 1e-9"},
                 "ls_refine_ms": dt_ls * 1e3, "ls_median_err_m": float(np.median(err_ls)), "ls_median_rms_m": float(np.median(rms)),
-                "roofline_stage": {"stage": "k_grid_cost", "bound": "fp64 alu (no HBM traffic to speak of: 24 B per cell-set out)",
-                                   "flop_per_cell_set": 16 * 33.0, "achieved_tflops": 1e6 * sets * 16 * 33.0 / dt / 1e12,
-                                   "peak_tflops": 37.0, "frac": 1e6 * sets * 16 * 33.0 / dt / 1e12 / 37.0,
-                                   "note": "16 stations x (3 sub, 3 mul-add, sqrt ~ 20) per cell + 120 pair residuals; peak = "
-                                           "148 SMs x 64 FP64 lanes x 2 x 1.965 GHz"},
-                "ok": bool(np.median(err_m) < 60.0 and int(status.max()) == 0)})
+                "roofline_stage": {"stage": "tdoa_grid call (k_grid_rank + k_grid_bound + k_grid_refine + k_grid_exact + k_grid_pick, copies and the one synchronisation included)",
+                                   "bound": "fp64 alu (no HBM traffic to speak of)",
+                                   "fp64_instr_per_cell_set": {"ranked": 30, "exhaustive": 480},
+                                   "achieved_ginstr_s": 1e6 * sets * 30 / dt / 1e9, "peak_ginstr_s": fp64_peak / 1e9,
+                                   "frac": 1e6 * sets * 30 / dt / fp64_peak,
+                                   "exhaustive_frac": 1e6 * sets * 480 / dt_ex / fp64_peak,
+                                   "note": "ranked: 16 FMA of the expanded cost + bound and minima per cell and set (solve.cu); exhaustive: "
+                                           "4 operations x 120 pairs; peak = 148 SMs x 64 FP64 lanes x 1.965 GHz; kernel-only times: profiles/"},
+                "ok": bool(np.median(err_m) < 60.0 and int(status.max()) == 0 and same and orc_ok)})
 
 
 def main():
