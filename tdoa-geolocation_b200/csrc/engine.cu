@@ -640,10 +640,16 @@ int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_stations, co
                                rd_stride, d_cost + s0, d_idx + s0, d_out + 3 * s0, d_rscratch, d_count + c, e->stream);
             count_launch(e, 5);
         }
+        std::vector<i64> h_idx((size_t)n_sets, 0);
         CU(cudaMemcpyAsync(h_count.data(), d_count, (size_t)n_chunks * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));   // tab and h_count are this frame's
+        CU(cudaMemcpyAsync(h_idx.data(), d_idx, (size_t)n_sets * sizeof(i64), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));   // tab, h_count and h_idx are this frame's
         for (int c = 0; c < n_chunks; c++)
             if (h_count[c] > grid_rank_cand_cap(std::min(chunk, n_sets - c * chunk))) exhaustive = true;   // a plateau of ties
+        // a set without a survivor (range differences that are not numbers: every comparison of the bound fails):
+        // the statement decides such sets too
+        for (int s = 0; s < n_sets; s++)
+            if (h_idx[s] < 0) exhaustive = true;
     }
     if (exhaustive) {
         launch_grid_cells(d_llh, n_stations, d_desc, nlat, nlon, d_rd, n_sets, rd_stride, d_cost, d_idx, d_out, d_scratch,

@@ -852,7 +852,7 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
                 Unit U;
                 U.grp = (int)gi; U.c0 = c0; U.lw = std::min(lw, K.n_lags - c0); U.seg = kFftN - lw;
                 U.n_seg = (int)std::max<i64>(1, (K.n_t + U.seg - 1) / U.seg);
-                U.spec_elems = (size_t)U.n_seg * n_pk * kFftN;
+                U.spec_elems = (size_t)U.n_seg * spec_seg_elems(2 * n_pk);
                 std::vector<int> idx;
                 for (int p : G.plans) {
                     const PairJob &J = plans[p]->job;
@@ -900,21 +900,45 @@ int run_fft(tdoa_engine *e, std::vector<CorrPlan *> &plans)
                     F.stride = U.seg; F.n_seg = U.n_seg;
                     if (tpl) { F.base = K.t_off; F.lo = K.t_off; F.hi = K.t_off + K.n_t; F.seg_len = U.seg; }
                     else { F.base = (i64)K.lag0 + U.c0; F.lo = 0; F.hi = K.sl; F.seg_len = kFftN; }
-                    F.out = spec + (size_t)m * kFftN; F.out_seg_stride = (i64)n_pk * kFftN;
+                    F.out = spec; F.row0 = 2 * m; F.n_rows = 2 * n_pk;
                     fj.push_back(F);
                 }
-                // pairs of the group, <= kSpecMaxPairs per accumulation job
-                for (size_t q0 = 0; q0 < G.plans.size(); q0 += kSpecMaxPairs) {
-                    SpecAccJob A{};
-                    A.spec = spec; A.n_pk_t = n_pk_t; A.n_pk_s = n_pk_s; A.n_seg = U.n_seg;
-                    A.n_pairs = (int)std::min<size_t>(kSpecMaxPairs, G.plans.size() - q0);
-                    for (int q = 0; q < A.n_pairs; q++) {
-                        const PairJob &J = plans[G.plans[q0 + q]]->job;
-                        A.pair_t[q] = (unsigned char)(std::find(G.rows.begin(), G.rows.end(), J.t_re) - G.rows.begin());
-                        A.pair_s[q] = (unsigned char)(std::find(G.cols.begin(), G.cols.end(), J.s_re) - G.cols.begin());
-                        A.spectrum[q] = sf[unit_fjob[u1][q0 + q]].spectrum;
+                // the pairs of the group as 4 x 4 register tiles over (template row, signal row); <= kSpecMaxTiles per job
+                {
+                    struct TileOut { int I, J; float2 *out[kSpecTile * kSpecTile]; };
+                    std::vector<TileOut> tl;
+                    for (size_t q = 0; q < G.plans.size(); q++) {
+                        const PairJob &J = plans[G.plans[q]]->job;
+                        const int tr = (int)(std::find(G.rows.begin(), G.rows.end(), J.t_re) - G.rows.begin());
+                        const int sc = (int)(std::find(G.cols.begin(), G.cols.end(), J.s_re) - G.cols.begin());
+                        const int I = tr / kSpecTile, Jb = sc / kSpecTile;
+                        TileOut *T = nullptr;
+                        for (auto &x : tl)
+                            if (x.I == I && x.J == Jb) T = &x;
+                        if (!T) {
+                            tl.push_back(TileOut{I, Jb, {}});
+                            T = &tl.back();
+                            for (auto &o : T->out) o = nullptr;
+                        }
+                        T->out[kSpecTile * (tr % kSpecTile) + sc % kSpecTile] = sf[unit_fjob[u1][q]].spectrum;
                     }
-                    aj.push_back(A);
+                    for (size_t t0 = 0; t0 < tl.size(); t0 += kSpecMaxTiles) {
+                        SpecAccJob A{};
+                        A.spec = spec; A.n_rows = 2 * n_pk; A.n_seg = U.n_seg;
+                        A.n_tiles = (int)std::min<size_t>(kSpecMaxTiles, tl.size() - t0);
+                        for (int t = 0; t < A.n_tiles; t++) {
+                            const TileOut &T = tl[t0 + t];
+                            for (int a = 0; a < kSpecTile; a++) {
+                                // rows beyond the group's stations: any valid row (their products have no output)
+                                const int tr = std::min<int>(T.I * kSpecTile + a, (int)G.rows.size() - 1);
+                                const int sc = std::min<int>(T.J * kSpecTile + a, (int)G.cols.size() - 1);
+                                A.t_row[t][a] = (unsigned char)tr;
+                                A.s_row[t][a] = (unsigned char)(2 * n_pk_t + sc);
+                            }
+                            for (int q = 0; q < kSpecTile * kSpecTile; q++) A.out[t][q] = T.out[q];
+                        }
+                        aj.push_back(A);
+                    }
                 }
                 used += U.spec_elems;
                 max_seg = std::max(max_seg, U.n_seg);

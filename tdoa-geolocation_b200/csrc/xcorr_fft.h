@@ -93,9 +93,15 @@ void launch_big_out(const BigOutJob *d_jobs, int n_jobs, const float2 *d_tw, cud
 // ---- many stations per window: each station-segment transformed once, pairs formed from the
 // parked spectra (xcorr_spec.cu)
 constexpr int kSpecMaxPacked = 16;   // packed transforms (two stations each) per job: templates + signals
-constexpr int kSpecMaxPairs = 128;   // pairs accumulated by one job
-constexpr int kSpecBins = 64;        // frequency bins per accumulation CTA
+constexpr int kSpecBins = 32;        // frequency bins per accumulation CTA (one warp per register tile)
+constexpr int kSpecChunks = 8192 / 2 / kSpecBins + 1;   // 129: the last chunk holds the Nyquist bin alone
 constexpr int kSpecMinPairs = 10;    // smaller groups stay with the 2 x 2 tiles
+constexpr int kSpecTile = 4;         // register tile: 4 template rows x 4 signal rows per thread
+constexpr int kSpecMaxTiles = 10;    // tiles per accumulation job (16 stations, all pairs: 10)
+
+// Parked spectra of one unit: [segment][chunk][row][kSpecBins] float2, row = 2 m + {0, 1} for the two stations of
+// packed transform m (templates first): what one accumulation CTA reads per segment is ONE contiguous block.
+__host__ __device__ inline size_t spec_seg_elems(int n_rows) { return (size_t)kSpecChunks * n_rows * kSpecBins; }
 
 struct SpecFftJob {     // one packed transform, all its segments
     const float *x0, *x1;   // planes: z = x0 + i x1
@@ -104,15 +110,15 @@ struct SpecFftJob {     // one packed transform, all its segments
     i64 lo, hi;             // plane indices outside [lo, hi) read as zero
     int seg_len;            // samples of a segment that carry data (the rest of the 8192 is zero)
     int n_seg;
-    float2 *out;            // spectrum of segment g at out + g * out_seg_stride
-    i64 out_seg_stride;     // floats2 between segments (n_packed * 8192)
+    float2 *out;            // parked spectra of the unit
+    int row0, n_rows;       // this transform fills rows row0 and row0 + 1 of n_rows
 };
 struct SpecAccJob {
-    const float2 *spec;     // [n_seg][n_pk_t + n_pk_s][8192]
-    int n_pk_t, n_pk_s, n_seg, n_pairs;
-    unsigned char pair_t[kSpecMaxPairs];   // template slot (0 .. 2 n_pk_t - 1) of each pair
-    unsigned char pair_s[kSpecMaxPairs];   // signal slot   (0 .. 2 n_pk_s - 1)
-    float2 *spectrum[kSpecMaxPairs];       // [4097] summed cross-spectrum conj(T) S of each pair
+    const float2 *spec;     // parked spectra of the unit
+    int n_rows, n_seg, n_tiles;
+    unsigned char t_row[kSpecMaxTiles][kSpecTile];   // rows of the tile's templates / signals (absent slots: any valid row)
+    unsigned char s_row[kSpecMaxTiles][kSpecTile];
+    float2 *out[kSpecMaxTiles][kSpecTile * kSpecTile];   // [4097] summed cross-spectrum conj(T_a) S_c of slot 4 a + c, or nullptr
 };
 int spec_setup();
 void launch_spec_fft(const SpecFftJob *d_jobs, int n_jobs, int max_seg, const float2 *d_tw, cudaStream_t st);

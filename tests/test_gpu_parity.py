@@ -566,6 +566,24 @@ def test_grid_ranked_equals_exhaustive(n_st, n_sets, nlat, nlon, dlat):
     assert idx[k] == wi and cost[k] == pytest.approx(wc, rel=1e-9)
 
 
+def test_grid_ranked_falls_back_on_sets_that_are_not_numbers():
+    """A set of range differences holding a NaN leaves the ranked path without a survivor (every comparison with
+    its bound fails); tdoa_grid then lets the exhaustive kernel decide, so both engines answer alike."""
+    st = np.vstack([STATION_LLH, STATION_LLH[:1] + [0.05, 0.07, 10.0]])
+    tx = np.array([41.25, -96.0, 350.0])
+    r = [np.linalg.norm(oracle.llh_to_ecef(*tx) - oracle.llh_to_ecef(*s)) for s in st]
+    rd = np.array([r[j] - r[i] for i in range(4) for j in range(i + 1, 4)])
+    rds = np.stack([rd, rd.copy(), rd + 5.0])
+    rds[1, 2] = np.nan
+    desc = [41.20, -96.06, 0.002, 0.002, 60, 70, 350.0]
+    with T.Engine(T.MODE_BINARY) as e, T.Engine(T.MODE_BINARY, use_fft=0) as ex:
+        out, cost, idx = e.grid(st, desc, rds)
+        out0, cost0, idx0 = ex.grid(st, desc, rds)
+    assert idx.tolist() == idx0.tolist()
+    assert cost.view(np.uint64)[[0, 2]].tolist() == cost0.view(np.uint64)[[0, 2]].tolist()
+    assert np.isnan(cost[1]) and np.isnan(cost0[1])
+
+
 # ------------------------------------------------------------------ the reference-interface mirror
 def test_processor_mirror_stdout(tmp_path):
     raws, meta = load_golden("fm_strong")
