@@ -1249,12 +1249,14 @@ long long demod_selftest(cudaStream_t st, unsigned *first_bad_out, int which, lo
 
 void launch_boxcar_small(const SigJob *d_jobs, int n_jobs, i64 max_n, cudaStream_t st)
 {
-    // all jobs together: 8 CTAs per SM, each walking its tiles with the next one's loads in flight.  (One CTA per
-    // tile for every job -- 62 528 single-tile CTAs for 64 windows of 2 000 000 samples -- left nothing for the
-    // software pipeline to hide: 2.35 TB/s where the three long signals of config 2 reach 5.)
+    // all jobs together: six waves of the 4 x 148 resident CTAs, each CTA walking its tiles with the next one's loads
+    // in flight.  (One CTA per tile for every job -- 62 528 single-tile CTAs for 64 windows of 2 000 000 samples --
+    // left nothing for the software pipeline to hide: 2.35 TB/s where the three long signals of config 2 reach 5;
+    // two waves of long CTAs cost those three signals 15 %: the tail.)
     const i64 tiles = (max_n + kTile - 1) / kTile;
-    i64 per_job = (148 * 8 + n_jobs - 1) / (n_jobs > 0 ? n_jobs : 1);
+    i64 per_job = (148 * 24 + n_jobs - 1) / (n_jobs > 0 ? n_jobs : 1);
     if (per_job < 1) per_job = 1;
+    if (per_job > 148 * 8) per_job = 148 * 8;
     const i64 gx = tiles < 1 ? 1 : (tiles > per_job ? per_job : tiles);   // <= fast_grid_x(max_n): the partial-sum slots suffice
     k_boxcar_small<<<dim3((unsigned)gx, n_jobs), kThreads, 0, st>>>(d_jobs);
 }
