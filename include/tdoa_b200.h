@@ -253,8 +253,15 @@ TDOA_API int tdoa_solve_binary(tdoa_engine *e, const double *stations_llh, int32
                                int32_t *n_valid, int32_t *n_iter, int32_t *converged, double *trace);
 
 /* Dense lat-lon grid multilateration (no reference equivalent): for each set the
- * cell minimising sum_{i<j} ((r_j - r_i) - rd_ij)^2.
- * grid_desc = {lat0, lon0, dlat, dlon, nlat, nlon, elev}. */
+ * cell minimising sum_{i<j} ((r_j - r_i) - rd_ij)^2, the terms added pair by pair in
+ * that order; ties go to the lowest linear index lat_index * nlon + lon_index.
+ * grid_desc = {lat0, lon0, dlat, dlon, nlat, nlon, elev}.
+ * The cells are RANKED by an expanded form of the cost (16 multiply-adds per cell and
+ * set) whose rounding error is bounded; only cells within that bound of the minimum are
+ * evaluated by the sum above, and the arg-min is taken over those values -- index and
+ * cost are what evaluating every cell gives, bit for bit (use_fft = 0 does evaluate
+ * every cell; a set holding a NaN, or a plateau of more than 64 ties per set, falls
+ * back to that).  range_diffs is read on the host as well (one pass, n_sets * pairs). */
 TDOA_API int tdoa_grid(tdoa_engine *e, const double *stations_llh, int32_t n_stations,
                        const double *grid_desc, const double *range_diffs, int32_t n_sets,
                        int32_t rd_stride, double *out_llh, double *out_cost, int64_t *out_index);
