@@ -16,8 +16,11 @@
 //
 // Arithmetic: EXTENDED mode's own statement of the chain (oracle: orc_preprocess_binary with
 // orc_set_wide_boxcar_f64) -- the 1001-tap window sum is the difference of two entries of an f64 prefix sum
-// of the staged tile, rounded once at the divide, exactly as k_boxcar_slide does it; the 5-tap low-pass is the
-// reference's sequential f32 sum and f32 divide, bit for bit; DC and power as in k_unpack / k_boxcar.
+// of the staged tile, rounded to f32 once after the divide, as k_boxcar_slide does it (full windows multiply by
+// RN(1 / taps) instead: an ulp of f64 from the quotient, 2^-29 of the f32 step, far inside what the prefix sums'
+// own rounding already moves); the 5-tap low-pass is the reference's sequential f32 sum and f32 divide, bit for
+// bit; DC and power as in k_unpack / k_boxcar.  Against the oracle's statement: at most a handful of samples per
+// 10^5 differ in their last f32 bit (tests/test_gpu_parity.py).
 // BINARY mode keeps the tap-by-tap kernels: only that walk reproduces the reference's f32 rounding chain.
 #include "kernels.h"
 
